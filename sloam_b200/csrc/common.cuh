@@ -1,0 +1,220 @@
+// common.cuh -- context, scratch layout and small device helpers shared by the
+// sm_100a kernels of the SLOAM hot path.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "../../include/sloam_b200.h"
+#include "proj_math.h"
+
+#define SLOAM_HD_FN __host__ __device__ __forceinline__
+
+namespace sb {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xFFFFFFFFu;
+constexpr int kMaxCells = 256;        // groundRadiiBins * groundThetaBins upper bound
+constexpr int kSplitTile = 2048;      // points per CTA in the project/split kernel
+constexpr int kMaxBigClusters = 1024; // clusters with > min_cluster_points per keyframe
+
+// Device copy of the parameters plus derived constants.
+struct DevParams {
+  sloam_params p;
+  int N;          // img_h * img_w
+  int B;          // ground cells
+  float fov_up, fov_down, fov;  // radians, float like the reference members
+  ProjGeom pg;
+  GroundGeom gg;
+};
+
+// Scratch owned by the context, sized for max_keyframes.
+struct Workspace {
+  // K1
+  int32_t *pix = nullptr;            // [K][N]
+  sloam_point *tree = nullptr;       // [K][N]
+  sloam_point *ground = nullptr;     // [K][N]
+  int32_t *ground_count = nullptr;   // [K]
+  uint8_t *ground_cell = nullptr;    // [K][N] polar cell of each ground point (255 = none)
+  int32_t *cell_count = nullptr;     // [K][kMaxCells]
+  unsigned long long *tile_state = nullptr; // [K][tiles] decoupled look-back
+  float *range_image = nullptr;      // [K][N] (when the caller passes none)
+  // K2
+  sloam_cell_plane *cells = nullptr; // [K][B]
+  sloam_point *cell_features = nullptr; // [K][B][Fg]
+  sloam_plane *planes_acc = nullptr; // [K][B] accepted planes, compact, sensor frame
+  int32_t *planes_acc_cell = nullptr;// [K][B] cell index of each accepted plane
+  int32_t *n_planes_acc = nullptr;   // [K]
+  unsigned long long *gscratch = nullptr; // [K][N] (z key, index) lists of oversized cells
+  double *qscratch = nullptr;        // [K][N][3] QR workspace of oversized cells
+  float *pscratch = nullptr;         // [K][N][3] point staging of oversized cells
+  // K3
+  int32_t *parent = nullptr;         // [K][N] union-find
+  uint8_t *cc_flags = nullptr;       // [K][N]
+  int32_t *csize = nullptr;          // [K][N] size at root
+  int32_t *big_roots = nullptr;      // [K][kMaxBigClusters] sorted root pixel of big clusters
+  int32_t *n_big = nullptr;          // [K]
+  int32_t *n_roots = nullptr;        // [K]
+  int32_t *big_rank = nullptr;       // [K][kMaxBigClusters] PCL label of each big cluster
+  int32_t *bbox = nullptr;           // [K][max_trees][4] cmin,cmax,rmin,rmax of each big cluster
+  int32_t *ccol_min = nullptr;       // [K][N] at root pixels: min column of the component
+  int32_t *ccol_max = nullptr;       // [K][N] at root pixels: max column
+  int32_t *crow_max = nullptr;       // [K][N] at root pixels: max row
+  int32_t *root_rank = nullptr;      // [K][N] at root pixels: PCL label (find_clusters entry)
+  int32_t *row_roots = nullptr;      // [K][H] number of component roots per row
+  sloam_vertex *slot_vertices = nullptr; // [K][max_trees][H] one candidate vertex per (cluster,row)
+  int32_t *vpool_count = nullptr;    // [K]
+  int32_t *vwork = nullptr;          // [K*max_trees*H] (k, slot, row) work items, packed
+  int32_t *overflow_list = nullptr;  // [K*max_trees*H] work items needing the wide path
+  int32_t *n_overflow = nullptr;     // [4] counters: [0] ticket/overflow, [1] n_vwork
+  int32_t *kf_flags = nullptr;       // [K] capacity-exceeded flags
+  sloam_tree *trees = nullptr;       // [K][max_trees]
+  int32_t *n_trees = nullptr;        // [K]
+  sloam_vertex *vertices = nullptr;  // [K][max_trees*max_tree_vertices]
+  sloam_point *vertex_points = nullptr; // [K][N]
+  // K4
+  sloam_tree_model *tree_models = nullptr; // [K][max_trees]
+  sloam_point *tree_features = nullptr;    // [K][max_trees][Ft]
+  int32_t *ransac_pairs = nullptr;   // draw tables per V (device copy)
+  int32_t *ransac_pairs_offset = nullptr; // [max_tree_vertices+1]
+  // K5/K6
+  sloam_cylinder *lm_cyl = nullptr;  // [K][max_trees] valid cylinders, compact (sensor frame)
+  int32_t *lm_src = nullptr;         // [K][max_trees] tree index of each compact cylinder
+  int32_t *n_lm = nullptr;           // [K]
+  int32_t *assoc_idx = nullptr;      // [K][max_trees]
+  double *assoc_dist = nullptr;      // [K][max_trees]
+  double *res_tree_feat = nullptr;   // [K][max_trees*Ft][3] matched tree features (sensor frame)
+  sloam_cylinder *res_tree_obj = nullptr; // [K][max_trees*Ft] matched map cylinder per feature
+  double *res_plane_feat = nullptr;  // [K][B*Fg][3]
+  sloam_plane *res_plane_obj = nullptr;   // [K][B*Fg]
+  int32_t *n_tree_res = nullptr;     // [K]
+  int32_t *n_plane_res = nullptr;    // [K]
+  uint8_t *optim_flags = nullptr;    // [K][2] treeCheck, groundCheck
+  uint8_t *kf_mode = nullptr;        // [K] 0 optimise, 1 first scan, 2 bailed out
+  double *lm_x = nullptr;            // [K][2][8] solver output parameters
+  int32_t *lm_info = nullptr;        // [K][2][2] iterations, termination
+  sloam_pose *curr_pose = nullptr;   // [K]
+  sloam_kf_result *results = nullptr;// [K]
+  int32_t *matches = nullptr;        // [K][max_trees]
+  sloam_cylinder *tm = nullptr;      // [K][max_trees]
+  int32_t *tm_id = nullptr;          // [K][max_trees]
+  sloam_plane *planes_out = nullptr; // [K][max_prev_planes]
+  int32_t *n_planes_out = nullptr;   // [K]
+};
+
+}  // namespace sb
+
+struct sloam_ctx {
+  int device = 0;
+  int max_k = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  sb::DevParams hp;              // host copy
+  sb::DevParams *dp = nullptr;   // device copy
+  sb::Workspace ws;
+  void *arena = nullptr;         // one allocation backing the workspace
+  size_t arena_bytes = 0;
+  int64_t launches = 0;
+  std::string err;
+  // host staging for the *_host entry points
+  void *pinned = nullptr;
+  size_t pinned_bytes = 0;
+  void *stage_dev = nullptr;
+  size_t stage_dev_bytes = 0;
+  int last_k = 0;
+  // partial results of split association (large maps), grown on demand
+  int32_t *assoc_part_i = nullptr;
+  double *assoc_part_d = nullptr;
+  size_t assoc_part_cap = 0;
+};
+
+namespace sb {
+
+inline int set_err(sloam_ctx *c, int code, const std::string &m) {
+  if (c) c->err = m;
+  return code;
+}
+
+#define SB_CUDA(ctx, call)                                                        \
+  do {                                                                            \
+    cudaError_t e__ = (call);                                                     \
+    if (e__ != cudaSuccess)                                                       \
+      return sb::set_err(ctx, SLOAM_E_CUDA,                                       \
+                         std::string(#call) + ": " + cudaGetErrorString(e__));    \
+  } while (0)
+
+#define SB_LAUNCH_CHECK(ctx)                                                      \
+  do {                                                                            \
+    (ctx)->launches++;                                                            \
+    cudaError_t e__ = cudaGetLastError();                                         \
+    if (e__ != cudaSuccess)                                                       \
+      return sb::set_err(ctx, SLOAM_E_CUDA,                                       \
+                         std::string("kernel launch: ") + cudaGetErrorString(e__)); \
+  } while (0)
+
+// ---- float helpers with the reference's operation order -----------------
+// Eigen Vector3f::norm / squaredNorm: x^2 + (y^2 + z^2)  (Redux.h unroller)
+SLOAM_HD_FN float sqnorm3f(float dx, float dy, float dz) { return dx * dx + (dy * dy + dz * dz); }
+SLOAM_HD_FN float dist3f(float ax, float ay, float az, float bx, float by, float bz) {
+  return sqrtf(sqnorm3f(ax - bx, ay - by, az - bz));
+}
+SLOAM_HD_FN double dot3d(const double *a, const double *b) {
+  return a[0] * b[0] + (a[1] * b[1] + a[2] * b[2]);
+}
+
+// order-preserving map float -> uint32 (for sorting / selection keys)
+__device__ __forceinline__ uint32_t float_key(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// ---- quaternion / pose (double) -------------------------------------------
+SLOAM_HD_FN void q_rotate(const double q[4] /*x y z w*/, const double v[3], double out[3]) {
+  // Eigen QuaternionBase::_transformVector
+  double uvx = q[1] * v[2] - q[2] * v[1];
+  double uvy = q[2] * v[0] - q[0] * v[2];
+  double uvz = q[0] * v[1] - q[1] * v[0];
+  uvx += uvx; uvy += uvy; uvz += uvz;
+  out[0] = v[0] + q[3] * uvx + (q[1] * uvz - q[2] * uvy);
+  out[1] = v[1] + q[3] * uvy + (q[2] * uvx - q[0] * uvz);
+  out[2] = v[2] + q[3] * uvz + (q[0] * uvy - q[1] * uvx);
+}
+SLOAM_HD_FN void pose_apply(const sloam_pose &T, const double v[3], double out[3]) {
+  q_rotate(T.q, v, out);
+  out[0] += T.t[0]; out[1] += T.t[1]; out[2] += T.t[2];
+}
+SLOAM_HD_FN void q_to_matrix(const double q[4], double R[9]) {
+  const double tx = 2 * q[0], ty = 2 * q[1], tz = 2 * q[2];
+  const double twx = tx * q[3], twy = ty * q[3], twz = tz * q[3];
+  const double txx = tx * q[0], txy = ty * q[0], txz = tz * q[0];
+  const double tyy = ty * q[1], tyz = tz * q[1], tzz = tz * q[2];
+  R[0] = 1 - (tyy + tzz); R[1] = txy - twz;       R[2] = txz + twy;
+  R[3] = txy + twz;       R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy;       R[7] = tyz + twx;       R[8] = 1 - (txx + tyy);
+}
+// plane' = (T^-1)^T plane : n' = R n, d' = d - n'.t   (Plane::project, plane.cpp:168)
+SLOAM_HD_FN void plane_transform(const sloam_pose &T, const double pl[4], double out[4]) {
+  double n[3] = {pl[0], pl[1], pl[2]}, rn[3];
+  q_rotate(T.q, n, rn);
+  out[0] = rn[0]; out[1] = rn[1]; out[2] = rn[2];
+  out[3] = pl[3] - (rn[0] * T.t[0] + rn[1] * T.t[1] + rn[2] * T.t[2]);
+}
+
+}  // namespace sb

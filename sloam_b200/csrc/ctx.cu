@@ -1,0 +1,321 @@
+// ctx.cu -- context life cycle, parameters and scratch arena of the C ABI.
+#include <algorithm>
+#include <cstring>
+#include <random>
+#include <vector>
+
+#include "common.cuh"
+
+namespace sb {
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Bump {
+  char *base;
+  size_t off = 0;
+  template <typename T>
+  void take(T *&ptr, size_t count) {
+    off = align_up(off, 256);
+    if (base) ptr = reinterpret_cast<T *>(base + off);
+    off += sizeof(T) * count;
+  }
+};
+
+// PCL sampling stream (SampleConsensusModel::drawIndexSample, seed 12345,
+// uniform_int<>(0, INT_MAX) over mt19937 == mt() >> 1; the shuffled index
+// vector persists across draws).  A fresh model is built per tree
+// (sloam/src/objects/cylinder.cpp:116-124), so the draw sequence depends only
+// on the number of vertices V.  Precomputed on the host per V.
+static void ransac_table(int V, int n_draws, std::vector<int32_t> &out) {
+  std::mt19937 rng(12345u);
+  std::vector<int> shuf(V);
+  for (int i = 0; i < V; ++i) shuf[i] = i;
+  for (int t = 0; t < n_draws; ++t) {
+    for (unsigned i = 0; i < 2; ++i) {
+      const unsigned r = (unsigned)(rng() >> 1);
+      std::swap(shuf[i], shuf[i + (r % ((unsigned)V - i))]);
+    }
+    out.push_back(shuf[0]);
+    out.push_back(shuf[1]);
+  }
+}
+
+int ransac_draws_per_tree(const sloam_params &p) {
+  // hypotheses + head-room for rejected (not "good") draws
+  const int hyp = p.ransac_fixed_hypotheses > 0 ? p.ransac_fixed_hypotheses : p.ransac_max_iterations + 1;
+  return hyp + 64;
+}
+
+static void layout(sloam_ctx *c, Bump &b) {
+  Workspace &w = c->ws;
+  const sloam_params &p = c->hp.p;
+  const size_t K = (size_t)c->max_k, N = (size_t)c->hp.N, B = (size_t)c->hp.B;
+  const size_t T = (size_t)p.max_trees, H = (size_t)p.img_h;
+  const size_t tiles = (N + kSplitTile - 1) / kSplitTile;
+  b.take(w.pix, K * N);
+  b.take(w.tree, K * N);
+  b.take(w.ground, K * N);
+  b.take(w.ground_count, K);
+  b.take(w.ground_cell, K * N);
+  b.take(w.cell_count, K * kMaxCells);
+  b.take(w.tile_state, K * tiles);
+  b.take(w.range_image, K * N);
+  b.take(w.cells, K * B);
+  b.take(w.cell_features, K * B * (size_t)p.numGroundFeatures);
+  b.take(w.planes_acc, K * B);
+  b.take(w.planes_acc_cell, K * B);
+  b.take(w.n_planes_acc, K);
+  b.take(w.gscratch, K * N);
+  b.take(w.qscratch, K * N * 3);
+  b.take(w.pscratch, K * N * 3);
+  b.take(w.parent, K * N);
+  b.take(w.cc_flags, K * N);
+  b.take(w.csize, K * N);
+  b.take(w.big_roots, K * T);
+  b.take(w.n_big, K);
+  b.take(w.n_roots, K);
+  b.take(w.big_rank, K * T);
+  b.take(w.bbox, K * T * 4);
+  b.take(w.ccol_min, K * N);
+  b.take(w.ccol_max, K * N);
+  b.take(w.crow_max, K * N);
+  b.take(w.root_rank, K * N);
+  b.take(w.row_roots, K * H);
+  b.take(w.slot_vertices, K * T * H);
+  b.take(w.vpool_count, K);
+  b.take(w.vwork, K * T * H);
+  b.take(w.overflow_list, K * T * H);
+  b.take(w.n_overflow, 4);
+  b.take(w.kf_flags, K);
+  b.take(w.trees, K * T);
+  b.take(w.n_trees, K);
+  b.take(w.vertices, K * T * (size_t)p.max_tree_vertices);
+  b.take(w.vertex_points, K * N);
+  b.take(w.tree_models, K * T);
+  b.take(w.tree_features, K * T * (size_t)p.featuresPerTree);
+  b.take(w.ransac_pairs, (size_t)(p.max_tree_vertices + 1) * ransac_draws_per_tree(p) * 2);
+  b.take(w.ransac_pairs_offset, (size_t)p.max_tree_vertices + 2);
+  b.take(w.lm_cyl, K * T);
+  b.take(w.lm_src, K * T);
+  b.take(w.n_lm, K);
+  b.take(w.assoc_idx, K * T);
+  b.take(w.assoc_dist, K * T);
+  b.take(w.res_tree_feat, K * T * (size_t)p.featuresPerTree * 3);
+  b.take(w.res_tree_obj, K * T * (size_t)p.featuresPerTree);
+  b.take(w.res_plane_feat, K * B * (size_t)p.numGroundFeatures * 3);
+  b.take(w.res_plane_obj, K * B * (size_t)p.numGroundFeatures);
+  b.take(w.n_tree_res, K);
+  b.take(w.n_plane_res, K);
+  b.take(w.optim_flags, K * 2);
+  b.take(w.kf_mode, K);
+  b.take(w.lm_x, K * 16);
+  b.take(w.lm_info, K * 4);
+  b.take(w.curr_pose, K);
+  b.take(w.results, K);
+  b.take(w.matches, K * T);
+  b.take(w.tm, K * T);
+  b.take(w.tm_id, K * T);
+  b.take(w.planes_out, K * (size_t)p.max_prev_planes);
+  b.take(w.n_planes_out, K);
+}
+
+static int validate(const sloam_params &p, std::string &why) {
+  if (p.img_h <= 0 || p.img_w <= 0) { why = "img_h/img_w must be positive"; return -1; }
+  if ((long long)p.img_h * p.img_w >= (1ll << 24)) { why = "image larger than 2^24 pixels"; return -1; }
+  if (p.groundRadiiBins <= 0 || p.groundThetaBins <= 0 ||
+      p.groundRadiiBins * p.groundThetaBins > kMaxCells - 1) { why = "ground bins out of range"; return -1; }
+  if (!(p.groundRetainThresh > 0.0 && p.groundRetainThresh <= 1.0)) {
+    why = "groundRetainThresh must be in (0,1] (the reference erases past end() above 1, SURVEY B-5)";
+    return -1;
+  }
+  if (p.numGroundFeatures <= 0 || p.featuresPerTree <= 0) { why = "feature counts must be positive"; return -1; }
+  if (p.max_tree_vertices < 3 || p.max_tree_vertices > 64) { why = "max_tree_vertices must be in [3,64]"; return -1; }
+  if (p.min_tree_vertices < 2) { why = "min_tree_vertices must be >= 2 (cylinder.cpp:11,78 index vertices[2])"; return -1; }
+  if (p.max_trees <= 0 || p.max_map_models <= 0) { why = "capacities must be positive"; return -1; }
+  if (p.max_prev_planes < p.groundRadiiBins * p.groundThetaBins) { why = "max_prev_planes < number of ground cells"; return -1; }
+  if (p.do_destagger) { why = "do_destagger is not implemented (sim.yaml:5 uses false)"; return -1; }
+  if (p.ransac_fixed_hypotheses < 0 || p.ransac_max_iterations <= 0) { why = "ransac counts"; return -1; }
+  return 0;
+}
+
+static void derive(DevParams &d) {
+  const sloam_params &p = d.p;
+  d.N = p.img_h * p.img_w;
+  d.B = p.groundRadiiBins * p.groundThetaBins;
+  // Segmentation constructor, inference.cpp:7-9: double expressions stored to float members
+  d.fov_up = (float)((double)p.fov_up_deg / 180.0 * 3.14159265358979323846);
+  d.fov_down = (float)((double)p.fov_down_deg / 180.0 * 3.14159265358979323846);
+  d.fov = fabsf(d.fov_down) + fabsf(d.fov_up);
+  d.pg.fov_down_abs = fabsf(d.fov_down);
+  d.pg.fov = d.fov;
+  d.pg.Wf = (float)p.img_w;
+  d.pg.Hf = (float)p.img_h;
+  // sloam.cpp:348-352
+  d.gg.max_dist = p.maxGroundLidarDist;
+  d.gg.min_dist = p.minGroundLidarDist;
+  d.gg.radial_step = p.maxGroundLidarDist / (double)p.groundRadiiBins;
+  d.gg.theta_step = 2 * 3.14159265 / (double)p.groundThetaBins;
+  d.gg.RB = p.groundRadiiBins;
+  d.gg.TB = p.groundThetaBins;
+}
+
+static int upload_tables(sloam_ctx *c) {
+  const sloam_params &p = c->hp.p;
+  const int draws = ransac_draws_per_tree(p);
+  std::vector<int32_t> pairs, offs(p.max_tree_vertices + 2, 0);
+  for (int V = 0; V <= p.max_tree_vertices; ++V) {
+    offs[V] = (int32_t)(pairs.size() / 2);
+    if (V >= 2) ransac_table(V, draws, pairs);
+    else pairs.resize(pairs.size() + (size_t)2 * draws, 0);
+  }
+  offs[p.max_tree_vertices + 1] = (int32_t)(pairs.size() / 2);
+  SB_CUDA(c, cudaMemcpyAsync(c->ws.ransac_pairs, pairs.data(), pairs.size() * sizeof(int32_t),
+                             cudaMemcpyHostToDevice, c->stream));
+  SB_CUDA(c, cudaMemcpyAsync(c->ws.ransac_pairs_offset, offs.data(), offs.size() * sizeof(int32_t),
+                             cudaMemcpyHostToDevice, c->stream));
+  SB_CUDA(c, cudaMemcpyAsync(c->dp, &c->hp, sizeof(DevParams), cudaMemcpyHostToDevice, c->stream));
+  SB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return SLOAM_OK;
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" {
+
+const char *sloam_b200_version(void) { return "sloam_b200 0.1 (sm_100a)"; }
+
+void sloam_b200_default_params(sloam_params *p) {
+  std::memset(p, 0, sizeof *p);
+  p->img_h = 64; p->img_w = 1024;
+  p->fov_up_deg = 22.5f; p->fov_down_deg = -22.5f;  // sloamNode.cpp:77,81
+  p->do_destagger = 0;                              // params/sim.yaml:5
+  // params/sloam.yaml over the code defaults of sloamNode.cpp:57-128
+  p->scansPerSweep = 1;
+  p->minTreeModels = 5; p->minGroundModels = 36;
+  p->maxLidarDist = 20; p->maxGroundLidarDist = 25; p->minGroundLidarDist = 5;
+  p->twoStepOptim = 1;
+  p->groundRadiiBins = 2; p->groundThetaBins = 18;
+  p->groundRetainThresh = 0.05;
+  p->groundMatchThresh = 2.0; p->roughTreeMatchThresh = 3.0;
+  p->treeMatchThresh = 0.5;
+  p->maxTreeRadius = 0.3; p->maxAxisTheta = 10; p->maxFocusOutlierDistance = 0.5;
+  p->AddNewTreeThreshDist = 1.5;
+  p->featuresPerTree = 20; p->numGroundFeatures = 5;
+  p->defaultTreeRadius = 0.2;
+  p->max_dist_to_centroid = 0.2f;
+  p->cluster_dist_thresh = 1.0f;
+  p->min_cluster_points = 80; p->min_vertex_points = 3;
+  p->min_tree_vertices = 16; p->max_tree_vertices = 56;
+  p->ransac_threshold = 0.25; p->ransac_max_iterations = 50; p->ransac_probability = 0.99;
+  p->ransac_fixed_hypotheses = 0;
+  p->min_tree_height_sq = 1.5; p->root_plane_max_dist = 2.0;
+  p->plane_match_thresh = 1.0; p->ground_angle_tol = 0.1; p->huber_delta = 0.1;
+  p->lm_max_iterations = 50;
+  p->max_trees = 512; p->max_map_models = 512; p->max_prev_planes = 64;
+}
+
+int sloam_b200_create(const sloam_params *p, int device, int max_keyframes, sloam_ctx **out) {
+  if (!p || !out || max_keyframes <= 0) return SLOAM_E_INVALID;
+  *out = nullptr;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || device < 0 || device >= n_dev)
+    return SLOAM_E_NODEVICE;  // no CPU fallback
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SLOAM_E_NODEVICE;
+  if (prop.major < 10) return SLOAM_E_NODEVICE;  // built for sm_100a only
+  std::string why;
+  if (validate(*p, why) != 0) return SLOAM_E_INVALID;
+  sloam_ctx *c = new (std::nothrow) sloam_ctx();
+  if (!c) return SLOAM_E_NOMEM;
+  c->device = device;
+  c->max_k = max_keyframes;
+  c->sm_count = prop.multiProcessorCount;
+  c->hp.p = *p;
+  derive(c->hp);
+  if (cudaSetDevice(device) != cudaSuccess) { delete c; return SLOAM_E_CUDA; }
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return SLOAM_E_CUDA; }
+  c->own_stream = true;
+  Bump dry{nullptr};
+  layout(c, dry);
+  c->arena_bytes = align_up(dry.off, 256);
+  if (cudaMalloc(&c->arena, c->arena_bytes) != cudaSuccess) {
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return SLOAM_E_NOMEM;
+  }
+  Bump real{(char *)c->arena};
+  layout(c, real);
+  if (cudaMalloc((void **)&c->dp, sizeof(DevParams)) != cudaSuccess) {
+    cudaFree(c->arena); cudaStreamDestroy(c->stream); delete c;
+    return SLOAM_E_NOMEM;
+  }
+  const int rc = upload_tables(c);
+  if (rc != SLOAM_OK) { sloam_b200_destroy(c); return rc; }
+  *out = c;
+  return SLOAM_OK;
+}
+
+void sloam_b200_destroy(sloam_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  if (c->arena) cudaFree(c->arena);
+  if (c->dp) cudaFree(c->dp);
+  if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->stage_dev) cudaFree(c->stage_dev);
+  if (c->assoc_part_i) cudaFree(c->assoc_part_i);
+  if (c->assoc_part_d) cudaFree(c->assoc_part_d);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int sloam_b200_set_params(sloam_ctx *c, const sloam_params *p) {
+  if (!c || !p) return SLOAM_E_INVALID;
+  std::string why;
+  if (validate(*p, why) != 0) return set_err(c, SLOAM_E_INVALID, why);
+  const sloam_params &o = c->hp.p;
+  // anything that sizes the arena must not grow
+  if (p->img_h * p->img_w > o.img_h * o.img_w || p->img_h > o.img_h ||
+      p->groundRadiiBins * p->groundThetaBins > o.groundRadiiBins * o.groundThetaBins ||
+      p->numGroundFeatures > o.numGroundFeatures || p->featuresPerTree > o.featuresPerTree ||
+      p->max_trees > o.max_trees || p->max_tree_vertices > o.max_tree_vertices ||
+      p->max_prev_planes > o.max_prev_planes ||
+      ransac_draws_per_tree(*p) > ransac_draws_per_tree(o))
+    return set_err(c, SLOAM_E_INVALID, "set_params: capacities/image size must not grow; create a new context");
+  // keep the arena layout of the creation-time parameters: only values change
+  sloam_params np = *p;
+  c->hp.p = np;
+  derive(c->hp);
+  return upload_tables(c);
+}
+
+int sloam_b200_get_params(const sloam_ctx *c, sloam_params *p) {
+  if (!c || !p) return SLOAM_E_INVALID;
+  *p = c->hp.p;
+  return SLOAM_OK;
+}
+
+int sloam_b200_set_stream(sloam_ctx *c, void *s) {
+  if (!c) return SLOAM_E_INVALID;
+  if (c->own_stream && c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+  if (s) { c->stream = (cudaStream_t)s; c->own_stream = false; }
+  else {
+    SB_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+  }
+  return SLOAM_OK;
+}
+
+int sloam_b200_sync(sloam_ctx *c) {
+  if (!c) return SLOAM_E_INVALID;
+  SB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return SLOAM_OK;
+}
+
+const char *sloam_b200_last_error(const sloam_ctx *c) { return c ? c->err.c_str() : "null context"; }
+int64_t sloam_b200_kernel_launches(const sloam_ctx *c) { return c ? c->launches : 0; }
+int64_t sloam_b200_workspace_bytes(const sloam_ctx *c) { return c ? (int64_t)c->arena_bytes : 0; }
+
+}  // extern "C"

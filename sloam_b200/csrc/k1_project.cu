@@ -1,0 +1,281 @@
+// k1_project.cu -- stage a1 + a2: spherical projection, closest-point-wins
+// range image, mask gather, dense tree cloud and order-preserving ground
+// compaction in ONE pass over the points.
+//
+// Replaces Segmentation::_doProjection (inference.cpp:80-165) and the two
+// Segmentation::maskCloud calls of SLOAMNode::run (inference.cpp:230-273,
+// sloamNode.cpp:212,215).  Also tags every ground point with its polar cell
+// (sloam::binGroundPoints, sloam.cpp:339-358) while it is in registers, so
+// stage a3 never re-reads the cloud to bin it.
+//
+// HBM-bound streaming kernel.  Algorithmic bytes per keyframe: 16N points +
+// 1N mask + 4N pix + 4N range image + 16N tree cloud + 16G ground = 41N + 16G
+// (+ 1G cell tags).  One CTA = one tile of 2048 consecutive points of one
+// keyframe; float4 loads/stores are fully coalesced; the ground points of a
+// tile are staged in shared memory in input order and written out as one
+// contiguous run whose base comes from a decoupled look-back scan over the
+// tiles of the keyframe (single pass, no second read of the input).
+#include "common.cuh"
+
+namespace sb {
+
+constexpr int kThreads = 256;
+constexpr int kRounds = kSplitTile / kThreads;  // 8
+
+// tile_state word: [63:62] flag (0 empty, 1 aggregate, 2 inclusive prefix), [31:0] value
+__device__ __forceinline__ unsigned long long pack_state(unsigned flag, unsigned v) {
+  return ((unsigned long long)flag << 62) | v;
+}
+
+template <bool DO_PROJECT, bool DO_SPLIT>
+__global__ void __launch_bounds__(kThreads)
+project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point *__restrict__ points,
+                     const uint8_t *__restrict__ mask, int32_t *__restrict__ pix_io,
+                     unsigned *__restrict__ range_bits, sloam_point *__restrict__ tree,
+                     sloam_point *__restrict__ ground, int32_t *__restrict__ ground_count,
+                     uint8_t *__restrict__ ground_cell, int32_t *__restrict__ cell_count,
+                     unsigned long long *__restrict__ tile_state, unsigned *__restrict__ ticket,
+                     int ground_stride) {
+  __shared__ sloam_point s_ground[DO_SPLIT ? kSplitTile : 1];
+  __shared__ uint8_t s_cell[DO_SPLIT ? kSplitTile : 1];
+  __shared__ int s_hist[DO_SPLIT ? kMaxCells : 1];
+  __shared__ int s_warp[kThreads / 32];
+  __shared__ unsigned s_tile;
+  __shared__ int s_base;
+
+  const int N = dp->N;
+  const int tiles = (N + kSplitTile - 1) / kSplitTile;
+  // tiles are handed out in scheduling order so the look-back never waits on
+  // a CTA that has not started
+  if (threadIdx.x == 0) s_tile = DO_SPLIT ? atomicAdd(ticket, 1u) : blockIdx.x;
+  if (DO_SPLIT)
+    for (int c = threadIdx.x; c < kMaxCells; c += kThreads) s_hist[c] = 0;
+  __syncthreads();
+  const unsigned tile_id = s_tile;
+  const int k = tile_id / tiles, tile = tile_id % tiles;
+  if (k >= K) return;
+  const ProjGeom pg = dp->pg;
+  const GroundGeom gg = dp->gg;
+  const size_t kbase = (size_t)k * N;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float qnan = __int_as_float(0x7fc00000);
+  int base = 0;
+
+#pragma unroll 2
+  for (int j = 0; j < kRounds; ++j) {
+    const int i = tile * kSplitTile + j * kThreads + threadIdx.x;
+    const bool in = i < N;
+    sloam_point p = {0.f, 0.f, 0.f, 0.f};
+    int pix = 0;
+    if (in) {
+      p = points[kbase + i];
+      if (DO_PROJECT) {
+        float range;
+        pix = project_pixel(pg, p.x, p.y, p.z, &range);
+        pix_io[kbase + i] = pix;
+        // closest point wins (inference.cpp:135,160-162): minimum over the
+        // bit pattern of the non-negative range; NaN ranges never write
+        if (range_bits != nullptr && range == range)
+          atomicMin(&range_bits[kbase + pix], __float_as_uint(range));
+      } else {
+        pix = pix_io[kbase + i];
+      }
+    }
+    if (DO_SPLIT) {
+      unsigned char m = 0;
+      if (in) m = mask[kbase + pix];  // inference.cpp:242-243
+      if (in) {
+        sloam_point t;  // dense mode (:247-251): the point or a NaN point with intensity 0
+        if (m == 255) t = p;
+        else { t.x = qnan; t.y = qnan; t.z = qnan; t.intensity = 0.f; }
+        tree[kbase + i] = t;
+      }
+      const bool is_g = in && (m == 1);
+      const unsigned bal = __ballot_sync(kFull, is_g);
+      if (lane == 0) s_warp[warp] = __popc(bal);
+      __syncthreads();
+      int off = base, total = 0;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) {
+        const int c = s_warp[w];
+        if (w < warp) off += c;
+        total += c;
+      }
+      if (is_g) {
+        const int slot = off + __popc(bal & ((1u << lane) - 1u));
+        const int cell = ground_cell_of(gg, p.x, p.y);
+        s_ground[slot] = p;
+        s_cell[slot] = (uint8_t)(cell < 0 ? 255 : cell);
+        if (cell >= 0) atomicAdd(&s_hist[cell], 1);
+      }
+      base += total;
+      __syncthreads();
+    }
+  }
+  if (!DO_SPLIT) return;
+
+  // ---- decoupled look-back over the tiles of this keyframe ----
+  if (warp == 0) {
+    unsigned long long *st = tile_state + (size_t)k * tiles;
+    if (lane == 0) {
+      __threadfence();
+      atomicExch(&st[tile], pack_state(tile == 0 ? 2u : 1u, (unsigned)base));
+    }
+    int excl = 0;
+    if (tile > 0) {
+      int look = tile - 1;
+      while (true) {
+        const int t = look - lane;
+        unsigned long long s = 0;
+        if (t >= 0) {
+          do { s = *((volatile unsigned long long *)&st[t]); } while ((s >> 62) == 0);
+        } else {
+          s = pack_state(2u, 0u);  // virtual tile -1: inclusive prefix 0
+        }
+        const unsigned is_prefix = __ballot_sync(kFull, (s >> 62) == 2);
+        const int first = __ffs(is_prefix) - 1;  // nearest tile carrying a prefix
+        int v = (first < 0 || lane <= first) ? (int)(s & 0xFFFFFFFFu) : 0;
+        v = warp_sum(v);
+        excl += v;
+        if (first >= 0) break;
+        look -= 32;
+      }
+      if (lane == 0) {
+        __threadfence();
+        atomicExch(&st[tile], pack_state(2u, (unsigned)(excl + base)));
+      }
+    }
+    if (lane == 0) {
+      s_base = excl;
+      if (tile == tiles - 1) ground_count[k] = excl + base;
+    }
+  }
+  __syncthreads();
+  const int gbase = s_base;
+  sloam_point *gout = ground + (size_t)k * ground_stride + gbase;
+  uint8_t *cout = ground_cell + (size_t)k * ground_stride + gbase;
+  for (int s = threadIdx.x; s < base; s += kThreads) {
+    gout[s] = s_ground[s];
+    cout[s] = s_cell[s];
+  }
+  for (int c = threadIdx.x; c < kMaxCells; c += kThreads) {
+    const int h = s_hist[c];
+    if (h) atomicAdd(&cell_count[(size_t)k * kMaxCells + c], h);
+  }
+}
+
+// empty pixels (still 0xFFFFFFFF) become 0 (inference.cpp:150-158)
+__global__ void range_finalize_kernel(unsigned *__restrict__ range_bits, long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    uint4 v = *reinterpret_cast<uint4 *>(range_bits + i);
+    const bool any = (v.x == 0xFFFFFFFFu) | (v.y == 0xFFFFFFFFu) | (v.z == 0xFFFFFFFFu) | (v.w == 0xFFFFFFFFu);
+    if (any) {
+      if (v.x == 0xFFFFFFFFu) v.x = 0;
+      if (v.y == 0xFFFFFFFFu) v.y = 0;
+      if (v.z == 0xFFFFFFFFu) v.z = 0;
+      if (v.w == 0xFFFFFFFFu) v.w = 0;
+      *reinterpret_cast<uint4 *>(range_bits + i) = v;
+    }
+  } else {
+    for (long long j = i; j < n; ++j)
+      if (range_bits[j] == 0xFFFFFFFFu) range_bits[j] = 0;
+  }
+}
+
+// Polar cell tags for a ground cloud that did not come through the split
+// kernel (stage entry sloam_b200_ground_planes_dev on caller-supplied clouds).
+__global__ void ground_tag_kernel(const DevParams *__restrict__ dp, int K,
+                                  const sloam_point *__restrict__ ground,
+                                  const int32_t *__restrict__ ground_count, int stride,
+                                  uint8_t *__restrict__ ground_cell, int32_t *__restrict__ cell_count) {
+  __shared__ int s_hist[kMaxCells];
+  const int k = blockIdx.y;
+  for (int c = threadIdx.x; c < kMaxCells; c += blockDim.x) s_hist[c] = 0;
+  __syncthreads();
+  const int n = ground_count[k];
+  const GroundGeom gg = dp->gg;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const sloam_point p = ground[(size_t)k * stride + i];
+    const int cell = ground_cell_of(gg, p.x, p.y);
+    ground_cell[(size_t)k * stride + i] = (uint8_t)(cell < 0 ? 255 : cell);
+    if (cell >= 0) atomicAdd(&s_hist[cell], 1);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < kMaxCells; c += blockDim.x)
+    if (s_hist[c]) atomicAdd(&cell_count[(size_t)k * kMaxCells + c], s_hist[c]);
+}
+
+int launch_ground_tag(sloam_ctx *c, int K, const sloam_point *ground, const int32_t *ground_count,
+                      int stride) {
+  SB_CUDA(c, cudaMemsetAsync(c->ws.cell_count, 0, sizeof(int32_t) * (size_t)K * kMaxCells, c->stream));
+  dim3 grid((unsigned)std::min(64, (stride + 255) / 256), (unsigned)K);
+  ground_tag_kernel<<<grid, 256, 0, c->stream>>>(c->dp, K, ground, ground_count, stride,
+                                                 c->ws.ground_cell, c->ws.cell_count);
+  SB_LAUNCH_CHECK(c);
+  return SLOAM_OK;
+}
+
+int launch_project_split(sloam_ctx *c, int K, bool do_project, bool do_split,
+                         const sloam_point *points, const uint8_t *mask, int32_t *pix,
+                         float *range_image, sloam_point *tree, sloam_point *ground,
+                         int32_t *ground_count) {
+  const int N = c->hp.N;
+  const int tiles = (N + kSplitTile - 1) / kSplitTile;
+  const long long total = (long long)K * N;
+  unsigned *rb = reinterpret_cast<unsigned *>(range_image);
+  if (do_project && rb) SB_CUDA(c, cudaMemsetAsync(rb, 0xFF, sizeof(unsigned) * total, c->stream));
+  unsigned *ticket = nullptr;
+  if (do_split) {
+    // tile states + the ticket counter live in one allocation: [K*tiles] states, then the ticket
+    SB_CUDA(c, cudaMemsetAsync(c->ws.tile_state, 0, sizeof(unsigned long long) * ((size_t)K * tiles), c->stream));
+    SB_CUDA(c, cudaMemsetAsync(c->ws.n_overflow, 0, sizeof(int32_t), c->stream));
+    SB_CUDA(c, cudaMemsetAsync(c->ws.cell_count, 0, sizeof(int32_t) * (size_t)K * kMaxCells, c->stream));
+    ticket = reinterpret_cast<unsigned *>(c->ws.n_overflow);
+  }
+  const unsigned grid = (unsigned)(K * tiles);
+#define SB_K1_ARGS c->dp, K, points, mask, pix, rb, tree, ground, ground_count, c->ws.ground_cell, \
+                   c->ws.cell_count, c->ws.tile_state, ticket, N
+  if (do_project && do_split) project_split_kernel<true, true><<<grid, kThreads, 0, c->stream>>>(SB_K1_ARGS);
+  else if (do_project) project_split_kernel<true, false><<<grid, kThreads, 0, c->stream>>>(SB_K1_ARGS);
+  else project_split_kernel<false, true><<<grid, kThreads, 0, c->stream>>>(SB_K1_ARGS);
+#undef SB_K1_ARGS
+  SB_LAUNCH_CHECK(c);
+  if (do_project && rb) {
+    const long long nvec = (total + 3) / 4;
+    range_finalize_kernel<<<(unsigned)((nvec + 255) / 256), 256, 0, c->stream>>>(rb, total);
+    SB_LAUNCH_CHECK(c);
+  }
+  return SLOAM_OK;
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" {
+
+int sloam_b200_project_dev(sloam_ctx *c, int K, const sloam_point *points, int32_t *pix,
+                           float *range_image) {
+  if (!c || K <= 0 || K > c->max_k || !points || !pix) return set_err(c, SLOAM_E_INVALID, "project: bad arguments");
+  return launch_project_split(c, K, true, false, points, nullptr, pix, range_image, nullptr, nullptr, nullptr);
+}
+
+int sloam_b200_mask_cloud_dev(sloam_ctx *c, int K, const sloam_point *points, const int32_t *pix,
+                              const uint8_t *mask, sloam_point *tree, sloam_point *ground,
+                              int32_t *ground_count) {
+  if (!c || K <= 0 || K > c->max_k || !points || !pix || !mask || !tree || !ground || !ground_count)
+    return set_err(c, SLOAM_E_INVALID, "mask_cloud: bad arguments");
+  return launch_project_split(c, K, false, true, points, mask, const_cast<int32_t *>(pix), nullptr,
+                              tree, ground, ground_count);
+}
+
+int sloam_b200_project_split_dev(sloam_ctx *c, int K, const sloam_point *points, const uint8_t *mask,
+                                 int32_t *pix, float *range_image, sloam_point *tree,
+                                 sloam_point *ground, int32_t *ground_count) {
+  if (!c || K <= 0 || K > c->max_k || !points || !mask || !pix || !tree || !ground || !ground_count)
+    return set_err(c, SLOAM_E_INVALID, "project_split: bad arguments");
+  return launch_project_split(c, K, true, true, points, mask, pix, range_image, tree, ground, ground_count);
+}
+
+}  // extern "C"

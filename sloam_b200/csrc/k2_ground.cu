@@ -1,0 +1,411 @@
+// k2_ground.cu -- stages a3 + a4 + a5: polar ground cells, bottom-k% retention,
+// per-cell plane fit and acceptance.
+//
+// Replaces sloam::binGroundPoints (sloam/src/core/sloam.cpp:330-386), the Plane
+// constructor + computeModel (sloam/src/objects/plane.cpp:3-17,96-128) and the
+// acceptance test in sloam::computeModels (sloam.cpp:394-412).
+//
+// One CTA per (keyframe, cell).  The cell tag of every ground point was written
+// by the split kernel (k1_project.cu), so a cell collects its members with one
+// coalesced pass over G bytes, gathers their z keys, selects the r lowest with
+// an 8-bit radix select (ties by input index: SURVEY B-3 total order
+// (z, input index)), sorts only those r, and fits the plane:
+//   - centroid: float32 sequential sum in sorted order (utils.h:14-28), one lane;
+//   - 3 x n JacobiSVD: column-pivoted Householder QR of the n x 3 adjoint with
+//     warp-shuffle reductions, then the 3x3 two-sided Jacobi of dev_plane.h.
+// Algorithmic bytes: 16 G in, B * (72 + 16 F_g) out per keyframe.
+#include "common.cuh"
+#include "dev_plane.h"
+
+namespace sb {
+
+constexpr int kGThreads = 256;
+constexpr int kSelCap = 3072;   // members kept in shared memory (else global scratch)
+constexpr int kQrCap = 512;     // retained points whose fit lives in shared memory
+
+struct SelKey { uint32_t z; uint32_t j; };
+
+__device__ __forceinline__ bool sel_less(const SelKey &a, const SelKey &b) {
+  return a.z < b.z || (a.z == b.z && a.j < b.j);
+}
+
+// exclusive block scan of one int per thread (256 threads); returns total in *total
+__device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int *total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(kFull, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  int off = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < kGThreads / 32; ++w) {
+    const int c = s_warp[w];
+    if (w < warp) off += c;
+    tot += c;
+  }
+  __syncthreads();
+  *total = tot;
+  return off + inc - v;
+}
+
+__global__ void __launch_bounds__(kGThreads)
+ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ ground,
+                    const int32_t *__restrict__ ground_count, int stride,
+                    const uint8_t *__restrict__ ground_cell, const int32_t *__restrict__ cell_count,
+                    const sloam_pose *__restrict__ pose_est, SelKey *__restrict__ gscratch,
+                    double *__restrict__ qscratch, float *__restrict__ pscratch,
+                    sloam_cell_plane *__restrict__ cells,
+                    sloam_point *__restrict__ cell_features, sloam_point *__restrict__ kept_points,
+                    int32_t *__restrict__ kept_offsets) {
+  __shared__ SelKey s_list[kSelCap];
+  __shared__ double s_qr[3 * kQrCap];
+  __shared__ float s_pts[3 * kQrCap];
+  __shared__ int s_hist[256];
+  __shared__ int s_warp[kGThreads / 32];
+  __shared__ int s_misc[8];
+  __shared__ double s_red[4];
+
+  const int B = dp->B, Fg = dp->p.numGroundFeatures;
+  const int k = blockIdx.y, cell = blockIdx.x;
+  const int G = ground_count[k];
+  const int n_c = cell_count[(size_t)k * kMaxCells + cell];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const sloam_point *gk = ground + (size_t)k * stride;
+  const uint8_t *ck = ground_cell + (size_t)k * stride;
+  sloam_cell_plane *out = cells + (size_t)k * B + cell;
+  sloam_point *fout = cell_features + ((size_t)k * B + cell) * Fg;
+
+  // retained count r (sloam.cpp:366-384) of every cell -> this cell's offsets
+  const double retainNum = 1.0 / dp->p.groundRetainThresh;
+  auto kept_of = [&](int n) {
+    if (n > 0 && retainNum < (double)n) { const int b = (int)((double)n / retainNum); return b < n ? b : n; }
+    return n;
+  };
+  if (threadIdx.x == 0) {
+    int off_all = 0, off_kept = 0;
+    for (int c = 0; c < cell; ++c) {
+      const int n = cell_count[(size_t)k * kMaxCells + c];
+      off_all += n; off_kept += kept_of(n);
+    }
+    s_misc[0] = off_all; s_misc[1] = off_kept;
+    if (kept_offsets) {
+      kept_offsets[(size_t)k * (B + 1) + cell] = off_kept;
+      if (cell == B - 1) kept_offsets[(size_t)k * (B + 1) + B] = off_kept + kept_of(n_c);
+    }
+  }
+  __syncthreads();
+  const int off_all = s_misc[0], off_kept = s_misc[1];
+  const bool do_sort = n_c > 0 && retainNum < (double)n_c;
+  const int r = kept_of(n_c);
+
+  if (n_c == 0 || r < Fg || r < 3) {
+    // Plane::Plane: features.size() < numGroundFeatures -> invalid (plane.cpp:7-10);
+    // n < 3 is out-of-range in the reference's ThinU access: declared invalid.
+    // (kept point lists of such cells are still emitted below when requested.)
+    if (threadIdx.x == 0) {
+      sloam_cell_plane c;
+      for (int i = 0; i < 4; ++i) c.model.plane[i] = 0.0;
+      for (int i = 0; i < 3; ++i) c.model.centroid[i] = 0.0;
+      c.n_cell = n_c; c.n_kept = r; c.is_valid = 0; c.accepted = 0;
+      *out = c;
+    }
+    for (int f = threadIdx.x; f < Fg; f += kGThreads) fout[f] = sloam_point{0.f, 0.f, 0.f, 0.f};
+    if (kept_points == nullptr || n_c == 0) return;
+  }
+
+  // ---- collect the members (z key, input index) in input order ----
+  SelKey *list = n_c <= kSelCap ? s_list : gscratch + (size_t)k * stride + off_all;
+  int filled = 0;
+  for (int base = 0; base < G; base += kGThreads * 16) {
+    const int i0 = base + threadIdx.x * 16;
+    uint32_t bytes[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    if (i0 + 15 < G && ((((size_t)k * stride + i0) & 15) == 0)) {
+      const uint4 v = *reinterpret_cast<const uint4 *>(ck + i0);
+      bytes[0] = v.x; bytes[1] = v.y; bytes[2] = v.z; bytes[3] = v.w;
+    } else {
+      for (int q = 0; q < 16; ++q)
+        if (i0 + q < G) {
+          const uint32_t b = ck[i0 + q];
+          bytes[q >> 2] = (bytes[q >> 2] & ~(0xFFu << (8 * (q & 3)))) | (b << (8 * (q & 3)));
+        }
+    }
+    int cnt = 0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) cnt += ((bytes[q >> 2] >> (8 * (q & 3))) & 0xFF) == (uint32_t)cell;
+    int total;
+    int pos = filled + block_excl_scan(cnt, s_warp, &total);
+    if (cnt)
+      for (int q = 0; q < 16; ++q)
+        if (((bytes[q >> 2] >> (8 * (q & 3))) & 0xFF) == (uint32_t)cell) {
+          SelKey e; e.j = (uint32_t)(i0 + q); e.z = float_key(gk[i0 + q].z);
+          list[pos++] = e;
+        }
+    filled += total;
+  }
+  __syncthreads();
+
+  // ---- select the r lowest (z, j) keys ----
+  SelKey *keep = list;  // compacted in place
+  if (do_sort) {
+    // 8-bit MSD radix select on z for the r-th smallest (rank r-1)
+    uint32_t prefix = 0, pmask = 0;
+    int want = r - 1;  // 0-based rank among members matching the prefix
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      s_hist[threadIdx.x] = 0;
+      __syncthreads();
+      for (int i = threadIdx.x; i < n_c; i += kGThreads) {
+        const uint32_t z = list[i].z;
+        if ((z & pmask) == prefix) atomicAdd(&s_hist[(z >> shift) & 0xFF], 1);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int acc = 0, d = 0;
+        for (; d < 256; ++d) { if (acc + s_hist[d] > want) break; acc += s_hist[d]; }
+        s_misc[2] = d; s_misc[3] = want - acc;
+      }
+      __syncthreads();
+      prefix |= (uint32_t)s_misc[2] << shift;
+      pmask |= 0xFFu << shift;
+      want = s_misc[3];
+      __syncthreads();
+    }
+    const uint32_t pivot = prefix;   // z key of the r-th smallest
+    const int tie_quota = want + 1;  // members with z == pivot to keep, lowest j first
+    // order-preserving compaction (the list is in j order, so ties come lowest j first)
+    int kept = 0, ties_seen = 0;
+    for (int base = 0; base < n_c; base += kGThreads) {
+      const int i = base + threadIdx.x;
+      SelKey e = {0, 0};
+      bool lt = false, eq = false;
+      if (i < n_c) { e = list[i]; lt = e.z < pivot; eq = e.z == pivot; }
+      int tot_eq, tot_keep;
+      const int eq_before = ties_seen + block_excl_scan(eq ? 1 : 0, s_warp, &tot_eq);
+      const bool take = lt || (eq && eq_before < tie_quota);
+      const int pos = kept + block_excl_scan(take ? 1 : 0, s_warp, &tot_keep);
+      if (take) keep[pos] = e;  // pos <= i, and every slot < base is already consumed
+      kept += tot_keep; ties_seen += tot_eq;
+      __syncthreads();
+    }
+    // ---- sort the r kept keys: rank sort in place via shared ranks ----
+    // (r is a few hundred; O(r^2 / threads))
+    SelKey *tmp = (r * (int)sizeof(SelKey) <= (int)sizeof(s_qr))
+                      ? reinterpret_cast<SelKey *>(s_qr)
+                      : reinterpret_cast<SelKey *>(qscratch + ((size_t)k * stride + off_all) * 3);
+    for (int i = threadIdx.x; i < r; i += kGThreads) {
+      const SelKey e = keep[i];
+      int rank = 0;
+      for (int j = 0; j < r; ++j) rank += sel_less(keep[j], e);
+      tmp[rank] = e;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < r; i += kGThreads) keep[i] = tmp[i];
+    __syncthreads();
+  }
+
+  if (kept_points) {
+    sloam_point *kp = kept_points + (size_t)k * stride + off_kept;
+    for (int i = threadIdx.x; i < r; i += kGThreads) kp[i] = gk[keep[i].j];
+  }
+  if (n_c == 0 || r < Fg || r < 3) return;
+
+  // ---- Plane::computeModel on the r retained points, in order ----
+  const int n = r;
+  // stage the retained points (x | y | z planes) so the serial float sum reads shared memory
+  float *P = n <= kQrCap ? s_pts : pscratch + ((size_t)k * stride + off_all) * 3;
+  for (int i = threadIdx.x; i < n; i += kGThreads) {
+    const sloam_point p = gk[keep[i].j];
+    P[i] = p.x; P[n + i] = p.y; P[2 * n + i] = p.z;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {  // computeCentroid: float32 sequential sums (utils.h:14-28)
+    const float *a = P + threadIdx.x * n;
+    float acc = 0.f;
+    for (int i = 0; i < n; ++i) acc += a[i];
+    s_red[threadIdx.x] = (double)(float)((double)acc / (double)n);
+  }
+  __syncthreads();
+  const float cxf = (float)s_red[0], cyf = (float)s_red[1], czf = (float)s_red[2];
+  // adjoint matrix A^T (n x 3), column-major in Q; entries (double)(float diff) (plane.cpp:106-108)
+  double *Q = n <= kQrCap ? s_qr : qscratch + ((size_t)k * stride + off_all) * 3;
+  double lmax = 0.0;
+  for (int i = threadIdx.x; i < n; i += kGThreads) {
+    const double dx = (double)(P[i] - cxf), dy = (double)(P[n + i] - cyf), dz = (double)(P[2 * n + i] - czf);
+    Q[i] = dx; Q[n + i] = dy; Q[2 * n + i] = dz;
+    lmax = fmax(lmax, fmax(fabs(dx), fmax(fabs(dy), fabs(dz))));
+  }
+  // scale = max |coeff| (JacobiSVD::compute)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(kFull, lmax, o));
+  if (lane == 0) reinterpret_cast<double *>(s_hist)[warp] = lmax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = 0.0;
+    for (int w = 0; w < kGThreads / 32; ++w) m = fmax(m, reinterpret_cast<double *>(s_hist)[w]);
+    s_red[3] = (m == 0.0) ? 1.0 : m;
+  }
+  __syncthreads();
+  const double scale = s_red[3];
+  for (int i = threadIdx.x; i < 3 * n; i += kGThreads) Q[i] = Q[i] / scale;
+  __syncthreads();
+
+  if (warp != 0) return;  // the tiny QR + Jacobi runs on one warp
+  double Wm[9], U[9];
+  if (n > 3) {
+    // ColPivHouseholderQR of the n x 3 matrix (Eigen/src/QR/ColPivHouseholderQR.h)
+    auto col_sq = [&](int c, int from) {
+      double s = 0.0;
+      for (int rr = from + lane; rr < n; rr += 32) s += Q[c * n + rr] * Q[c * n + rr];
+      return warp_sum_d(s);
+    };
+    double nUpd[3], nDir[3];
+    for (int c = 0; c < 3; ++c) nUpd[c] = nDir[c] = sqrt(col_sq(c, 0));
+    const double downdate_thr = sqrt(DBL_EPSILON);
+    int colmap[3] = {0, 1, 2};  // physical column of logical column
+    int transp[3];
+    for (int kk = 0; kk < 3; ++kk) {
+      int big = kk;
+      for (int j = kk + 1; j < 3; ++j) if (nUpd[j] > nUpd[big]) big = j;
+      transp[kk] = big;
+      if (big != kk) {
+        const int tc = colmap[kk]; colmap[kk] = colmap[big]; colmap[big] = tc;
+        const double tu = nUpd[kk]; nUpd[kk] = nUpd[big]; nUpd[big] = tu;
+        const double td = nDir[kk]; nDir[kk] = nDir[big]; nDir[big] = td;
+      }
+      double *ck2 = Q + colmap[kk] * n;
+      double tailSq = 0.0;
+      for (int rr = kk + 1 + lane; rr < n; rr += 32) tailSq += ck2[rr] * ck2[rr];
+      tailSq = warp_sum_d(tailSq);
+      const double c0 = ck2[kk];
+      double tau, beta;
+      __syncwarp();
+      if (tailSq <= DBL_MIN) {
+        tau = 0.0; beta = c0;
+        for (int rr = kk + 1 + lane; rr < n; rr += 32) ck2[rr] = 0.0;
+      } else {
+        beta = sqrt(c0 * c0 + tailSq);
+        if (c0 >= 0.0) beta = -beta;
+        for (int rr = kk + 1 + lane; rr < n; rr += 32) ck2[rr] = ck2[rr] / (c0 - beta);
+        tau = (beta - c0) / beta;
+      }
+      if (lane == 0) ck2[kk] = beta;
+      __syncwarp();
+      if (tau != 0.0) {
+        for (int j = kk + 1; j < 3; ++j) {
+          double *cj = Q + colmap[j] * n;
+          double tmp = 0.0;
+          for (int rr = kk + 1 + lane; rr < n; rr += 32) tmp += ck2[rr] * cj[rr];
+          tmp = warp_sum_d(tmp);
+          tmp += cj[kk];
+          __syncwarp();
+          if (lane == 0) cj[kk] -= tau * tmp;
+          for (int rr = kk + 1 + lane; rr < n; rr += 32) cj[rr] -= tau * ck2[rr] * tmp;
+          __syncwarp();
+        }
+      }
+      for (int j = kk + 1; j < 3; ++j) {  // LAPACK-style norm downdate
+        if (nUpd[j] != 0.0) {
+          double temp = fabs(Q[colmap[j] * n + kk]) / nUpd[j];
+          temp = (1.0 + temp) * (1.0 - temp);
+          temp = temp < 0.0 ? 0.0 : temp;
+          const double r2 = nUpd[j] / nDir[j];
+          const double temp2 = temp * r2 * r2;
+          if (temp2 <= downdate_thr) {
+            nDir[j] = sqrt(col_sq(colmap[j], kk + 1));
+            nUpd[j] = nDir[j];
+          } else {
+            nUpd[j] *= sqrt(temp);
+          }
+        }
+      }
+    }
+    int perm[3] = {0, 1, 2};
+    for (int kk = 0; kk < 3; ++kk) { const int t = perm[kk]; perm[kk] = perm[transp[kk]]; perm[transp[kk]] = t; }
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        U[i * 3 + j] = (i == perm[j]) ? 1.0 : 0.0;
+        Wm[i * 3 + j] = (j <= i) ? Q[colmap[i] * n + j] : 0.0;  // R^T
+      }
+  } else {  // n == 3: square, no preconditioner
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        Wm[i * 3 + j] = Q[i * n + j];
+        U[i * 3 + j] = (i == j) ? 1.0 : 0.0;
+      }
+  }
+  if (lane != 0) return;
+  double nrm[3];
+  jacobi_svd3_last_u(Wm, U, nrm);
+  sloam_cell_plane c;
+  const double cx = (double)cxf, cy = (double)cyf, cz = (double)czf;
+  c.model.plane[0] = nrm[0]; c.model.plane[1] = nrm[1]; c.model.plane[2] = nrm[2];
+  c.model.plane[3] = -(nrm[0] * cx + nrm[1] * cy + nrm[2] * cz);  // plane.cpp:117
+  c.model.centroid[0] = cx; c.model.centroid[1] = cy; c.model.centroid[2] = cz;
+  c.n_cell = n_c; c.n_kept = r; c.is_valid = 1;
+  c.accepted = plane_accept(pose_est[k], c.model.plane, c.model.centroid, dp->p.ground_angle_tol) ? 1 : 0;
+  *out = c;
+  for (int f = 0; f < Fg; ++f) fout[f] = gk[keep[f].j];  // features.resize(numGroundFeatures)
+}
+
+// accepted planes of each keyframe, compact, in (radius bin, theta bin) order
+__global__ void planes_compact_kernel(const DevParams *__restrict__ dp, const sloam_cell_plane *__restrict__ cells,
+                                      sloam_plane *__restrict__ planes_acc, int32_t *__restrict__ acc_cell,
+                                      int32_t *__restrict__ n_acc) {
+  const int B = dp->B;
+  const int k = blockIdx.x, lane = threadIdx.x;
+  int cnt = 0;
+  for (int base = 0; base < B; base += 32) {
+    const int c = base + lane;
+    const bool a = c < B && cells[(size_t)k * B + c].accepted;
+    const unsigned b = __ballot_sync(kFull, a);
+    if (a) {
+      const int pos = cnt + __popc(b & ((1u << lane) - 1u));
+      planes_acc[(size_t)k * B + pos] = cells[(size_t)k * B + c].model;
+      acc_cell[(size_t)k * B + pos] = c;
+    }
+    cnt += __popc(b);
+  }
+  if (lane == 0) n_acc[k] = cnt;
+}
+
+int launch_ground_tag(sloam_ctx *c, int K, const sloam_point *ground, const int32_t *ground_count, int stride);
+
+int launch_planes_compact(sloam_ctx *c, int K, const sloam_cell_plane *cells) {
+  planes_compact_kernel<<<K, 32, 0, c->stream>>>(c->dp, cells, c->ws.planes_acc, c->ws.planes_acc_cell,
+                                                 c->ws.n_planes_acc);
+  SB_LAUNCH_CHECK(c);
+  return SLOAM_OK;
+}
+
+int launch_ground_planes(sloam_ctx *c, int K, const sloam_point *ground, const int32_t *ground_count,
+                         int stride, const sloam_pose *pose_est, sloam_cell_plane *cells,
+                         sloam_point *cell_features, sloam_point *kept_points, int32_t *kept_offsets) {
+  Workspace &w = c->ws;
+  dim3 grid((unsigned)c->hp.B, (unsigned)K);
+  ground_cells_kernel<<<grid, kGThreads, 0, c->stream>>>(
+      c->dp, ground, ground_count, stride, w.ground_cell, w.cell_count, pose_est,
+      reinterpret_cast<SelKey *>(w.gscratch), w.qscratch, w.pscratch, cells, cell_features, kept_points, kept_offsets);
+  SB_LAUNCH_CHECK(c);
+  return launch_planes_compact(c, K, cells);
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" int sloam_b200_ground_planes_dev(sloam_ctx *c, int K, const sloam_point *ground,
+                                            const int32_t *ground_count, int ground_stride,
+                                            const sloam_pose *pose_est, sloam_cell_plane *cells,
+                                            sloam_point *cell_features, sloam_point *kept_points,
+                                            int32_t *kept_offsets) {
+  if (!c || K <= 0 || K > c->max_k || !ground || !ground_count || !pose_est || !cells || !cell_features ||
+      ground_stride <= 0 || ground_stride > c->hp.N)
+    return set_err(c, SLOAM_E_INVALID, "ground_planes: bad arguments (ground_stride must be <= H*W)");
+  int rc = launch_ground_tag(c, K, ground, ground_count, ground_stride);
+  if (rc != SLOAM_OK) return rc;
+  return launch_ground_planes(c, K, ground, ground_count, ground_stride, pose_est, cells, cell_features,
+                              kept_points, kept_offsets);
+}

@@ -1,0 +1,602 @@
+// k3_trellis.cu -- stage a6 + a7: tree instance detection.
+//
+// Replaces Instance::computeGraph (sloam/src/segmentation/trellis.cpp:134-140):
+//   findClusters -> PCL OrganizedConnectedComponentSegmentation with an
+//   EuclideanClusterComparator(1.0 m) over the organized H x W tree cloud
+//   (trellis.cpp:15-29), i.e. connected components of the grid graph whose
+//   edges are (left, up) neighbour pairs with ||pa - pb|| < threshold; the
+//   PCL label of a component is its rank by the raster index of its first
+//   pixel.
+//   findTrees -> per cluster with > 80 points, per scan line from the bottom
+//   row up, a TreeVertex from the cluster's points of that row
+//   (trellis.cpp:104-132, computeVertexProperties :63-102).
+//
+// GPU formulation: lock-free union-find over pixels (init / merge / flatten),
+// where the smaller raster index always wins a union so that every root IS the
+// first pixel of its component; component size, column extent and last row are
+// accumulated at the root with warp-aggregated atomics; a per-keyframe planning
+// CTA sorts the big components (= PCL label order), ranks them and emits
+// (cluster, row) work items; one warp per work item builds the vertex with
+// rank-based order statistics in shared memory.
+#include "common.cuh"
+
+namespace sb {
+
+constexpr int kVtxWarps = 8;
+constexpr int kVtxCap = 128;   // members per (cluster,row) handled by the warp path
+constexpr int kInvalid = -1;
+
+__device__ __forceinline__ int uf_find(const int32_t *parent, int x) {
+  int p = *((volatile const int32_t *)&parent[x]);
+  while (p != x) {
+    x = p;
+    p = *((volatile const int32_t *)&parent[x]);
+  }
+  return x;
+}
+__device__ __forceinline__ void uf_union(int32_t *parent, int a, int b) {
+  while (true) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b) return;
+    if (a < b) { const int t = a; a = b; b = t; }
+    const int old = atomicMin(&parent[a], b);  // attach the larger root under the smaller
+    if (old == a) return;
+    a = old;
+  }
+}
+
+// ---- 1. init: link every valid pixel to its left (else up) neighbour ------
+__global__ void cc_init_kernel(const DevParams *__restrict__ dp, int K,
+                               const sloam_point *__restrict__ tree, int32_t *__restrict__ parent,
+                               uint8_t *__restrict__ flags, int32_t *__restrict__ csize,
+                               int32_t *__restrict__ cmin, int32_t *__restrict__ cmax,
+                               int32_t *__restrict__ rmax) {
+  const int N = dp->N, W = dp->p.img_w;
+  const float thr = dp->p.cluster_dist_thresh;
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)K * N) return;
+  const int i = (int)(g % N);
+  const int row = i / W, col = i - row * W;
+  const sloam_point p = tree[g];
+  // PCL skips a pixel iff !isfinite(x); EuclideanClusterComparator::compare is
+  // dist < threshold in float (NaN compares false)
+  const bool valid = isfinite(p.x);
+  bool left_ok = false, up_ok = false;
+  if (valid) {
+    if (col > 0) {
+      const sloam_point q = tree[g - 1];
+      left_ok = dist3f(p.x, p.y, p.z, q.x, q.y, q.z) < thr;
+    }
+    if (row > 0) {
+      const sloam_point q = tree[g - W];
+      up_ok = dist3f(p.x, p.y, p.z, q.x, q.y, q.z) < thr;
+    }
+    parent[g] = left_ok ? i - 1 : (up_ok ? i - W : i);
+    csize[g] = 0;
+    cmin[g] = col; cmax[g] = col; rmax[g] = row;
+  } else {
+    parent[g] = kInvalid;
+  }
+  flags[g] = (left_ok && up_ok) ? 1 : 0;
+}
+
+// ---- 2. merge: pixels linked left that are also connected upwards ---------
+__global__ void cc_merge_kernel(const DevParams *__restrict__ dp, int K,
+                                const uint8_t *__restrict__ flags, int32_t *__restrict__ parent) {
+  const int N = dp->N, W = dp->p.img_w;
+  const long long g4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const long long total = (long long)K * N;
+  if (g4 >= total) return;
+  uint32_t f4;
+  if (g4 + 3 < total) f4 = *reinterpret_cast<const uint32_t *>(flags + g4);
+  else { f4 = 0; for (int j = 0; g4 + j < total; ++j) f4 |= (uint32_t)flags[g4 + j] << (8 * j); }
+  if (f4 == 0) return;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if ((f4 >> (8 * j)) & 0xFF) {
+      const long long g = g4 + j;
+      const int k = (int)(g / N), i = (int)(g - (long long)k * N);
+      uf_union(parent + (size_t)k * N, i, i - W);
+    }
+  }
+}
+
+// ---- 3. flatten + statistics at the root ----------------------------------
+__global__ void cc_flatten_kernel(const DevParams *__restrict__ dp, int K,
+                                  int32_t *__restrict__ parent, int32_t *__restrict__ csize,
+                                  int32_t *__restrict__ cmin, int32_t *__restrict__ cmax,
+                                  int32_t *__restrict__ rmax, int32_t *__restrict__ row_roots,
+                                  int32_t *__restrict__ n_roots, int32_t *__restrict__ big_roots,
+                                  int32_t *__restrict__ n_big, int32_t *__restrict__ kf_flags) {
+  const int N = dp->N, W = dp->p.img_w, H = dp->p.img_h;
+  const int min_pts = dp->p.min_cluster_points, T = dp->p.max_trees;
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in = g < (long long)K * N;
+  int k = 0, i = 0, root = kInvalid;
+  if (in) {
+    k = (int)(g / N); i = (int)(g - (long long)k * N);
+    if (parent[g] != kInvalid) {
+      root = uf_find(parent + (size_t)k * N, i);
+      parent[g] = root;
+    }
+  }
+  const int row = i / W, col = i - row * W;
+  // lanes of a warp that share (keyframe, root): one atomic per group
+  const long long key = root == kInvalid ? -1ll : ((long long)k << 32 | (unsigned)root);
+  const unsigned act = __ballot_sync(kFull, root != kInvalid);
+  if (root == kInvalid) return;
+  const unsigned grp = __match_any_sync(act, key);
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(grp) - 1;
+  if (lane == leader) {
+    const size_t r = (size_t)k * N + root;
+    const int cnt = __popc(grp);
+    const int old = atomicAdd(&csize[r], cnt);
+    if (old <= min_pts && old + cnt > min_pts) {  // exactly one group sees the crossing
+      const int slot = atomicAdd(&n_big[k], 1);
+      if (slot < T) big_roots[(size_t)k * T + slot] = root;
+      else atomicOr(&kf_flags[k], 1);
+    }
+  }
+  // extents of the component: a member only issues an atomic when it improves the
+  // value it sees (monotone, so the racy pre-check is safe)
+  {
+    const size_t r = (size_t)k * N + root;
+    if (col < cmin[r]) atomicMin(&cmin[r], col);
+    if (col > cmax[r]) atomicMax(&cmax[r], col);
+    if (row > rmax[r]) atomicMax(&rmax[r], row);
+  }
+  if (root == i) {
+    atomicAdd(&row_roots[(size_t)k * H + row], 1);
+    atomicAdd(&n_roots[k], 1);
+  }
+}
+
+// ---- 4. plan: sort big clusters, rank them, emit work items ----------------
+__global__ void cc_plan_kernel(const DevParams *__restrict__ dp, const int32_t *__restrict__ parent,
+                               const int32_t *__restrict__ cmin, const int32_t *__restrict__ cmax,
+                               const int32_t *__restrict__ rmax, const int32_t *__restrict__ row_roots,
+                               int32_t *__restrict__ big_roots, int32_t *__restrict__ n_big,
+                               int32_t *__restrict__ big_rank, int32_t *__restrict__ bbox,
+                               int32_t *__restrict__ vwork, int32_t *__restrict__ n_vwork) {
+  extern __shared__ int32_t sm[];
+  const int N = dp->N, W = dp->p.img_w, H = dp->p.img_h, T = dp->p.max_trees;
+  const int k = blockIdx.x;
+  int32_t *s_roots = sm;            // [T]
+  int32_t *s_sorted = sm + T;       // [T]
+  int32_t *s_rowpre = sm + 2 * T;   // [H+1]
+  const int nb = min(n_big[k], T);
+  for (int s = threadIdx.x; s < nb; s += blockDim.x) s_roots[s] = big_roots[(size_t)k * T + s];
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int r = 0; r < H; ++r) { s_rowpre[r] = acc; acc += row_roots[(size_t)k * H + r]; }
+    s_rowpre[H] = acc;
+  }
+  __syncthreads();
+  for (int s = threadIdx.x; s < nb; s += blockDim.x) {  // rank sort (roots are distinct)
+    const int v = s_roots[s];
+    int r = 0;
+    for (int j = 0; j < nb; ++j) r += s_roots[j] < v;
+    s_sorted[r] = v;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int s = warp; s < nb; s += nwarps) {
+    const int root = s_sorted[s];
+    const int row = root / W, col = root - row * W;
+    // PCL label = number of component roots before this one in raster order
+    int cnt = 0;
+    const int32_t *prow = parent + (size_t)k * N + (size_t)row * W;
+    for (int c = lane; c < col; c += 32) cnt += (prow[c] == row * W + c);
+    cnt = warp_sum(cnt);
+    if (lane == 0) {
+      const size_t r = (size_t)k * N + root;
+      big_roots[(size_t)k * T + s] = root;
+      big_rank[(size_t)k * T + s] = s_rowpre[row] + cnt;
+      int32_t *bb = bbox + ((size_t)k * T + s) * 4;
+      const int r1 = rmax[r];
+      bb[0] = cmin[r]; bb[1] = cmax[r]; bb[2] = row; bb[3] = r1;
+      const int nrows = r1 - row + 1;
+      const int base = atomicAdd(n_vwork, nrows);
+      for (int q = 0; q < nrows; ++q) vwork[base + q] = (k << 18) | (s << 8) | (row + q);
+    }
+  }
+  if (threadIdx.x == 0) n_big[k] = nb;
+}
+
+// ---- 5. one vertex per (cluster, row) --------------------------------------
+struct VtxSmem {
+  float x[kVtxCap], y[kVtxCap], z[kVtxCap], w[kVtxCap];
+  int16_t col[kVtxCap];
+  int16_t order[kVtxCap];
+};
+
+// lexicographic (z, y, x, col): the order the reference's three std::sort calls
+// produce (SURVEY B-3); col is unique so this is a total order
+__device__ __forceinline__ bool key_less(float za, float ya, float xa, int ca, float zb, float yb,
+                                         float xb, int cb) {
+  if (za != zb) return za < zb;
+  if (ya != yb) return ya < yb;
+  if (xa != xb) return xa < xb;
+  return ca < cb;
+}
+
+__device__ void build_vertex(const DevParams *dp, VtxSmem &s, int n, int row, sloam_vertex *out,
+                             sloam_point *pool, int32_t *pool_count) {
+  const int lane = threadIdx.x & 31;
+  const int middle = (int)(n / 2.0);  // trellis.cpp:66
+  // order statistics by ranking: every member counts the members before it
+  float med[3] = {0.f, 0.f, 0.f};
+  for (int m = lane; m < ((n + 31) & ~31); m += 32) {
+    int rx = 0, ry = 0, rz = 0, rk = 0;
+    float xm = 0.f, ym = 0.f, zm = 0.f;
+    int cm = 0;
+    if (m < n) {
+      xm = s.x[m]; ym = s.y[m]; zm = s.z[m]; cm = s.col[m];
+      for (int j = 0; j < n; ++j) {
+        const float xj = s.x[j], yj = s.y[j], zj = s.z[j];
+        rx += (xj < xm) || (xj == xm && j < m);
+        ry += (yj < ym) || (yj == ym && j < m);
+        rz += (zj < zm) || (zj == zm && j < m);
+        rk += key_less(zj, yj, xj, s.col[j], zm, ym, xm, cm);
+      }
+      s.order[rk] = (int16_t)m;
+    }
+    // the member whose rank is `middle` holds the median of that axis
+    const unsigned bx = __ballot_sync(kFull, m < n && rx == middle);
+    const unsigned by = __ballot_sync(kFull, m < n && ry == middle);
+    const unsigned bz = __ballot_sync(kFull, m < n && rz == middle);
+    if (bx) med[0] = __shfl_sync(kFull, xm, __ffs(bx) - 1);
+    if (by) med[1] = __shfl_sync(kFull, ym, __ffs(by) - 1);
+    if (bz) med[2] = __shfl_sync(kFull, zm, __ffs(bz) - 1);
+  }
+  __syncwarp();
+  // keep points within max_dist_to_centroid of the median, in z order (trellis.cpp:89-93)
+  const float maxd = dp->p.max_dist_to_centroid;
+  int kept = 0;
+  for (int sidx = lane; sidx < ((n + 31) & ~31); sidx += 32) {
+    bool keep = false;
+    int m = 0;
+    if (sidx < n) {
+      m = s.order[sidx];
+      keep = dist3f(s.x[m], s.y[m], s.z[m], med[0], med[1], med[2]) < maxd;
+    }
+    const unsigned b = __ballot_sync(kFull, keep);
+    if (keep) s.order[kept + __popc(b & ((1u << lane) - 1u))] = (int16_t)m;  // in-place: kept+pos <= sidx
+    kept += __popc(b);
+    __syncwarp();
+  }
+  sloam_vertex v;
+  v.cx = med[0]; v.cy = med[1]; v.cz = med[2];
+  v.radius = 0.f; v.n_points = 0; v.point_begin = 0; v.row = row; v.is_valid = 0;
+  if (kept > 1) {  // trellis.cpp:95-100
+    const int a = s.order[0], b = s.order[kept - 1];
+    v.radius = dist3f(s.x[a], s.y[a], s.z[a], s.x[b], s.y[b], s.z[b]);
+    int base = 0;
+    if (lane == 0) base = atomicAdd(pool_count, kept);
+    base = __shfl_sync(kFull, base, 0);
+    for (int q = lane; q < kept; q += 32) {
+      const int m = s.order[q];
+      sloam_point p; p.x = s.x[m]; p.y = s.y[m]; p.z = s.z[m]; p.intensity = s.w[m];
+      pool[base + q] = p;
+    }
+    v.n_points = kept; v.point_begin = base; v.is_valid = 1;
+  }
+  if (lane == 0) *out = v;
+}
+
+__global__ void __launch_bounds__(kVtxWarps * 32)
+vertex_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ tree,
+              const int32_t *__restrict__ parent, const int32_t *__restrict__ big_roots,
+              const int32_t *__restrict__ bbox, const int32_t *__restrict__ vwork,
+              const int32_t *__restrict__ n_vwork, sloam_vertex *__restrict__ slot_vertices,
+              sloam_point *__restrict__ pool, int32_t *__restrict__ pool_count,
+              int32_t *__restrict__ overflow, int32_t *__restrict__ n_overflow) {
+  __shared__ VtxSmem sm[kVtxWarps];
+  const int N = dp->N, W = dp->p.img_w, H = dp->p.img_h, T = dp->p.max_trees;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  VtxSmem &s = sm[warp];
+  const int total = *n_vwork;
+  for (int item = blockIdx.x * kVtxWarps + warp; item < total; item += gridDim.x * kVtxWarps) {
+    const int w = vwork[item];
+    const int k = w >> 18, slot = (w >> 8) & 0x3FF, row = w & 0xFF;
+    const int root = big_roots[(size_t)k * T + slot];
+    const int32_t *bb = bbox + ((size_t)k * T + slot) * 4;
+    const int c0 = bb[0], c1 = bb[1];
+    const size_t rbase = (size_t)k * N + (size_t)row * W;
+    sloam_vertex *out = slot_vertices + ((size_t)k * T + slot) * H + row;
+    // members of this cluster in this row, in column order (trellis.cpp:113-118)
+    int n = 0;
+    for (int c = c0 + lane; c < ((c1 - c0 + 32) & ~31) + c0; c += 32) {
+      const bool mem = c <= c1 && parent[rbase + c] == root;
+      const unsigned b = __ballot_sync(kFull, mem);
+      if (mem) {
+        const int pos = n + __popc(b & ((1u << lane) - 1u));
+        if (pos < kVtxCap) {
+          const sloam_point p = tree[rbase + c];
+          s.x[pos] = p.x; s.y[pos] = p.y; s.z[pos] = p.z; s.w[pos] = p.intensity;
+          s.col[pos] = (int16_t)c;
+        }
+      }
+      n += __popc(b);
+    }
+    __syncwarp();
+    if (n > kVtxCap) {  // rare: very wide cluster, handled by the wide kernel
+      if (lane == 0) overflow[atomicAdd(n_overflow, 1)] = w;
+      continue;
+    }
+    if (n > dp->p.min_vertex_points) {  // trellis.cpp:119
+      build_vertex(dp, s, n, row, out, pool + (size_t)k * N, pool_count + k);
+    } else if (lane == 0) {
+      sloam_vertex v;
+      v.cx = v.cy = v.cz = 0.f; v.radius = 0.f; v.n_points = 0; v.point_begin = 0; v.row = row; v.is_valid = 0;
+      *out = v;
+    }
+    __syncwarp();
+  }
+}
+
+// wide path: one CTA per overflow item, all members in global scratch order --
+// same algorithm with a block-wide rank sort; members live in dynamic smem.
+__global__ void vertex_wide_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ tree,
+                                   const int32_t *__restrict__ parent, const int32_t *__restrict__ big_roots,
+                                   const int32_t *__restrict__ bbox, const int32_t *__restrict__ overflow,
+                                   const int32_t *__restrict__ n_overflow,
+                                   sloam_vertex *__restrict__ slot_vertices, sloam_point *__restrict__ pool,
+                                   int32_t *__restrict__ pool_count) {
+  extern __shared__ float dsm[];
+  const int N = dp->N, W = dp->p.img_w, H = dp->p.img_h, T = dp->p.max_trees;
+  float *sx = dsm, *sy = dsm + W, *sz = dsm + 2 * W, *sw = dsm + 3 * W;
+  int *scol = (int *)(dsm + 4 * W);
+  int *sorder = scol + W;
+  int *skeep = sorder + W;
+  __shared__ int s_n, s_kept, s_base;
+  __shared__ float s_med[3];
+  const int total = *n_overflow;
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int w = overflow[item];
+    const int k = w >> 18, slot = (w >> 8) & 0x3FF, row = w & 0xFF;
+    const int root = big_roots[(size_t)k * T + slot];
+    const size_t rbase = (size_t)k * N + (size_t)row * W;
+    sloam_vertex *out = slot_vertices + ((size_t)k * T + slot) * H + row;
+    __syncthreads();
+    if (threadIdx.x == 0) {  // serial member collection keeps column order (rare path)
+      int n = 0;
+      const int32_t *bb = bbox + ((size_t)k * T + slot) * 4;
+      for (int c = bb[0]; c <= bb[1]; ++c)
+        if (parent[rbase + c] == root) {
+          const sloam_point p = tree[rbase + c];
+          sx[n] = p.x; sy[n] = p.y; sz[n] = p.z; sw[n] = p.intensity; scol[n] = c; ++n;
+        }
+      s_n = n;
+    }
+    __syncthreads();
+    const int n = s_n;
+    const int middle = (int)(n / 2.0);
+    for (int m = threadIdx.x; m < n; m += blockDim.x) {
+      int rx = 0, ry = 0, rz = 0, rk = 0;
+      const float xm = sx[m], ym = sy[m], zm = sz[m];
+      for (int j = 0; j < n; ++j) {
+        rx += (sx[j] < xm) || (sx[j] == xm && j < m);
+        ry += (sy[j] < ym) || (sy[j] == ym && j < m);
+        rz += (sz[j] < zm) || (sz[j] == zm && j < m);
+        rk += key_less(sz[j], sy[j], sx[j], scol[j], zm, ym, xm, scol[m]);
+      }
+      sorder[rk] = m;
+      if (rx == middle) s_med[0] = xm;
+      if (ry == middle) s_med[1] = ym;
+      if (rz == middle) s_med[2] = zm;
+    }
+    __syncthreads();
+    const float maxd = dp->p.max_dist_to_centroid;
+    for (int q = threadIdx.x; q < n; q += blockDim.x) {
+      const int m = sorder[q];
+      skeep[q] = dist3f(sx[m], sy[m], sz[m], s_med[0], s_med[1], s_med[2]) < maxd;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int kept = 0;
+      for (int q = 0; q < n; ++q) if (skeep[q]) sorder[kept++] = sorder[q];
+      s_kept = kept;
+      sloam_vertex v;
+      v.cx = s_med[0]; v.cy = s_med[1]; v.cz = s_med[2];
+      v.radius = 0.f; v.n_points = 0; v.point_begin = 0; v.row = row; v.is_valid = 0;
+      if (kept > 1) {
+        const int a = sorder[0], b = sorder[kept - 1];
+        v.radius = dist3f(sx[a], sy[a], sz[a], sx[b], sy[b], sz[b]);
+        s_base = atomicAdd(pool_count + k, kept);
+        v.n_points = kept; v.point_begin = s_base; v.is_valid = 1;
+      }
+      *out = v;
+    }
+    __syncthreads();
+    if (s_kept > 1)
+      for (int q = threadIdx.x; q < s_kept; q += blockDim.x) {
+        const int m = sorder[q];
+        sloam_point p; p.x = sx[m]; p.y = sy[m]; p.z = sz[m]; p.intensity = sw[m];
+        pool[(size_t)k * N + s_base + q] = p;
+      }
+  }
+}
+
+// ---- 6. trees: keep clusters with enough vertices, bottom row first --------
+__global__ void tree_compact_kernel(const DevParams *__restrict__ dp, const int32_t *__restrict__ n_big,
+                                    const int32_t *__restrict__ big_rank, const int32_t *__restrict__ bbox,
+                                    const sloam_vertex *__restrict__ slot_vertices,
+                                    sloam_tree *__restrict__ trees, int32_t *__restrict__ n_trees,
+                                    sloam_vertex *__restrict__ vertices) {
+  extern __shared__ int32_t sm[];
+  const int H = dp->p.img_h, T = dp->p.max_trees;
+  const int minv = dp->p.min_tree_vertices, maxv = dp->p.max_tree_vertices;
+  const int k = blockIdx.x;
+  const int nb = n_big[k];
+  int32_t *s_nv = sm;        // [T] vertices of the slot (0 when rejected)
+  int32_t *s_idx = sm + T;   // [T] tree index
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int s = warp; s < nb; s += nwarps) {
+    const int32_t *bb = bbox + ((size_t)k * T + s) * 4;
+    const sloam_vertex *sv = slot_vertices + ((size_t)k * T + s) * H;
+    int cnt = 0;
+    for (int top = bb[3]; top >= bb[2]; top -= 32) {  // rows from the bottom up (trellis.cpp:111)
+      const int r = top - lane;
+      const bool v = r >= bb[2] && sv[r].is_valid;
+      cnt += __popc(__ballot_sync(kFull, v));
+    }
+    if (lane == 0) s_nv[s] = cnt > minv ? min(cnt, maxv) : 0;  // trellis.cpp:124-127
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int s = 0; s < nb; ++s) { s_idx[s] = t; t += s_nv[s] > 0; }
+    n_trees[k] = t;
+  }
+  __syncthreads();
+  for (int s = warp; s < nb; s += nwarps) {
+    const int nv = s_nv[s];
+    if (nv == 0) continue;
+    const int t = s_idx[s];
+    const int32_t *bb = bbox + ((size_t)k * T + s) * 4;
+    const sloam_vertex *sv = slot_vertices + ((size_t)k * T + s) * H;
+    sloam_vertex *dst = vertices + ((size_t)k * T + t) * maxv;
+    int cnt = 0, npts = 0;
+    for (int top = bb[3]; top >= bb[2]; top -= 32) {
+      const int r = top - lane;
+      const bool v = r >= bb[2] && sv[r].is_valid;
+      const unsigned b = __ballot_sync(kFull, v);
+      const int pos = cnt + __popc(b & ((1u << lane) - 1u));
+      int np = 0;
+      if (v && pos < nv) { const sloam_vertex vv = sv[r]; dst[pos] = vv; np = vv.n_points; }
+      npts += warp_sum(np);
+      cnt += __popc(b);
+    }
+    if (lane == 0) {
+      sloam_tree tr;
+      tr.tree_id = big_rank[(size_t)k * T + s];
+      tr.n_vertices = nv;
+      tr.vertex_begin = t * maxv;
+      tr.n_points = npts;
+      trees[(size_t)k * T + t] = tr;
+    }
+  }
+}
+
+// ---- labels for the find_clusters stage entry -------------------------------
+__global__ void cc_rank_rows_kernel(const DevParams *__restrict__ dp, const int32_t *__restrict__ parent,
+                                    const int32_t *__restrict__ row_roots, int32_t *__restrict__ root_rank) {
+  const int N = dp->N, W = dp->p.img_w, H = dp->p.img_h;
+  const int k = blockIdx.y;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= H) return;
+  const int lane = threadIdx.x & 31;
+  int pre = 0;
+  for (int r = lane; r < row; r += 32) pre += row_roots[(size_t)k * H + r];
+  pre = warp_sum(pre);
+  const size_t rbase = (size_t)k * N + (size_t)row * W;
+  for (int c = lane; c < ((W + 31) & ~31); c += 32) {
+    const bool is_root = c < W && parent[rbase + c] == row * W + c;
+    const unsigned b = __ballot_sync(kFull, is_root);
+    if (is_root) root_rank[rbase + c] = pre + __popc(b & ((1u << lane) - 1u));
+    pre += __popc(b);
+  }
+}
+__global__ void cc_labels_kernel(const DevParams *__restrict__ dp, int K, const int32_t *__restrict__ parent,
+                                 const int32_t *__restrict__ root_rank, uint32_t *__restrict__ labels) {
+  const int N = dp->N;
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)K * N) return;
+  const int k = (int)(g / N);
+  const int r = parent[g];
+  labels[g] = r == kInvalid ? 0xFFFFFFFFu : (uint32_t)root_rank[(size_t)k * N + r];
+}
+
+static int run_cc(sloam_ctx *c, int K, const sloam_point *tree) {
+  Workspace &w = c->ws;
+  const long long total = (long long)K * c->hp.N;
+  const int H = c->hp.p.img_h;
+  SB_CUDA(c, cudaMemsetAsync(w.row_roots, 0, sizeof(int32_t) * (size_t)K * H, c->stream));
+  SB_CUDA(c, cudaMemsetAsync(w.n_roots, 0, sizeof(int32_t) * K, c->stream));
+  SB_CUDA(c, cudaMemsetAsync(w.n_big, 0, sizeof(int32_t) * K, c->stream));
+  SB_CUDA(c, cudaMemsetAsync(w.kf_flags, 0, sizeof(int32_t) * K, c->stream));
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  cc_init_kernel<<<blocks, 256, 0, c->stream>>>(c->dp, K, tree, w.parent, w.cc_flags, w.csize,
+                                                w.ccol_min, w.ccol_max, w.crow_max);
+  SB_LAUNCH_CHECK(c);
+  cc_merge_kernel<<<(unsigned)((total / 4 + 255) / 256 + 1), 256, 0, c->stream>>>(c->dp, K, w.cc_flags, w.parent);
+  SB_LAUNCH_CHECK(c);
+  cc_flatten_kernel<<<blocks, 256, 0, c->stream>>>(c->dp, K, w.parent, w.csize, w.ccol_min, w.ccol_max,
+                                                   w.crow_max, w.row_roots, w.n_roots, w.big_roots,
+                                                   w.n_big, w.kf_flags);
+  SB_LAUNCH_CHECK(c);
+  return SLOAM_OK;
+}
+
+int launch_compute_graph(sloam_ctx *c, int K, const sloam_point *tree, sloam_tree *trees,
+                         int32_t *n_trees, sloam_vertex *vertices, sloam_point *vertex_points) {
+  Workspace &w = c->ws;
+  const sloam_params &p = c->hp.p;
+  const int T = p.max_trees, H = p.img_h, W = p.img_w;
+  int rc = run_cc(c, K, tree);
+  if (rc != SLOAM_OK) return rc;
+  SB_CUDA(c, cudaMemsetAsync(w.n_overflow, 0, sizeof(int32_t) * 4, c->stream));
+  SB_CUDA(c, cudaMemsetAsync(w.vpool_count, 0, sizeof(int32_t) * K, c->stream));
+  cc_plan_kernel<<<K, 256, sizeof(int32_t) * (2 * T + H + 1), c->stream>>>(
+      c->dp, w.parent, w.ccol_min, w.ccol_max, w.crow_max, w.row_roots, w.big_roots, w.n_big,
+      w.big_rank, w.bbox, w.vwork, w.n_overflow + 1);
+  SB_LAUNCH_CHECK(c);
+  const int vgrid = c->sm_count * 4;
+  vertex_kernel<<<vgrid, kVtxWarps * 32, 0, c->stream>>>(c->dp, tree, w.parent, w.big_roots, w.bbox,
+                                                         w.vwork, w.n_overflow + 1, w.slot_vertices,
+                                                         vertex_points, w.vpool_count, w.overflow_list,
+                                                         w.n_overflow);
+  SB_LAUNCH_CHECK(c);
+  const size_t wide_smem = sizeof(float) * 4 * W + sizeof(int) * 3 * W;
+  static bool attr_set = false;
+  if (!attr_set && wide_smem > 48 * 1024) {
+    SB_CUDA(c, cudaFuncSetAttribute(vertex_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem));
+    attr_set = true;
+  }
+  vertex_wide_kernel<<<c->sm_count, 256, wide_smem, c->stream>>>(c->dp, tree, w.parent, w.big_roots, w.bbox,
+                                                                 w.overflow_list, w.n_overflow,
+                                                                 w.slot_vertices, vertex_points,
+                                                                 w.vpool_count);
+  SB_LAUNCH_CHECK(c);
+  tree_compact_kernel<<<K, 256, sizeof(int32_t) * 2 * T, c->stream>>>(c->dp, w.n_big, w.big_rank, w.bbox,
+                                                                       w.slot_vertices, trees, n_trees,
+                                                                       vertices);
+  SB_LAUNCH_CHECK(c);
+  return SLOAM_OK;
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" {
+
+int sloam_b200_find_clusters_dev(sloam_ctx *c, int K, const sloam_point *tree, uint32_t *labels,
+                                 int32_t *n_clusters) {
+  if (!c || K <= 0 || K > c->max_k || !tree || !labels) return set_err(c, SLOAM_E_INVALID, "find_clusters: bad arguments");
+  int rc = run_cc(c, K, tree);
+  if (rc != SLOAM_OK) return rc;
+  const int H = c->hp.p.img_h;
+  dim3 grid((unsigned)((H + 7) / 8), (unsigned)K);
+  cc_rank_rows_kernel<<<grid, 256, 0, c->stream>>>(c->dp, c->ws.parent, c->ws.row_roots, c->ws.root_rank);
+  SB_LAUNCH_CHECK(c);
+  const long long total = (long long)K * c->hp.N;
+  cc_labels_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(c->dp, K, c->ws.parent,
+                                                                          c->ws.root_rank, labels);
+  SB_LAUNCH_CHECK(c);
+  if (n_clusters)
+    SB_CUDA(c, cudaMemcpyAsync(n_clusters, c->ws.n_roots, sizeof(int32_t) * K, cudaMemcpyDeviceToDevice, c->stream));
+  return SLOAM_OK;
+}
+
+int sloam_b200_compute_graph_dev(sloam_ctx *c, int K, const sloam_point *tree, sloam_tree *trees,
+                                 int32_t *n_trees, sloam_vertex *vertices, sloam_point *vertex_points) {
+  if (!c || K <= 0 || K > c->max_k || !tree || !trees || !n_trees || !vertices || !vertex_points)
+    return set_err(c, SLOAM_E_INVALID, "compute_graph: bad arguments");
+  return launch_compute_graph(c, K, tree, trees, n_trees, vertices, vertex_points);
+}
+
+}  // extern "C"

@@ -1,0 +1,141 @@
+// pipeline.cu -- the fused batched path: Segmentation::run (projection) +
+// maskCloud x2 + Instance::computeGraph + sloam::RunSloam for K keyframes
+// (the call sequence of SLOAMNode::run, sloam/src/core/sloamNode.cpp:208-236,
+// minus the segmentation network whose H x W {0,1,255} mask is an input).
+#include "common.cuh"
+
+namespace sb {
+
+int launch_project_split(sloam_ctx *c, int K, bool do_project, bool do_split, const sloam_point *points,
+                         const uint8_t *mask, int32_t *pix, float *range_image, sloam_point *tree,
+                         sloam_point *ground, int32_t *ground_count);
+int launch_ground_planes(sloam_ctx *c, int K, const sloam_point *ground, const int32_t *ground_count,
+                         int stride, const sloam_pose *pose_est, sloam_cell_plane *cells,
+                         sloam_point *cell_features, sloam_point *kept_points, int32_t *kept_offsets);
+int launch_compute_graph(sloam_ctx *c, int K, const sloam_point *tree, sloam_tree *trees, int32_t *n_trees,
+                         sloam_vertex *vertices, sloam_point *vertex_points);
+int launch_cylinders(sloam_ctx *c, int K, const sloam_tree *trees, const int32_t *n_trees,
+                     const sloam_vertex *vertices, const sloam_point *vpoints, const sloam_plane *planes_acc,
+                     const int32_t *n_planes_acc, sloam_tree_model *models, sloam_point *features);
+int launch_sloam_core(sloam_ctx *c, int K, const sloam_batch_in *in, const sloam_batch_out *out);
+
+static int check_batch(sloam_ctx *c, int K, const sloam_batch_in *in, const sloam_batch_out *out) {
+  if (!c) return SLOAM_E_INVALID;
+  if (K <= 0 || K > c->max_k) return set_err(c, SLOAM_E_INVALID, "run_keyframes: K out of range");
+  if (!in || !out || !in->points || !in->mask || !in->pose_est || !in->first_scan || !in->map_models ||
+      !in->n_map_models || !in->prev_planes || !in->n_prev_planes || !out->results || !out->matches ||
+      !out->tm || !out->tm_id || !out->planes || !out->n_planes)
+    return set_err(c, SLOAM_E_INVALID, "run_keyframes: null buffer");
+  return SLOAM_OK;
+}
+
+static int run_dev(sloam_ctx *c, int K, const sloam_batch_in *in, const sloam_batch_out *out) {
+  Workspace &w = c->ws;
+  float *range = out->range_image;  // optional output
+  int rc = launch_project_split(c, K, true, true, in->points, in->mask, w.pix, range, w.tree, w.ground,
+                                w.ground_count);
+  if (rc != SLOAM_OK) return rc;
+  rc = launch_ground_planes(c, K, w.ground, w.ground_count, c->hp.N, in->pose_est, w.cells,
+                            w.cell_features, nullptr, nullptr);
+  if (rc != SLOAM_OK) return rc;
+  rc = launch_compute_graph(c, K, w.tree, w.trees, w.n_trees, w.vertices, w.vertex_points);
+  if (rc != SLOAM_OK) return rc;
+  rc = launch_cylinders(c, K, w.trees, w.n_trees, w.vertices, w.vertex_points, w.planes_acc,
+                        w.n_planes_acc, w.tree_models, w.tree_features);
+  if (rc != SLOAM_OK) return rc;
+  rc = launch_sloam_core(c, K, in, out);
+  c->last_k = K;
+  return rc;
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" {
+
+int sloam_b200_run_keyframes_dev(sloam_ctx *c, int K, const sloam_batch_in *in, const sloam_batch_out *out) {
+  const int rc = check_batch(c, K, in, out);
+  if (rc != SLOAM_OK) return rc;
+  return run_dev(c, K, in, out);
+}
+
+int sloam_b200_run_keyframes_host(sloam_ctx *c, int K, const sloam_batch_in *in, const sloam_batch_out *out) {
+  int rc = check_batch(c, K, in, out);
+  if (rc != SLOAM_OK) return rc;
+  const sloam_params &p = c->hp.p;
+  const size_t N = (size_t)c->hp.N, T = (size_t)p.max_trees, M = (size_t)p.max_map_models,
+               PP = (size_t)p.max_prev_planes, Kc = (size_t)c->max_k;
+  // device staging for the largest batch, allocated once
+  struct Part { size_t off, bytes; };
+  size_t off = 0;
+  auto part = [&](size_t bytes) { Part q{off, bytes}; off = (off + bytes + 255) / 256 * 256; return q; };
+  const Part d_points = part(Kc * N * sizeof(sloam_point)), d_mask = part(Kc * N), d_pose = part(Kc * sizeof(sloam_pose)),
+             d_first = part(Kc), d_map = part(Kc * M * sizeof(sloam_cylinder)), d_nmap = part(Kc * 4),
+             d_prev = part(Kc * PP * sizeof(sloam_plane)), d_nprev = part(Kc * 4),
+             d_res = part(Kc * sizeof(sloam_kf_result)), d_match = part(Kc * T * 4),
+             d_tm = part(Kc * T * sizeof(sloam_cylinder)), d_tmid = part(Kc * T * 4),
+             d_planes = part(Kc * PP * sizeof(sloam_plane)), d_npl = part(Kc * 4),
+             d_range = part(Kc * N * 4);
+  if (c->stage_dev_bytes < off) {
+    if (c->stage_dev) cudaFree(c->stage_dev);
+    c->stage_dev = nullptr; c->stage_dev_bytes = 0;
+    SB_CUDA(c, cudaMalloc(&c->stage_dev, off));
+    c->stage_dev_bytes = off;
+  }
+  char *base = (char *)c->stage_dev;
+  cudaStream_t s = c->stream;
+  const size_t Ks = (size_t)K;
+#define H2D(partv, src, bytes) SB_CUDA(c, cudaMemcpyAsync(base + partv.off, src, bytes, cudaMemcpyHostToDevice, s))
+  H2D(d_points, in->points, Ks * N * sizeof(sloam_point));
+  H2D(d_mask, in->mask, Ks * N);
+  H2D(d_pose, in->pose_est, Ks * sizeof(sloam_pose));
+  H2D(d_first, in->first_scan, Ks);
+  H2D(d_map, in->map_models, (in->map_shared ? 1 : Ks) * M * sizeof(sloam_cylinder));
+  H2D(d_nmap, in->n_map_models, (in->map_shared ? 1 : Ks) * 4);
+  H2D(d_prev, in->prev_planes, Ks * PP * sizeof(sloam_plane));
+  H2D(d_nprev, in->n_prev_planes, Ks * 4);
+#undef H2D
+  sloam_batch_in din = *in;
+  din.points = (const sloam_point *)(base + d_points.off);
+  din.mask = (const uint8_t *)(base + d_mask.off);
+  din.pose_est = (const sloam_pose *)(base + d_pose.off);
+  din.first_scan = (const uint8_t *)(base + d_first.off);
+  din.map_models = (const sloam_cylinder *)(base + d_map.off);
+  din.n_map_models = (const int32_t *)(base + d_nmap.off);
+  din.prev_planes = (const sloam_plane *)(base + d_prev.off);
+  din.n_prev_planes = (const int32_t *)(base + d_nprev.off);
+  sloam_batch_out dout;
+  dout.results = (sloam_kf_result *)(base + d_res.off);
+  dout.matches = (int32_t *)(base + d_match.off);
+  dout.tm = (sloam_cylinder *)(base + d_tm.off);
+  dout.tm_id = (int32_t *)(base + d_tmid.off);
+  dout.planes = (sloam_plane *)(base + d_planes.off);
+  dout.n_planes = (int32_t *)(base + d_npl.off);
+  dout.range_image = out->range_image ? (float *)(base + d_range.off) : nullptr;
+  rc = run_dev(c, K, &din, &dout);
+  if (rc != SLOAM_OK) return rc;
+#define D2H(dst, partv, bytes) SB_CUDA(c, cudaMemcpyAsync(dst, base + partv.off, bytes, cudaMemcpyDeviceToHost, s))
+  D2H(out->results, d_res, Ks * sizeof(sloam_kf_result));
+  D2H(out->matches, d_match, Ks * T * 4);
+  D2H(out->tm, d_tm, Ks * T * sizeof(sloam_cylinder));
+  D2H(out->tm_id, d_tmid, Ks * T * 4);
+  D2H(out->planes, d_planes, Ks * PP * sizeof(sloam_plane));
+  D2H(out->n_planes, d_npl, Ks * 4);
+  if (out->range_image) D2H(out->range_image, d_range, Ks * N * 4);
+#undef D2H
+  SB_CUDA(c, cudaStreamSynchronize(s));
+  return SLOAM_OK;
+}
+
+int sloam_b200_get_intermediates(sloam_ctx *c, sloam_intermediates *o) {
+  if (!c || !o) return SLOAM_E_INVALID;
+  const Workspace &w = c->ws;
+  o->pix = w.pix; o->tree = w.tree; o->ground = w.ground; o->ground_count = w.ground_count;
+  o->cells = w.cells; o->cell_features = w.cell_features; o->trees = w.trees; o->n_trees = w.n_trees;
+  o->vertices = w.vertices; o->vertex_points = w.vertex_points; o->tree_models = w.tree_models;
+  o->tree_features = w.tree_features;
+  return SLOAM_OK;
+}
+
+}  // extern "C"
