@@ -352,6 +352,27 @@ int sloam_b200_run_keyframes_host(sloam_ctx *ctx, int K,
                                   const sloam_batch_in *in,
                                   const sloam_batch_out *out);
 
+/* sloam::RunSloam (sloam.cpp:453-532) alone, for callers that already hold the
+ * SloamInput of the reference: ground clouds [K][ground_stride] with counts,
+ * landmarks as produced by compute_graph (trees [K][max_trees], vertices
+ * [K][vertex_stride], vertex_points [K][point_stride]); in->points / in->mask
+ * are ignored.  Device pointers. */
+int sloam_b200_run_sloam_dev(sloam_ctx *ctx, int K, const sloam_point *ground,
+                             const int32_t *ground_count, int ground_stride,
+                             const sloam_tree *trees, const int32_t *n_trees,
+                             const sloam_vertex *vertices, int vertex_stride,
+                             const sloam_point *vertex_points, int point_stride,
+                             const sloam_batch_in *in,
+                             const sloam_batch_out *out);
+
+/* Device-memory helpers so that a host-language binding (cgo / JNI / the C++
+ * classes in sloam_b200/host) needs no CUDA headers.  copy_d2h synchronises
+ * the context stream before returning. */
+void *sloam_b200_dev_alloc(sloam_ctx *ctx, uint64_t bytes);
+void sloam_b200_dev_free(sloam_ctx *ctx, void *ptr);
+int sloam_b200_copy_h2d(sloam_ctx *ctx, void *dst_dev, const void *src_host, uint64_t bytes);
+int sloam_b200_copy_d2h(sloam_ctx *ctx, void *dst_host, const void *src_dev, uint64_t bytes);
+
 /* Intermediate device buffers of the last run_keyframes call (for tests and
  * for callers that want the landmarks): pointers into context scratch. */
 typedef struct sloam_intermediates {

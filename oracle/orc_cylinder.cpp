@@ -327,8 +327,9 @@ Cylinder make_cylinder(const Options &o, const std::vector<TreeVertex> &vertices
   const TreeVertex &firstVtx = vertices[1];
   const bool withinMaxDist = euclideanDist2D(firstVtx.coords, centroid) < o.p.maxLidarDist;
   c.isValid = false;
-  /* ray is uninitialised in the reference on the early-return paths; the
-   * oracle defines it as zero (the cylinder is invalid there anyway). */
+  /* id and ray are uninitialised in the reference on the early-return paths; the
+   * oracle defines them as vertices[2].treeId and zero (the cylinder is invalid there). */
+  c.id = (size_t)vertices[2].treeId;
   if (!withinMaxDist) return c;
   compute_model(o, c, vertices);
   /* groundBasedRoot, :41-55 */

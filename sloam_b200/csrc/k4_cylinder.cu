@@ -443,14 +443,28 @@ __global__ void cylinders_compact_kernel(const DevParams *__restrict__ dp, const
   if (lane == 0) n_lm[k] = cnt;
 }
 
+int launch_cylinders_strided(sloam_ctx *c, int K, const sloam_tree *trees, const int32_t *n_trees,
+                             const sloam_vertex *vertices, int vstride, const sloam_point *vpoints,
+                             int pstride, const sloam_plane *planes_acc, const int32_t *n_planes_acc,
+                             sloam_tree_model *models, sloam_point *features);
+
 int launch_cylinders(sloam_ctx *c, int K, const sloam_tree *trees, const int32_t *n_trees,
                      const sloam_vertex *vertices, const sloam_point *vpoints,
                      const sloam_plane *planes_acc, const int32_t *n_planes_acc,
                      sloam_tree_model *models, sloam_point *features) {
   const sloam_params &p = c->hp.p;
+  return launch_cylinders_strided(c, K, trees, n_trees, vertices, p.max_trees * p.max_tree_vertices, vpoints,
+                                  c->hp.N, planes_acc, n_planes_acc, models, features);
+}
+
+int launch_cylinders_strided(sloam_ctx *c, int K, const sloam_tree *trees, const int32_t *n_trees,
+                             const sloam_vertex *vertices, int vstride, const sloam_point *vpoints,
+                             int pstride, const sloam_plane *planes_acc, const int32_t *n_planes_acc,
+                             sloam_tree_model *models, sloam_point *features) {
+  const sloam_params &p = c->hp.p;
   dim3 grid((unsigned)((p.max_trees + kCylWarps - 1) / kCylWarps), (unsigned)K);
   cylinder_kernel<<<grid, kCylWarps * 32, 0, c->stream>>>(
-      c->dp, trees, n_trees, vertices, vpoints, p.max_trees * p.max_tree_vertices, c->hp.N, planes_acc,
+      c->dp, trees, n_trees, vertices, vpoints, vstride, pstride, planes_acc,
       n_planes_acc, c->ws.ransac_pairs, c->ws.ransac_pairs_offset, models, features);
   SB_LAUNCH_CHECK(c);
   cylinders_compact_kernel<<<K, 32, 0, c->stream>>>(c->dp, n_trees, models, c->ws.lm_cyl, c->ws.lm_src, c->ws.n_lm);

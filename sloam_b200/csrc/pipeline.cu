@@ -18,6 +18,11 @@ int launch_cylinders(sloam_ctx *c, int K, const sloam_tree *trees, const int32_t
                      const sloam_vertex *vertices, const sloam_point *vpoints, const sloam_plane *planes_acc,
                      const int32_t *n_planes_acc, sloam_tree_model *models, sloam_point *features);
 int launch_sloam_core(sloam_ctx *c, int K, const sloam_batch_in *in, const sloam_batch_out *out);
+int launch_ground_tag(sloam_ctx *c, int K, const sloam_point *ground, const int32_t *ground_count, int stride);
+int launch_cylinders_strided(sloam_ctx *c, int K, const sloam_tree *trees, const int32_t *n_trees,
+                             const sloam_vertex *vertices, int vstride, const sloam_point *vpoints,
+                             int pstride, const sloam_plane *planes_acc, const int32_t *n_planes_acc,
+                             sloam_tree_model *models, sloam_point *features);
 
 static int check_batch(sloam_ctx *c, int K, const sloam_batch_in *in, const sloam_batch_out *out) {
   if (!c) return SLOAM_E_INVALID;
@@ -125,6 +130,59 @@ int sloam_b200_run_keyframes_host(sloam_ctx *c, int K, const sloam_batch_in *in,
   if (out->range_image) D2H(out->range_image, d_range, Ks * N * 4);
 #undef D2H
   SB_CUDA(c, cudaStreamSynchronize(s));
+  return SLOAM_OK;
+}
+
+int sloam_b200_run_sloam_dev(sloam_ctx *c, int K, const sloam_point *ground, const int32_t *ground_count,
+                             int ground_stride, const sloam_tree *trees, const int32_t *n_trees,
+                             const sloam_vertex *vertices, int vertex_stride,
+                             const sloam_point *vertex_points, int point_stride, const sloam_batch_in *in,
+                             const sloam_batch_out *out) {
+  if (!c || K <= 0 || K > c->max_k || !ground || !ground_count || !trees || !n_trees || !vertices ||
+      !vertex_points || !in || !out || !in->pose_est || !in->first_scan || !in->map_models ||
+      !in->n_map_models || !in->prev_planes || !in->n_prev_planes || !out->results || !out->matches ||
+      !out->tm || !out->tm_id || !out->planes || !out->n_planes || ground_stride <= 0 ||
+      ground_stride > c->hp.N)
+    return set_err(c, SLOAM_E_INVALID, "run_sloam: bad arguments (ground_stride must be <= H*W)");
+  Workspace &w = c->ws;
+  int rc = launch_ground_tag(c, K, ground, ground_count, ground_stride);
+  if (rc != SLOAM_OK) return rc;
+  rc = launch_ground_planes(c, K, ground, ground_count, ground_stride, in->pose_est, w.cells,
+                            w.cell_features, nullptr, nullptr);
+  if (rc != SLOAM_OK) return rc;
+  rc = launch_cylinders_strided(c, K, trees, n_trees, vertices, vertex_stride, vertex_points, point_stride,
+                                w.planes_acc, w.n_planes_acc, w.tree_models, w.tree_features);
+  if (rc != SLOAM_OK) return rc;
+  // the core reads the per-keyframe counts from the workspace for its result records
+  SB_CUDA(c, cudaMemcpyAsync(w.ground_count, ground_count, sizeof(int32_t) * K, cudaMemcpyDeviceToDevice, c->stream));
+  SB_CUDA(c, cudaMemcpyAsync(w.n_trees, n_trees, sizeof(int32_t) * K, cudaMemcpyDeviceToDevice, c->stream));
+  return launch_sloam_core(c, K, in, out);
+}
+
+void *sloam_b200_dev_alloc(sloam_ctx *c, uint64_t bytes) {
+  if (!c) return nullptr;
+  void *p = nullptr;
+  cudaSetDevice(c->device);
+  if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) { c->err = "dev_alloc: cudaMalloc failed"; return nullptr; }
+  return p;
+}
+
+void sloam_b200_dev_free(sloam_ctx *c, void *p) {
+  if (!c || !p) return;
+  cudaStreamSynchronize(c->stream);
+  cudaFree(p);
+}
+
+int sloam_b200_copy_h2d(sloam_ctx *c, void *dst, const void *src, uint64_t bytes) {
+  if (!c || (!dst && bytes) || (!src && bytes)) return SLOAM_E_INVALID;
+  if (bytes) SB_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  return SLOAM_OK;
+}
+
+int sloam_b200_copy_d2h(sloam_ctx *c, void *dst, const void *src, uint64_t bytes) {
+  if (!c || (!dst && bytes) || (!src && bytes)) return SLOAM_E_INVALID;
+  if (bytes) SB_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  SB_CUDA(c, cudaStreamSynchronize(c->stream));
   return SLOAM_OK;
 }
 
