@@ -19,7 +19,7 @@ namespace sb {
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr int kMaxCells = 256;        // groundRadiiBins * groundThetaBins upper bound
-constexpr int kSplitTile = 2048;      // points per CTA in the project/split kernel
+constexpr int kSplitTile = 1024;      // points per CTA in the project/split kernel
 constexpr int kMaxBigClusters = 1024; // clusters with > min_cluster_points per keyframe
 
 // Device copy of the parameters plus derived constants.

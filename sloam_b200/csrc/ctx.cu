@@ -157,6 +157,8 @@ static void derive(DevParams &d) {
   d.gg.theta_step = 2 * 3.14159265 / (double)p.groundThetaBins;
   d.gg.RB = p.groundRadiiBins;
   d.gg.TB = p.groundThetaBins;
+  d.gg.inv_radial_step_f = (float)(1.0 / d.gg.radial_step);
+  d.gg.inv_theta_step_f = (float)(1.0 / d.gg.theta_step);
 }
 
 static int upload_tables(sloam_ctx *c) {

@@ -27,8 +27,57 @@ __device__ __forceinline__ unsigned long long pack_state(unsigned flag, unsigned
   return ((unsigned long long)flag << 62) | v;
 }
 
+// fp32 estimate of project_pixel(): returns the pixel index when both image
+// coordinates are provably (margins mx, my, in pixels) on the same side of every
+// pixel boundary as the bit-exact evaluation, else -1.  Error budget (W = 2048):
+// CUDA atan2f <= 3 ulp (7.2e-7 rad), asinf <= 4 ulp; fp32 evaluation of
+// 0.5 (yaw / pi + 1) W deviates from the exact pipeline by < 9e-4 px, of
+// (1 - (pitch + |fov_down|) / fov) H by < 2e-4 px.  NaN / out-of-image -> -1.
+__device__ __forceinline__ int project_pixel_fast(const ProjGeom &g, float x, float y, float z, float mx,
+                                                  float my, float inv_fov, float *yaw_out) {
+  // no-return beams (NaN x or y): yaw and pitch are NaN, both coordinates take the
+  // clamp of inference.cpp:120,125 (std::min keeps its first argument) -> last pixel
+  *yaw_out = __int_as_float(0x7fc00000);
+  if (x != x || y != y) return (int)((g.Hf - 1.0f) * g.Wf + (g.Wf - 1.0f));
+  const float yaw = -atan2f(y, x);
+  *yaw_out = yaw;
+  // z / range via rsqrt (<= 2 ulp): the estimate only has to be inside the margins
+  const float pitch = asinf(z * rsqrtf(x * x + y * y + z * z));
+  const float px = (0.5f * (yaw * 0.318309886f + 1.0f)) * g.Wf;
+  const float py = (1.0f - (pitch + g.fov_down_abs) * inv_fov) * g.Hf;
+  const float fx = floorf(px), fy = floorf(py);
+  const bool ok = (px - fx > mx) && (fx + 1.0f - px > mx) && (py - fy > my) && (fy + 1.0f - py > my) &&
+                  fx >= 0.0f && fx <= g.Wf - 1.0f && fy >= 0.0f && fy <= g.Hf - 1.0f;
+  return ok ? (int)(fy * g.Wf + fx) : -1;
+}
+
+// Same idea for the polar ground cell: the radius bin is evaluated exactly (one
+// fp64 division), the theta bin from atan2f with a margin of 1e-4 bins, falling
+// back to the exact ground_cell_of() next to a bin edge (~2e-4 of the points).
+// `yaw` is the fp32 estimate of -atan2f(y, x) from the projection (NaN when unknown).
+__device__ __forceinline__ int ground_cell_fast(const GroundGeom &g, float x, float y, float yaw) {
+  // pow_2 rounds the exact fp64 square of a float to float == the fp32 product
+  const float rf = sqrtf(x * x + y * y);  // bit-identical to euclideanDist2D (utils.h:9-12)
+  const double radius = (double)rf;
+  if (!(radius < g.max_dist && radius > g.min_dist)) return -1;
+  const float theta = (yaw == yaw) ? -yaw : atan2f(y, x);
+  const float tb_f = (3.14159265f + theta) * g.inv_theta_step_f;
+  const float rb_f = rf * g.inv_radial_step_f;
+  const float fl = floorf(tb_f), flr = floorf(rb_f);
+  // margins: atan2f 3 ulp + fp32 evaluation < 2e-5 bins for up to 255 bins
+  if (!(tb_f - fl > 1e-3f && fl + 1.0f - tb_f > 1e-3f && rb_f - flr > 1e-3f && flr + 1.0f - rb_f > 1e-3f))
+    return ground_cell_of(g, x, y);
+  int rb = (int)flr;
+  int tb = (int)fl;
+  rb = rb < g.RB - 1 ? rb : g.RB - 1;
+  rb = rb > 0 ? rb : 0;
+  tb = tb < g.TB - 1 ? tb : g.TB - 1;
+  tb = tb > 0 ? tb : 0;
+  return rb * g.TB + tb;
+}
+
 template <bool DO_PROJECT, bool DO_SPLIT>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point *__restrict__ points,
                      const uint8_t *__restrict__ mask, int32_t *__restrict__ pix_io,
                      unsigned *__restrict__ range_bits, sloam_point *__restrict__ tree,
@@ -36,18 +85,27 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
                      uint8_t *__restrict__ ground_cell, int32_t *__restrict__ cell_count,
                      unsigned long long *__restrict__ tile_state, unsigned *__restrict__ ticket,
                      int ground_stride) {
-  __shared__ sloam_point s_ground[DO_SPLIT ? kSplitTile : 1];
+  __shared__ __align__(16) unsigned char s_raw[(DO_SPLIT ? sizeof(sloam_point) : sizeof(int)) * kSplitTile];
+  sloam_point *s_ground = reinterpret_cast<sloam_point *>(s_raw);
   __shared__ uint8_t s_cell[DO_SPLIT ? kSplitTile : 1];
   __shared__ int s_hist[DO_SPLIT ? kMaxCells : 1];
   __shared__ int s_warp[kThreads / 32];
   __shared__ unsigned s_tile;
   __shared__ int s_base;
+  __shared__ uint16_t s_slow[DO_PROJECT ? kSplitTile : 1];
+  __shared__ int s_nslow;
+  __shared__ int s_cnt[kRounds * (kThreads / 32)];
+  // exact pixel indices of the queued points (phases A/B only): aliases the ground staging
+  int *s_pix = reinterpret_cast<int *>(s_raw);
 
   const int N = dp->N;
   const int tiles = (N + kSplitTile - 1) / kSplitTile;
   // tiles are handed out in scheduling order so the look-back never waits on
   // a CTA that has not started
-  if (threadIdx.x == 0) s_tile = DO_SPLIT ? atomicAdd(ticket, 1u) : blockIdx.x;
+  if (threadIdx.x == 0) {
+    s_tile = DO_SPLIT ? atomicAdd(ticket, 1u) : blockIdx.x;
+    s_nslow = 0;
+  }
   if (DO_SPLIT)
     for (int c = threadIdx.x; c < kMaxCells; c += kThreads) s_hist[c] = 0;
   __syncthreads();
@@ -61,58 +119,112 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
   const float qnan = __int_as_float(0x7fc00000);
   int base = 0;
 
-#pragma unroll 2
+  // ---- phase A: load the tile (8 float4 per thread stay in registers) and project.
+  // The pixel index is an integer derived from atan2f/asinf; the bit-exact evaluation
+  // (proj_math.h, fp64) is ~230 DP instructions, so it only runs for the ~1.5 % of points
+  // whose fast fp32 estimate lies within a proven error margin of a pixel boundary.
+  // Those are queued and re-projected densely in phase B instead of diverging here.
+  sloam_point pts[kRounds];
+  int pixr[kRounds];
+  float yawr[kRounds];
+  const float mx = pg.Wf * 2.5e-6f + 1e-3f, my = 2e-3f, inv_fov = 1.0f / pg.fov;
+#pragma unroll
+  for (int j = 0; j < kRounds; ++j) {
+    const int i = tile * kSplitTile + j * kThreads + threadIdx.x;
+    pts[j] = sloam_point{0.f, 0.f, 0.f, 0.f};
+    pixr[j] = 0;
+    yawr[j] = qnan;
+    if (i < N) {
+      pts[j] = points[kbase + i];
+      if (DO_PROJECT) {
+        pixr[j] = project_pixel_fast(pg, pts[j].x, pts[j].y, pts[j].z, mx, my, inv_fov, &yawr[j]);
+        if (pixr[j] < 0) s_slow[atomicAdd(&s_nslow, 1)] = j * kThreads + threadIdx.x;
+      } else {
+        pixr[j] = pix_io[kbase + i];
+      }
+    }
+  }
+  if (DO_PROJECT) {
+    __syncthreads();
+    // ---- phase B: exact projection of the queued points, one per thread
+    const int ns = s_nslow;
+    for (int q = threadIdx.x; q < ns; q += kThreads) {
+      const int idx = s_slow[q];
+      const sloam_point p = points[kbase + tile * kSplitTile + idx];
+      float range;
+      s_pix[idx] = project_pixel(pg, p.x, p.y, p.z, &range);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kRounds; ++j) {
+      const int i = tile * kSplitTile + j * kThreads + threadIdx.x;
+      if (i < N) {
+        if (pixr[j] < 0) pixr[j] = s_pix[j * kThreads + threadIdx.x];
+        pix_io[kbase + i] = pixr[j];
+        // closest point wins (inference.cpp:135,160-162): minimum over the
+        // bit pattern of the non-negative range; NaN ranges never write
+        const float range = sqrtf(pts[j].x * pts[j].x + pts[j].y * pts[j].y + pts[j].z * pts[j].z);
+        if (range_bits != nullptr && range == range)
+          atomicMin(&range_bits[kbase + pixr[j]], __float_as_uint(range));
+      }
+    }
+  }
+
+  // ---- phase C: mask gather, dense tree cloud, order-preserving ground compaction
+  if (!DO_SPLIT) return;
+  // all mask gathers of the thread are issued back to back; one block-wide scan over the
+  // (round, warp) ballot counts gives every ground point its slot in input order
+  unsigned bal[kRounds];
+  unsigned gmask = 0;  // bit j: point j of this thread is ground
+#pragma unroll
   for (int j = 0; j < kRounds; ++j) {
     const int i = tile * kSplitTile + j * kThreads + threadIdx.x;
     const bool in = i < N;
-    sloam_point p = {0.f, 0.f, 0.f, 0.f};
-    int pix = 0;
+    unsigned char m = 0;
+    if (in) m = mask[kbase + pixr[j]];  // inference.cpp:242-243
     if (in) {
-      p = points[kbase + i];
-      if (DO_PROJECT) {
-        float range;
-        pix = project_pixel(pg, p.x, p.y, p.z, &range);
-        pix_io[kbase + i] = pix;
-        // closest point wins (inference.cpp:135,160-162): minimum over the
-        // bit pattern of the non-negative range; NaN ranges never write
-        if (range_bits != nullptr && range == range)
-          atomicMin(&range_bits[kbase + pix], __float_as_uint(range));
-      } else {
-        pix = pix_io[kbase + i];
-      }
+      sloam_point t;  // dense mode (:247-251): the point or a NaN point with intensity 0
+      if (m == 255) t = pts[j];
+      else { t.x = qnan; t.y = qnan; t.z = qnan; t.intensity = 0.f; }
+      tree[kbase + i] = t;
     }
-    if (DO_SPLIT) {
-      unsigned char m = 0;
-      if (in) m = mask[kbase + pix];  // inference.cpp:242-243
-      if (in) {
-        sloam_point t;  // dense mode (:247-251): the point or a NaN point with intensity 0
-        if (m == 255) t = p;
-        else { t.x = qnan; t.y = qnan; t.z = qnan; t.intensity = 0.f; }
-        tree[kbase + i] = t;
-      }
-      const bool is_g = in && (m == 1);
-      const unsigned bal = __ballot_sync(kFull, is_g);
-      if (lane == 0) s_warp[warp] = __popc(bal);
-      __syncthreads();
-      int off = base, total = 0;
+    const bool is_g = in && (m == 1);
+    bal[j] = __ballot_sync(kFull, is_g);
+    gmask |= (is_g ? 1u : 0u) << j;
+    if (lane == 0) s_cnt[j * (kThreads / 32) + warp] = __popc(bal[j]);
+  }
+  __syncthreads();
+  if (warp == 0) {  // exclusive scan of the kRounds * 8 counts, round-major
+    constexpr int kEnt = kRounds * (kThreads / 32);
+    constexpr int kPer = (kEnt + 31) / 32;
+    int v[kPer], s = 0;
 #pragma unroll
-      for (int w = 0; w < kThreads / 32; ++w) {
-        const int c = s_warp[w];
-        if (w < warp) off += c;
-        total += c;
-      }
-      if (is_g) {
-        const int slot = off + __popc(bal & ((1u << lane) - 1u));
-        const int cell = ground_cell_of(gg, p.x, p.y);
-        s_ground[slot] = p;
-        s_cell[slot] = (uint8_t)(cell < 0 ? 255 : cell);
-        if (cell >= 0) atomicAdd(&s_hist[cell], 1);
-      }
-      base += total;
-      __syncthreads();
+    for (int q = 0; q < kPer; ++q) { const int e = lane * kPer + q; v[q] = e < kEnt ? s_cnt[e] : 0; s += v[q]; }
+    int inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(kFull, inc, o);
+      if (lane >= o) inc += t;
+    }
+    int run = inc - s;
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) { const int e = lane * kPer + q; if (e < kEnt) s_cnt[e] = run; run += v[q]; }
+    if (lane == 31) s_base = inc;
+  }
+  __syncthreads();
+  base = s_base;
+#pragma unroll
+  for (int j = 0; j < kRounds; ++j) {
+    if ((gmask >> j) & 1u) {
+      const sloam_point p = pts[j];
+      const int slot = s_cnt[j * (kThreads / 32) + warp] + __popc(bal[j] & ((1u << lane) - 1u));
+      const int cell = ground_cell_fast(gg, p.x, p.y, yawr[j]);
+      s_ground[slot] = p;
+      s_cell[slot] = (uint8_t)(cell < 0 ? 255 : cell);
+      if (cell >= 0) atomicAdd(&s_hist[cell], 1);
     }
   }
-  if (!DO_SPLIT) return;
+  __syncthreads();
 
   // ---- decoupled look-back over the tiles of this keyframe ----
   if (warp == 0) {

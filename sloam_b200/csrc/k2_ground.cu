@@ -19,9 +19,13 @@
 
 namespace sb {
 
-constexpr int kGThreads = 256;
-constexpr int kSelCap = 3072;   // members kept in shared memory (else global scratch)
-constexpr int kQrCap = 512;     // retained points whose fit lives in shared memory
+// A cell is a few hundred points: the work per CTA is latency-bound (dependent
+// passes separated by barriers), so the CTA is kept small (2 warps, ~16 KB of
+// shared memory) to have many cells resident per SM.  Larger cells spill their
+// member list / fit workspace to global scratch (L2-resident).
+constexpr int kGThreads = 64;
+constexpr int kSelCap = 1024;   // members kept in shared memory (else global scratch)
+constexpr int kQrCap = 192;     // retained points whose fit lives in shared memory
 
 struct SelKey { uint32_t z; uint32_t j; };
 
@@ -85,16 +89,20 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
     if (n > 0 && retainNum < (double)n) { const int b = (int)((double)n / retainNum); return b < n ? b : n; }
     return n;
   };
-  if (threadIdx.x == 0) {
+  if (warp == 0) {  // prefix over the preceding cells, one warp, loads in parallel
     int off_all = 0, off_kept = 0;
-    for (int c = 0; c < cell; ++c) {
+    for (int c = lane; c < cell; c += 32) {
       const int n = cell_count[(size_t)k * kMaxCells + c];
       off_all += n; off_kept += kept_of(n);
     }
-    s_misc[0] = off_all; s_misc[1] = off_kept;
-    if (kept_offsets) {
-      kept_offsets[(size_t)k * (B + 1) + cell] = off_kept;
-      if (cell == B - 1) kept_offsets[(size_t)k * (B + 1) + B] = off_kept + kept_of(n_c);
+    off_all = warp_sum(off_all);
+    off_kept = warp_sum(off_kept);
+    if (lane == 0) {
+      s_misc[0] = off_all; s_misc[1] = off_kept;
+      if (kept_offsets) {
+        kept_offsets[(size_t)k * (B + 1) + cell] = off_kept;
+        if (cell == B - 1) kept_offsets[(size_t)k * (B + 1) + B] = off_kept + kept_of(n_c);
+      }
     }
   }
   __syncthreads();
@@ -155,17 +163,29 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
     uint32_t prefix = 0, pmask = 0;
     int want = r - 1;  // 0-based rank among members matching the prefix
     for (int shift = 24; shift >= 0; shift -= 8) {
-      s_hist[threadIdx.x] = 0;
+      for (int b = threadIdx.x; b < 256; b += kGThreads) s_hist[b] = 0;
       __syncthreads();
       for (int i = threadIdx.x; i < n_c; i += kGThreads) {
         const uint32_t z = list[i].z;
         if ((z & pmask) == prefix) atomicAdd(&s_hist[(z >> shift) & 0xFF], 1);
       }
       __syncthreads();
-      if (threadIdx.x == 0) {
-        int acc = 0, d = 0;
-        for (; d < 256; ++d) { if (acc + s_hist[d] > want) break; acc += s_hist[d]; }
-        s_misc[2] = d; s_misc[3] = want - acc;
+      if (warp == 0) {  // bin that holds rank `want`: 8 bins per lane + a warp scan
+        int loc[8], s = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { loc[q] = s_hist[lane * 8 + q]; s += loc[q]; }
+        int inc = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(kFull, inc, o);
+          if (lane >= o) inc += t;
+        }
+        const int excl = inc - s;
+        if (excl <= want && want < inc) {  // exactly one lane
+          int acc = excl, d = 0;
+          for (; d < 7; ++d) { if (acc + loc[d] > want) break; acc += loc[d]; }
+          s_misc[2] = lane * 8 + d; s_misc[3] = want - acc;
+        }
       }
       __syncthreads();
       prefix |= (uint32_t)s_misc[2] << shift;

@@ -62,7 +62,7 @@ __global__ void cc_init_kernel(const DevParams *__restrict__ dp, int K,
   // PCL skips a pixel iff !isfinite(x); EuclideanClusterComparator::compare is
   // dist < threshold in float (NaN compares false)
   const bool valid = isfinite(p.x);
-  bool left_ok = false, up_ok = false;
+  bool left_ok = false, up_ok = false, upleft_ok = false;  // upleft_ok: (i-W) -- (i-W-1)
   if (valid) {
     if (col > 0) {
       const sloam_point q = tree[g - 1];
@@ -71,14 +71,44 @@ __global__ void cc_init_kernel(const DevParams *__restrict__ dp, int K,
     if (row > 0) {
       const sloam_point q = tree[g - W];
       up_ok = dist3f(p.x, p.y, p.z, q.x, q.y, q.z) < thr;
+      if (up_ok && left_ok) {
+        const sloam_point ql = tree[g - W - 1];
+        upleft_ok = dist3f(q.x, q.y, q.z, ql.x, ql.y, ql.z) < thr;
+      }
     }
-    parent[g] = left_ok ? i - 1 : (up_ok ? i - W : i);
+  }
+  // the whole warp is alive here (the grid is padded to a multiple of 32 and
+  // out-of-range threads returned warp-uniformly only in the last warp)
+  const int lane = threadIdx.x & 31;
+  const unsigned act = __activemask();
+  // is the left neighbour connected to ITS upper neighbour?
+  int left_up = __shfl_up_sync(act, up_ok ? 1 : 0, 1);
+  if (lane == 0 || !((act >> (lane - 1)) & 1u)) {
+    left_up = 0;
+    if (left_ok && row > 0) {
+      const sloam_point a = tree[g - 1], b = tree[g - 1 - W];
+      left_up = dist3f(a.x, a.y, a.z, b.x, b.y, b.z) < thr;
+    }
+  }
+  // run starts inside the warp: link to the start of the row run (short find chains)
+  const unsigned starts = __ballot_sync(act, !left_ok);
+  if (valid) {
+    int par;
+    if (left_ok) {
+      const unsigned s = starts & ((2u << lane) - 1u);   // starts at or below this lane
+      par = s ? i - (lane - (31 - __clz(s))) : i - (lane + 1);
+    } else {
+      par = up_ok ? i - W : i;
+    }
+    parent[g] = par;
     csize[g] = 0;
     cmin[g] = col; cmax[g] = col; rmax[g] = row;
   } else {
     parent[g] = kInvalid;
   }
-  flags[g] = (left_ok && up_ok) ? 1 : 0;
+  // A union with the upper neighbour is only needed when it is not implied by
+  // i ~ i-1 (row link), i-1 ~ i-1-W (left neighbour's own up link) and i-W ~ i-W-1.
+  flags[g] = (left_ok && up_ok && !(left_up && upleft_ok)) ? 1 : 0;
 }
 
 // ---- 2. merge: pixels linked left that are also connected upwards ---------

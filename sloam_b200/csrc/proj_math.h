@@ -44,6 +44,7 @@ struct GroundGeom {
   double radial_step;         // maxGroundLidarDist / groundRadiiBins
   double theta_step;          // 2 * PIDEF / groundThetaBins
   int RB, TB;
+  float inv_radial_step_f, inv_theta_step_f;  // for the fp32 estimate in k1_project.cu
 };
 
 // Polar cell (rb * TB + tb) of a ground point seen from the origin, or -1 when

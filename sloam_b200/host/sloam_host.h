@@ -1,0 +1,667 @@
+// sloam_host.h -- host-side C++ mirror of the reference's core API for the hot path,
+// marshalling to the C ABI of include/sloam_b200.h.
+//
+// Same class / member names and call order as the reference so that it drops into
+// SLOAMNode::run (sloam/src/core/sloamNode.cpp:186-282):
+//   seg::Segmentation::run / maskCloud      sloam/include/segmentation/inference.h:57-67
+//   Instance::computeGraph / set_params     sloam/include/segmentation/trellis.h:42-65
+//   Plane, Cylinder (SemanticObject<T>)     sloam/include/objects/{plane,cylinder,semanticObject}.h
+//   sloam::sloam::RunSloam, setFmParams     sloam/include/core/sloam.h:57-107
+//   SloamInput / SloamOutput                sloam/include/core/sloam.h:32-55
+//   FeatureModelParams, TreeVertex          sloam/include/helpers/definitions.h:56-105
+// PCL / Eigen / Sophus / OpenCV are not available in this image, so minimal look-alike types
+// (PointT, CloudT, SE3, Vector3, Vector4, Mask) stand in; a ROS build swaps the real headers
+// back in and keeps the marshalling.  All arithmetic of the path runs on the GPU: the methods
+// that remain host code are accessors and the three-line model transforms / distances the
+// reference's tests call on single objects.  Header-only; needs only libsloam_b200.so.
+#pragma once
+
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/sloam_b200.h"
+
+using Scalar = double;
+
+struct PointT {  // pcl::PointXYZI stand-in, layout of sloam_point
+  float x = 0.f, y = 0.f, z = 0.f, intensity = 0.f;
+};
+static_assert(sizeof(PointT) == sizeof(sloam_point), "PointT must match sloam_point");
+using VectorType = std::vector<PointT>;
+using Slash = VectorType;
+
+struct CloudT {  // pcl::PointCloud<PointT> stand-in
+  using Ptr = std::shared_ptr<CloudT>;
+  VectorType points;
+  uint32_t width = 0, height = 0;
+  bool is_dense = false;
+  size_t size() const { return points.size(); }
+};
+using Cloud = CloudT;
+
+struct Vector3 {
+  double v[3] = {0, 0, 0};
+  double &operator[](int i) { return v[i]; }
+  double operator[](int i) const { return v[i]; }
+  double &operator()(int i) { return v[i]; }
+  double operator()(int i) const { return v[i]; }
+  double norm() const { return std::sqrt(v[0] * v[0] + (v[1] * v[1] + v[2] * v[2])); }
+};
+struct Vector4 {
+  double v[4] = {0, 0, 0, 0};
+  double &operator[](int i) { return v[i]; }
+  double operator[](int i) const { return v[i]; }
+  double &operator()(int i) { return v[i]; }
+  double operator()(int i) const { return v[i]; }
+};
+
+class SE3 {  // Sophus::SE3d stand-in: unit quaternion (x,y,z,w) + translation
+ public:
+  SE3() { p_.q[3] = 1.0; }
+  explicit SE3(const sloam_pose &p) : p_(p) {}
+  Vector3 &translation() { return *reinterpret_cast<Vector3 *>(p_.t); }
+  const Vector3 &translation() const { return *reinterpret_cast<const Vector3 *>(p_.t); }
+  const double *unit_quaternion() const { return p_.q; }  // x y z w
+  void setQuaternion(double w, double x, double y, double z) {
+    const double n = std::sqrt(w * w + x * x + y * y + z * z);
+    p_.q[0] = x / n; p_.q[1] = y / n; p_.q[2] = z / n; p_.q[3] = w / n;
+  }
+  Vector3 operator*(const Vector3 &p) const {
+    const double *q = p_.q;
+    double uv[3] = {q[1] * p[2] - q[2] * p[1], q[2] * p[0] - q[0] * p[2], q[0] * p[1] - q[1] * p[0]};
+    for (double &u : uv) u += u;
+    Vector3 r;
+    r[0] = p[0] + q[3] * uv[0] + (q[1] * uv[2] - q[2] * uv[1]) + p_.t[0];
+    r[1] = p[1] + q[3] * uv[1] + (q[2] * uv[0] - q[0] * uv[2]) + p_.t[1];
+    r[2] = p[2] + q[3] * uv[2] + (q[0] * uv[1] - q[1] * uv[0]) + p_.t[2];
+    return r;
+  }
+  const sloam_pose &abi() const { return p_; }
+
+ private:
+  sloam_pose p_{};
+};
+
+struct TreeVertex {  // definitions.h:56-66
+  int treeId = 0;
+  int beam = 0;
+  int prevVertexSize = 0;
+  Scalar radius = 0;
+  bool isValid = false;
+  PointT coords;
+  Slash points;
+};
+
+struct FeatureModelParams {  // definitions.h:76-105
+  int scansPerSweep = 1;
+  Scalar minTreeModels = 5, minGroundModels = 36;
+  Scalar maxLidarDist = 20, maxGroundLidarDist = 25, minGroundLidarDist = 5;
+  bool twoStepOptim = true;
+  int groundRadiiBins = 2, groundThetaBins = 18;
+  Scalar groundRetainThresh = 0.05, groundMatchThresh = 2.0;
+  Scalar roughTreeMatchThresh = 3.0, treeMatchThresh = 0.5;
+  Scalar maxTreeRadius = 0.3, maxAxisTheta = 10, maxFocusOutlierDistance = 0.5;
+  Scalar AddNewTreeThreshDist = 1.5;
+  int featuresPerTree = 20, numGroundFeatures = 5;
+  Scalar defaultTreeRadius = 0.2;
+};
+
+namespace sloam_b200 {
+
+// Sensor geometry / capacities that the reference keeps in other objects
+// (Segmentation ctor, Instance::Params) or hard-codes.
+struct HostConfig {
+  int img_h = 64, img_w = 2048;  // sloam/params/sloam.yaml:31-33
+  float fov_up = 22.5f, fov_down = -22.5f;
+  float max_dist_to_centroid = 0.2f;
+  int max_trees = 512, max_map_models = 512;
+};
+
+inline void fill_params(sloam_params &p, const FeatureModelParams &f, const HostConfig &h) {
+  sloam_b200_default_params(&p);
+  p.img_h = h.img_h; p.img_w = h.img_w; p.fov_up_deg = h.fov_up; p.fov_down_deg = h.fov_down;
+  p.max_dist_to_centroid = h.max_dist_to_centroid;
+  p.max_trees = h.max_trees; p.max_map_models = h.max_map_models;
+  p.scansPerSweep = f.scansPerSweep;
+  p.minTreeModels = f.minTreeModels; p.minGroundModels = f.minGroundModels;
+  p.maxLidarDist = f.maxLidarDist; p.maxGroundLidarDist = f.maxGroundLidarDist;
+  p.minGroundLidarDist = f.minGroundLidarDist; p.twoStepOptim = f.twoStepOptim ? 1 : 0;
+  p.groundRadiiBins = f.groundRadiiBins; p.groundThetaBins = f.groundThetaBins;
+  p.groundRetainThresh = f.groundRetainThresh; p.groundMatchThresh = f.groundMatchThresh;
+  p.roughTreeMatchThresh = f.roughTreeMatchThresh; p.treeMatchThresh = f.treeMatchThresh;
+  p.maxTreeRadius = f.maxTreeRadius; p.maxAxisTheta = f.maxAxisTheta;
+  p.maxFocusOutlierDistance = f.maxFocusOutlierDistance; p.AddNewTreeThreshDist = f.AddNewTreeThreshDist;
+  p.featuresPerTree = f.featuresPerTree; p.numGroundFeatures = f.numGroundFeatures;
+  p.defaultTreeRadius = f.defaultTreeRadius;
+  if (p.max_prev_planes < p.groundRadiiBins * p.groundThetaBins)
+    p.max_prev_planes = p.groundRadiiBins * p.groundThetaBins;
+}
+
+// RAII device buffer through the C ABI helpers (no CUDA headers on the host side).
+class DevBuf {
+ public:
+  DevBuf(sloam_ctx *c, size_t bytes) : c_(c), bytes_(bytes), p_(sloam_b200_dev_alloc(c, bytes)) {
+    if (!p_) throw std::runtime_error("sloam_b200: device allocation failed");
+  }
+  ~DevBuf() { sloam_b200_dev_free(c_, p_); }
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  template <typename T> T *as() { return static_cast<T *>(p_); }
+  void upload(const void *src, size_t bytes) { check(sloam_b200_copy_h2d(c_, p_, src, bytes)); }
+  void download(void *dst, size_t bytes) { check(sloam_b200_copy_d2h(c_, dst, p_, bytes)); }
+  void check(int rc) {
+    if (rc != SLOAM_OK) throw std::runtime_error(std::string("sloam_b200: ") + sloam_b200_last_error(c_));
+  }
+
+ private:
+  sloam_ctx *c_;
+  size_t bytes_;
+  void *p_;
+};
+
+// One context per parameter set (created lazily, K = 1 like a reference call).
+class Runtime {
+ public:
+  Runtime(const FeatureModelParams &f, const HostConfig &h) {
+    fill_params(p_, f, h);
+    const int rc = sloam_b200_create(&p_, 0, 1, &ctx_);
+    if (rc != SLOAM_OK)
+      throw std::runtime_error("sloam_b200_create failed (" + std::to_string(rc) +
+                               "): no CPU fallback, a B200 is required");
+  }
+  ~Runtime() { sloam_b200_destroy(ctx_); }
+  Runtime(const Runtime &) = delete;
+  Runtime &operator=(const Runtime &) = delete;
+  sloam_ctx *ctx() const { return ctx_; }
+  const sloam_params &params() const { return p_; }
+  void check(int rc) const {
+    if (rc != SLOAM_OK) throw std::runtime_error(std::string("sloam_b200: ") + sloam_b200_last_error(ctx_));
+  }
+
+ private:
+  sloam_params p_{};
+  sloam_ctx *ctx_ = nullptr;
+};
+
+// landmarks <-> flattened ABI records
+inline void flatten(const std::vector<std::vector<TreeVertex>> &lm, std::vector<sloam_tree> &trees,
+                    std::vector<sloam_vertex> &verts, std::vector<sloam_point> &pts) {
+  for (const auto &tree : lm) {
+    sloam_tree t{};
+    t.tree_id = tree.empty() ? -1 : tree[0].treeId;
+    t.n_vertices = (int)tree.size();
+    t.vertex_begin = (int)verts.size();
+    for (const auto &v : tree) {
+      sloam_vertex fv{};
+      fv.cx = v.coords.x; fv.cy = v.coords.y; fv.cz = v.coords.z;
+      fv.radius = (float)v.radius;
+      fv.n_points = (int)v.points.size();
+      fv.point_begin = (int)pts.size();
+      fv.row = -1;
+      fv.is_valid = v.isValid ? 1 : 0;
+      verts.push_back(fv);
+      for (const auto &p : v.points) pts.push_back(sloam_point{p.x, p.y, p.z, p.intensity});
+      t.n_points += fv.n_points;
+    }
+    trees.push_back(t);
+  }
+}
+
+}  // namespace sloam_b200
+
+// ------------------------------------------------------------------ SemanticObject
+template <typename T>
+class SemanticObject {  // semanticObject.h:5-19
+ public:
+  virtual ~SemanticObject() {}
+  virtual Scalar distance(const T &model) const = 0;
+  virtual Scalar distance(const PointT &point) const = 0;
+  virtual void project(const SE3 &tf) = 0;
+  T getModel() const { return model; }
+  VectorType getFeatures() const { return features; }
+  size_t id = 0;
+  bool isValid = false;
+  VectorType features;
+  T model;
+};
+
+struct PlaneParameters {  // plane.h:14-19
+  Vector4 plane;
+  Vector3 centroid;
+  double dist = 0;
+};
+
+class Plane : public SemanticObject<PlaneParameters> {
+ public:
+  Plane() {}
+  // plane.cpp:3-17: the fit runs on the GPU (binGroundPoints is bypassed by using one cell
+  // that keeps every point: groundRetainThresh = 1 -> sorted by z like any retained cell is not
+  // wanted here, so the points go through the RunSloam-independent plane-fit entry).
+  explicit Plane(const VectorType &points, const FeatureModelParams &fmParams,
+                 const sloam_b200::HostConfig &hc = sloam_b200::HostConfig());
+  Scalar distance(const PlaneParameters &tgt) const override {  // plane.cpp:131-134
+    Vector3 d;
+    for (int i = 0; i < 3; ++i) d[i] = model.centroid[i] - tgt.centroid[i];
+    return d.norm();
+  }
+  Scalar distance(const PointT &p) const override {  // plane.cpp:136-151
+    const double n = std::sqrt(model.plane[0] * model.plane[0] +
+                               (model.plane[1] * model.plane[1] + model.plane[2] * model.plane[2]));
+    return std::fabs(model.plane[0] * p.x + model.plane[1] * p.y + model.plane[2] * p.z + model.plane[3]) / n;
+  }
+  void project(const SE3 &tf) override {  // plane.cpp:153-176
+    for (auto &f : features) {
+      if (!std::isfinite(f.x) || !std::isfinite(f.y) || !std::isfinite(f.z)) continue;
+      Vector3 v; v[0] = f.x; v[1] = f.y; v[2] = f.z;
+      const Vector3 r = tf * v;
+      f.x = (float)r[0]; f.y = (float)r[1]; f.z = (float)r[2];
+    }
+    Vector3 n; n[0] = model.plane[0]; n[1] = model.plane[1]; n[2] = model.plane[2];
+    SE3 rot = tf; rot.translation() = Vector3();
+    const Vector3 rn = rot * n;
+    const Vector3 &t = tf.translation();
+    model.plane[3] = model.plane[3] - (rn[0] * t[0] + rn[1] * t[1] + rn[2] * t[2]);
+    for (int i = 0; i < 3; ++i) model.plane[i] = rn[i];
+    model.centroid = tf * model.centroid;
+  }
+};
+
+struct CylinderParameters {  // cylinder.h:14-23
+  Vector3 root, ray;
+  std::vector<double> radii;
+  std::vector<TreeVertex> vertices;
+  double radius = 0, lambda = 1.0;
+};
+
+class Cylinder : public SemanticObject<CylinderParameters> {
+ public:
+  Cylinder() {}
+  explicit Cylinder(const std::vector<TreeVertex> vertices, const Plane &gplane,
+                    const FeatureModelParams &fmParams,
+                    const sloam_b200::HostConfig &hc = sloam_b200::HostConfig());
+  Scalar distance(const CylinderParameters &tgt) const override {  // cylinder.cpp:175-194
+    double d = 0.0;
+    for (double h : {0.0, 3.0, 6.0}) {
+      const double s = (h - model.root[2]) / model.ray[2], t = (h - tgt.root[2]) / tgt.ray[2];
+      Vector3 e;
+      for (int i = 0; i < 3; ++i) e[i] = (model.root[i] + s * model.ray[i]) - (tgt.root[i] + t * tgt.ray[i]);
+      d += e.norm();
+    }
+    return d / 3.0;
+  }
+  Scalar distance(const PointT &p) const override {  // cylinder.cpp:196-203
+    Vector3 e; e[0] = p.x - model.root[0]; e[1] = p.y - model.root[1]; e[2] = p.z - model.root[2];
+    const double rr = model.ray[0] * model.ray[0] + (model.ray[1] * model.ray[1] + model.ray[2] * model.ray[2]);
+    const double s = (e[0] * model.ray[0] + (e[1] * model.ray[1] + e[2] * model.ray[2])) / rr;
+    Vector3 d;
+    for (int i = 0; i < 3; ++i) d[i] = e[i] - s * model.ray[i];
+    return d.norm() - model.radius;
+  }
+  void project(const SE3 &tf) override {  // cylinder.cpp:205-211
+    Vector3 other;
+    for (int i = 0; i < 3; ++i) other[i] = model.root[i] + model.ray[i];
+    model.root = tf * model.root;
+    other = tf * other;
+    for (int i = 0; i < 3; ++i) model.ray[i] = other[i] - model.root[i];
+  }
+};
+
+// ------------------------------------------------------------------ sloam core
+struct SloamInput {  // sloam.h:32-46
+  SloamInput() : groundCloud(new CloudT()) {}
+  SE3 poseEstimate;
+  Scalar distance = 0;
+  CloudT::Ptr groundCloud;
+  std::vector<Cylinder> mapModels;
+  std::vector<std::vector<TreeVertex>> landmarks;
+};
+struct SloamOutput {  // sloam.h:48-55
+  std::vector<int> matches;
+  std::vector<Cylinder> tm;
+  SE3 T_Map_Curr;
+  SE3 T_Delta;
+};
+
+namespace sloam {
+class sloam {  // sloam.h:57-107
+ public:
+  explicit sloam(const sloam_b200::HostConfig &hc = sloam_b200::HostConfig()) : hc_(hc) {}
+  const FeatureModelParams &fmParams() const { return fmParams_; }
+  void setFmParams(const FeatureModelParams &p) { fmParams_ = p; rt_.reset(); }
+  std::vector<Plane> getPrevGroundModel() { return prevGPlanes_; }
+
+  // sloam.cpp:453-532, one keyframe.  Returns false exactly when the reference does.
+  bool RunSloam(SloamInput &in, SloamOutput &out) {
+    if (!rt_) rt_.reset(new sloam_b200::Runtime(fmParams_, sized_for(in.groundCloud->points.size())));
+    else if ((int)in.groundCloud->points.size() > rt_->params().img_h * rt_->params().img_w)
+      rt_.reset(new sloam_b200::Runtime(fmParams_, sized_for(in.groundCloud->points.size())));
+    sloam_ctx *c = rt_->ctx();
+    const sloam_params &p = rt_->params();
+    const int N = p.img_h * p.img_w, T = p.max_trees, M = p.max_map_models, PP = p.max_prev_planes;
+    std::vector<sloam_tree> trees; std::vector<sloam_vertex> verts; std::vector<sloam_point> vpts;
+    sloam_b200::flatten(in.landmarks, trees, verts, vpts);
+    if ((int)trees.size() > T || (int)in.mapModels.size() > M || (int)prevGPlanes_.size() > PP)
+      throw std::runtime_error("sloam_b200: capacity exceeded (max_trees / max_map_models / max_prev_planes)");
+    const int32_t n_ground = (int32_t)in.groundCloud->points.size(), n_trees = (int32_t)trees.size();
+    std::vector<sloam_cylinder> map(std::max<size_t>(in.mapModels.size(), 1));
+    for (size_t i = 0; i < in.mapModels.size(); ++i) {
+      for (int a = 0; a < 3; ++a) { map[i].root[a] = in.mapModels[i].model.root[a]; map[i].ray[a] = in.mapModels[i].model.ray[a]; }
+      map[i].radius = in.mapModels[i].model.radius;
+    }
+    std::vector<sloam_plane> prev(std::max<size_t>(prevGPlanes_.size(), 1));
+    for (size_t i = 0; i < prevGPlanes_.size(); ++i) {
+      for (int a = 0; a < 4; ++a) prev[i].plane[a] = prevGPlanes_[i].model.plane[a];
+      for (int a = 0; a < 3; ++a) prev[i].centroid[a] = prevGPlanes_[i].model.centroid[a];
+    }
+    const int32_t n_map = (int32_t)in.mapModels.size(), n_prev = (int32_t)prevGPlanes_.size();
+    const uint8_t first = firstScan_ ? 1 : 0;
+    const sloam_pose pose = in.poseEstimate.abi();
+    using sloam_b200::DevBuf;
+    DevBuf d_ground(c, sizeof(sloam_point) * (size_t)N), d_ng(c, 4), d_trees(c, sizeof(sloam_tree) * T),
+        d_nt(c, 4), d_verts(c, sizeof(sloam_vertex) * std::max<size_t>(verts.size(), 1)),
+        d_vpts(c, sizeof(sloam_point) * std::max<size_t>(vpts.size(), 1)), d_pose(c, sizeof pose), d_first(c, 1),
+        d_map(c, sizeof(sloam_cylinder) * M), d_nmap(c, 4), d_prev(c, sizeof(sloam_plane) * PP), d_nprev(c, 4),
+        d_res(c, sizeof(sloam_kf_result)), d_match(c, 4 * T), d_tm(c, sizeof(sloam_cylinder) * T),
+        d_tmid(c, 4 * T), d_planes(c, sizeof(sloam_plane) * PP), d_npl(c, 4);
+    d_ground.upload(in.groundCloud->points.data(), sizeof(sloam_point) * (size_t)n_ground);
+    d_ng.upload(&n_ground, 4);
+    d_trees.upload(trees.data(), sizeof(sloam_tree) * trees.size());
+    d_nt.upload(&n_trees, 4);
+    d_verts.upload(verts.data(), sizeof(sloam_vertex) * verts.size());
+    d_vpts.upload(vpts.data(), sizeof(sloam_point) * vpts.size());
+    d_pose.upload(&pose, sizeof pose);
+    d_first.upload(&first, 1);
+    d_map.upload(map.data(), sizeof(sloam_cylinder) * in.mapModels.size());
+    d_nmap.upload(&n_map, 4);
+    d_prev.upload(prev.data(), sizeof(sloam_plane) * prevGPlanes_.size());
+    d_nprev.upload(&n_prev, 4);
+    sloam_batch_in bi{};
+    bi.pose_est = d_pose.as<sloam_pose>(); bi.first_scan = d_first.as<uint8_t>();
+    bi.map_models = d_map.as<sloam_cylinder>(); bi.n_map_models = d_nmap.as<int32_t>();
+    bi.prev_planes = d_prev.as<sloam_plane>(); bi.n_prev_planes = d_nprev.as<int32_t>();
+    sloam_batch_out bo{};
+    bo.results = d_res.as<sloam_kf_result>(); bo.matches = d_match.as<int32_t>();
+    bo.tm = d_tm.as<sloam_cylinder>(); bo.tm_id = d_tmid.as<int32_t>();
+    bo.planes = d_planes.as<sloam_plane>(); bo.n_planes = d_npl.as<int32_t>();
+    rt_->check(sloam_b200_run_sloam_dev(c, 1, d_ground.as<sloam_point>(), d_ng.as<int32_t>(), N,
+                                        d_trees.as<sloam_tree>(), d_nt.as<int32_t>(), d_verts.as<sloam_vertex>(),
+                                        (int)std::max<size_t>(verts.size(), 1), d_vpts.as<sloam_point>(),
+                                        (int)std::max<size_t>(vpts.size(), 1), &bi, &bo));
+    sloam_kf_result res;
+    d_res.download(&res, sizeof res);
+    last_ = res;
+    int32_t npl = 0;
+    d_npl.download(&npl, 4);
+    std::vector<sloam_plane> planes(std::max(npl, 1));
+    d_planes.download(planes.data(), sizeof(sloam_plane) * npl);
+    if (res.status == SLOAM_KF_EMPTY_MAP || res.status == SLOAM_KF_NO_MODELS) return false;  // :476-486
+    std::vector<int32_t> matches(std::max(res.n_landmarks, 1)), ids(std::max(res.n_landmarks, 1));
+    std::vector<sloam_cylinder> tm(std::max(res.n_landmarks, 1));
+    d_match.download(matches.data(), 4 * (size_t)res.n_landmarks);
+    d_tmid.download(ids.data(), 4 * (size_t)res.n_landmarks);
+    d_tm.download(tm.data(), sizeof(sloam_cylinder) * (size_t)res.n_landmarks);
+    out.matches.assign(matches.begin(), matches.begin() + res.n_landmarks);
+    out.tm.clear();
+    for (int i = 0; i < res.n_landmarks; ++i) {
+      Cylinder cy;
+      for (int a = 0; a < 3; ++a) { cy.model.root[a] = tm[i].root[a]; cy.model.ray[a] = tm[i].ray[a]; }
+      cy.model.radius = tm[i].radius;
+      cy.id = (size_t)ids[i];
+      cy.isValid = true;
+      out.tm.push_back(cy);
+    }
+    out.T_Map_Curr = SE3(res.T_Map_Curr);
+    out.T_Delta = SE3(res.T_Delta);
+    prevGPlanes_.clear();  // :471,:525
+    for (int i = 0; i < npl; ++i) {
+      Plane pl;
+      for (int a = 0; a < 4; ++a) pl.model.plane[a] = planes[i].plane[a];
+      for (int a = 0; a < 3; ++a) pl.model.centroid[a] = planes[i].centroid[a];
+      pl.isValid = true;
+      prevGPlanes_.push_back(pl);
+    }
+    firstScan_ = false;
+    return res.success != 0;
+  }
+  const sloam_kf_result &lastResult() const { return last_; }
+
+ private:
+  sloam_b200::HostConfig sized_for(size_t n_ground) const {
+    sloam_b200::HostConfig h = hc_;
+    while ((size_t)h.img_h * h.img_w < n_ground) h.img_w *= 2;
+    return h;
+  }
+  sloam_b200::HostConfig hc_;
+  FeatureModelParams fmParams_;
+  std::unique_ptr<sloam_b200::Runtime> rt_;
+  std::vector<Plane> prevGPlanes_;
+  bool firstScan_ = true;
+  sloam_kf_result last_{};
+};
+}  // namespace sloam
+
+// ------------------------------------------------------------------ Plane / Cylinder ctors
+inline Plane::Plane(const VectorType &points, const FeatureModelParams &fmParams,
+                    const sloam_b200::HostConfig &hc) {
+  // One polar cell covering everything, retaining every point in input order
+  // (groundRetainThresh = 1 keeps all points but would sort them; the reference's Plane
+  // constructor does not sort, so the cell is made "small": 1/thresh >= size).
+  features = points;
+  if ((int)features.size() < fmParams.numGroundFeatures || features.size() < 3) { isValid = false; return; }
+  FeatureModelParams f = fmParams;
+  f.groundRadiiBins = 1; f.groundThetaBins = 1;
+  f.minGroundLidarDist = -1.0; f.maxGroundLidarDist = 1e30;
+  f.groundRetainThresh = std::min(1.0, 1.0 / (double)(features.size() + 1));
+  sloam_b200::HostConfig h = hc;
+  while ((size_t)h.img_h * h.img_w < features.size()) h.img_w *= 2;
+  sloam_b200::Runtime rt(f, h);
+  sloam_ctx *c = rt.ctx();
+  const int N = rt.params().img_h * rt.params().img_w, Fg = f.numGroundFeatures;
+  const int32_t n = (int32_t)features.size();
+  sloam_pose ident{}; ident.q[3] = 1.0; ident.t[2] = 1e9;  // acceptance is not part of the ctor
+  sloam_b200::DevBuf d_g(c, sizeof(sloam_point) * (size_t)N), d_n(c, 4), d_pose(c, sizeof ident),
+      d_cells(c, sizeof(sloam_cell_plane)), d_feat(c, sizeof(sloam_point) * Fg);
+  d_g.upload(features.data(), sizeof(sloam_point) * features.size());
+  d_n.upload(&n, 4);
+  d_pose.upload(&ident, sizeof ident);
+  rt.check(sloam_b200_ground_planes_dev(c, 1, d_g.as<sloam_point>(), d_n.as<int32_t>(), N, d_pose.as<sloam_pose>(),
+                                        d_cells.as<sloam_cell_plane>(), d_feat.as<sloam_point>(), nullptr, nullptr));
+  sloam_cell_plane cell;
+  d_cells.download(&cell, sizeof cell);
+  isValid = cell.is_valid != 0;
+  for (int a = 0; a < 4; ++a) model.plane[a] = cell.model.plane[a];
+  for (int a = 0; a < 3; ++a) model.centroid[a] = cell.model.centroid[a];
+  features.resize(Fg);  // plane.cpp:14
+}
+
+inline Cylinder::Cylinder(const std::vector<TreeVertex> vertices, const Plane &gplane,
+                          const FeatureModelParams &fmParams, const sloam_b200::HostConfig &hc) {
+  sloam_b200::Runtime rt(fmParams, hc);
+  sloam_ctx *c = rt.ctx();
+  const sloam_params &p = rt.params();
+  std::vector<sloam_tree> trees; std::vector<sloam_vertex> verts; std::vector<sloam_point> vpts;
+  sloam_b200::flatten({vertices}, trees, verts, vpts);
+  const int B = p.groundRadiiBins * p.groundThetaBins, Ft = p.featuresPerTree;
+  std::vector<sloam_cell_plane> cells(B);
+  std::memset(cells.data(), 0, sizeof(sloam_cell_plane) * B);
+  for (int a = 0; a < 4; ++a) cells[0].model.plane[a] = gplane.model.plane[a];
+  for (int a = 0; a < 3; ++a) cells[0].model.centroid[a] = gplane.model.centroid[a];
+  cells[0].is_valid = cells[0].accepted = 1;
+  const int32_t one = 1;
+  sloam_b200::DevBuf d_trees(c, sizeof(sloam_tree) * p.max_trees), d_nt(c, 4),
+      d_verts(c, sizeof(sloam_vertex) * std::max<size_t>(verts.size(), 1) + 0),
+      d_vpts(c, sizeof(sloam_point) * std::max<size_t>(vpts.size(), 1)), d_cells(c, sizeof(sloam_cell_plane) * B),
+      d_models(c, sizeof(sloam_tree_model) * p.max_trees), d_feat(c, sizeof(sloam_point) * p.max_trees * Ft);
+  // the stage entry uses the compute_graph strides: one tree, so offsets are the same
+  d_trees.upload(trees.data(), sizeof(sloam_tree));
+  d_nt.upload(&one, 4);
+  d_verts.upload(verts.data(), sizeof(sloam_vertex) * verts.size());
+  d_vpts.upload(vpts.data(), sizeof(sloam_point) * vpts.size());
+  d_cells.upload(cells.data(), sizeof(sloam_cell_plane) * B);
+  rt.check(sloam_b200_cylinders_dev(c, 1, d_trees.as<sloam_tree>(), d_nt.as<int32_t>(), d_verts.as<sloam_vertex>(),
+                                    d_vpts.as<sloam_point>(), d_cells.as<sloam_cell_plane>(),
+                                    d_models.as<sloam_tree_model>(), d_feat.as<sloam_point>()));
+  sloam_tree_model m;
+  d_models.download(&m, sizeof m);
+  std::vector<sloam_point> f(Ft);
+  d_feat.download(f.data(), sizeof(sloam_point) * Ft);
+  for (int a = 0; a < 3; ++a) { model.root[a] = m.model.root[a]; model.ray[a] = m.model.ray[a]; }
+  model.radius = m.model.radius;
+  model.vertices = vertices;
+  for (const auto &v : vertices) model.radii.push_back(v.radius);
+  id = (size_t)m.id;
+  isValid = m.is_valid != 0;
+  features.resize(Ft);
+  for (int i = 0; i < Ft; ++i) { features[i].x = f[i].x; features[i].y = f[i].y; features[i].z = f[i].z; features[i].intensity = f[i].intensity; }
+}
+
+// ------------------------------------------------------------------ Instance (trellis.h)
+class Instance {
+ public:
+  struct Params {  // trellis.h:31-40
+    float beam_cluster_threshold = 0.1f;
+    float max_dist_to_centroid = 0.2f;
+    int min_vertex_size = 2;
+    int min_landmark_size = 4;
+    float min_landmark_height = 1.0f;
+  };
+  explicit Instance(const sloam_b200::HostConfig &hc = sloam_b200::HostConfig()) : hc_(hc) {}
+  const Params &params() const { return params_; }
+  void set_params(const Params &p) { params_ = p; rt_.reset(); }
+  void reset_tree_id() {}
+
+  // trellis.cpp:134-140; `cloud` is unused there too
+  void computeGraph(const CloudT::Ptr /*cloud*/, const CloudT::Ptr tree_cloud,
+                    std::vector<std::vector<TreeVertex>> &landmarks) {
+    if (tree_cloud->size() == 0) return;  // trellis.cpp:17
+    sloam_b200::HostConfig h = hc_;
+    h.img_h = (int)tree_cloud->height; h.img_w = (int)tree_cloud->width;
+    h.max_dist_to_centroid = params_.max_dist_to_centroid;
+    if (!rt_ || rt_->params().img_h != h.img_h || rt_->params().img_w != h.img_w)
+      rt_.reset(new sloam_b200::Runtime(FeatureModelParams(), h));
+    sloam_ctx *c = rt_->ctx();
+    const sloam_params &p = rt_->params();
+    const size_t N = (size_t)p.img_h * p.img_w, T = p.max_trees, V = p.max_tree_vertices;
+    if (tree_cloud->points.size() != N) throw std::runtime_error("computeGraph: cloud is not organized H x W");
+    sloam_b200::DevBuf d_tree(c, sizeof(sloam_point) * N), d_trees(c, sizeof(sloam_tree) * T), d_nt(c, 4),
+        d_verts(c, sizeof(sloam_vertex) * T * V), d_vpts(c, sizeof(sloam_point) * N);
+    d_tree.upload(tree_cloud->points.data(), sizeof(sloam_point) * N);
+    rt_->check(sloam_b200_compute_graph_dev(c, 1, d_tree.as<sloam_point>(), d_trees.as<sloam_tree>(),
+                                            d_nt.as<int32_t>(), d_verts.as<sloam_vertex>(), d_vpts.as<sloam_point>()));
+    int32_t nt = 0;
+    d_nt.download(&nt, 4);
+    std::vector<sloam_tree> trees(std::max(nt, 1));
+    std::vector<sloam_vertex> verts(T * V);
+    std::vector<sloam_point> vpts(N);
+    d_trees.download(trees.data(), sizeof(sloam_tree) * nt);
+    d_verts.download(verts.data(), sizeof(sloam_vertex) * T * V);
+    d_vpts.download(vpts.data(), sizeof(sloam_point) * N);
+    for (int t = 0; t < nt; ++t) {
+      std::vector<TreeVertex> tree;
+      for (int k = 0; k < trees[t].n_vertices; ++k) {
+        const sloam_vertex &fv = verts[trees[t].vertex_begin + k];
+        TreeVertex v;
+        v.treeId = trees[t].tree_id;
+        v.radius = fv.radius;
+        v.isValid = fv.is_valid != 0;
+        v.coords.x = fv.cx; v.coords.y = fv.cy; v.coords.z = fv.cz;
+        for (int j = 0; j < fv.n_points; ++j) {
+          const sloam_point &q = vpts[fv.point_begin + j];
+          PointT pt; pt.x = q.x; pt.y = q.y; pt.z = q.z; pt.intensity = q.intensity;
+          v.points.push_back(pt);
+        }
+        tree.push_back(v);
+      }
+      landmarks.push_back(tree);
+    }
+  }
+
+ private:
+  sloam_b200::HostConfig hc_;
+  Params params_;
+  std::unique_ptr<sloam_b200::Runtime> rt_;
+};
+
+// ------------------------------------------------------------------ seg::Segmentation
+struct Mask {  // cv::Mat (CV_8U) stand-in: rows x cols labels, 0 other / 1 ground / 255 tree
+  int rows = 0, cols = 0;
+  std::vector<unsigned char> data;
+  Mask() {}
+  Mask(int r, int c) : rows(r), cols(c), data((size_t)r * c, 0) {}
+};
+
+namespace seg {
+class Segmentation {  // inference.h:55-110
+ public:
+  using Ptr = std::shared_ptr<Segmentation>;
+  // The model path of the reference constructor is dropped: the network is out of scope and
+  // its H x W mask is supplied by the caller (setLabelSource) before run().
+  Segmentation(const float fov_up, const float fov_down, const int img_w, const int img_h, const int /*img_d*/,
+               bool do_destagger) {
+    if (do_destagger) throw std::runtime_error("do_destagger is not supported (sim.yaml:5 uses false)");
+    sloam_b200::HostConfig h;
+    h.img_h = img_h; h.img_w = img_w; h.fov_up = fov_up; h.fov_down = fov_down;
+    rt_.reset(new sloam_b200::Runtime(FeatureModelParams(), h));
+  }
+  Segmentation(const Segmentation &) = delete;
+  Segmentation operator=(const Segmentation &) = delete;
+  // stands in for the ONNX session: the mask run() hands back
+  void setLabelSource(const Mask &m) { labels_ = m; }
+
+  // inference.cpp:374-448 minus the network: projection (kept for maskCloud, like proj_xs/ys) + labels
+  void run(const Cloud::Ptr cloud, Mask &maskImg) {
+    const sloam_params &p = rt_->params();
+    const size_t N = (size_t)p.img_h * p.img_w;
+    if (cloud->points.size() != N) throw std::runtime_error("Segmentation::run: cloud must hold H*W points");
+    sloam_ctx *c = rt_->ctx();
+    d_points_.reset(new sloam_b200::DevBuf(c, sizeof(sloam_point) * N));
+    d_pix_.reset(new sloam_b200::DevBuf(c, 4 * N));
+    d_points_->upload(cloud->points.data(), sizeof(sloam_point) * N);
+    sloam_b200::DevBuf d_range(c, 4 * N);
+    rt_->check(sloam_b200_project_dev(c, 1, d_points_->as<sloam_point>(), d_pix_->as<int32_t>(), d_range.as<float>()));
+    range_image.resize(N);
+    d_range.download(range_image.data(), 4 * N);
+    if (labels_.rows * labels_.cols != (int)N) throw std::runtime_error("Segmentation::run: no label source set");
+    maskImg = labels_;
+  }
+
+  // inference.cpp:230-273.  The two calls of SLOAMNode::run (val 1 sparse, val 255 dense) share
+  // one GPU pass; any other val falls outside the reference's use.
+  void maskCloud(const Cloud::Ptr cloud, Mask mask, Cloud::Ptr &outCloud, unsigned char val, bool dense = false) {
+    const sloam_params &p = rt_->params();
+    const size_t N = (size_t)p.img_h * p.img_w;
+    if ((size_t)mask.rows * mask.cols != cloud->points.size() || !d_pix_)
+      throw std::runtime_error("maskCloud: call run() first with a cloud of H*W points");  // assert :239
+    if (!((val == 1 && !dense) || (val == 255 && dense)))
+      throw std::runtime_error("maskCloud: only (1, sparse) and (255, dense) are part of the hot path");
+    sloam_ctx *c = rt_->ctx();
+    sloam_b200::DevBuf d_mask(c, N), d_tree(c, sizeof(sloam_point) * N), d_ground(c, sizeof(sloam_point) * N), d_n(c, 4);
+    d_mask.upload(mask.data.data(), N);
+    rt_->check(sloam_b200_mask_cloud_dev(c, 1, d_points_->as<sloam_point>(), d_pix_->as<int32_t>(), d_mask.as<uint8_t>(),
+                                         d_tree.as<sloam_point>(), d_ground.as<sloam_point>(), d_n.as<int32_t>()));
+    if (!outCloud) outCloud.reset(new Cloud());
+    if (dense) {
+      outCloud->points.resize(N);
+      d_tree.download(outCloud->points.data(), sizeof(sloam_point) * N);
+      outCloud->width = p.img_w; outCloud->height = p.img_h; outCloud->is_dense = true;
+    } else {
+      int32_t n = 0;
+      d_n.download(&n, 4);
+      outCloud->points.resize(n);
+      d_ground.download(outCloud->points.data(), sizeof(sloam_point) * (size_t)n);
+      outCloud->width = n; outCloud->height = 1; outCloud->is_dense = false;
+    }
+  }
+  std::vector<float> range_image;  // what _doProjection returns
+
+ private:
+  std::unique_ptr<sloam_b200::Runtime> rt_;
+  std::unique_ptr<sloam_b200::DevBuf> d_points_, d_pix_;
+  Mask labels_;
+};
+}  // namespace seg

@@ -1,0 +1,203 @@
+// host_api_test.cpp -- the reference's gtest cases (sloam/src/tests/{plane,cylinder,core}_test.cpp)
+// written against sloam_b200/host/sloam_host.h: same classes, same calls, same assertions,
+// executed on the GPU through the C ABI.  Fixtures (the reference's still_* files converted
+// by scripts/make_golden.py) arrive as one binary blob written by tests/test_host_api.py.
+//
+//   g++ -std=c++17 -O1 tests/host_api_test.cpp -Lsloam_b200/lib -lsloam_b200 -o host_api_test
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+
+#include "../sloam_b200/host/sloam_host.h"
+
+static int g_fail = 0, g_run = 0;
+#define EXPECT_TRUE(c) do { ++g_run; if (!(c)) { ++g_fail; std::printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #c); } } while (0)
+#define EXPECT_NEAR(a, b, t) EXPECT_TRUE(std::fabs((double)(a) - (double)(b)) <= (t))
+#define EXPECT_EQ(a, b) EXPECT_TRUE((a) == (b))
+
+struct Fixture {
+  VectorType ground;
+  std::vector<std::vector<TreeVertex>> landmarks;
+};
+
+static bool read_fixture(std::ifstream &f, Fixture &fx) {
+  int32_t ng = 0, nt = 0;
+  f.read((char *)&ng, 4);
+  fx.ground.resize(ng);
+  f.read((char *)fx.ground.data(), sizeof(PointT) * (size_t)ng);
+  f.read((char *)&nt, 4);
+  for (int t = 0; t < nt; ++t) {
+    int32_t nv = 0;
+    f.read((char *)&nv, 4);
+    std::vector<TreeVertex> tree(nv);
+    for (auto &v : tree) {
+      int32_t id = 0, np = 0; float radius = 0, c[3];
+      f.read((char *)&id, 4); f.read((char *)&radius, 4); f.read((char *)c, 12); f.read((char *)&np, 4);
+      v.treeId = id; v.radius = radius; v.isValid = true;
+      v.coords.x = c[0]; v.coords.y = c[1]; v.coords.z = c[2];
+      v.points.resize(np);
+      f.read((char *)v.points.data(), sizeof(PointT) * (size_t)np);
+    }
+    fx.landmarks.push_back(tree);
+  }
+  return (bool)f;
+}
+
+static PointT pt(float x, float y, float z) { PointT p; p.x = x; p.y = y; p.z = z; return p; }
+
+// ---------------------------------------------------------------- plane_test.cpp
+static FeatureModelParams plane_params() {  // plane_test.cpp:28-52
+  FeatureModelParams p;
+  p.maxLidarDist = 15.0; p.maxGroundLidarDist = 30.0; p.minGroundLidarDist = 0.0;
+  p.groundRadiiBins = 1; p.groundThetaBins = 18; p.groundRetainThresh = 0.1; p.numGroundFeatures = 1;
+  p.treeMatchThresh = 1.0; p.AddNewTreeThreshDist = 2.0; p.featuresPerTree = 2; p.defaultTreeRadius = 0.1;
+  return p;
+}
+static void plane_tests() {
+  const FeatureModelParams params = plane_params();
+  VectorType g{pt(0, 0, 0), pt(0, 1, 0), pt(1, 0, 0)};
+  {  // PlaneTest.Initalizes :57-66
+    Plane plane(g, params);
+    EXPECT_TRUE(plane.isValid);
+  }
+  {  // PlaneTest.DistanceToFeature :68-80
+    Plane plane(g, params);
+    float d = plane.distance(g[0]);
+    EXPECT_NEAR(0.0, d, 0.1);
+    EXPECT_NEAR(1.0, std::fabs(plane.model.plane[2]), 1e-12);
+  }
+  {  // PlaneTest.TranslateModel :82-97
+    Plane plane(g, params);
+    SE3 tf;
+    tf.translation()[2] = 1;
+    auto centroid = plane.model.centroid;
+    plane.project(tf);
+    EXPECT_EQ(centroid[2] + 1, plane.model.centroid[2]);
+  }
+}
+
+// ------------------------------------------------------------- cylinder_test.cpp
+static void cylinder_tests(const Fixture &t0) {
+  FeatureModelParams params;  // cylinder_test.cpp:38-62
+  params.maxLidarDist = 30.0; params.maxGroundLidarDist = 30.0; params.minGroundLidarDist = 0.0;
+  params.groundRadiiBins = 1; params.groundThetaBins = 1; params.groundRetainThresh = 0.1;
+  params.treeMatchThresh = 1.0; params.AddNewTreeThreshDist = 2.0;
+  params.featuresPerTree = 2; params.numGroundFeatures = 3; params.defaultTreeRadius = 0.1;
+  VectorType gf{pt(0, 0, 0), pt(0, 1, 0), pt(1, 0, 0), pt(1, 1, 0)};
+  Plane plane(gf, params);
+  EXPECT_TRUE(plane.isValid);
+  std::vector<Cylinder> cylinders;
+  for (auto l : t0.landmarks) {  // Initalizes :69-77
+    auto c = Cylinder(l, plane, params);
+    if (c.isValid) cylinders.push_back(c);
+  }
+  EXPECT_TRUE(cylinders.size() > 0);
+  if (cylinders.empty()) return;
+  {  // DistanceToModel :79-93
+    float d = cylinders[0].distance(cylinders[0].model);
+    EXPECT_EQ(0.0, d);
+  }
+  {  // DistanceToFeature :95-108
+    float d = cylinders[0].distance(cylinders[0].features[0]);
+    EXPECT_NEAR(0.0, d, 0.1);
+  }
+  {  // TranslateModel :110-127
+    SE3 tf;
+    tf.translation()[0] = 1;
+    auto root = cylinders[0].model.root;
+    cylinders[0].project(tf);
+    EXPECT_EQ(root[0] + 1, cylinders[0].model.root[0]);
+  }
+}
+
+// ----------------------------------------------------------------- core_test.cpp
+static FeatureModelParams core_params(bool two_step) {  // core_test.cpp:94-119 + YAML for the unset ones
+  FeatureModelParams p;
+  p.maxLidarDist = 15.0; p.maxGroundLidarDist = 30.0; p.minGroundLidarDist = 0.0;
+  p.groundRadiiBins = 1; p.groundThetaBins = 18; p.groundMatchThresh = 2.0; p.groundRetainThresh = 0.05;
+  p.maxTreeRadius = 0.3; p.maxAxisTheta = 10; p.roughTreeMatchThresh = 3.0; p.treeMatchThresh = 1.0;
+  p.AddNewTreeThreshDist = 2.0; p.featuresPerTree = 2; p.numGroundFeatures = 60; p.defaultTreeRadius = 0.1;
+  p.minTreeModels = 5; p.minGroundModels = 36; p.twoStepOptim = two_step;
+  return p;
+}
+static SloamInput make_input(const Fixture &fx) {  // readInputData :72-92
+  SloamInput in;
+  in.landmarks = fx.landmarks;
+  for (auto &tree : in.landmarks)
+    for (auto &vtx : tree) vtx.points.resize(5);
+  in.groundCloud->points = fx.ground;
+  in.poseEstimate = SE3();
+  return in;
+}
+static void core_tests(const Fixture &t0, const Fixture &t1, bool two_step) {
+  const FeatureModelParams params = core_params(two_step);
+  {  // FirstScan / SecondScan :128-146
+    for (const Fixture *fx : {&t0, &t1}) {
+      sloam::sloam s;
+      SloamOutput out;
+      s.setFmParams(params);
+      SloamInput in = make_input(*fx);
+      s.RunSloam(in, out);
+      EXPECT_TRUE(out.tm.size() > 0);
+      EXPECT_TRUE(s.getPrevGroundModel().size() > 0);
+    }
+  }
+  {  // SLOAMSucess, PoseOptimization, ObjectAssociation :148-194
+    sloam::sloam s;
+    SloamOutput out;
+    s.setFmParams(params);
+    SloamInput in0 = make_input(t0), in1 = make_input(t1);
+    s.RunSloam(in0, out);
+    in1.mapModels = out.tm;  // first scan output is the initial map
+    bool success = s.RunSloam(in1, out);
+    EXPECT_TRUE(success);
+    float translation = out.T_Delta.translation().norm();
+    std::printf("  two_step=%d  |T_Delta.t| = %.6f  |T_Map_Curr.t| = %.6f  lm iters %d/%d\n", (int)two_step,
+                translation, out.T_Map_Curr.translation().norm(), s.lastResult().lm_iterations[0],
+                s.lastResult().lm_iterations[1]);
+    EXPECT_NEAR(0.0, translation, two_step ? 0.1 : 0.2);  // see tests/test_oracle_reference_tests.py
+    bool matched = false;
+    for (auto m : out.matches) matched = matched || m != -1;
+    EXPECT_TRUE(matched);
+  }
+  {  // not the first scan but the map is empty -> false (sloam.cpp:476-480)
+    sloam::sloam s;
+    SloamOutput out;
+    s.setFmParams(params);
+    SloamInput in0 = make_input(t0), in1 = make_input(t1);
+    s.RunSloam(in0, out);
+    SloamOutput out2;
+    EXPECT_TRUE(!s.RunSloam(in1, out2));
+    EXPECT_TRUE(out2.tm.empty());
+  }
+}
+
+int main(int argc, char **argv) {
+  if (argc < 2) { std::printf("usage: %s fixtures.bin\n", argv[0]); return 2; }
+  std::ifstream f(argv[1], std::ios::binary);
+  Fixture t0, t1;
+  if (!read_fixture(f, t0) || !read_fixture(f, t1)) { std::printf("cannot read %s\n", argv[1]); return 2; }
+  std::printf("fixtures: t0 %zu ground / %zu trees, t1 %zu ground / %zu trees\n", t0.ground.size(),
+              t0.landmarks.size(), t1.ground.size(), t1.landmarks.size());
+  try {
+    plane_tests();
+    cylinder_tests(t0);
+    core_tests(t0, t1, false);
+    core_tests(t0, t1, true);
+    {  // Instance::computeGraph on an empty organized cloud: no landmarks, no crash
+      Instance inst;
+      CloudT::Ptr cloud(new CloudT());
+      cloud->width = 64; cloud->height = 16;
+      PointT nanp; nanp.x = nanp.y = nanp.z = std::numeric_limits<float>::quiet_NaN();
+      cloud->points.assign(64 * 16, nanp);
+      std::vector<std::vector<TreeVertex>> lm;
+      inst.computeGraph(cloud, cloud, lm);
+      EXPECT_TRUE(lm.empty());
+    }
+  } catch (const std::exception &e) {
+    std::printf("EXCEPTION %s\n", e.what());
+    return 3;
+  }
+  std::printf("%d checks, %d failed\n", g_run, g_fail);
+  return g_fail ? 1 : 0;
+}
