@@ -32,6 +32,14 @@ struct DevParams {
   GroundGeom gg;
 };
 
+// hand-over record between the per-cell QR (one CTA per cell) and the per-cell
+// 3x3 Jacobi + acceptance (one THREAD per cell): k2_ground.cu
+struct FitRec {
+  double W[9], U[9];
+  float c[3];
+  int32_t n_cell, n_kept, valid;
+};
+
 // Scratch owned by the context, sized for max_keyframes.
 struct Workspace {
   // K1
@@ -52,6 +60,7 @@ struct Workspace {
   unsigned long long *gscratch = nullptr; // [K][N] (z key, index) lists of oversized cells
   double *qscratch = nullptr;        // [K][N][3] QR workspace of oversized cells
   float *pscratch = nullptr;         // [K][N][3] point staging of oversized cells
+  FitRec *fit_rec = nullptr;         // [K][B]
   // K3
   int32_t *parent = nullptr;         // [K][N] union-find
   uint8_t *cc_flags = nullptr;       // [K][N]
@@ -156,6 +165,17 @@ inline int set_err(sloam_ctx *c, int code, const std::string &m) {
       return sb::set_err(ctx, SLOAM_E_CUDA,                                       \
                          std::string("kernel launch: ") + cudaGetErrorString(e__)); \
   } while (0)
+
+// 16-byte vector access to points (sloam_point is four floats; every point array
+// of the ABI must be 16-byte aligned, which cudaMalloc / torch allocations are)
+__device__ __forceinline__ sloam_point ld_point(const sloam_point *p) {
+  const float4 v = *reinterpret_cast<const float4 *>(p);
+  sloam_point r; r.x = v.x; r.y = v.y; r.z = v.z; r.intensity = v.w;
+  return r;
+}
+__device__ __forceinline__ void st_point(sloam_point *p, const sloam_point &v) {
+  *reinterpret_cast<float4 *>(p) = make_float4(v.x, v.y, v.z, v.intensity);
+}
 
 // ---- float helpers with the reference's operation order -----------------
 // Eigen Vector3f::norm / squaredNorm: x^2 + (y^2 + z^2)  (Redux.h unroller)

@@ -68,6 +68,7 @@ static void layout(sloam_ctx *c, Bump &b) {
   b.take(w.gscratch, K * N);
   b.take(w.qscratch, K * N * 3);
   b.take(w.pscratch, K * N * 3);
+  b.take(w.fit_rec, K * B);
   b.take(w.parent, K * N);
   b.take(w.cc_flags, K * N);
   b.take(w.csize, K * N);

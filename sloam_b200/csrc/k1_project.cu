@@ -135,7 +135,7 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
     pixr[j] = 0;
     yawr[j] = qnan;
     if (i < N) {
-      pts[j] = points[kbase + i];
+      pts[j] = ld_point(points + kbase + i);
       if (DO_PROJECT) {
         pixr[j] = project_pixel_fast(pg, pts[j].x, pts[j].y, pts[j].z, mx, my, inv_fov, &yawr[j]);
         if (pixr[j] < 0) s_slow[atomicAdd(&s_nslow, 1)] = j * kThreads + threadIdx.x;
@@ -150,7 +150,7 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
     const int ns = s_nslow;
     for (int q = threadIdx.x; q < ns; q += kThreads) {
       const int idx = s_slow[q];
-      const sloam_point p = points[kbase + tile * kSplitTile + idx];
+      const sloam_point p = ld_point(points + kbase + tile * kSplitTile + idx);
       float range;
       s_pix[idx] = project_pixel(pg, p.x, p.y, p.z, &range);
     }
@@ -186,7 +186,7 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
       sloam_point t;  // dense mode (:247-251): the point or a NaN point with intensity 0
       if (m == 255) t = pts[j];
       else { t.x = qnan; t.y = qnan; t.z = qnan; t.intensity = 0.f; }
-      tree[kbase + i] = t;
+      st_point(tree + kbase + i, t);
     }
     const bool is_g = in && (m == 1);
     bal[j] = __ballot_sync(kFull, is_g);
@@ -219,7 +219,7 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
       const sloam_point p = pts[j];
       const int slot = s_cnt[j * (kThreads / 32) + warp] + __popc(bal[j] & ((1u << lane) - 1u));
       const int cell = ground_cell_fast(gg, p.x, p.y, yawr[j]);
-      s_ground[slot] = p;
+      st_point(s_ground + slot, p);
       s_cell[slot] = (uint8_t)(cell < 0 ? 255 : cell);
       if (cell >= 0) atomicAdd(&s_hist[cell], 1);
     }
@@ -267,7 +267,7 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
   sloam_point *gout = ground + (size_t)k * ground_stride + gbase;
   uint8_t *cout = ground_cell + (size_t)k * ground_stride + gbase;
   for (int s = threadIdx.x; s < base; s += kThreads) {
-    gout[s] = s_ground[s];
+    st_point(gout + s, ld_point(s_ground + s));
     cout[s] = s_cell[s];
   }
   for (int c = threadIdx.x; c < kMaxCells; c += kThreads) {

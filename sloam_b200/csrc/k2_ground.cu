@@ -62,7 +62,7 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
                     const uint8_t *__restrict__ ground_cell, const int32_t *__restrict__ cell_count,
                     const sloam_pose *__restrict__ pose_est, SelKey *__restrict__ gscratch,
                     double *__restrict__ qscratch, float *__restrict__ pscratch,
-                    sloam_cell_plane *__restrict__ cells,
+                    FitRec *__restrict__ fit, sloam_cell_plane *__restrict__ cells,
                     sloam_point *__restrict__ cell_features, sloam_point *__restrict__ kept_points,
                     int32_t *__restrict__ kept_offsets) {
   __shared__ SelKey s_list[kSelCap];
@@ -120,6 +120,7 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
       for (int i = 0; i < 3; ++i) c.model.centroid[i] = 0.0;
       c.n_cell = n_c; c.n_kept = r; c.is_valid = 0; c.accepted = 0;
       *out = c;
+      fit[(size_t)k * B + cell].valid = 0;
     }
     for (int f = threadIdx.x; f < Fg; f += kGThreads) fout[f] = sloam_point{0.f, 0.f, 0.f, 0.f};
     if (kept_points == nullptr || n_c == 0) return;
@@ -128,30 +129,48 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
   // ---- collect the members (z key, input index) in input order ----
   SelKey *list = n_c <= kSelCap ? s_list : gscratch + (size_t)k * stride + off_all;
   int filled = 0;
-  for (int base = 0; base < G; base += kGThreads * 16) {
-    const int i0 = base + threadIdx.x * 16;
-    uint32_t bytes[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-    if (i0 + 15 < G && ((((size_t)k * stride + i0) & 15) == 0)) {
-      const uint4 v = *reinterpret_cast<const uint4 *>(ck + i0);
-      bytes[0] = v.x; bytes[1] = v.y; bytes[2] = v.z; bytes[3] = v.w;
-    } else {
-      for (int q = 0; q < 16; ++q)
-        if (i0 + q < G) {
-          const uint32_t b = ck[i0 + q];
-          bytes[q >> 2] = (bytes[q >> 2] & ~(0xFFu << (8 * (q & 3)))) | (b << (8 * (q & 3)));
-        }
-    }
+  const uint32_t cell4 = (uint32_t)cell * 0x01010101u;
+  constexpr int kPerThread = 16;  // tag bytes per thread per pass: one 16-byte load, SIMD byte compare
+  for (int base = 0; base < G; base += kGThreads * kPerThread) {
+    const int i0 = base + threadIdx.x * kPerThread;
+    uint32_t eq[kPerThread / 4];
     int cnt = 0;
+    if (i0 + kPerThread - 1 < G && ((((size_t)k * stride + i0) & 15) == 0)) {
 #pragma unroll
-    for (int q = 0; q < 16; ++q) cnt += ((bytes[q >> 2] >> (8 * (q & 3))) & 0xFF) == (uint32_t)cell;
+      for (int v4 = 0; v4 < kPerThread / 16; ++v4) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(ck + i0 + 16 * v4);
+        eq[4 * v4 + 0] = __vcmpeq4(v.x, cell4) & 0x80808080u;
+        eq[4 * v4 + 1] = __vcmpeq4(v.y, cell4) & 0x80808080u;
+        eq[4 * v4 + 2] = __vcmpeq4(v.z, cell4) & 0x80808080u;
+        eq[4 * v4 + 3] = __vcmpeq4(v.w, cell4) & 0x80808080u;
+      }
+    } else {
+#pragma unroll
+      for (int w = 0; w < kPerThread / 4; ++w) {
+        uint32_t word = 0xFFFFFFFFu;  // tag 255 = "no cell": never matches
+        for (int b = 0; b < 4; ++b) {
+          const int i = i0 + 4 * w + b;
+          if (i < G) word = (word & ~(0xFFu << (8 * b))) | ((uint32_t)ck[i] << (8 * b));
+        }
+        eq[w] = __vcmpeq4(word, cell4) & 0x80808080u;
+      }
+    }
+#pragma unroll
+    for (int w = 0; w < kPerThread / 4; ++w) cnt += __popc(eq[w]);
     int total;
     int pos = filled + block_excl_scan(cnt, s_warp, &total);
-    if (cnt)
-      for (int q = 0; q < 16; ++q)
-        if (((bytes[q >> 2] >> (8 * (q & 3))) & 0xFF) == (uint32_t)cell) {
-          SelKey e; e.j = (uint32_t)(i0 + q); e.z = float_key(gk[i0 + q].z);
+    if (cnt) {
+#pragma unroll
+      for (int w = 0; w < kPerThread / 4; ++w) {
+        uint32_t m = eq[w];
+        while (m) {
+          const int i = i0 + 4 * w + ((__ffs(m) - 1) >> 3);
+          SelKey e; e.j = (uint32_t)i; e.z = float_key(gk[i].z);
           list[pos++] = e;
+          m &= m - 1;
         }
+      }
+    }
     filled += total;
   }
   __syncthreads();
@@ -228,7 +247,7 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
 
   if (kept_points) {
     sloam_point *kp = kept_points + (size_t)k * stride + off_kept;
-    for (int i = threadIdx.x; i < r; i += kGThreads) kp[i] = gk[keep[i].j];
+    for (int i = threadIdx.x; i < r; i += kGThreads) st_point(kp + i, ld_point(gk + keep[i].j));
   }
   if (n_c == 0 || r < Fg || r < 3) return;
 
@@ -237,7 +256,7 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
   // stage the retained points (x | y | z planes) so the serial float sum reads shared memory
   float *P = n <= kQrCap ? s_pts : pscratch + ((size_t)k * stride + off_all) * 3;
   for (int i = threadIdx.x; i < n; i += kGThreads) {
-    const sloam_point p = gk[keep[i].j];
+    const sloam_point p = ld_point(gk + keep[i].j);
     P[i] = p.x; P[n + i] = p.y; P[2 * n + i] = p.z;
   }
   __syncthreads();
@@ -356,18 +375,38 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
         U[i * 3 + j] = (i == j) ? 1.0 : 0.0;
       }
   }
-  if (lane != 0) return;
-  double nrm[3];
+  // hand the 3x3 problem to plane_finish_kernel (one thread per cell: the Jacobi sweeps and
+  // the acceptance test are scalar fp64 code, 32 cells per warp instead of one)
+  FitRec *rec = fit + (size_t)k * B + cell;
+  if (lane < 9) { rec->W[lane] = Wm[lane]; rec->U[lane] = U[lane]; }
+  if (lane == 0) {
+    rec->c[0] = cxf; rec->c[1] = cyf; rec->c[2] = czf;
+    rec->n_cell = n_c; rec->n_kept = r; rec->valid = 1;
+  }
+  for (int f = lane; f < Fg; f += 32) st_point(fout + f, ld_point(gk + keep[f].j));  // features.resize(numGroundFeatures)
+}
+
+// Steps 2-4 of JacobiSVD on the QR-preconditioned 3x3, plane assembly (plane.cpp:115-127)
+// and the acceptance test (sloam.cpp:401-409): one thread per (keyframe, cell).
+__global__ void plane_finish_kernel(const DevParams *__restrict__ dp, int K, const FitRec *__restrict__ fit,
+                                    const sloam_pose *__restrict__ pose_est,
+                                    sloam_cell_plane *__restrict__ cells) {
+  const int B = dp->B;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= K * B) return;
+  const FitRec rec = fit[g];
+  if (!rec.valid) return;  // the invalid record was written by ground_cells_kernel
+  double Wm[9], U[9], nrm[3];
+  for (int i = 0; i < 9; ++i) { Wm[i] = rec.W[i]; U[i] = rec.U[i]; }
   jacobi_svd3_last_u(Wm, U, nrm);
   sloam_cell_plane c;
-  const double cx = (double)cxf, cy = (double)cyf, cz = (double)czf;
+  const double cx = (double)rec.c[0], cy = (double)rec.c[1], cz = (double)rec.c[2];
   c.model.plane[0] = nrm[0]; c.model.plane[1] = nrm[1]; c.model.plane[2] = nrm[2];
   c.model.plane[3] = -(nrm[0] * cx + nrm[1] * cy + nrm[2] * cz);  // plane.cpp:117
   c.model.centroid[0] = cx; c.model.centroid[1] = cy; c.model.centroid[2] = cz;
-  c.n_cell = n_c; c.n_kept = r; c.is_valid = 1;
-  c.accepted = plane_accept(pose_est[k], c.model.plane, c.model.centroid, dp->p.ground_angle_tol) ? 1 : 0;
-  *out = c;
-  for (int f = 0; f < Fg; ++f) fout[f] = gk[keep[f].j];  // features.resize(numGroundFeatures)
+  c.n_cell = rec.n_cell; c.n_kept = rec.n_kept; c.is_valid = 1;
+  c.accepted = plane_accept(pose_est[g / B], c.model.plane, c.model.centroid, dp->p.ground_angle_tol) ? 1 : 0;
+  cells[g] = c;
 }
 
 // accepted planes of each keyframe, compact, in (radius bin, theta bin) order
@@ -407,7 +446,10 @@ int launch_ground_planes(sloam_ctx *c, int K, const sloam_point *ground, const i
   dim3 grid((unsigned)c->hp.B, (unsigned)K);
   ground_cells_kernel<<<grid, kGThreads, 0, c->stream>>>(
       c->dp, ground, ground_count, stride, w.ground_cell, w.cell_count, pose_est,
-      reinterpret_cast<SelKey *>(w.gscratch), w.qscratch, w.pscratch, cells, cell_features, kept_points, kept_offsets);
+      reinterpret_cast<SelKey *>(w.gscratch), w.qscratch, w.pscratch, w.fit_rec, cells, cell_features, kept_points,
+      kept_offsets);
+  SB_LAUNCH_CHECK(c);
+  plane_finish_kernel<<<(K * c->hp.B + 127) / 128, 128, 0, c->stream>>>(c->dp, K, w.fit_rec, pose_est, cells);
   SB_LAUNCH_CHECK(c);
   return launch_planes_compact(c, K, cells);
 }

@@ -58,21 +58,21 @@ __global__ void cc_init_kernel(const DevParams *__restrict__ dp, int K,
   if (g >= (long long)K * N) return;
   const int i = (int)(g % N);
   const int row = i / W, col = i - row * W;
-  const sloam_point p = tree[g];
+  const sloam_point p = ld_point(tree + g);
   // PCL skips a pixel iff !isfinite(x); EuclideanClusterComparator::compare is
   // dist < threshold in float (NaN compares false)
   const bool valid = isfinite(p.x);
   bool left_ok = false, up_ok = false, upleft_ok = false;  // upleft_ok: (i-W) -- (i-W-1)
   if (valid) {
     if (col > 0) {
-      const sloam_point q = tree[g - 1];
+      const sloam_point q = ld_point(tree + g - 1);
       left_ok = dist3f(p.x, p.y, p.z, q.x, q.y, q.z) < thr;
     }
     if (row > 0) {
-      const sloam_point q = tree[g - W];
+      const sloam_point q = ld_point(tree + g - W);
       up_ok = dist3f(p.x, p.y, p.z, q.x, q.y, q.z) < thr;
       if (up_ok && left_ok) {
-        const sloam_point ql = tree[g - W - 1];
+        const sloam_point ql = ld_point(tree + g - W - 1);
         upleft_ok = dist3f(q.x, q.y, q.z, ql.x, ql.y, ql.z) < thr;
       }
     }
@@ -86,7 +86,7 @@ __global__ void cc_init_kernel(const DevParams *__restrict__ dp, int K,
   if (lane == 0 || !((act >> (lane - 1)) & 1u)) {
     left_up = 0;
     if (left_ok && row > 0) {
-      const sloam_point a = tree[g - 1], b = tree[g - 1 - W];
+      const sloam_point a = ld_point(tree + g - 1), b = ld_point(tree + g - 1 - W);
       left_up = dist3f(a.x, a.y, a.z, b.x, b.y, b.z) < thr;
     }
   }
@@ -258,21 +258,23 @@ __device__ void build_vertex(const DevParams *dp, VtxSmem &s, int n, int row, sl
   const int middle = (int)(n / 2.0);  // trellis.cpp:66
   // order statistics by ranking: every member counts the members before it
   float med[3] = {0.f, 0.f, 0.f};
+  unsigned any_ztie = 0;
   for (int m = lane; m < ((n + 31) & ~31); m += 32) {
-    int rx = 0, ry = 0, rz = 0, rk = 0;
+    int rx = 0, ry = 0, rz = 0;
+    bool ztie = false;
     float xm = 0.f, ym = 0.f, zm = 0.f;
-    int cm = 0;
     if (m < n) {
-      xm = s.x[m]; ym = s.y[m]; zm = s.z[m]; cm = s.col[m];
+      xm = s.x[m]; ym = s.y[m]; zm = s.z[m];
       for (int j = 0; j < n; ++j) {
         const float xj = s.x[j], yj = s.y[j], zj = s.z[j];
         rx += (xj < xm) || (xj == xm && j < m);
         ry += (yj < ym) || (yj == ym && j < m);
         rz += (zj < zm) || (zj == zm && j < m);
-        rk += key_less(zj, yj, xj, s.col[j], zm, ym, xm, cm);
+        ztie |= (zj == zm) && (j != m);
       }
-      s.order[rk] = (int16_t)m;
+      s.order[rz] = (int16_t)m;  // final order when z has no ties (the common case)
     }
+    any_ztie |= __ballot_sync(kFull, ztie);
     // the member whose rank is `middle` holds the median of that axis
     const unsigned bx = __ballot_sync(kFull, m < n && rx == middle);
     const unsigned by = __ballot_sync(kFull, m < n && ry == middle);
@@ -282,6 +284,16 @@ __device__ void build_vertex(const DevParams *dp, VtxSmem &s, int n, int row, sl
     if (bz) med[2] = __shfl_sync(kFull, zm, __ffs(bz) - 1);
   }
   __syncwarp();
+  if (any_ztie) {  // exact z ties: full (z, y, x, column) key
+    for (int m = lane; m < n; m += 32) {
+      const float xm = s.x[m], ym = s.y[m], zm = s.z[m];
+      const int cm = s.col[m];
+      int rk = 0;
+      for (int j = 0; j < n; ++j) rk += key_less(s.z[j], s.y[j], s.x[j], s.col[j], zm, ym, xm, cm);
+      s.order[rk] = (int16_t)m;
+    }
+    __syncwarp();
+  }
   // keep points within max_dist_to_centroid of the median, in z order (trellis.cpp:89-93)
   const float maxd = dp->p.max_dist_to_centroid;
   int kept = 0;
@@ -309,7 +321,7 @@ __device__ void build_vertex(const DevParams *dp, VtxSmem &s, int n, int row, sl
     for (int q = lane; q < kept; q += 32) {
       const int m = s.order[q];
       sloam_point p; p.x = s.x[m]; p.y = s.y[m]; p.z = s.z[m]; p.intensity = s.w[m];
-      pool[base + q] = p;
+      st_point(pool + base + q, p);
     }
     v.n_points = kept; v.point_begin = base; v.is_valid = 1;
   }
@@ -344,7 +356,7 @@ vertex_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ 
       if (mem) {
         const int pos = n + __popc(b & ((1u << lane) - 1u));
         if (pos < kVtxCap) {
-          const sloam_point p = tree[rbase + c];
+          const sloam_point p = ld_point(tree + rbase + c);
           s.x[pos] = p.x; s.y[pos] = p.y; s.z[pos] = p.z; s.w[pos] = p.intensity;
           s.col[pos] = (int16_t)c;
         }
@@ -396,7 +408,7 @@ __global__ void vertex_wide_kernel(const DevParams *__restrict__ dp, const sloam
       const int32_t *bb = bbox + ((size_t)k * T + slot) * 4;
       for (int c = bb[0]; c <= bb[1]; ++c)
         if (parent[rbase + c] == root) {
-          const sloam_point p = tree[rbase + c];
+          const sloam_point p = ld_point(tree + rbase + c);
           sx[n] = p.x; sy[n] = p.y; sz[n] = p.z; sw[n] = p.intensity; scol[n] = c; ++n;
         }
       s_n = n;

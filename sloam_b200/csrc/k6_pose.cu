@@ -173,8 +173,10 @@ struct BlockEval {
       }
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int cnt = want_jac ? 28 : 1;
-    for (int i = want_jac ? 0 : 27; i < 28; ++i) {
+    // only the live accumulators are reduced: np packed J^T J entries, n of J^T r, the cost
+    for (int i = 0; i < 28; ++i) {
+      const bool live = i == 27 || (want_jac && (i < np || (i >= 21 && i < 21 + n)));
+      if (!live) continue;
       double v = warp_sum_d(acc[i]);
       if (lane == 0) s_red[warp * 28 + i] = v;
     }
@@ -191,12 +193,11 @@ struct BlockEval {
       for (int i = 0; i < n; ++i) g[i] = s_red[4 * 28 + 21 + i];
     }
     __syncthreads();
-    (void)cnt;
   }
 };
 
 // grid (problems, K): joint -> 1 problem; two-step -> problem 0 = XYYaw (trees), 1 = ZRollPitch (planes)
-__global__ void __launch_bounds__(kLmThreads)
+__global__ void __launch_bounds__(kLmThreads, 4)
 lm_kernel(const DevParams *__restrict__ dp, int two_step, const sloam_pose *__restrict__ pose_est,
           const double *__restrict__ tree_feat, const sloam_cylinder *__restrict__ tree_obj,
           const int32_t *__restrict__ n_tree_res, int tf_stride, const double *__restrict__ plane_feat,

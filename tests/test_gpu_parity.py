@@ -597,3 +597,59 @@ def test_c_abi_rejects_bad_arguments(capi):
     h = C.c_void_p()
     assert capi.lib().sloam_b200_create(C.byref(bad), 0, 1, C.byref(h)) == -1
     ctx.close()
+
+
+# ------------------------------------------------------------ BASELINE.json configurations
+@pytest.mark.parametrize("preset", ["os1-64-dense", "os1-128"])
+def test_baseline_configs_full_size(capi, oracle, preset):
+    """configs[2] (dense forest, 4096 fixed RANSAC hypotheses per tree) and configs[3]
+    (OS1-128, 128 x 2048) through the fused path against the oracle."""
+    from sloam_b200 import configs
+    K = 3
+    p, cfg = configs.make(capi, preset)
+    inp, exp = run_sequence(capi, oracle, p, cfg, K, True)
+    T, PP = p.max_trees, p.max_prev_planes
+    ctx = capi.Context(p, K)
+    out = dict(results=np.zeros(K, abi.KF_RESULT), matches=np.zeros((K, T), np.int32),
+               tm=np.zeros((K, T), abi.CYLINDER), tm_id=np.zeros((K, T), np.int32),
+               planes=np.zeros((K, PP), abi.PLANE), n_planes=np.zeros(K, np.int32), range_image=None)
+    ctx.run_keyframes_host(K, inp, out)
+    for k in range(K):
+        compare_keyframe(out["results"][k], out["matches"][k], out["tm"][k], out["tm_id"][k], out["planes"][k],
+                         out["n_planes"][k], exp[k])
+    # inlier counts / winning hypotheses of every tree, bit-exact
+    it = ctx.intermediates()
+    models = capi.read_dev(it.tree_models, K * T * abi.TREE_MODEL.itemsize, ctx.device).view(abi.TREE_MODEL).reshape(K, T)
+    for k in range(K):
+        n = exp[k].n_trees
+        for f in ("n_inliers", "best_hypothesis", "n_hypotheses", "n_refit_inliers", "is_valid", "plane_index"):
+            assert np.array_equal(models[k][:n][f], exp[k].tree_models[:n][f]), f
+    if preset == "os1-64-dense":
+        ran = exp[0].tree_models[:exp[0].n_trees]["n_hypotheses"]
+        assert np.all(ran[ran > 0] == 4096) and exp[0].n_trees > 50
+    ctx.close()
+
+
+def test_large_map_association_config5(capi, oracle):
+    """configs[4]: 100 000 map cylinders, 2 000 detections per keyframe (split-map path)."""
+    rng = np.random.default_rng(55)
+    n_map, n_det, K = 100000, 2000, 1
+    mp_ = random_cylinders(rng, n_map, 1000.0)
+    det = np.zeros((K, n_det), abi.CYLINDER)
+    pick = rng.integers(0, n_map, n_det)
+    det[0] = mp_[pick]
+    det[0]["root"][:, :2] += rng.normal(0, 0.2, (n_det, 2))
+    det[0]["root"][:200, :2] += 5000.0                     # 10 % unmatched
+    tf = np.zeros(K, abi.POSE); tf["q"][:, 3] = 1.0; tf["t"][0] = (0.1, -0.2, 0.05)
+    p = capi.default_params()
+    ctx = capi.Context(p, K)
+    bi, bd = ctx.associate(capi.to_dev(det), capi.to_dev(np.full(K, n_det, np.int32)), n_det, capi.to_dev(tf),
+                           capi.to_dev(mp_), capi.to_dev(np.array([n_map], np.int32)), n_map, True, K)
+    ctx.sync()
+    bi = capi.to_host(bi, np.int32, (K, n_det)); bd = capi.to_host(bd, np.float64, (K, n_det))
+    ei, ed = oracle.associate(det[0], tf[0:1], mp_)
+    assert np.array_equal(bi[0], ei) and np.array_equal(bd[0], ed)
+    # property at full size: a matched detection's best map entry is the one it was sampled from
+    near = bd[0] < 1.0
+    assert near.sum() >= 1700 and np.mean(bi[0][near] == pick[near]) > 0.99
+    ctx.close()
