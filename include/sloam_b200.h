@@ -365,6 +365,35 @@ int sloam_b200_run_sloam_dev(sloam_ctx *ctx, int K, const sloam_point *ground,
                              const sloam_batch_in *in,
                              const sloam_batch_out *out);
 
+/* ---------------------------------------------- semantic map + sequential mode
+ * SURVEY 8(f)-1/2.  MapManager (sloam/src/core/mapManager.cpp:8-71) and the
+ * state-carrying call sequence of SLOAMNode::run (sloamNode.cpp:186-282), both
+ * device-resident.  map_init allocates the map (capacity landmarks) and resets
+ * firstScan_ / prevGPlanes_; the context must have been created with
+ * max_keyframes >= 1. */
+int sloam_b200_map_init(sloam_ctx *ctx, int capacity);
+void sloam_b200_map_free(sloam_ctx *ctx);
+/* MapManager::getSubmap (:41-71): kNN(100) around (pose.x, pose.y, 1) over the landmark
+ * roots, then the "last 200 landmarks" filter.  pose, submap [max_map_models], n_submap:
+ * device pointers.  The submap-index -> map-index table is kept for update. */
+int sloam_b200_map_get_submap_dev(sloam_ctx *ctx, const sloam_pose *pose,
+                                  sloam_cylinder *submap, int32_t *n_submap);
+/* MapManager::updateMap (:8-28) with the outputs of run_keyframes (K = 1): device pointers. */
+int sloam_b200_map_update_dev(sloam_ctx *ctx, const sloam_kf_result *res,
+                              const sloam_cylinder *tm, const int32_t *tm_id,
+                              const int32_t *matches);
+/* Whole map to the host (treeModels_, treeHits_); returns the map size (getMap (:30-39) is
+ * the subset with hits > 2).  Synchronises. */
+int sloam_b200_map_dump_host(sloam_ctx *ctx, sloam_cylinder *models, int32_t *hits, int cap);
+/* SLOAMNode::run for one keyframe: HOST points [H*W], mask [H*W], poseEstimate
+ * (= prevKeyPose * initialGuess, sloamNode.cpp:192); getSubmap -> projection/split ->
+ * computeGraph -> RunSloam -> updateMap on the device; result (and optionally matches /
+ * tm / tm_id, [max_trees]) back on the host.  result->success is run()'s return value. */
+int sloam_b200_sequence_step_host(sloam_ctx *ctx, const sloam_point *points,
+                                  const uint8_t *mask, const sloam_pose *pose_estimate,
+                                  sloam_kf_result *result, int32_t *matches,
+                                  sloam_cylinder *tm, int32_t *tm_id);
+
 /* Device-memory helpers so that a host-language binding (cgo / JNI / the C++
  * classes in sloam_b200/host) needs no CUDA headers.  copy_d2h synchronises
  * the context stream before returning. */

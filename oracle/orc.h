@@ -185,6 +185,8 @@ class Sloam { /* sloam::sloam, sloam.h:57-107 */
   std::vector<Plane> cellPlanes;      /* all RB*TB cells */
   std::vector<char> cellAccepted;
   std::vector<Cylinder> treeModels;   /* one per input landmark */
+  std::vector<TreeMatch> lastTreeMatches;   /* match lists handed to the optimiser */
+  std::vector<PlaneMatch> lastPlaneMatches;
  private:
   Options o_;
 };

@@ -125,7 +125,26 @@ sloam_tree_model tree_model_to_abi(const Cylinder &c) {
 }
 }  // namespace
 
+static thread_local std::vector<TreeMatch> g_last_tm;
+static thread_local std::vector<PlaneMatch> g_last_gm;
+
 extern "C" {
+
+/* match lists of the last orc_run_keyframe call on this thread (debugging / LM tests) */
+int orc_last_matches(double *tree_feat, sloam_cylinder *tree_obj, int tcap, double *plane_feat,
+                     sloam_plane *plane_obj, int pcap, int32_t *n_plane) {
+  const int nt = std::min<int>((int)g_last_tm.size(), tcap), np = std::min<int>((int)g_last_gm.size(), pcap);
+  for (int i = 0; i < nt; ++i) {
+    tree_feat[3 * i] = g_last_tm[i].feature.x; tree_feat[3 * i + 1] = g_last_tm[i].feature.y; tree_feat[3 * i + 2] = g_last_tm[i].feature.z;
+    Cylinder c; c.model = g_last_tm[i].object; tree_obj[i] = cyl_to_abi(c.model);
+  }
+  for (int i = 0; i < np; ++i) {
+    plane_feat[3 * i] = g_last_gm[i].feature.x; plane_feat[3 * i + 1] = g_last_gm[i].feature.y; plane_feat[3 * i + 2] = g_last_gm[i].feature.z;
+    Plane pl; pl.model = g_last_gm[i].object; plane_obj[i] = plane_to_abi(pl);
+  }
+  *n_plane = np;
+  return nt;
+}
 
 void orc_default_params(sloam_params *p) {
   std::memset(p, 0, sizeof *p);
@@ -362,6 +381,8 @@ void orc_run_keyframe(const sloam_params *p, int use_libm, const sloam_point *po
   for (int k = 0; k < n_prev; ++k) s.prevGPlanes.push_back(plane_from_abi(prev_planes[k]));
   SloamOutput out;
   s.RunSloam(in, out);
+  g_last_tm = s.lastTreeMatches;
+  g_last_gm = s.lastPlaneMatches;
   *result = s.last;
   const int T = std::min((int)out.tm.size(), p->max_trees);
   for (int i = 0; i < T; ++i) {

@@ -123,6 +123,8 @@ bool Sloam::RunSloam(SloamInput &in, SloamOutput &out) {
         match_tree_features(in.poseEstimate, landmarks, in.mapModels, fm.treeMatchThresh);
     const std::vector<PlaneMatch> planeMatches =
         match_plane_features(in.poseEstimate, planes, prevGPlanes, fm.plane_match_thresh);
+    lastTreeMatches = treeMatches;
+    lastPlaneMatches = planeMatches;
     last.n_tree_matches = (int)treeMatches.size();
     last.n_plane_matches = (int)planeMatches.size();
     SE3 T_Delta;

@@ -22,6 +22,9 @@ EXPORTS = [
     "sloam_b200_ground_planes_dev", "sloam_b200_find_clusters_dev", "sloam_b200_compute_graph_dev",
     "sloam_b200_cylinders_dev", "sloam_b200_associate_dev", "sloam_b200_optimize_pose_dev",
     "sloam_b200_run_keyframes_dev", "sloam_b200_run_keyframes_host", "sloam_b200_get_intermediates",
+    "sloam_b200_run_sloam_dev", "sloam_b200_dev_alloc", "sloam_b200_dev_free", "sloam_b200_copy_h2d",
+    "sloam_b200_copy_d2h", "sloam_b200_map_init", "sloam_b200_map_free", "sloam_b200_map_get_submap_dev",
+    "sloam_b200_map_update_dev", "sloam_b200_map_dump_host", "sloam_b200_sequence_step_host",
     "sloam_synth_default_config", "sloam_synth_scene", "sloam_synth_pose",
     "sloam_synth_generate_host", "sloam_synth_generate_dev",
 ]

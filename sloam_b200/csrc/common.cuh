@@ -123,6 +123,10 @@ struct sloam_ctx {
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  // side stream: the tree detector (K3) runs concurrently with the ground stage (K2);
+  // both only depend on the split kernel (K1)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   sb::DevParams hp;              // host copy
   sb::DevParams *dp = nullptr;   // device copy
   sb::Workspace ws;
@@ -140,6 +144,7 @@ struct sloam_ctx {
   int32_t *assoc_part_i = nullptr;
   double *assoc_part_d = nullptr;
   size_t assoc_part_cap = 0;
+  void *seq = nullptr;  // sloam_seq_state (k7_map.cu): semantic map + sequential state
 };
 
 namespace sb {

@@ -240,6 +240,12 @@ int sloam_b200_create(const sloam_params *p, int device, int max_keyframes, sloa
   if (cudaSetDevice(device) != cudaSuccess) { delete c; return SLOAM_E_CUDA; }
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return SLOAM_E_CUDA; }
   c->own_stream = true;
+  if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    delete c;
+    return SLOAM_E_CUDA;
+  }
   Bump dry{nullptr};
   layout(c, dry);
   c->arena_bytes = align_up(dry.off, 256);
@@ -260,9 +266,12 @@ int sloam_b200_create(const sloam_params *p, int device, int max_keyframes, sloa
   return SLOAM_OK;
 }
 
+void sloam_b200_map_free(sloam_ctx *c);
+
 void sloam_b200_destroy(sloam_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  sloam_b200_map_free(c);
   cudaDeviceSynchronize();
   if (c->arena) cudaFree(c->arena);
   if (c->dp) cudaFree(c->dp);
@@ -271,6 +280,9 @@ void sloam_b200_destroy(sloam_ctx *c) {
   if (c->assoc_part_i) cudaFree(c->assoc_part_i);
   if (c->assoc_part_d) cudaFree(c->assoc_part_d);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  if (c->side) cudaStreamDestroy(c->side);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   delete c;
 }
 

@@ -197,8 +197,10 @@ SLOAM_HD_FN void lm_plus(int mode, const double *x, const double *d, double *out
 
 // Solve (A + diag(D2)) y = b for symmetric positive definite A (n <= 6, packed
 // upper triangle row-major) by Cholesky.  Returns false on breakdown.
-SLOAM_HD_FN bool chol_solve(int n, const double *A, const double *D2, const double *b, double *y) {
-  double L[6][6];
+// L (36) and z (6) are caller-provided scratch: they live in the caller's single work
+// struct on purpose (see LMWork).
+SLOAM_HD_FN bool chol_solve(int n, const double *A, const double *D2, const double *b, double *y,
+                            double (*L)[6], double *z) {
   for (int i = 0; i < n; ++i)
     for (int j = 0; j <= i; ++j) {
       // packed index of (j, i), j <= i
@@ -212,7 +214,6 @@ SLOAM_HD_FN bool chol_solve(int n, const double *A, const double *D2, const doub
         L[i][j] = s / L[j][j];
       }
     }
-  double z[6];
   for (int i = 0; i < n; ++i) {
     double s = b[i];
     for (int k = 0; k < i; ++k) s -= L[i][k] * z[k];
@@ -227,6 +228,11 @@ SLOAM_HD_FN bool chol_solve(int n, const double *A, const double *D2, const doub
     if (!isfinite(y[i])) return false;
   return true;
 }
+
+struct LMWork {
+  double xc[7], cand[7], tmp[7], A[21], g[6], scale[6], diag[6], D2[6], rhs[6], step[6], delta[6], neg[6];
+  double L[6][6], z[6];
+};
 
 struct LMOut { int iterations; int termination; double initial_cost, final_cost; };
 
@@ -247,7 +253,13 @@ SLOAM_HD_FN LMOut lm_minimize(Eval &ev, int mode, int n_res, int max_iterations,
   double radius = 1e4, decrease_factor = 2.0;
   bool reuse_diagonal = false;
   int invalid_steps = 0;
-  double xc[7], cand[7], tmp[7], A[21], g[6], scale[6], diag[6], D2[6], rhs[6], step[6], delta[6], neg[6];
+  // Every array of the state machine lives in ONE zero-initialised object.  As separate
+  // locals nvcc 12.9 assigned `A` and chol_solve's `z` the same local-memory slot (its
+  // stack colouring starts a slot's lifetime at the first use and got the loop wrong), which
+  // corrupted A whenever a step was rejected and A had to be reused.
+  LMWork w = {};
+  double *xc = w.xc, *cand = w.cand, *tmp = w.tmp, *A = w.A, *g = w.g, *scale = w.scale, *diag = w.diag,
+         *D2 = w.D2, *rhs = w.rhs, *step = w.step, *delta = w.delta, *neg = w.neg;
   for (int i = 0; i < na; ++i) xc[i] = x[i];
   for (int i = 0; i < 6; ++i) { scale[i] = 1.0; diag[i] = 0.0; }
   double cost = 0.0, gmax = 0.0, x_norm = 0.0;
@@ -285,7 +297,7 @@ SLOAM_HD_FN LMOut lm_minimize(Eval &ev, int mode, int n_res, int max_iterations,
       rhs[c] = g[c] * scale[c];                   // J_s^T r
     }
     reuse_diagonal = true;
-    const bool solved = chol_solve(n, A, D2, rhs, step);
+    const bool solved = chol_solve(n, A, D2, rhs, step, w.L, w.z);
     bool step_valid = false;
     double model_cost_change = 0.0;
     if (solved) {
@@ -302,6 +314,10 @@ SLOAM_HD_FN LMOut lm_minimize(Eval &ev, int mode, int n_res, int max_iterations,
       model_cost_change = -lin - 0.5 * quad;
       step_valid = model_cost_change > 0.0;
     }
+#ifdef SLOAM_LM_DEBUG
+    printf("it %d cost %.12g solved %d mcc %.6g radius %.4g gmax %.4g A00 %.6g A55 %.6g rhs0 %.6g step0 %.6g\n", iteration, cost,
+           (int)solved, model_cost_change, radius, gmax, A[0], A[n * (n + 1) / 2 - 1], rhs[0], step[0]);
+#endif
     if (!step_valid) {
       if (++invalid_steps >= 5) { out.termination = 2; break; }
       radius /= decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;

@@ -209,7 +209,13 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
     int run = inc - s;
 #pragma unroll
     for (int q = 0; q < kPer; ++q) { const int e = lane * kPer + q; if (e < kEnt) s_cnt[e] = run; run += v[q]; }
-    if (lane == 31) s_base = inc;
+    if (lane == 31) {
+      s_base = inc;
+      // publish this tile's ground count for the look-back of later tiles as early as
+      // possible (before the staging work below)
+      __threadfence();
+      atomicExch(&tile_state[(size_t)k * tiles + tile], pack_state(tile == 0 ? 2u : 1u, (unsigned)inc));
+    }
   }
   __syncthreads();
   base = s_base;
@@ -229,10 +235,6 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
   // ---- decoupled look-back over the tiles of this keyframe ----
   if (warp == 0) {
     unsigned long long *st = tile_state + (size_t)k * tiles;
-    if (lane == 0) {
-      __threadfence();
-      atomicExch(&st[tile], pack_state(tile == 0 ? 2u : 1u, (unsigned)base));
-    }
     int excl = 0;
     if (tile > 0) {
       int look = tile - 1;

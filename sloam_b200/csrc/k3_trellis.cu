@@ -54,14 +54,20 @@ __global__ void cc_init_kernel(const DevParams *__restrict__ dp, int K,
                                int32_t *__restrict__ rmax) {
   const int N = dp->N, W = dp->p.img_w;
   const float thr = dp->p.cluster_dist_thresh;
-  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= (long long)K * N) return;
-  const int i = (int)(g % N);
+  // grid = (ceil(N / 256), K): no 64-bit division on the index path
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const long long g = (long long)blockIdx.y * N + i;
   const int row = i / W, col = i - row * W;
   const sloam_point p = ld_point(tree + g);
   // PCL skips a pixel iff !isfinite(x); EuclideanClusterComparator::compare is
   // dist < threshold in float (NaN compares false)
   const bool valid = isfinite(p.x);
+  if (__ballot_sync(__activemask(), valid) == 0u) {  // most warps: no tree pixel at all
+    parent[g] = kInvalid;
+    flags[g] = 0;
+    return;
+  }
   bool left_ok = false, up_ok = false, upleft_ok = false;  // upleft_ok: (i-W) -- (i-W-1)
   if (valid) {
     if (col > 0) {
@@ -141,40 +147,41 @@ __global__ void cc_flatten_kernel(const DevParams *__restrict__ dp, int K,
                                   int32_t *__restrict__ n_big, int32_t *__restrict__ kf_flags) {
   const int N = dp->N, W = dp->p.img_w, H = dp->p.img_h;
   const int min_pts = dp->p.min_cluster_points, T = dp->p.max_trees;
-  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool in = g < (long long)K * N;
-  int k = 0, i = 0, root = kInvalid;
-  if (in) {
-    k = (int)(g / N); i = (int)(g - (long long)k * N);
-    if (parent[g] != kInvalid) {
-      root = uf_find(parent + (size_t)k * N, i);
-      parent[g] = root;
-    }
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y;
+  const long long g = (long long)k * N + i;
+  const bool in = i < N;
+  int root = kInvalid;
+  const int par0 = in ? parent[g] : kInvalid;
+  if (__ballot_sync(kFull, par0 != kInvalid) == 0u) return;  // most warps: no tree pixel
+  if (par0 != kInvalid) {
+    root = par0 == i ? i : uf_find(parent + (size_t)k * N, par0);
+    parent[g] = root;
   }
   const int row = i / W, col = i - row * W;
-  // lanes of a warp that share (keyframe, root): one atomic per group
-  const long long key = root == kInvalid ? -1ll : ((long long)k << 32 | (unsigned)root);
-  const unsigned act = __ballot_sync(kFull, root != kInvalid);
-  if (root == kInvalid) return;
-  const unsigned grp = __match_any_sync(act, key);
+  // Consecutive lanes are consecutive pixels of a row, so the members of a component come
+  // in runs: a run = maximal stretch of lanes with the same (keyframe, root, row).  One
+  // lane per run (its head) issues the atomics for the whole run.
   const int lane = threadIdx.x & 31;
-  const int leader = __ffs(grp) - 1;
-  if (lane == leader) {
+  const long long key = root == kInvalid ? -1ll - lane : (((long long)k * N + root) * 4096ll + row);
+  const long long prev = __shfl_up_sync(kFull, key, 1);
+  const bool head = root != kInvalid && (lane == 0 || prev != key);
+  const unsigned heads = __ballot_sync(kFull, head || root == kInvalid);
+  if (root == kInvalid) return;
+  if (head) {
+    // run length = distance to the next head / invalid lane (or the end of the warp)
+    const unsigned above = heads & ~((2u << lane) - 1u);
+    const int len = (above ? __ffs(above) - 1 : 32) - lane;
     const size_t r = (size_t)k * N + root;
-    const int cnt = __popc(grp);
-    const int old = atomicAdd(&csize[r], cnt);
-    if (old <= min_pts && old + cnt > min_pts) {  // exactly one group sees the crossing
+    const int old = atomicAdd(&csize[r], len);
+    if (old <= min_pts && old + len > min_pts) {  // exactly one run sees the crossing
       const int slot = atomicAdd(&n_big[k], 1);
       if (slot < T) big_roots[(size_t)k * T + slot] = root;
       else atomicOr(&kf_flags[k], 1);
     }
-  }
-  // extents of the component: a member only issues an atomic when it improves the
-  // value it sees (monotone, so the racy pre-check is safe)
-  {
-    const size_t r = (size_t)k * N + root;
+    // extents of the component (monotone, so the racy pre-checks are safe)
     if (col < cmin[r]) atomicMin(&cmin[r], col);
-    if (col > cmax[r]) atomicMax(&cmax[r], col);
+    if (col + len - 1 > cmax[r]) atomicMax(&cmax[r], col + len - 1);
     if (row > rmax[r]) atomicMax(&rmax[r], row);
   }
   if (root == i) {
@@ -560,7 +567,7 @@ static int run_cc(sloam_ctx *c, int K, const sloam_point *tree) {
   SB_CUDA(c, cudaMemsetAsync(w.n_roots, 0, sizeof(int32_t) * K, c->stream));
   SB_CUDA(c, cudaMemsetAsync(w.n_big, 0, sizeof(int32_t) * K, c->stream));
   SB_CUDA(c, cudaMemsetAsync(w.kf_flags, 0, sizeof(int32_t) * K, c->stream));
-  const unsigned blocks = (unsigned)((total + 255) / 256);
+  const dim3 blocks((unsigned)((c->hp.N + 255) / 256), (unsigned)K);
   cc_init_kernel<<<blocks, 256, 0, c->stream>>>(c->dp, K, tree, w.parent, w.cc_flags, w.csize,
                                                 w.ccol_min, w.ccol_max, w.crow_max);
   SB_LAUNCH_CHECK(c);

@@ -184,26 +184,26 @@ struct BlockEval {
     if (threadIdx.x < 28 && (want_jac || threadIdx.x == 27)) {
       double v = 0.0;
       for (int w = 0; w < kLmThreads / 32; ++w) v += s_red[w * 28 + threadIdx.x];
-      s_red[4 * 28 + threadIdx.x] = v;
+      s_red[(kLmThreads / 32) * 28 + threadIdx.x] = v;
     }
     __syncthreads();
-    *cost = s_red[4 * 28 + 27];
+    *cost = s_red[(kLmThreads / 32) * 28 + 27];
     if (want_jac) {
-      for (int i = 0; i < np; ++i) A[i] = s_red[4 * 28 + i];
-      for (int i = 0; i < n; ++i) g[i] = s_red[4 * 28 + 21 + i];
+      for (int i = 0; i < np; ++i) A[i] = s_red[(kLmThreads / 32) * 28 + i];
+      for (int i = 0; i < n; ++i) g[i] = s_red[(kLmThreads / 32) * 28 + 21 + i];
     }
     __syncthreads();
   }
 };
 
 // grid (problems, K): joint -> 1 problem; two-step -> problem 0 = XYYaw (trees), 1 = ZRollPitch (planes)
-__global__ void __launch_bounds__(kLmThreads, 4)
+__global__ void __launch_bounds__(kLmThreads)
 lm_kernel(const DevParams *__restrict__ dp, int two_step, const sloam_pose *__restrict__ pose_est,
           const double *__restrict__ tree_feat, const sloam_cylinder *__restrict__ tree_obj,
           const int32_t *__restrict__ n_tree_res, int tf_stride, const double *__restrict__ plane_feat,
           const sloam_plane *__restrict__ plane_obj, const int32_t *__restrict__ n_plane_res, int pf_stride,
           const uint8_t *__restrict__ optim_flags, double *__restrict__ lm_x, int32_t *__restrict__ lm_info) {
-  __shared__ double s_red[5 * 28];
+  __shared__ double s_red[(kLmThreads / 32 + 1) * 28];
   const int k = blockIdx.y, prob = blockIdx.x;
   const bool optimTrees = optim_flags[2 * k] != 0, optimGround = optim_flags[2 * k + 1] != 0;
   double *xo = lm_x + ((size_t)k * 2 + prob) * 8;

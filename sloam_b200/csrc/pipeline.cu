@@ -40,11 +40,20 @@ static int run_dev(sloam_ctx *c, int K, const sloam_batch_in *in, const sloam_ba
   int rc = launch_project_split(c, K, true, true, in->points, in->mask, w.pix, range, w.tree, w.ground,
                                 w.ground_count);
   if (rc != SLOAM_OK) return rc;
+  // fork: ground cells + plane fits (K2, main stream) and the tree detector (K3, side
+  // stream) both depend only on K1 and are latency-bound, so they run concurrently
+  cudaStream_t main_stream = c->stream;
+  SB_CUDA(c, cudaEventRecord(c->ev_fork, main_stream));
+  SB_CUDA(c, cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+  c->stream = c->side;
+  rc = launch_compute_graph(c, K, w.tree, w.trees, w.n_trees, w.vertices, w.vertex_points);
+  c->stream = main_stream;
+  if (rc != SLOAM_OK) return rc;
+  SB_CUDA(c, cudaEventRecord(c->ev_join, c->side));
   rc = launch_ground_planes(c, K, w.ground, w.ground_count, c->hp.N, in->pose_est, w.cells,
                             w.cell_features, nullptr, nullptr);
   if (rc != SLOAM_OK) return rc;
-  rc = launch_compute_graph(c, K, w.tree, w.trees, w.n_trees, w.vertices, w.vertex_points);
-  if (rc != SLOAM_OK) return rc;
+  SB_CUDA(c, cudaStreamWaitEvent(main_stream, c->ev_join, 0));  // join
   rc = launch_cylinders(c, K, w.trees, w.n_trees, w.vertices, w.vertex_points, w.planes_acc,
                         w.n_planes_acc, w.tree_models, w.tree_features);
   if (rc != SLOAM_OK) return rc;

@@ -208,3 +208,39 @@ def identity_pose(n=1):
     p = np.zeros(n, abi.POSE)
     p["q"][:, 3] = 1.0
     return p
+
+
+class OracleMap:
+    """MapManager restatement (oracle/orc_map.cpp)."""
+
+    def __init__(self):
+        lib().orc_map_create.restype = C.c_void_p
+        self.h = C.c_void_p(lib().orc_map_create())
+
+    def __del__(self):
+        try:
+            lib().orc_map_destroy(self.h)
+        except Exception:
+            pass
+
+    def size(self):
+        return lib().orc_map_size(self.h)
+
+    def get_submap(self, pose, cap):
+        sub = np.zeros(cap, abi.CYLINDER)
+        idx = np.zeros(cap, np.int32)
+        pose = np.ascontiguousarray(pose)
+        n = lib().orc_map_get_submap(self.h, abi.ptr(pose), abi.ptr(sub), abi.ptr(idx), cap)
+        return sub[:n].copy(), idx[:n].copy()
+
+    def update(self, tm, ids, matches):
+        tm = np.ascontiguousarray(tm)
+        ids = np.ascontiguousarray(ids, np.int32)
+        matches = np.ascontiguousarray(matches, np.int32)
+        lib().orc_map_update(self.h, abi.ptr(tm), abi.ptr(ids), abi.ptr(matches), len(tm))
+
+    def dump(self, cap=1 << 16):
+        models = np.zeros(cap, abi.CYLINDER)
+        hits = np.zeros(cap, np.int32)
+        n = lib().orc_map_dump(self.h, abi.ptr(models), abi.ptr(hits), cap)
+        return models[:n].copy(), hits[:n].copy()
