@@ -195,54 +195,68 @@ SLOAM_HD_FN void lm_plus(int mode, const double *x, const double *d, double *out
   }
 }
 
-// Solve (A + diag(D2)) y = b for symmetric positive definite A (n <= 6, packed
-// upper triangle row-major) by Cholesky.  Returns false on breakdown.
-// L (36) and z (6) are caller-provided scratch: they live in the caller's single work
-// struct on purpose (see LMWork).
-SLOAM_HD_FN bool chol_solve(int n, const double *A, const double *D2, const double *b, double *y,
-                            double (*L)[6], double *z) {
-  for (int i = 0; i < n; ++i)
-    for (int j = 0; j <= i; ++j) {
-      // packed index of (j, i), j <= i
-      const int idx = j * n - j * (j - 1) / 2 + (i - j);
-      double s = A[idx] + (i == j ? D2[i] : 0.0);
-      for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
-      if (i == j) {
-        if (!(s > 0.0)) return false;
-        L[i][i] = sqrt(s);
-      } else {
-        L[i][j] = s / L[j][j];
-      }
+// Work area of one trust-region solve.  Every array of the state machine lives in ONE
+// object on purpose: as separate locals nvcc 12.9 gave the normal matrix and the solver's
+// scratch the same local-memory slot (its stack colouring starts a slot's lifetime at the
+// first use and got the loop wrong), which corrupted the matrix whenever a step was
+// rejected and the matrix had to be reused.  On the device the object sits in shared
+// memory, one per warp (k6_pose.cu); on the host it is a local of the caller.
+struct LMWork {
+  double xc[7], cand[7], tmp[7];
+  double A[21], g[6];    // linearisation at xc (A Jacobi-scaled in place)
+  double A2[21], g2[6];  // linearisation at the candidate (evaluated speculatively)
+  double scale[6], diag[6], D2[6], rhs[6], step[6], delta[6], neg[6];
+  double L[6][6], inv[6], z[6];
+};
+
+// Solve (A + diag(D2)) y = b for symmetric positive definite A (n <= 6, packed upper
+// triangle row-major) by a square-root-free Cholesky (L D L^T): n divisions in total, the
+// substitutions multiply by the stored reciprocals.  Returns false on breakdown.
+SLOAM_HD_FN bool ldl_solve(int n, const double *A, const double *D2, const double *b, double *y, LMWork &w) {
+  double(*L)[6] = w.L;
+  double *inv = w.inv, *z = w.z;
+  for (int j = 0; j < n; ++j) {
+    const int dj = j * n - j * (j - 1) / 2;  // packed index of (j, j)
+    // below the diagonal L holds l_jk * d_k (the products the later columns need)
+    double d = A[dj] + D2[j];
+    for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k] * inv[k];
+    if (!(d > 0.0)) return false;
+    inv[j] = 1.0 / d;
+    for (int i = j + 1; i < n; ++i) {
+      double s = A[dj + (i - j)];
+      for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k] * inv[k];
+      L[i][j] = s;  // = l_ij * d_j
     }
-  for (int i = 0; i < n; ++i) {
-    double s = b[i];
-    for (int k = 0; k < i; ++k) s -= L[i][k] * z[k];
-    z[i] = s / L[i][i];
   }
-  for (int i = n - 1; i >= 0; --i) {
-    double s = z[i];
-    for (int k = i + 1; k < n; ++k) s -= L[k][i] * y[k];
-    y[i] = s / L[i][i];
+  for (int i = 0; i < n; ++i) {  // L z = b, with l_ik = L[i][k] * inv[k]
+    double s = b[i];
+    for (int k = 0; k < i; ++k) s -= L[i][k] * inv[k] * z[k];
+    z[i] = s;
+  }
+  for (int i = n - 1; i >= 0; --i) {  // D L^T y = z
+    double s = z[i] * inv[i];
+    for (int k = i + 1; k < n; ++k) s -= L[k][i] * inv[i] * y[k];
+    y[i] = s;
   }
   for (int i = 0; i < n; ++i)
     if (!isfinite(y[i])) return false;
   return true;
 }
 
-struct LMWork {
-  double xc[7], cand[7], tmp[7], A[21], g[6], scale[6], diag[6], D2[6], rhs[6], step[6], delta[6], neg[6];
-  double L[6][6], z[6];
-};
-
 struct LMOut { int iterations; int termination; double initial_cost, final_cost; };
 
-// The trust-region loop.  `ev(x, want_jac, &cost, JtJ, g)` evaluates the robustified
-// problem at x: cost = sum 0.5 rho(r^2); with want_jac also the packed upper
-// triangle of J~^T J~ (n(n+1)/2) and g = J~^T r~.  x holds the start point and
-// receives the last accepted point.  When evaluated by a thread block every
-// thread runs this loop with identical values (ev reduces and broadcasts).
+// The trust-region loop.  `ev(x, &cost, JtJ, g)` evaluates the robustified problem at x:
+// cost = sum 0.5 rho(r^2), the packed upper triangle of J~^T J~ (n(n+1)/2) and
+// g = J~^T r~.  x holds the start point and receives the last accepted point.
+//
+// Ceres evaluates a candidate cost-only and re-evaluates it with Jacobians once the step is
+// accepted.  Here the candidate is linearised speculatively (into A2/g2) in the same pass,
+// so an accepted step costs one evaluation round instead of two; the values are the ones
+// the second evaluation would produce, so the iterates are unchanged.
+// On the device every lane of a warp runs this loop with identical values (ev reduces over
+// the lanes and broadcasts).
 template <class Eval>
-SLOAM_HD_FN LMOut lm_minimize(Eval &ev, int mode, int n_res, int max_iterations, double *x) {
+SLOAM_HD_FN LMOut lm_minimize(Eval &ev, LMWork &w, int mode, int n_res, int max_iterations, double *x) {
   LMOut out;
   out.iterations = 0; out.termination = -1; out.initial_cost = 0.0; out.final_cost = 0.0;
   const int n = mode == LM_JOINT ? 6 : 3, na = mode == LM_JOINT ? 7 : 6, np = n * (n + 1) / 2;
@@ -253,11 +267,6 @@ SLOAM_HD_FN LMOut lm_minimize(Eval &ev, int mode, int n_res, int max_iterations,
   double radius = 1e4, decrease_factor = 2.0;
   bool reuse_diagonal = false;
   int invalid_steps = 0;
-  // Every array of the state machine lives in ONE zero-initialised object.  As separate
-  // locals nvcc 12.9 assigned `A` and chol_solve's `z` the same local-memory slot (its
-  // stack colouring starts a slot's lifetime at the first use and got the loop wrong), which
-  // corrupted A whenever a step was rejected and A had to be reused.
-  LMWork w = {};
   double *xc = w.xc, *cand = w.cand, *tmp = w.tmp, *A = w.A, *g = w.g, *scale = w.scale, *diag = w.diag,
          *D2 = w.D2, *rhs = w.rhs, *step = w.step, *delta = w.delta, *neg = w.neg;
   for (int i = 0; i < na; ++i) xc[i] = x[i];
@@ -277,7 +286,7 @@ SLOAM_HD_FN LMOut lm_minimize(Eval &ev, int mode, int n_res, int max_iterations,
     for (int i = 0; i < na; ++i) gmax = fmax(gmax, fabs(xc[i] - tmp[i]));
   };
   x_norm = norm_of(xc);
-  ev(xc, true, &cost, A, g);
+  ev(xc, &cost, A, g);
   after_eval(true);
   out.initial_cost = cost;
   int iteration = 0;
@@ -297,7 +306,7 @@ SLOAM_HD_FN LMOut lm_minimize(Eval &ev, int mode, int n_res, int max_iterations,
       rhs[c] = g[c] * scale[c];                   // J_s^T r
     }
     reuse_diagonal = true;
-    const bool solved = chol_solve(n, A, D2, rhs, step, w.L, w.z);
+    const bool solved = ldl_solve(n, A, D2, rhs, step, w);
     bool step_valid = false;
     double model_cost_change = 0.0;
     if (solved) {
@@ -314,10 +323,6 @@ SLOAM_HD_FN LMOut lm_minimize(Eval &ev, int mode, int n_res, int max_iterations,
       model_cost_change = -lin - 0.5 * quad;
       step_valid = model_cost_change > 0.0;
     }
-#ifdef SLOAM_LM_DEBUG
-    printf("it %d cost %.12g solved %d mcc %.6g radius %.4g gmax %.4g A00 %.6g A55 %.6g rhs0 %.6g step0 %.6g\n", iteration, cost,
-           (int)solved, model_cost_change, radius, gmax, A[0], A[n * (n + 1) / 2 - 1], rhs[0], step[0]);
-#endif
     if (!step_valid) {
       if (++invalid_steps >= 5) { out.termination = 2; break; }
       radius /= decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
@@ -327,7 +332,7 @@ SLOAM_HD_FN LMOut lm_minimize(Eval &ev, int mode, int n_res, int max_iterations,
     for (int c = 0; c < n; ++c) delta[c] = step[c] * scale[c];
     lm_plus(mode, xc, delta, cand);
     double cand_cost = 0.0;
-    ev(cand, false, &cand_cost, nullptr, nullptr);
+    ev(cand, &cand_cost, w.A2, w.g2);
     {
       double s = 0.0;
       for (int i = 0; i < na; ++i) s += (xc[i] - cand[i]) * (xc[i] - cand[i]);
@@ -338,7 +343,9 @@ SLOAM_HD_FN LMOut lm_minimize(Eval &ev, int mode, int n_res, int max_iterations,
     if (relative_decrease > min_relative_decrease) {
       for (int i = 0; i < na; ++i) xc[i] = cand[i];
       x_norm = norm_of(xc);
-      ev(xc, true, &cost, A, g);
+      cost = cand_cost;
+      for (int i = 0; i < np; ++i) A[i] = w.A2[i];
+      for (int i = 0; i < n; ++i) g[i] = w.g2[i];
       after_eval(false);
       last_successful = true;
       const double t = 2.0 * relative_decrease - 1.0;
@@ -352,7 +359,6 @@ SLOAM_HD_FN LMOut lm_minimize(Eval &ev, int mode, int n_res, int max_iterations,
   }
   out.iterations = iteration;
   out.final_cost = cost;
-  (void)np;
   return out;
 }
 

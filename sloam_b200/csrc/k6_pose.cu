@@ -19,7 +19,7 @@
 
 namespace sb {
 
-constexpr int kLmThreads = 128;
+constexpr int kLmThreads = 64;  // 2 problems (warps) per CTA
 
 // ---------------------------------------------------------------- matching --
 __global__ void __launch_bounds__(128)
@@ -142,69 +142,86 @@ build_matches_kernel(const DevParams *__restrict__ dp, const uint8_t *__restrict
 }
 
 // ---------------------------------------------------------------- LM solve --
-struct BlockEval {
+// One WARP per (keyframe, problem).  The 32 lanes split the residual rows of an evaluation
+// (row r on lane r % 32), reduce the J^T J / J^T r / cost partial sums with shuffles, and
+// then all run the scalar trust-region state machine of dev_lm.h on identical values: a
+// warp instruction costs the same issue slots with one lane or 32, so the redundancy is
+// free, and no block barrier or master/worker hand-over sits on the critical path.  The
+// scalar state (LMWork) is in shared memory, one copy per warp: every lane reads it by
+// broadcast and writes the same value to the same address.
+// The kernel is latency-bound on the dependent FP64 chain of one iteration, so what
+// matters is how many independent chains an SM holds: 2 warps per CTA, as many CTAs per SM
+// as the register file allows.
+struct WarpEval {
   int mode;
   const double *tree_feat; const sloam_cylinder *tree_obj; int n_tree;
   const double *plane_feat; const sloam_plane *plane_obj; int n_plane;
   double huber_a;
-  double *s_red;  // [4 warps][28] + [28] broadcast
 
-  __device__ void operator()(const double *x, bool want_jac, double *cost, double *A, double *g) {
-    const int n = mode == LM_JOINT ? 6 : 3, np = n * (n + 1) / 2;
-    double acc[28];
+  // N = tangent dimension (6 joint, 3 for the two-step problems): a compile-time N keeps
+  // the accumulators in registers
+  template <int N>
+  __device__ __forceinline__ void eval(const double *xs, double *cost, double *A, double *g) {
+    constexpr int NP = N * (N + 1) / 2;
+    const int lane = threadIdx.x & 31;
+    double x[7];
 #pragma unroll
-    for (int i = 0; i < 28; ++i) acc[i] = 0.0;
+    for (int i = 0; i < 7; ++i) x[i] = xs[i];
+    double acc[NP], accg[N], accc = 0.0;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) acc[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) accg[i] = 0.0;
     const int total = n_tree + n_plane;
-    for (int r = threadIdx.x; r < total; r += kLmThreads) {
+    for (int r = lane; r < total; r += 32) {
       double J[6];
       double res;
-      if (r < n_tree) res = residual_row(mode, x, tree_feat + 3 * (size_t)r, tree_obj + r, nullptr, want_jac ? J : nullptr);
-      else { const int q = r - n_tree; res = residual_row(mode, x, plane_feat + 3 * (size_t)q, nullptr, plane_obj + q, want_jac ? J : nullptr); }
+      if (r < n_tree) res = residual_row(mode, x, tree_feat + 3 * (size_t)r, tree_obj + r, nullptr, J);
+      else { const int q = r - n_tree; res = residual_row(mode, x, plane_feat + 3 * (size_t)q, nullptr, plane_obj + q, J); }
       double sc;
-      acc[27] += huber(res, huber_a, &sc);
-      if (want_jac) {
-        const double rr = res * sc;
-        int p = 0;
-        for (int i = 0; i < n; ++i) {
-          const double ji = J[i] * sc;
-          for (int j = i; j < n; ++j) acc[p++] += ji * (J[j] * sc);
-          acc[21 + i] += ji * rr;
-        }
+      accc += huber(res, huber_a, &sc);
+      const double rr = res * sc;
+      int p = 0;
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const double ji = J[i] * sc;
+#pragma unroll
+        for (int j = i; j < N; ++j) acc[p++] += ji * (J[j] * sc);
+        accg[i] += ji * rr;
       }
     }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // only the live accumulators are reduced: np packed J^T J entries, n of J^T r, the cost
-    for (int i = 0; i < 28; ++i) {
-      const bool live = i == 27 || (want_jac && (i < np || (i >= 21 && i < 21 + n)));
-      if (!live) continue;
-      double v = warp_sum_d(acc[i]);
-      if (lane == 0) s_red[warp * 28 + i] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < 28 && (want_jac || threadIdx.x == 27)) {
-      double v = 0.0;
-      for (int w = 0; w < kLmThreads / 32; ++w) v += s_red[w * 28 + threadIdx.x];
-      s_red[(kLmThreads / 32) * 28 + threadIdx.x] = v;
-    }
-    __syncthreads();
-    *cost = s_red[(kLmThreads / 32) * 28 + 27];
-    if (want_jac) {
-      for (int i = 0; i < np; ++i) A[i] = s_red[(kLmThreads / 32) * 28 + i];
-      for (int i = 0; i < n; ++i) g[i] = s_red[(kLmThreads / 32) * 28 + 21 + i];
-    }
-    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NP; ++i) A[i] = warp_sum_d(acc[i]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) g[i] = warp_sum_d(accg[i]);
+    *cost = warp_sum_d(accc);
+  }
+
+  __device__ void operator()(const double *xs, double *cost, double *A, double *g) {
+    __syncwarp();
+    if (mode == LM_JOINT) eval<6>(xs, cost, A, g);
+    else eval<3>(xs, cost, A, g);
+    __syncwarp();
   }
 };
 
-// grid (problems, K): joint -> 1 problem; two-step -> problem 0 = XYYaw (trees), 1 = ZRollPitch (planes)
-__global__ void __launch_bounds__(kLmThreads)
-lm_kernel(const DevParams *__restrict__ dp, int two_step, const sloam_pose *__restrict__ pose_est,
+// problems: joint -> one per keyframe; two-step -> 2 per keyframe, problem 0 = XYYaw (trees),
+// 1 = ZRollPitch (planes).  Warp w of the grid solves problem w.
+#ifndef SLOAM_LM_MIN_CTAS
+#define SLOAM_LM_MIN_CTAS 8  // 128 registers: measured best of 4 / 6 / 8 (latency-bound, occupancy wins)
+#endif
+__global__ void __launch_bounds__(kLmThreads, SLOAM_LM_MIN_CTAS)
+lm_kernel(const DevParams *__restrict__ dp, int two_step, int K, const sloam_pose *__restrict__ pose_est,
           const double *__restrict__ tree_feat, const sloam_cylinder *__restrict__ tree_obj,
           const int32_t *__restrict__ n_tree_res, int tf_stride, const double *__restrict__ plane_feat,
           const sloam_plane *__restrict__ plane_obj, const int32_t *__restrict__ n_plane_res, int pf_stride,
           const uint8_t *__restrict__ optim_flags, double *__restrict__ lm_x, int32_t *__restrict__ lm_info) {
-  __shared__ double s_red[(kLmThreads / 32 + 1) * 28];
-  const int k = blockIdx.y, prob = blockIdx.x;
+  __shared__ LMWork s_work[kLmThreads / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pid = blockIdx.x * (kLmThreads / 32) + warp;
+  const int per_kf = two_step ? 2 : 1;
+  if (pid >= K * per_kf) return;  // warp-uniform; no block barrier below
+  const int k = pid / per_kf, prob = pid % per_kf;
   const bool optimTrees = optim_flags[2 * k] != 0, optimGround = optim_flags[2 * k + 1] != 0;
   double *xo = lm_x + ((size_t)k * 2 + prob) * 8;
   int32_t *info = lm_info + ((size_t)k * 2 + prob) * 2;
@@ -228,7 +245,7 @@ lm_kernel(const DevParams *__restrict__ dp, int two_step, const sloam_pose *__re
   LMOut o;
   o.iterations = 0; o.termination = -1; o.initial_cost = 0; o.final_cost = 0;
   if (run) {
-    BlockEval ev;
+    WarpEval ev;
     ev.mode = mode;
     const bool use_trees = mode != LM_ZROLLPITCH, use_planes = mode != LM_XYYAW;
     ev.tree_feat = tree_feat + (size_t)k * tf_stride * 3;
@@ -238,14 +255,17 @@ lm_kernel(const DevParams *__restrict__ dp, int two_step, const sloam_pose *__re
     ev.plane_obj = plane_obj + (size_t)k * pf_stride;
     ev.n_plane = use_planes ? n_plane_res[k] : 0;
     ev.huber_a = dp->p.huber_delta;
-    ev.s_red = s_red;
-    o = lm_minimize(ev, mode, ev.n_tree + ev.n_plane, dp->p.lm_max_iterations, x);
+    o = lm_minimize(ev, s_work[warp], mode, ev.n_tree + ev.n_plane, dp->p.lm_max_iterations, x);
   }
-  if (threadIdx.x == 0) {
+  if (lane == 0) {
     for (int i = 0; i < 7; ++i) xo[i] = x[i];
     xo[7] = o.final_cost;
     info[0] = o.iterations;
     info[1] = run ? o.termination : -1;
+  }
+  if (!two_step && lane == 1) {  // the unused second problem slot of a joint solve
+    int32_t *info1 = lm_info + ((size_t)k * 2 + 1) * 2;
+    info1[0] = 0; info1[1] = -1;
   }
 }
 
@@ -364,8 +384,8 @@ int launch_lm(sloam_ctx *c, int K, int two_step, const sloam_pose *pose_est, con
               const sloam_cylinder *tree_obj, const int32_t *n_tree_res, int tf_stride,
               const double *plane_feat, const sloam_plane *plane_obj, const int32_t *n_plane_res,
               int pf_stride, const uint8_t *optim_flags) {
-  dim3 grid(two_step ? 2u : 1u, (unsigned)K);
-  lm_kernel<<<grid, kLmThreads, 0, c->stream>>>(c->dp, two_step, pose_est, tree_feat, tree_obj, n_tree_res,
+  const int problems = K * (two_step ? 2 : 1), per_cta = kLmThreads / 32;
+  lm_kernel<<<(problems + per_cta - 1) / per_cta, kLmThreads, 0, c->stream>>>(c->dp, two_step, K, pose_est, tree_feat, tree_obj, n_tree_res,
                                                 tf_stride, plane_feat, plane_obj, n_plane_res, pf_stride,
                                                 optim_flags, c->ws.lm_x, c->ws.lm_info);
   SB_LAUNCH_CHECK(c);

@@ -13,7 +13,8 @@ struct SerialEval {
   const double *tf; const sloam_cylinder *to; int nt;
   const double *pf; const sloam_plane *po; int np_;
   double huber_a;
-  void operator()(const double *x, bool want_jac, double *cost, double *A, double *g) {
+  void operator()(const double *x, double *cost, double *A, double *g) {
+    const bool want_jac = true;
     const int n = mode == LM_JOINT ? 6 : 3, npk = n * (n + 1) / 2;
     double acc[28];
     for (double &a : acc) a = 0.0;
@@ -49,7 +50,8 @@ int hd_lm_solve(int mode, double *x, const double *tf, const sloam_cylinder *to,
   const bool use_t = mode != LM_ZROLLPITCH, use_p = mode != LM_XYYAW;
   if (!use_t) ev.nt = 0;
   if (!use_p) ev.np_ = 0;
-  const LMOut o = lm_minimize(ev, mode, ev.nt + ev.np_, max_it, x);
+  LMWork w = {};
+  const LMOut o = lm_minimize(ev, w, mode, ev.nt + ev.np_, max_it, x);
   *iterations = o.iterations;
   costs[0] = o.initial_cost; costs[1] = o.final_cost;
   return o.termination;
