@@ -56,11 +56,85 @@ __device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int *total) {
   return off + inc - v;
 }
 
+// Stable multisplit of one keyframe's ground points by polar cell: members[k] receives the
+// (z key, input index) records of cell 0, then cell 1, ... each in input order, so that a
+// cell's CTA reads its n_c members with one contiguous load instead of scanning all G tags.
+// One CTA per keyframe walks the tags in chunks of kBinThreads; inside a chunk the rank of a
+// point among the points of its cell is  (points of the cell in earlier warps) + (points of
+// the cell on lower lanes, from match_any).
+constexpr int kBinThreads = 1024;
+constexpr int kBinWarps = kBinThreads / 32;
+
+__global__ void __launch_bounds__(kBinThreads)
+ground_bin_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ ground,
+                  const int32_t *__restrict__ ground_count, int stride,
+                  const uint8_t *__restrict__ ground_cell, const int32_t *__restrict__ cell_count,
+                  SelKey *__restrict__ members) {
+  extern __shared__ int s_bin[];  // [B] running offsets, then [kBinWarps][B] per-warp counts
+  const int B = dp->B;
+  int *s_run = s_bin, *s_wc = s_bin + B;
+  const int k = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int G = ground_count[k];
+  const sloam_point *gk = ground + (size_t)k * stride;
+  const uint8_t *ck = ground_cell + (size_t)k * stride;
+  SelKey *mk = members + (size_t)k * stride;
+  if (warp == 0) {  // exclusive prefix of the cell counts -> first slot of every cell
+    int carry = 0;
+    for (int base = 0; base < B; base += 32) {
+      const int c = base + lane;
+      const int v = c < B ? cell_count[(size_t)k * kMaxCells + c] : 0;
+      int inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (c < B) s_run[c] = carry + inc - v;
+      carry += __shfl_sync(kFull, inc, 31);
+    }
+  }
+  for (int base = 0; base < G; base += kBinThreads) {
+    for (int i = threadIdx.x; i < kBinWarps * B; i += kBinThreads) s_wc[i] = 0;
+    __syncthreads();
+    const int i = base + threadIdx.x;
+    const int c = i < G ? (int)ck[i] : 255;
+    const bool valid = c < B;
+    uint32_t zk = 0;
+    if (valid) zk = float_key(gk[i].z);
+    // lanes of this warp in the same cell (invalid lanes get a private key)
+    const unsigned same = __match_any_sync(kFull, valid ? c : 256 + lane);
+    const int rank = __popc(same & ((1u << lane) - 1u));
+    if (valid && rank == 0) s_wc[warp * B + c] = __popc(same);
+    __syncthreads();
+    // per cell: exclusive scan of the counts over the warps (one warp per cell, lane = warp
+    // index), turned into absolute output slots; the running offset advances by the total
+    for (int cc = warp; cc < B; cc += kBinWarps) {
+      const int v = s_wc[lane * B + cc];
+      int inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += t;
+      }
+      const int run = s_run[cc];
+      __syncwarp();
+      s_wc[lane * B + cc] = run + inc - v;
+      if (lane == 31) s_run[cc] = run + inc;
+    }
+    __syncthreads();
+    if (valid) {
+      SelKey e; e.z = zk; e.j = (uint32_t)i;
+      mk[s_wc[warp * B + c] + rank] = e;
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(kGThreads)
 ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ ground,
                     const int32_t *__restrict__ ground_count, int stride,
-                    const uint8_t *__restrict__ ground_cell, const int32_t *__restrict__ cell_count,
-                    const sloam_pose *__restrict__ pose_est, SelKey *__restrict__ gscratch,
+                    SelKey *__restrict__ members, const int32_t *__restrict__ cell_count,
+                    const sloam_pose *__restrict__ pose_est,
                     double *__restrict__ qscratch, float *__restrict__ pscratch,
                     FitRec *__restrict__ fit, sloam_cell_plane *__restrict__ cells,
                     sloam_point *__restrict__ cell_features, sloam_point *__restrict__ kept_points,
@@ -79,7 +153,6 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
   const int n_c = cell_count[(size_t)k * kMaxCells + cell];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const sloam_point *gk = ground + (size_t)k * stride;
-  const uint8_t *ck = ground_cell + (size_t)k * stride;
   sloam_cell_plane *out = cells + (size_t)k * B + cell;
   sloam_point *fout = cell_features + ((size_t)k * B + cell) * Fg;
 
@@ -126,52 +199,12 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
     if (kept_points == nullptr || n_c == 0) return;
   }
 
-  // ---- collect the members (z key, input index) in input order ----
-  SelKey *list = n_c <= kSelCap ? s_list : gscratch + (size_t)k * stride + off_all;
-  int filled = 0;
-  const uint32_t cell4 = (uint32_t)cell * 0x01010101u;
-  constexpr int kPerThread = 16;  // tag bytes per thread per pass: one 16-byte load, SIMD byte compare
-  for (int base = 0; base < G; base += kGThreads * kPerThread) {
-    const int i0 = base + threadIdx.x * kPerThread;
-    uint32_t eq[kPerThread / 4];
-    int cnt = 0;
-    if (i0 + kPerThread - 1 < G && ((((size_t)k * stride + i0) & 15) == 0)) {
-#pragma unroll
-      for (int v4 = 0; v4 < kPerThread / 16; ++v4) {
-        const uint4 v = *reinterpret_cast<const uint4 *>(ck + i0 + 16 * v4);
-        eq[4 * v4 + 0] = __vcmpeq4(v.x, cell4) & 0x80808080u;
-        eq[4 * v4 + 1] = __vcmpeq4(v.y, cell4) & 0x80808080u;
-        eq[4 * v4 + 2] = __vcmpeq4(v.z, cell4) & 0x80808080u;
-        eq[4 * v4 + 3] = __vcmpeq4(v.w, cell4) & 0x80808080u;
-      }
-    } else {
-#pragma unroll
-      for (int w = 0; w < kPerThread / 4; ++w) {
-        uint32_t word = 0xFFFFFFFFu;  // tag 255 = "no cell": never matches
-        for (int b = 0; b < 4; ++b) {
-          const int i = i0 + 4 * w + b;
-          if (i < G) word = (word & ~(0xFFu << (8 * b))) | ((uint32_t)ck[i] << (8 * b));
-        }
-        eq[w] = __vcmpeq4(word, cell4) & 0x80808080u;
-      }
-    }
-#pragma unroll
-    for (int w = 0; w < kPerThread / 4; ++w) cnt += __popc(eq[w]);
-    int total;
-    int pos = filled + block_excl_scan(cnt, s_warp, &total);
-    if (cnt) {
-#pragma unroll
-      for (int w = 0; w < kPerThread / 4; ++w) {
-        uint32_t m = eq[w];
-        while (m) {
-          const int i = i0 + 4 * w + ((__ffs(m) - 1) >> 3);
-          SelKey e; e.j = (uint32_t)i; e.z = float_key(gk[i].z);
-          list[pos++] = e;
-          m &= m - 1;
-        }
-      }
-    }
-    filled += total;
+  // ---- the members (z key, input index), in input order: contiguous in `members` ----
+  SelKey *src = members + (size_t)k * stride + off_all;
+  SelKey *list = src;  // oversized cells are processed in place (L2-resident workspace)
+  if (n_c <= kSelCap) {
+    list = s_list;
+    for (int i = threadIdx.x; i < n_c; i += kGThreads) s_list[i] = src[i];
   }
   __syncthreads();
 
@@ -444,9 +477,13 @@ int launch_ground_planes(sloam_ctx *c, int K, const sloam_point *ground, const i
                          sloam_point *cell_features, sloam_point *kept_points, int32_t *kept_offsets) {
   Workspace &w = c->ws;
   dim3 grid((unsigned)c->hp.B, (unsigned)K);
+  const size_t bin_smem = sizeof(int) * (size_t)(kBinWarps + 1) * c->hp.B;
+  ground_bin_kernel<<<K, kBinThreads, bin_smem, c->stream>>>(c->dp, ground, ground_count, stride, w.ground_cell,
+                                                             w.cell_count, reinterpret_cast<SelKey *>(w.gscratch));
+  SB_LAUNCH_CHECK(c);
   ground_cells_kernel<<<grid, kGThreads, 0, c->stream>>>(
-      c->dp, ground, ground_count, stride, w.ground_cell, w.cell_count, pose_est,
-      reinterpret_cast<SelKey *>(w.gscratch), w.qscratch, w.pscratch, w.fit_rec, cells, cell_features, kept_points,
+      c->dp, ground, ground_count, stride, reinterpret_cast<SelKey *>(w.gscratch), w.cell_count, pose_est,
+      w.qscratch, w.pscratch, w.fit_rec, cells, cell_features, kept_points,
       kept_offsets);
   SB_LAUNCH_CHECK(c);
   plane_finish_kernel<<<(K * c->hp.B + 127) / 128, 128, 0, c->stream>>>(c->dp, K, w.fit_rec, pose_est, cells);
