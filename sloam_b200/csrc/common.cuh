@@ -47,6 +47,9 @@ struct Workspace {
   sloam_point *tree = nullptr;       // [K][N]
   sloam_point *ground = nullptr;     // [K][N]
   int32_t *ground_count = nullptr;   // [K]
+  uint32_t *tree_bits = nullptr;     // [K][ceil(N/32)] bit i: pixel i may hold a tree point
+  int32_t *tree_words = nullptr;     // [K * ceil(N/32)] indices of the non-zero words of tree_bits
+  int32_t *n_tree_words = nullptr;   // [1]
   uint8_t *ground_cell = nullptr;    // [K][N] polar cell of each ground point (255 = none)
   int32_t *cell_count = nullptr;     // [K][kMaxCells]
   unsigned long long *tile_state = nullptr; // [K][tiles] decoupled look-back
@@ -140,6 +143,9 @@ struct sloam_ctx {
   void *stage_dev = nullptr;
   size_t stage_dev_bytes = 0;
   int last_k = 0;
+  // the fused path writes only the tree-labelled points of ws.tree (+ ws.tree_bits); the NaN
+  // points of the dense cloud are filled in when the intermediates are asked for
+  bool tree_sparse = false;
   // partial results of split association (large maps), grown on demand
   int32_t *assoc_part_i = nullptr;
   double *assoc_part_d = nullptr;

@@ -56,6 +56,9 @@ static void layout(sloam_ctx *c, Bump &b) {
   b.take(w.tree, K * N);
   b.take(w.ground, K * N);
   b.take(w.ground_count, K);
+  b.take(w.tree_bits, K * ((N + 31) / 32));
+  b.take(w.tree_words, 2 * K * ((N + 31) / 32));
+  b.take(w.n_tree_words, 4);
   b.take(w.ground_cell, K * N);
   b.take(w.cell_count, K * kMaxCells);
   b.take(w.tile_state, K * tiles);
@@ -220,7 +223,9 @@ void sloam_b200_default_params(sloam_params *p) {
 }
 
 int sloam_b200_create(const sloam_params *p, int device, int max_keyframes, sloam_ctx **out) {
-  if (!p || !out || max_keyframes <= 0) return SLOAM_E_INVALID;
+  // batch keyframe index and 32-pixel word index are packed 16 + 16 bits (k3_trellis.cu)
+  if (!p || !out || max_keyframes <= 0 || max_keyframes > 65535) return SLOAM_E_INVALID;
+  if ((long long)p->img_h * p->img_w > (1ll << 21)) return SLOAM_E_INVALID;
   *out = nullptr;
   int n_dev = 0;
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || device < 0 || device >= n_dev)

@@ -84,7 +84,7 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
                      sloam_point *__restrict__ ground, int32_t *__restrict__ ground_count,
                      uint8_t *__restrict__ ground_cell, int32_t *__restrict__ cell_count,
                      unsigned long long *__restrict__ tile_state, unsigned *__restrict__ ticket,
-                     int ground_stride) {
+                     int ground_stride, uint32_t *__restrict__ tree_bits, int sparse_tree) {
   __shared__ __align__(16) unsigned char s_raw[(DO_SPLIT ? sizeof(sloam_point) : sizeof(int)) * kSplitTile];
   sloam_point *s_ground = reinterpret_cast<sloam_point *>(s_raw);
   __shared__ uint8_t s_cell[DO_SPLIT ? kSplitTile : 1];
@@ -182,11 +182,19 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
     const bool in = i < N;
     unsigned char m = 0;
     if (in) m = mask[kbase + pixr[j]];  // inference.cpp:242-243
-    if (in) {
-      sloam_point t;  // dense mode (:247-251): the point or a NaN point with intensity 0
-      if (m == 255) t = pts[j];
+    // dense mode (:247-251): the point or a NaN point with intensity 0.  With sparse_tree
+    // (fused pipeline) only the tree points are written; tree_bits says which pixels hold one
+    // and the NaN points are materialised on demand (pipeline.cu).
+    const bool is_t = in && (m == 255);
+    if (in && (is_t || !sparse_tree)) {
+      sloam_point t;
+      if (is_t) t = pts[j];
       else { t.x = qnan; t.y = qnan; t.z = qnan; t.intensity = 0.f; }
       st_point(tree + kbase + i, t);
+    }
+    if (tree_bits != nullptr) {
+      const unsigned tb = __ballot_sync(kFull, is_t);
+      if (lane == 0 && in) tree_bits[(size_t)k * ((N + 31) >> 5) + (i >> 5)] = tb;
     }
     const bool is_g = in && (m == 1);
     bal[j] = __ballot_sync(kFull, is_g);
@@ -333,7 +341,7 @@ int launch_ground_tag(sloam_ctx *c, int K, const sloam_point *ground, const int3
 int launch_project_split(sloam_ctx *c, int K, bool do_project, bool do_split,
                          const sloam_point *points, const uint8_t *mask, int32_t *pix,
                          float *range_image, sloam_point *tree, sloam_point *ground,
-                         int32_t *ground_count) {
+                         int32_t *ground_count, uint32_t *tree_bits, bool sparse_tree) {
   const int N = c->hp.N;
   const int tiles = (N + kSplitTile - 1) / kSplitTile;
   const long long total = (long long)K * N;
@@ -349,7 +357,7 @@ int launch_project_split(sloam_ctx *c, int K, bool do_project, bool do_split,
   }
   const unsigned grid = (unsigned)(K * tiles);
 #define SB_K1_ARGS c->dp, K, points, mask, pix, rb, tree, ground, ground_count, c->ws.ground_cell, \
-                   c->ws.cell_count, c->ws.tile_state, ticket, N
+                   c->ws.cell_count, c->ws.tile_state, ticket, N, tree_bits, sparse_tree ? 1 : 0
   if (do_project && do_split) project_split_kernel<true, true><<<grid, kThreads, 0, c->stream>>>(SB_K1_ARGS);
   else if (do_project) project_split_kernel<true, false><<<grid, kThreads, 0, c->stream>>>(SB_K1_ARGS);
   else project_split_kernel<false, true><<<grid, kThreads, 0, c->stream>>>(SB_K1_ARGS);
@@ -372,7 +380,8 @@ extern "C" {
 int sloam_b200_project_dev(sloam_ctx *c, int K, const sloam_point *points, int32_t *pix,
                            float *range_image) {
   if (!c || K <= 0 || K > c->max_k || !points || !pix) return set_err(c, SLOAM_E_INVALID, "project: bad arguments");
-  return launch_project_split(c, K, true, false, points, nullptr, pix, range_image, nullptr, nullptr, nullptr);
+  return launch_project_split(c, K, true, false, points, nullptr, pix, range_image, nullptr, nullptr, nullptr,
+                              nullptr, false);
 }
 
 int sloam_b200_mask_cloud_dev(sloam_ctx *c, int K, const sloam_point *points, const int32_t *pix,
@@ -381,7 +390,7 @@ int sloam_b200_mask_cloud_dev(sloam_ctx *c, int K, const sloam_point *points, co
   if (!c || K <= 0 || K > c->max_k || !points || !pix || !mask || !tree || !ground || !ground_count)
     return set_err(c, SLOAM_E_INVALID, "mask_cloud: bad arguments");
   return launch_project_split(c, K, false, true, points, mask, const_cast<int32_t *>(pix), nullptr,
-                              tree, ground, ground_count);
+                              tree, ground, ground_count, nullptr, false);
 }
 
 int sloam_b200_project_split_dev(sloam_ctx *c, int K, const sloam_point *points, const uint8_t *mask,
@@ -389,7 +398,8 @@ int sloam_b200_project_split_dev(sloam_ctx *c, int K, const sloam_point *points,
                                  sloam_point *ground, int32_t *ground_count) {
   if (!c || K <= 0 || K > c->max_k || !points || !mask || !pix || !tree || !ground || !ground_count)
     return set_err(c, SLOAM_E_INVALID, "project_split: bad arguments");
-  return launch_project_split(c, K, true, true, points, mask, pix, range_image, tree, ground, ground_count);
+  return launch_project_split(c, K, true, true, points, mask, pix, range_image, tree, ground, ground_count,
+                              nullptr, false);
 }
 
 }  // extern "C"

@@ -46,152 +46,222 @@ __device__ __forceinline__ void uf_union(int32_t *parent, int a, int b) {
   }
 }
 
-// ---- 1. init: link every valid pixel to its left (else up) neighbour ------
-__global__ void cc_init_kernel(const DevParams *__restrict__ dp, int K,
-                               const sloam_point *__restrict__ tree, int32_t *__restrict__ parent,
-                               uint8_t *__restrict__ flags, int32_t *__restrict__ csize,
-                               int32_t *__restrict__ cmin, int32_t *__restrict__ cmax,
-                               int32_t *__restrict__ rmax) {
-  const int N = dp->N, W = dp->p.img_w;
-  const float thr = dp->p.cluster_dist_thresh;
-  // grid = (ceil(N / 256), K): no 64-bit division on the index path
+// tree_bits: one bit per pixel, [K][Nw] words (Nw = ceil(N / 32)).  Bit set = the pixel may
+// hold a tree point (the split kernel sets it for mask == 255; for caller-supplied clouds it
+// is isfinite(x)).  Pixels whose bit is clear are never read by the kernels below -- in the
+// fused pipeline their tree point, parent and flag entries are not even written.
+__device__ __forceinline__ bool tree_bit(const uint32_t *__restrict__ bits_k, int i) {
+  return i >= 0 && ((bits_k[i >> 5] >> (i & 31)) & 1u);
+}
+
+__global__ void tree_bits_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ tree,
+                                 uint32_t *__restrict__ bits) {
+  const int N = dp->N, Nw = (N + 31) >> 5;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y;
+  const bool v = i < N && isfinite(tree[(size_t)k * N + i].x);
+  const unsigned b = __ballot_sync(kFull, v);
+  if ((threadIdx.x & 31) == 0 && i < N) bits[(size_t)k * Nw + (i >> 5)] = b;
+}
+
+// dense organized cloud from the sparse one: NaN points (intensity 0) where the bit is clear
+__global__ void tree_fill_kernel(const DevParams *__restrict__ dp, const uint32_t *__restrict__ bits,
+                                 sloam_point *__restrict__ tree) {
+  const int N = dp->N, Nw = (N + 31) >> 5;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y;
   if (i >= N) return;
-  const long long g = (long long)blockIdx.y * N + i;
-  const int row = i / W, col = i - row * W;
-  const sloam_point p = ld_point(tree + g);
-  // PCL skips a pixel iff !isfinite(x); EuclideanClusterComparator::compare is
-  // dist < threshold in float (NaN compares false)
-  const bool valid = isfinite(p.x);
-  if (__ballot_sync(__activemask(), valid) == 0u) {  // most warps: no tree pixel at all
-    parent[g] = kInvalid;
-    flags[g] = 0;
-    return;
+  if (!((bits[(size_t)k * Nw + (i >> 5)] >> (i & 31)) & 1u)) {
+    const float qnan = __int_as_float(0x7fc00000);
+    st_point(tree + (size_t)k * N + i, sloam_point{qnan, qnan, qnan, 0.f});
   }
-  bool left_ok = false, up_ok = false, upleft_ok = false;  // upleft_ok: (i-W) -- (i-W-1)
-  if (valid) {
-    if (col > 0) {
-      const sloam_point q = ld_point(tree + g - 1);
-      left_ok = dist3f(p.x, p.y, p.z, q.x, q.y, q.z) < thr;
+}
+
+// The three connected-component passes below walk the NON-ZERO bit words, not the pixels
+// (a forest scan is ~90 % non-tree pixels).  tree_words_kernel lists the non-zero words of
+// the batch once; each pass then hands one listed word to a warp, 32 lanes = its 32 pixels,
+// so the work is balanced no matter how the trees cluster in the image.
+__global__ void tree_words_kernel(const DevParams *__restrict__ dp, int K, const uint32_t *__restrict__ bits,
+                                  int2 *__restrict__ list, int32_t *__restrict__ n_list) {
+  const int Nw = (dp->N + 31) >> 5;
+  const long long total_words = (long long)K * Nw;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long base = warp0 * 32; base < total_words; base += nwarps * 32) {
+    const uint32_t word = base + lane < total_words ? bits[base + lane] : 0u;
+    const bool nz = word != 0u;
+    const unsigned m = __ballot_sync(kFull, nz);
+    if (m == 0u) continue;
+    int at = 0;
+    if (lane == 0) at = atomicAdd(n_list, __popc(m));
+    at = __shfl_sync(kFull, at, 0);
+    if (nz) {  // entry = (keyframe << 16 | word index in the keyframe, the word itself)
+      const long long gw = base + lane;
+      const int k = (int)(gw / Nw);
+      list[at + __popc(m & ((1u << lane) - 1u))] = make_int2((k << 16) | (int)(gw - (long long)k * Nw), (int)word);
     }
-    if (row > 0) {
-      const sloam_point q = ld_point(tree + g - W);
-      up_ok = dist3f(p.x, p.y, p.z, q.x, q.y, q.z) < thr;
-      if (up_ok && left_ok) {
-        const sloam_point ql = ld_point(tree + g - W - 1);
-        upleft_ok = dist3f(q.x, q.y, q.z, ql.x, ql.y, ql.z) < thr;
+  }
+}
+
+template <class F>
+__device__ __forceinline__ void for_each_tree_word(const int2 *__restrict__ list,
+                                                   const int32_t *__restrict__ n_list, F body) {
+  const int lane = threadIdx.x & 31;
+  const int n = *n_list;
+  const int warp0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  for (int idx = warp0; idx < n; idx += nwarps) {
+    const int2 e = list[idx];
+    body((int)((unsigned)e.x >> 16), (e.x & 0xFFFF) * 32 + lane, (uint32_t)e.y, idx);
+  }
+}
+
+// ---- 1. init: link every valid pixel to its left (else up) neighbour ------
+__global__ void __launch_bounds__(256)
+cc_init_kernel(const DevParams *__restrict__ dp, int K, const sloam_point *__restrict__ tree,
+               const uint32_t *__restrict__ bits, const int2 *__restrict__ wlist,
+               const int32_t *__restrict__ n_wlist, int32_t *__restrict__ parent, uint32_t *__restrict__ mflags,
+               int32_t *__restrict__ csize, int32_t *__restrict__ cmin, int32_t *__restrict__ cmax,
+               int32_t *__restrict__ rmax) {
+  const int N = dp->N, W = dp->p.img_w, Nw = (N + 31) >> 5;
+  const float thr = dp->p.cluster_dist_thresh;
+  const int lane = threadIdx.x & 31;
+  for_each_tree_word(wlist, n_wlist, [&](int k, int i, uint32_t word, int idx) {
+    const uint32_t *bk = bits + (size_t)k * Nw;
+    const size_t g = (size_t)k * N + i;
+    const int row = i / W, col = i - row * W;
+    const bool bit = (word >> lane) & 1u;  // clear for the padding lanes of the last word
+    sloam_point p{0.f, 0.f, 0.f, 0.f};
+    if (bit) p = ld_point(tree + g);
+    // PCL skips a pixel iff !isfinite(x); EuclideanClusterComparator::compare is
+    // dist < threshold in float (NaN compares false)
+    const bool valid = bit && isfinite(p.x);
+    bool left_ok = false, up_ok = false, upleft_ok = false;  // upleft_ok: (i-W) -- (i-W-1)
+    if (valid) {
+      if (col > 0 && tree_bit(bk, i - 1)) {
+        const sloam_point q = ld_point(tree + g - 1);
+        left_ok = dist3f(p.x, p.y, p.z, q.x, q.y, q.z) < thr;
+      }
+      if (row > 0 && tree_bit(bk, i - W)) {
+        const sloam_point q = ld_point(tree + g - W);
+        up_ok = dist3f(p.x, p.y, p.z, q.x, q.y, q.z) < thr;
+        if (up_ok && left_ok && tree_bit(bk, i - W - 1)) {
+          const sloam_point ql = ld_point(tree + g - W - 1);
+          upleft_ok = dist3f(q.x, q.y, q.z, ql.x, ql.y, ql.z) < thr;
+        }
       }
     }
-  }
-  // the whole warp is alive here (the grid is padded to a multiple of 32 and
-  // out-of-range threads returned warp-uniformly only in the last warp)
-  const int lane = threadIdx.x & 31;
-  const unsigned act = __activemask();
-  // is the left neighbour connected to ITS upper neighbour?
-  int left_up = __shfl_up_sync(act, up_ok ? 1 : 0, 1);
-  if (lane == 0 || !((act >> (lane - 1)) & 1u)) {
-    left_up = 0;
-    if (left_ok && row > 0) {
-      const sloam_point a = ld_point(tree + g - 1), b = ld_point(tree + g - 1 - W);
-      left_up = dist3f(a.x, a.y, a.z, b.x, b.y, b.z) < thr;
+    // is the left neighbour connected to ITS upper neighbour?
+    int left_up = __shfl_up_sync(kFull, up_ok ? 1 : 0, 1);
+    if (lane == 0) {
+      left_up = 0;
+      if (left_ok && row > 0 && tree_bit(bk, i - 1 - W)) {
+        const sloam_point a = ld_point(tree + g - 1), b = ld_point(tree + g - 1 - W);
+        left_up = dist3f(a.x, a.y, a.z, b.x, b.y, b.z) < thr;
+      }
     }
-  }
-  // run starts inside the warp: link to the start of the row run (short find chains)
-  const unsigned starts = __ballot_sync(act, !left_ok);
-  if (valid) {
-    int par;
-    if (left_ok) {
-      const unsigned s = starts & ((2u << lane) - 1u);   // starts at or below this lane
-      par = s ? i - (lane - (31 - __clz(s))) : i - (lane + 1);
-    } else {
-      par = up_ok ? i - W : i;
+    // run starts inside the word: link to the start of the row run (short find chains)
+    const unsigned starts = __ballot_sync(kFull, !left_ok);
+    if (i < N) {
+      if (valid) {
+        int par;
+        if (left_ok) {
+          const unsigned s = starts & ((2u << lane) - 1u);   // starts at or below this lane
+          par = s ? i - (lane - (31 - __clz(s))) : i - (lane + 1);
+        } else {
+          par = up_ok ? i - W : i;
+        }
+        parent[g] = par;
+        if (par == i) {  // only a pixel that starts as its own parent can end up a root
+          csize[g] = 0;
+          cmin[g] = col; cmax[g] = col; rmax[g] = row;
+        }
+      } else {
+        parent[g] = kInvalid;
+      }
     }
-    parent[g] = par;
-    csize[g] = 0;
-    cmin[g] = col; cmax[g] = col; rmax[g] = row;
-  } else {
-    parent[g] = kInvalid;
-  }
-  // A union with the upper neighbour is only needed when it is not implied by
-  // i ~ i-1 (row link), i-1 ~ i-1-W (left neighbour's own up link) and i-W ~ i-W-1.
-  flags[g] = (left_ok && up_ok && !(left_up && upleft_ok)) ? 1 : 0;
+    // A union with the upper neighbour is only needed when it is not implied by
+    // i ~ i-1 (row link), i-1 ~ i-1-W (left neighbour's own up link) and i-W ~ i-W-1.
+    const unsigned mf = __ballot_sync(kFull, left_ok && up_ok && !(left_up && upleft_ok));
+    if (lane == 0) mflags[idx] = mf;  // one bit per pixel of the word, indexed like the word list
+  });
 }
 
 // ---- 2. merge: pixels linked left that are also connected upwards ---------
-__global__ void cc_merge_kernel(const DevParams *__restrict__ dp, int K,
-                                const uint8_t *__restrict__ flags, int32_t *__restrict__ parent) {
+__global__ void __launch_bounds__(256)
+cc_merge_kernel(const DevParams *__restrict__ dp, int K, const uint32_t *__restrict__ bits,
+                const int2 *__restrict__ wlist, const int32_t *__restrict__ n_wlist,
+                const uint32_t *__restrict__ mflags, int32_t *__restrict__ parent) {
   const int N = dp->N, W = dp->p.img_w;
-  const long long g4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  const long long total = (long long)K * N;
-  if (g4 >= total) return;
-  uint32_t f4;
-  if (g4 + 3 < total) f4 = *reinterpret_cast<const uint32_t *>(flags + g4);
-  else { f4 = 0; for (int j = 0; g4 + j < total; ++j) f4 |= (uint32_t)flags[g4 + j] << (8 * j); }
-  if (f4 == 0) return;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    if ((f4 >> (8 * j)) & 0xFF) {
-      const long long g = g4 + j;
-      const int k = (int)(g / N), i = (int)(g - (long long)k * N);
+  const int n = *n_wlist;
+  // thread per listed word: the few pixels whose flag is set are merged by that thread
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+    uint32_t mf = mflags[idx];
+    if (mf == 0u) continue;
+    const int2 e = wlist[idx];
+    const int k = (int)((unsigned)e.x >> 16), i0 = (e.x & 0xFFFF) * 32;
+    while (mf) {
+      const int i = i0 + __ffs(mf) - 1;
+      mf &= mf - 1;
       uf_union(parent + (size_t)k * N, i, i - W);
     }
   }
 }
 
 // ---- 3. flatten + statistics at the root ----------------------------------
-__global__ void cc_flatten_kernel(const DevParams *__restrict__ dp, int K,
-                                  int32_t *__restrict__ parent, int32_t *__restrict__ csize,
-                                  int32_t *__restrict__ cmin, int32_t *__restrict__ cmax,
-                                  int32_t *__restrict__ rmax, int32_t *__restrict__ row_roots,
-                                  int32_t *__restrict__ n_roots, int32_t *__restrict__ big_roots,
-                                  int32_t *__restrict__ n_big, int32_t *__restrict__ kf_flags) {
+__global__ void __launch_bounds__(256)
+cc_flatten_kernel(const DevParams *__restrict__ dp, int K, const uint32_t *__restrict__ bits,
+                  const int2 *__restrict__ wlist, const int32_t *__restrict__ n_wlist,
+                  int32_t *__restrict__ parent, int32_t *__restrict__ csize, int32_t *__restrict__ cmin,
+                  int32_t *__restrict__ cmax, int32_t *__restrict__ rmax, int32_t *__restrict__ row_roots,
+                  int32_t *__restrict__ n_roots, int32_t *__restrict__ big_roots,
+                  int32_t *__restrict__ n_big, int32_t *__restrict__ kf_flags) {
   const int N = dp->N, W = dp->p.img_w, H = dp->p.img_h;
   const int min_pts = dp->p.min_cluster_points, T = dp->p.max_trees;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int k = blockIdx.y;
-  const long long g = (long long)k * N + i;
-  const bool in = i < N;
-  int root = kInvalid;
-  const int par0 = in ? parent[g] : kInvalid;
-  if (__ballot_sync(kFull, par0 != kInvalid) == 0u) return;  // most warps: no tree pixel
-  if (par0 != kInvalid) {
-    root = par0 == i ? i : uf_find(parent + (size_t)k * N, par0);
-    parent[g] = root;
-  }
-  const int row = i / W, col = i - row * W;
-  // Consecutive lanes are consecutive pixels of a row, so the members of a component come
-  // in runs: a run = maximal stretch of lanes with the same (keyframe, root, row).  One
-  // lane per run (its head) issues the atomics for the whole run.
   const int lane = threadIdx.x & 31;
-  const long long key = root == kInvalid ? -1ll - lane : (((long long)k * N + root) * 4096ll + row);
-  const long long prev = __shfl_up_sync(kFull, key, 1);
-  const bool head = root != kInvalid && (lane == 0 || prev != key);
-  const unsigned heads = __ballot_sync(kFull, head || root == kInvalid);
-  if (root == kInvalid) return;
-  if (head) {
-    // run length = distance to the next head / invalid lane (or the end of the warp)
-    const unsigned above = heads & ~((2u << lane) - 1u);
-    const int len = (above ? __ffs(above) - 1 : 32) - lane;
-    const size_t r = (size_t)k * N + root;
-    const int old = atomicAdd(&csize[r], len);
-    if (old <= min_pts && old + len > min_pts) {  // exactly one run sees the crossing
-      const int slot = atomicAdd(&n_big[k], 1);
-      if (slot < T) big_roots[(size_t)k * T + slot] = root;
-      else atomicOr(&kf_flags[k], 1);
+  for_each_tree_word(wlist, n_wlist, [&](int k, int i, uint32_t word, int) {
+    const size_t g = (size_t)k * N + i;
+    int root = kInvalid;
+    const int par0 = ((word >> lane) & 1u) ? parent[g] : kInvalid;
+    if (par0 != kInvalid) {
+      root = par0 == i ? i : uf_find(parent + (size_t)k * N, par0);
+      parent[g] = root;
     }
-    // extents of the component (monotone, so the racy pre-checks are safe)
-    if (col < cmin[r]) atomicMin(&cmin[r], col);
-    if (col + len - 1 > cmax[r]) atomicMax(&cmax[r], col + len - 1);
-    if (row > rmax[r]) atomicMax(&rmax[r], row);
-  }
-  if (root == i) {
-    atomicAdd(&row_roots[(size_t)k * H + row], 1);
-    atomicAdd(&n_roots[k], 1);
-  }
+    const int row = i / W, col = i - row * W;
+    // Consecutive lanes are consecutive pixels of a row, so the members of a component come
+    // in runs: a run = maximal stretch of lanes with the same (root, row).  One lane per run
+    // (its head) issues the atomics for the whole run.
+    const long long key = root == kInvalid ? -1ll - lane : ((long long)root * 4096ll + row);
+    const long long prev = __shfl_up_sync(kFull, key, 1);
+    const bool head = root != kInvalid && (lane == 0 || prev != key);
+    const unsigned heads = __ballot_sync(kFull, head || root == kInvalid);
+    if (head) {
+      // run length = distance to the next head / invalid lane (or the end of the word)
+      const unsigned above = heads & ~((2u << lane) - 1u);
+      const int len = (above ? __ffs(above) - 1 : 32) - lane;
+      const size_t r = (size_t)k * N + root;
+      const int old = atomicAdd(&csize[r], len);
+      if (old <= min_pts && old + len > min_pts) {  // exactly one run sees the crossing
+        const int slot = atomicAdd(&n_big[k], 1);
+        if (slot < T) big_roots[(size_t)k * T + slot] = root;
+        else atomicOr(&kf_flags[k], 1);
+      }
+      // extents of the component (monotone, so the racy pre-checks are safe)
+      if (col < cmin[r]) atomicMin(&cmin[r], col);
+      if (col + len - 1 > cmax[r]) atomicMax(&cmax[r], col + len - 1);
+      if (row > rmax[r]) atomicMax(&rmax[r], row);
+    }
+    if (root == i) {
+      atomicAdd(&row_roots[(size_t)k * H + row], 1);
+      atomicAdd(&n_roots[k], 1);
+    }
+  });
 }
 
 // ---- 4. plan: sort big clusters, rank them, emit work items ----------------
-__global__ void cc_plan_kernel(const DevParams *__restrict__ dp, const int32_t *__restrict__ parent,
+__global__ void cc_plan_kernel(const DevParams *__restrict__ dp, const uint32_t *__restrict__ bits,
+                               const int32_t *__restrict__ parent,
                                const int32_t *__restrict__ cmin, const int32_t *__restrict__ cmax,
                                const int32_t *__restrict__ rmax, const int32_t *__restrict__ row_roots,
                                int32_t *__restrict__ big_roots, int32_t *__restrict__ n_big,
@@ -225,7 +295,8 @@ __global__ void cc_plan_kernel(const DevParams *__restrict__ dp, const int32_t *
     // PCL label = number of component roots before this one in raster order
     int cnt = 0;
     const int32_t *prow = parent + (size_t)k * N + (size_t)row * W;
-    for (int c = lane; c < col; c += 32) cnt += (prow[c] == row * W + c);
+    const uint32_t *bk = bits + (size_t)k * ((N + 31) >> 5);
+    for (int c = lane; c < col; c += 32) cnt += tree_bit(bk, row * W + c) && (prow[c] == row * W + c);
     cnt = warp_sum(cnt);
     if (lane == 0) {
       const size_t r = (size_t)k * N + root;
@@ -337,7 +408,7 @@ __device__ void build_vertex(const DevParams *dp, VtxSmem &s, int n, int row, sl
 
 __global__ void __launch_bounds__(kVtxWarps * 32)
 vertex_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ tree,
-              const int32_t *__restrict__ parent, const int32_t *__restrict__ big_roots,
+              const uint32_t *__restrict__ bits, const int32_t *__restrict__ parent, const int32_t *__restrict__ big_roots,
               const int32_t *__restrict__ bbox, const int32_t *__restrict__ vwork,
               const int32_t *__restrict__ n_vwork, sloam_vertex *__restrict__ slot_vertices,
               sloam_point *__restrict__ pool, int32_t *__restrict__ pool_count,
@@ -354,11 +425,16 @@ vertex_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ 
     const int32_t *bb = bbox + ((size_t)k * T + slot) * 4;
     const int c0 = bb[0], c1 = bb[1];
     const size_t rbase = (size_t)k * N + (size_t)row * W;
+    const uint32_t *bk = bits + (size_t)k * ((N + 31) >> 5);
     sloam_vertex *out = slot_vertices + ((size_t)k * T + slot) * H + row;
     // members of this cluster in this row, in column order (trellis.cpp:113-118)
     int n = 0;
     for (int c = c0 + lane; c < ((c1 - c0 + 32) & ~31) + c0; c += 32) {
-      const bool mem = c <= c1 && parent[rbase + c] == root;
+      // both loads are unconditional so that they are in flight together
+      const int cc = c <= c1 ? c : c1;
+      const int pc = parent[rbase + cc];  // stale where the bit is clear: never trusted alone
+      const uint32_t bw = bk[(row * W + cc) >> 5];
+      const bool mem = c <= c1 && ((bw >> ((row * W + cc) & 31)) & 1u) && pc == root;
       const unsigned b = __ballot_sync(kFull, mem);
       if (mem) {
         const int pos = n + __popc(b & ((1u << lane) - 1u));
@@ -389,7 +465,7 @@ vertex_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ 
 // wide path: one CTA per overflow item, all members in global scratch order --
 // same algorithm with a block-wide rank sort; members live in dynamic smem.
 __global__ void vertex_wide_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ tree,
-                                   const int32_t *__restrict__ parent, const int32_t *__restrict__ big_roots,
+                                   const uint32_t *__restrict__ bits, const int32_t *__restrict__ parent, const int32_t *__restrict__ big_roots,
                                    const int32_t *__restrict__ bbox, const int32_t *__restrict__ overflow,
                                    const int32_t *__restrict__ n_overflow,
                                    sloam_vertex *__restrict__ slot_vertices, sloam_point *__restrict__ pool,
@@ -414,7 +490,7 @@ __global__ void vertex_wide_kernel(const DevParams *__restrict__ dp, const sloam
       int n = 0;
       const int32_t *bb = bbox + ((size_t)k * T + slot) * 4;
       for (int c = bb[0]; c <= bb[1]; ++c)
-        if (parent[rbase + c] == root) {
+        if (tree_bit(bits + (size_t)k * ((N + 31) >> 5), row * W + c) && parent[rbase + c] == root) {
           const sloam_point p = ld_point(tree + rbase + c);
           sx[n] = p.x; sy[n] = p.y; sz[n] = p.z; sw[n] = p.intensity; scol[n] = c; ++n;
         }
@@ -531,7 +607,8 @@ __global__ void tree_compact_kernel(const DevParams *__restrict__ dp, const int3
 }
 
 // ---- labels for the find_clusters stage entry -------------------------------
-__global__ void cc_rank_rows_kernel(const DevParams *__restrict__ dp, const int32_t *__restrict__ parent,
+__global__ void cc_rank_rows_kernel(const DevParams *__restrict__ dp, const uint32_t *__restrict__ bits,
+                                    const int32_t *__restrict__ parent,
                                     const int32_t *__restrict__ row_roots, int32_t *__restrict__ root_rank) {
   const int N = dp->N, W = dp->p.img_w, H = dp->p.img_h;
   const int k = blockIdx.y;
@@ -543,23 +620,26 @@ __global__ void cc_rank_rows_kernel(const DevParams *__restrict__ dp, const int3
   pre = warp_sum(pre);
   const size_t rbase = (size_t)k * N + (size_t)row * W;
   for (int c = lane; c < ((W + 31) & ~31); c += 32) {
-    const bool is_root = c < W && parent[rbase + c] == row * W + c;
+    const bool is_root = c < W && tree_bit(bits + (size_t)k * ((N + 31) >> 5), row * W + c) &&
+                         parent[rbase + c] == row * W + c;
     const unsigned b = __ballot_sync(kFull, is_root);
     if (is_root) root_rank[rbase + c] = pre + __popc(b & ((1u << lane) - 1u));
     pre += __popc(b);
   }
 }
-__global__ void cc_labels_kernel(const DevParams *__restrict__ dp, int K, const int32_t *__restrict__ parent,
+__global__ void cc_labels_kernel(const DevParams *__restrict__ dp, int K, const uint32_t *__restrict__ bits,
+                                 const int32_t *__restrict__ parent,
                                  const int32_t *__restrict__ root_rank, uint32_t *__restrict__ labels) {
   const int N = dp->N;
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= (long long)K * N) return;
   const int k = (int)(g / N);
-  const int r = parent[g];
+  const int i = (int)(g - (long long)k * N);
+  const int r = tree_bit(bits + (size_t)k * ((N + 31) >> 5), i) ? parent[g] : kInvalid;
   labels[g] = r == kInvalid ? 0xFFFFFFFFu : (uint32_t)root_rank[(size_t)k * N + r];
 }
 
-static int run_cc(sloam_ctx *c, int K, const sloam_point *tree) {
+static int run_cc(sloam_ctx *c, int K, const sloam_point *tree, bool bits_ready) {
   Workspace &w = c->ws;
   const long long total = (long long)K * c->hp.N;
   const int H = c->hp.p.img_h;
@@ -568,12 +648,22 @@ static int run_cc(sloam_ctx *c, int K, const sloam_point *tree) {
   SB_CUDA(c, cudaMemsetAsync(w.n_big, 0, sizeof(int32_t) * K, c->stream));
   SB_CUDA(c, cudaMemsetAsync(w.kf_flags, 0, sizeof(int32_t) * K, c->stream));
   const dim3 blocks((unsigned)((c->hp.N + 255) / 256), (unsigned)K);
-  cc_init_kernel<<<blocks, 256, 0, c->stream>>>(c->dp, K, tree, w.parent, w.cc_flags, w.csize,
+  if (!bits_ready) {  // caller-supplied cloud: derive the bits from the points
+    tree_bits_kernel<<<blocks, 256, 0, c->stream>>>(c->dp, tree, w.tree_bits);
+    SB_LAUNCH_CHECK(c);
+  }
+  const unsigned wgrid = (unsigned)std::min<long long>((total / 32 / 32 / 8) + 1, (long long)c->sm_count * 8);
+  SB_CUDA(c, cudaMemsetAsync(w.n_tree_words, 0, sizeof(int32_t), c->stream));
+  tree_words_kernel<<<wgrid, 256, 0, c->stream>>>(c->dp, K, w.tree_bits, reinterpret_cast<int2 *>(w.tree_words), w.n_tree_words);
+  SB_LAUNCH_CHECK(c);
+  const int2 *wl = reinterpret_cast<const int2 *>(w.tree_words);
+  cc_init_kernel<<<wgrid, 256, 0, c->stream>>>(c->dp, K, tree, w.tree_bits, wl, w.n_tree_words, w.parent,
+                                               reinterpret_cast<uint32_t *>(w.cc_flags), w.csize,
                                                 w.ccol_min, w.ccol_max, w.crow_max);
   SB_LAUNCH_CHECK(c);
-  cc_merge_kernel<<<(unsigned)((total / 4 + 255) / 256 + 1), 256, 0, c->stream>>>(c->dp, K, w.cc_flags, w.parent);
+  cc_merge_kernel<<<wgrid, 256, 0, c->stream>>>(c->dp, K, w.tree_bits, wl, w.n_tree_words, reinterpret_cast<const uint32_t *>(w.cc_flags), w.parent);
   SB_LAUNCH_CHECK(c);
-  cc_flatten_kernel<<<blocks, 256, 0, c->stream>>>(c->dp, K, w.parent, w.csize, w.ccol_min, w.ccol_max,
+  cc_flatten_kernel<<<wgrid, 256, 0, c->stream>>>(c->dp, K, w.tree_bits, wl, w.n_tree_words, w.parent, w.csize, w.ccol_min, w.ccol_max,
                                                    w.crow_max, w.row_roots, w.n_roots, w.big_roots,
                                                    w.n_big, w.kf_flags);
   SB_LAUNCH_CHECK(c);
@@ -581,20 +671,21 @@ static int run_cc(sloam_ctx *c, int K, const sloam_point *tree) {
 }
 
 int launch_compute_graph(sloam_ctx *c, int K, const sloam_point *tree, sloam_tree *trees,
-                         int32_t *n_trees, sloam_vertex *vertices, sloam_point *vertex_points) {
+                         int32_t *n_trees, sloam_vertex *vertices, sloam_point *vertex_points,
+                         bool bits_ready) {
   Workspace &w = c->ws;
   const sloam_params &p = c->hp.p;
   const int T = p.max_trees, H = p.img_h, W = p.img_w;
-  int rc = run_cc(c, K, tree);
+  int rc = run_cc(c, K, tree, bits_ready);
   if (rc != SLOAM_OK) return rc;
   SB_CUDA(c, cudaMemsetAsync(w.n_overflow, 0, sizeof(int32_t) * 4, c->stream));
   SB_CUDA(c, cudaMemsetAsync(w.vpool_count, 0, sizeof(int32_t) * K, c->stream));
   cc_plan_kernel<<<K, 256, sizeof(int32_t) * (2 * T + H + 1), c->stream>>>(
-      c->dp, w.parent, w.ccol_min, w.ccol_max, w.crow_max, w.row_roots, w.big_roots, w.n_big,
+      c->dp, w.tree_bits, w.parent, w.ccol_min, w.ccol_max, w.crow_max, w.row_roots, w.big_roots, w.n_big,
       w.big_rank, w.bbox, w.vwork, w.n_overflow + 1);
   SB_LAUNCH_CHECK(c);
   const int vgrid = c->sm_count * 4;
-  vertex_kernel<<<vgrid, kVtxWarps * 32, 0, c->stream>>>(c->dp, tree, w.parent, w.big_roots, w.bbox,
+  vertex_kernel<<<vgrid, kVtxWarps * 32, 0, c->stream>>>(c->dp, tree, w.tree_bits, w.parent, w.big_roots, w.bbox,
                                                          w.vwork, w.n_overflow + 1, w.slot_vertices,
                                                          vertex_points, w.vpool_count, w.overflow_list,
                                                          w.n_overflow);
@@ -605,7 +696,7 @@ int launch_compute_graph(sloam_ctx *c, int K, const sloam_point *tree, sloam_tre
     SB_CUDA(c, cudaFuncSetAttribute(vertex_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem));
     attr_set = true;
   }
-  vertex_wide_kernel<<<c->sm_count, 256, wide_smem, c->stream>>>(c->dp, tree, w.parent, w.big_roots, w.bbox,
+  vertex_wide_kernel<<<c->sm_count, 256, wide_smem, c->stream>>>(c->dp, tree, w.tree_bits, w.parent, w.big_roots, w.bbox,
                                                                  w.overflow_list, w.n_overflow,
                                                                  w.slot_vertices, vertex_points,
                                                                  w.vpool_count);
@@ -613,6 +704,14 @@ int launch_compute_graph(sloam_ctx *c, int K, const sloam_point *tree, sloam_tre
   tree_compact_kernel<<<K, 256, sizeof(int32_t) * 2 * T, c->stream>>>(c->dp, w.n_big, w.big_rank, w.bbox,
                                                                        w.slot_vertices, trees, n_trees,
                                                                        vertices);
+  SB_LAUNCH_CHECK(c);
+  return SLOAM_OK;
+}
+
+// materialise the dense tree cloud of the last fused run (see sloam_ctx::tree_sparse)
+int launch_tree_fill(sloam_ctx *c, int K) {
+  const dim3 blocks((unsigned)((c->hp.N + 255) / 256), (unsigned)K);
+  tree_fill_kernel<<<blocks, 256, 0, c->stream>>>(c->dp, c->ws.tree_bits, c->ws.tree);
   SB_LAUNCH_CHECK(c);
   return SLOAM_OK;
 }
@@ -626,14 +725,14 @@ extern "C" {
 int sloam_b200_find_clusters_dev(sloam_ctx *c, int K, const sloam_point *tree, uint32_t *labels,
                                  int32_t *n_clusters) {
   if (!c || K <= 0 || K > c->max_k || !tree || !labels) return set_err(c, SLOAM_E_INVALID, "find_clusters: bad arguments");
-  int rc = run_cc(c, K, tree);
+  int rc = run_cc(c, K, tree, false);
   if (rc != SLOAM_OK) return rc;
   const int H = c->hp.p.img_h;
   dim3 grid((unsigned)((H + 7) / 8), (unsigned)K);
-  cc_rank_rows_kernel<<<grid, 256, 0, c->stream>>>(c->dp, c->ws.parent, c->ws.row_roots, c->ws.root_rank);
+  cc_rank_rows_kernel<<<grid, 256, 0, c->stream>>>(c->dp, c->ws.tree_bits, c->ws.parent, c->ws.row_roots, c->ws.root_rank);
   SB_LAUNCH_CHECK(c);
   const long long total = (long long)K * c->hp.N;
-  cc_labels_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(c->dp, K, c->ws.parent,
+  cc_labels_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(c->dp, K, c->ws.tree_bits, c->ws.parent,
                                                                           c->ws.root_rank, labels);
   SB_LAUNCH_CHECK(c);
   if (n_clusters)
@@ -645,7 +744,7 @@ int sloam_b200_compute_graph_dev(sloam_ctx *c, int K, const sloam_point *tree, s
                                  int32_t *n_trees, sloam_vertex *vertices, sloam_point *vertex_points) {
   if (!c || K <= 0 || K > c->max_k || !tree || !trees || !n_trees || !vertices || !vertex_points)
     return set_err(c, SLOAM_E_INVALID, "compute_graph: bad arguments");
-  return launch_compute_graph(c, K, tree, trees, n_trees, vertices, vertex_points);
+  return launch_compute_graph(c, K, tree, trees, n_trees, vertices, vertex_points, false);
 }
 
 }  // extern "C"

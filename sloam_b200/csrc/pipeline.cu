@@ -8,12 +8,13 @@ namespace sb {
 
 int launch_project_split(sloam_ctx *c, int K, bool do_project, bool do_split, const sloam_point *points,
                          const uint8_t *mask, int32_t *pix, float *range_image, sloam_point *tree,
-                         sloam_point *ground, int32_t *ground_count);
+                         sloam_point *ground, int32_t *ground_count, uint32_t *tree_bits, bool sparse_tree);
 int launch_ground_planes(sloam_ctx *c, int K, const sloam_point *ground, const int32_t *ground_count,
                          int stride, const sloam_pose *pose_est, sloam_cell_plane *cells,
                          sloam_point *cell_features, sloam_point *kept_points, int32_t *kept_offsets);
 int launch_compute_graph(sloam_ctx *c, int K, const sloam_point *tree, sloam_tree *trees, int32_t *n_trees,
-                         sloam_vertex *vertices, sloam_point *vertex_points);
+                         sloam_vertex *vertices, sloam_point *vertex_points, bool bits_ready);
+int launch_tree_fill(sloam_ctx *c, int K);
 int launch_cylinders(sloam_ctx *c, int K, const sloam_tree *trees, const int32_t *n_trees,
                      const sloam_vertex *vertices, const sloam_point *vpoints, const sloam_plane *planes_acc,
                      const int32_t *n_planes_acc, sloam_tree_model *models, sloam_point *features);
@@ -37,8 +38,11 @@ static int check_batch(sloam_ctx *c, int K, const sloam_batch_in *in, const sloa
 static int run_dev(sloam_ctx *c, int K, const sloam_batch_in *in, const sloam_batch_out *out) {
   Workspace &w = c->ws;
   float *range = out->range_image;  // optional output
+  // sparse tree cloud: only the tree-labelled points and the bit mask are written (the NaN
+  // points of the dense cloud are ~90 % of its bytes and nothing downstream needs them)
   int rc = launch_project_split(c, K, true, true, in->points, in->mask, w.pix, range, w.tree, w.ground,
-                                w.ground_count);
+                                w.ground_count, w.tree_bits, true);
+  c->tree_sparse = true;
   if (rc != SLOAM_OK) return rc;
   // fork: ground cells + plane fits (K2, main stream) and the tree detector (K3, side
   // stream) both depend only on K1 and are latency-bound, so they run concurrently
@@ -46,7 +50,7 @@ static int run_dev(sloam_ctx *c, int K, const sloam_batch_in *in, const sloam_ba
   SB_CUDA(c, cudaEventRecord(c->ev_fork, main_stream));
   SB_CUDA(c, cudaStreamWaitEvent(c->side, c->ev_fork, 0));
   c->stream = c->side;
-  rc = launch_compute_graph(c, K, w.tree, w.trees, w.n_trees, w.vertices, w.vertex_points);
+  rc = launch_compute_graph(c, K, w.tree, w.trees, w.n_trees, w.vertices, w.vertex_points, true);
   c->stream = main_stream;
   if (rc != SLOAM_OK) return rc;
   SB_CUDA(c, cudaEventRecord(c->ev_join, c->side));
@@ -198,6 +202,11 @@ int sloam_b200_copy_d2h(sloam_ctx *c, void *dst, const void *src, uint64_t bytes
 int sloam_b200_get_intermediates(sloam_ctx *c, sloam_intermediates *o) {
   if (!c || !o) return SLOAM_E_INVALID;
   const Workspace &w = c->ws;
+  if (c->tree_sparse && c->last_k > 0) {  // make ws.tree the dense organized cloud of stage a2
+    const int rc = launch_tree_fill(c, c->last_k);
+    if (rc != SLOAM_OK) return rc;
+    c->tree_sparse = false;
+  }
   o->pix = w.pix; o->tree = w.tree; o->ground = w.ground; o->ground_count = w.ground_count;
   o->cells = w.cells; o->cell_features = w.cell_features; o->trees = w.trees; o->n_trees = w.n_trees;
   o->vertices = w.vertices; o->vertex_points = w.vertex_points; o->tree_models = w.tree_models;

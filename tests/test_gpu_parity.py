@@ -630,6 +630,48 @@ def test_baseline_configs_full_size(capi, oracle, preset):
     ctx.close()
 
 
+def test_workspace_reuse_and_dense_tree_cloud(capi, oracle):
+    """Two DIFFERENT scenes through the same context.  The fused path writes only the
+    tree-labelled points of its organized tree cloud (plus a bit mask) and never touches the
+    connected-component state of the other pixels, so whatever the first batch left behind must
+    not leak into the second; the dense cloud handed out with the intermediates (NaN points
+    filled in on demand) must equal the reference's maskCloud output bit for bit."""
+    from sloam_b200 import configs
+    K = 3
+    p, cfg_a = configs.make(capi, "os1-64")
+    _, cfg_b = configs.make(capi, "os1-64")
+    cfg_b.seed, cfg_b.n_trees, cfg_b.azimuth_offset_cols = 977, 33, 311.5
+    T, PP, N = p.max_trees, p.max_prev_planes, p.img_h * p.img_w
+    ctx = capi.Context(p, K)
+
+    def run(cfg):
+        inp, exp = run_sequence(capi, oracle, p, cfg, K, True)
+        out = dict(results=np.zeros(K, abi.KF_RESULT), matches=np.zeros((K, T), np.int32),
+                   tm=np.zeros((K, T), abi.CYLINDER), tm_id=np.zeros((K, T), np.int32),
+                   planes=np.zeros((K, PP), abi.PLANE), n_planes=np.zeros(K, np.int32), range_image=None)
+        ctx.run_keyframes_host(K, inp, out)
+        for k in range(K):
+            compare_keyframe(out["results"][k], out["matches"][k], out["tm"][k], out["tm_id"][k],
+                             out["planes"][k], out["n_planes"][k], exp[k])
+        return inp, exp
+
+    run(cfg_a)
+    inp, exp = run(cfg_b)
+    it = ctx.intermediates()
+    tree = capi.read_dev(it.tree, K * N * abi.POINT.itemsize, ctx.device).view(np.uint32).reshape(K, N, 4)
+    pix = capi.read_dev(it.pix, K * N * 4, ctx.device).view(np.int32).reshape(K, N)
+    n_tree_px = 0
+    for k in range(K):
+        e_tree, _ = oracle.mask_cloud(p, inp["points"][k], exp[k].pix, inp["mask"][k])
+        assert np.array_equal(pix[k], exp[k].pix)
+        assert np.array_equal(tree[k], e_tree.view(np.uint32).reshape(N, 4))
+        n_tree_px += int(np.isfinite(e_tree["x"]).sum())
+    assert 0 < n_tree_px < K * N // 4
+    # and a third batch (scene A again) after the intermediates were materialised
+    run(cfg_a)
+    ctx.close()
+
+
 def test_large_map_association_config5(capi, oracle):
     """configs[4]: 100 000 map cylinders, 2 000 detections per keyframe (split-map path)."""
     rng = np.random.default_rng(55)
