@@ -52,7 +52,7 @@ struct Workspace {
   int32_t *n_tree_words = nullptr;   // [1]
   uint8_t *ground_cell = nullptr;    // [K][N] polar cell of each ground point (255 = none)
   int32_t *cell_count = nullptr;     // [K][kMaxCells]
-  unsigned long long *tile_state = nullptr; // [K][tiles] decoupled look-back
+  int32_t *tile_count = nullptr;     // [K][tiles] ground points of each K1 tile (tile-strided ground layout)
   float *range_image = nullptr;      // [K][N] (when the caller passes none)
   // K2
   sloam_cell_plane *cells = nullptr; // [K][B]
@@ -146,6 +146,9 @@ struct sloam_ctx {
   // the fused path writes only the tree-labelled points of ws.tree (+ ws.tree_bits); the NaN
   // points of the dense cloud are filled in when the intermediates are asked for
   bool tree_sparse = false;
+  // likewise ws.ground is tile-strided after a fused run; ground_dense (ws.qscratch) receives
+  // the contiguous cloud on demand
+  bool ground_strided = false;
   // partial results of split association (large maps), grown on demand
   int32_t *assoc_part_i = nullptr;
   double *assoc_part_d = nullptr;

@@ -61,7 +61,7 @@ static void layout(sloam_ctx *c, Bump &b) {
   b.take(w.n_tree_words, 4);
   b.take(w.ground_cell, K * N);
   b.take(w.cell_count, K * kMaxCells);
-  b.take(w.tile_state, K * tiles);
+  b.take(w.tile_count, K * tiles);
   b.take(w.range_image, K * N);
   b.take(w.cells, K * B);
   b.take(w.cell_features, K * B * (size_t)p.numGroundFeatures);

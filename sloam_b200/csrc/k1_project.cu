@@ -9,23 +9,23 @@
 // stage a3 never re-reads the cloud to bin it.
 //
 // HBM-bound streaming kernel.  Algorithmic bytes per keyframe: 16N points +
-// 1N mask + 4N pix + 4N range image + 16N tree cloud + 16G ground = 41N + 16G
-// (+ 1G cell tags).  One CTA = one tile of 2048 consecutive points of one
-// keyframe; float4 loads/stores are fully coalesced; the ground points of a
-// tile are staged in shared memory in input order and written out as one
-// contiguous run whose base comes from a decoupled look-back scan over the
-// tiles of the keyframe (single pass, no second read of the input).
+// 1N mask + 4N pix + 4N range image + 16T tree points + N/8 tree bits + 17G ground
+// points and cell tags (T tree-labelled, G ground-labelled points).  One CTA = one tile of
+// kSplitTile consecutive points of one keyframe; float4 loads/stores are coalesced.
+//
+// Ground layout: the ground points of tile t are written, in input order, to slots
+// [t * kSplitTile, t * kSplitTile + tile_count[t]) of the keyframe's ground array
+// ("tile-strided").  The order of the slots is the input order, which is all the ground
+// stage needs (it bins and sorts by (z, slot)), so no CTA ever waits for another one: the
+// single-pass compaction with a look-back scan that this replaces serialised the tiles of
+// a keyframe.  Callers that want the contiguous cloud of Segmentation::maskCloud (the stage
+// entries, the intermediates) get it from ground_compact_kernel.
 #include "common.cuh"
 
 namespace sb {
 
 constexpr int kThreads = 256;
 constexpr int kRounds = kSplitTile / kThreads;  // 8
-
-// tile_state word: [63:62] flag (0 empty, 1 aggregate, 2 inclusive prefix), [31:0] value
-__device__ __forceinline__ unsigned long long pack_state(unsigned flag, unsigned v) {
-  return ((unsigned long long)flag << 62) | v;
-}
 
 // fp32 estimate of project_pixel(): returns the pixel index when both image
 // coordinates are provably (margins mx, my, in pixels) on the same side of every
@@ -76,48 +76,37 @@ __device__ __forceinline__ int ground_cell_fast(const GroundGeom &g, float x, fl
   return rb * g.TB + tb;
 }
 
+#ifndef SLOAM_K1_MIN_CTAS
+#define SLOAM_K1_MIN_CTAS 5  // measured: 4 -> 427 us, 5 -> 384 us, 6 -> 390 us per 1000 VLP-16 keyframes
+#endif
 template <bool DO_PROJECT, bool DO_SPLIT>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, SLOAM_K1_MIN_CTAS)
 project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point *__restrict__ points,
                      const uint8_t *__restrict__ mask, int32_t *__restrict__ pix_io,
                      unsigned *__restrict__ range_bits, sloam_point *__restrict__ tree,
                      sloam_point *__restrict__ ground, int32_t *__restrict__ ground_count,
                      uint8_t *__restrict__ ground_cell, int32_t *__restrict__ cell_count,
-                     unsigned long long *__restrict__ tile_state, unsigned *__restrict__ ticket,
-                     int ground_stride, uint32_t *__restrict__ tree_bits, int sparse_tree) {
-  __shared__ __align__(16) unsigned char s_raw[(DO_SPLIT ? sizeof(sloam_point) : sizeof(int)) * kSplitTile];
-  sloam_point *s_ground = reinterpret_cast<sloam_point *>(s_raw);
-  __shared__ uint8_t s_cell[DO_SPLIT ? kSplitTile : 1];
+                     int32_t *__restrict__ tile_count, int ground_stride,
+                     uint32_t *__restrict__ tree_bits, int sparse_tree) {
+  __shared__ int s_pix[DO_PROJECT ? kSplitTile : 1];  // exact pixel indices of the queued points
   __shared__ int s_hist[DO_SPLIT ? kMaxCells : 1];
-  __shared__ int s_warp[kThreads / 32];
-  __shared__ unsigned s_tile;
-  __shared__ int s_base;
   __shared__ uint16_t s_slow[DO_PROJECT ? kSplitTile : 1];
   __shared__ int s_nslow;
   __shared__ int s_cnt[kRounds * (kThreads / 32)];
-  // exact pixel indices of the queued points (phases A/B only): aliases the ground staging
-  int *s_pix = reinterpret_cast<int *>(s_raw);
 
   const int N = dp->N;
   const int tiles = (N + kSplitTile - 1) / kSplitTile;
-  // tiles are handed out in scheduling order so the look-back never waits on
-  // a CTA that has not started
-  if (threadIdx.x == 0) {
-    s_tile = DO_SPLIT ? atomicAdd(ticket, 1u) : blockIdx.x;
-    s_nslow = 0;
-  }
+  if (threadIdx.x == 0) s_nslow = 0;
   if (DO_SPLIT)
     for (int c = threadIdx.x; c < kMaxCells; c += kThreads) s_hist[c] = 0;
   __syncthreads();
-  const unsigned tile_id = s_tile;
-  const int k = tile_id / tiles, tile = tile_id % tiles;
+  const int k = blockIdx.x / tiles, tile = blockIdx.x % tiles;
   if (k >= K) return;
   const ProjGeom pg = dp->pg;
   const GroundGeom gg = dp->gg;
   const size_t kbase = (size_t)k * N;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float qnan = __int_as_float(0x7fc00000);
-  int base = 0;
 
   // ---- phase A: load the tile (8 float4 per thread stay in registers) and project.
   // The pixel index is an integer derived from atan2f/asinf; the bit-exact evaluation
@@ -217,73 +206,54 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
     int run = inc - s;
 #pragma unroll
     for (int q = 0; q < kPer; ++q) { const int e = lane * kPer + q; if (e < kEnt) s_cnt[e] = run; run += v[q]; }
-    if (lane == 31) {
-      s_base = inc;
-      // publish this tile's ground count for the look-back of later tiles as early as
-      // possible (before the staging work below)
-      __threadfence();
-      atomicExch(&tile_state[(size_t)k * tiles + tile], pack_state(tile == 0 ? 2u : 1u, (unsigned)inc));
+    if (lane == 31) {  // inc = ground points of this tile
+      tile_count[(size_t)k * tiles + tile] = inc;
+      if (inc) atomicAdd(&ground_count[k], inc);
     }
   }
   __syncthreads();
-  base = s_base;
+  // ground points go straight from registers to their slots: the ground lanes of a warp
+  // own consecutive slots, so the 16-byte stores of a warp form contiguous runs
+  sloam_point *gout = ground + (size_t)k * ground_stride + (size_t)tile * kSplitTile;
+  uint8_t *cout = ground_cell + (size_t)k * ground_stride + (size_t)tile * kSplitTile;
 #pragma unroll
   for (int j = 0; j < kRounds; ++j) {
     if ((gmask >> j) & 1u) {
       const sloam_point p = pts[j];
       const int slot = s_cnt[j * (kThreads / 32) + warp] + __popc(bal[j] & ((1u << lane) - 1u));
       const int cell = ground_cell_fast(gg, p.x, p.y, yawr[j]);
-      st_point(s_ground + slot, p);
-      s_cell[slot] = (uint8_t)(cell < 0 ? 255 : cell);
+      st_point(gout + slot, p);
+      cout[slot] = (uint8_t)(cell < 0 ? 255 : cell);
       if (cell >= 0) atomicAdd(&s_hist[cell], 1);
     }
   }
   __syncthreads();
-
-  // ---- decoupled look-back over the tiles of this keyframe ----
-  if (warp == 0) {
-    unsigned long long *st = tile_state + (size_t)k * tiles;
-    int excl = 0;
-    if (tile > 0) {
-      int look = tile - 1;
-      while (true) {
-        const int t = look - lane;
-        unsigned long long s = 0;
-        if (t >= 0) {
-          do { s = *((volatile unsigned long long *)&st[t]); } while ((s >> 62) == 0);
-        } else {
-          s = pack_state(2u, 0u);  // virtual tile -1: inclusive prefix 0
-        }
-        const unsigned is_prefix = __ballot_sync(kFull, (s >> 62) == 2);
-        const int first = __ffs(is_prefix) - 1;  // nearest tile carrying a prefix
-        int v = (first < 0 || lane <= first) ? (int)(s & 0xFFFFFFFFu) : 0;
-        v = warp_sum(v);
-        excl += v;
-        if (first >= 0) break;
-        look -= 32;
-      }
-      if (lane == 0) {
-        __threadfence();
-        atomicExch(&st[tile], pack_state(2u, (unsigned)(excl + base)));
-      }
-    }
-    if (lane == 0) {
-      s_base = excl;
-      if (tile == tiles - 1) ground_count[k] = excl + base;
-    }
-  }
-  __syncthreads();
-  const int gbase = s_base;
-  sloam_point *gout = ground + (size_t)k * ground_stride + gbase;
-  uint8_t *cout = ground_cell + (size_t)k * ground_stride + gbase;
-  for (int s = threadIdx.x; s < base; s += kThreads) {
-    st_point(gout + s, ld_point(s_ground + s));
-    cout[s] = s_cell[s];
-  }
   for (int c = threadIdx.x; c < kMaxCells; c += kThreads) {
     const int h = s_hist[c];
     if (h) atomicAdd(&cell_count[(size_t)k * kMaxCells + c], h);
   }
+}
+
+// Contiguous ground cloud (Segmentation::maskCloud's output) from the tile-strided one:
+// grid (tiles, K); a CTA copies its tile's run to the offset given by the counts before it.
+__global__ void ground_compact_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ src,
+                                      int src_stride, const int32_t *__restrict__ tile_count,
+                                      sloam_point *__restrict__ dst, int dst_stride) {
+  __shared__ int s_off;
+  const int tiles = (dp->N + kSplitTile - 1) / kSplitTile;
+  const int k = blockIdx.y, tile = blockIdx.x;
+  const int32_t *tc = tile_count + (size_t)k * tiles;
+  if (threadIdx.x < 32) {
+    int off = 0;
+    for (int t = threadIdx.x; t < tile; t += 32) off += tc[t];
+    off = warp_sum(off);
+    if (threadIdx.x == 0) s_off = off;
+  }
+  __syncthreads();
+  const int n = tc[tile];
+  const sloam_point *s = src + (size_t)k * src_stride + (size_t)tile * kSplitTile;
+  sloam_point *d = dst + (size_t)k * dst_stride + s_off;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) st_point(d + i, ld_point(s + i));
 }
 
 // empty pixels (still 0xFFFFFFFF) become 0 (inference.cpp:150-158)
@@ -347,27 +317,39 @@ int launch_project_split(sloam_ctx *c, int K, bool do_project, bool do_split,
   const long long total = (long long)K * N;
   unsigned *rb = reinterpret_cast<unsigned *>(range_image);
   if (do_project && rb) SB_CUDA(c, cudaMemsetAsync(rb, 0xFF, sizeof(unsigned) * total, c->stream));
-  unsigned *ticket = nullptr;
+  // The kernel always writes the tile-strided ground layout.  The fused pipeline consumes it
+  // as is (ground == ws.ground); a stage entry gets the contiguous cloud by compaction.
+  const bool strided_out = ground == c->ws.ground;
   if (do_split) {
-    // tile states + the ticket counter live in one allocation: [K*tiles] states, then the ticket
-    SB_CUDA(c, cudaMemsetAsync(c->ws.tile_state, 0, sizeof(unsigned long long) * ((size_t)K * tiles), c->stream));
-    SB_CUDA(c, cudaMemsetAsync(c->ws.n_overflow, 0, sizeof(int32_t), c->stream));
+    SB_CUDA(c, cudaMemsetAsync(ground_count, 0, sizeof(int32_t) * (size_t)K, c->stream));
     SB_CUDA(c, cudaMemsetAsync(c->ws.cell_count, 0, sizeof(int32_t) * (size_t)K * kMaxCells, c->stream));
-    ticket = reinterpret_cast<unsigned *>(c->ws.n_overflow);
   }
   const unsigned grid = (unsigned)(K * tiles);
-#define SB_K1_ARGS c->dp, K, points, mask, pix, rb, tree, ground, ground_count, c->ws.ground_cell, \
-                   c->ws.cell_count, c->ws.tile_state, ticket, N, tree_bits, sparse_tree ? 1 : 0
+#define SB_K1_ARGS c->dp, K, points, mask, pix, rb, tree, c->ws.ground, ground_count, c->ws.ground_cell, \
+                   c->ws.cell_count, c->ws.tile_count, N, tree_bits, sparse_tree ? 1 : 0
   if (do_project && do_split) project_split_kernel<true, true><<<grid, kThreads, 0, c->stream>>>(SB_K1_ARGS);
   else if (do_project) project_split_kernel<true, false><<<grid, kThreads, 0, c->stream>>>(SB_K1_ARGS);
   else project_split_kernel<false, true><<<grid, kThreads, 0, c->stream>>>(SB_K1_ARGS);
 #undef SB_K1_ARGS
   SB_LAUNCH_CHECK(c);
+  if (do_split && !strided_out) {
+    ground_compact_kernel<<<dim3((unsigned)tiles, (unsigned)K), 256, 0, c->stream>>>(
+        c->dp, c->ws.ground, N, c->ws.tile_count, ground, N);
+    SB_LAUNCH_CHECK(c);
+  }
   if (do_project && rb) {
     const long long nvec = (total + 3) / 4;
     range_finalize_kernel<<<(unsigned)((nvec + 255) / 256), 256, 0, c->stream>>>(rb, total);
     SB_LAUNCH_CHECK(c);
   }
+  return SLOAM_OK;
+}
+
+int launch_ground_compact(sloam_ctx *c, int K, sloam_point *dst) {
+  const int N = c->hp.N, tiles = (N + kSplitTile - 1) / kSplitTile;
+  ground_compact_kernel<<<dim3((unsigned)tiles, (unsigned)K), 256, 0, c->stream>>>(c->dp, c->ws.ground, N,
+                                                                                   c->ws.tile_count, dst, N);
+  SB_LAUNCH_CHECK(c);
   return SLOAM_OK;
 }
 

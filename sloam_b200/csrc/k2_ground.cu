@@ -64,17 +64,18 @@ __device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int *total) {
 // the cell on lower lanes, from match_any).
 constexpr int kBinThreads = 1024;
 constexpr int kBinWarps = kBinThreads / 32;
+constexpr int kBinItems = 2;  // points per thread per chunk
 
 __global__ void __launch_bounds__(kBinThreads)
 ground_bin_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ ground,
                   const int32_t *__restrict__ ground_count, int stride,
                   const uint8_t *__restrict__ ground_cell, const int32_t *__restrict__ cell_count,
-                  SelKey *__restrict__ members) {
-  extern __shared__ int s_bin[];  // [B] running offsets, then [kBinWarps][B] per-warp counts
+                  const int32_t *__restrict__ tile_count, SelKey *__restrict__ members) {
+  extern __shared__ int s_bin[];  // [B] running offsets, [tiles + 1] tile prefix, [items][warps][B] counts
   const int B = dp->B;
-  int *s_run = s_bin, *s_wc = s_bin + B;
+  const int tiles = (dp->N + kSplitTile - 1) / kSplitTile;
+  int *s_run = s_bin, *s_tpre = s_bin + B, *s_wc = s_tpre + tiles + 1;
   const int k = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int G = ground_count[k];
   const sloam_point *gk = ground + (size_t)k * stride;
   const uint8_t *ck = ground_cell + (size_t)k * stride;
   SelKey *mk = members + (size_t)k * stride;
@@ -92,40 +93,78 @@ ground_bin_kernel(const DevParams *__restrict__ dp, const sloam_point *__restric
       if (c < B) s_run[c] = carry + inc - v;
       carry += __shfl_sync(kFull, inc, 31);
     }
-  }
-  for (int base = 0; base < G; base += kBinThreads) {
-    for (int i = threadIdx.x; i < kBinWarps * B; i += kBinThreads) s_wc[i] = 0;
-    __syncthreads();
-    const int i = base + threadIdx.x;
-    const int c = i < G ? (int)ck[i] : 255;
-    const bool valid = c < B;
-    uint32_t zk = 0;
-    if (valid) zk = float_key(gk[i].z);
-    // lanes of this warp in the same cell (invalid lanes get a private key)
-    const unsigned same = __match_any_sync(kFull, valid ? c : 256 + lane);
-    const int rank = __popc(same & ((1u << lane) - 1u));
-    if (valid && rank == 0) s_wc[warp * B + c] = __popc(same);
-    __syncthreads();
-    // per cell: exclusive scan of the counts over the warps (one warp per cell, lane = warp
-    // index), turned into absolute output slots; the running offset advances by the total
-    for (int cc = warp; cc < B; cc += kBinWarps) {
-      const int v = s_wc[lane * B + cc];
+  } else if (warp == 1 && tile_count) {
+    // tile-strided cloud: the v-th ground point (input order) is slot v - pre[t] of tile t
+    int carry = 0;
+    for (int base = 0; base < tiles; base += 32) {
+      const int t = base + lane;
+      const int v = t < tiles ? tile_count[(size_t)k * tiles + t] : 0;
       int inc = v;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(kFull, inc, o);
-        if (lane >= o) inc += t;
+        const int u = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += u;
       }
-      const int run = s_run[cc];
-      __syncwarp();
-      s_wc[lane * B + cc] = run + inc - v;
-      if (lane == 31) s_run[cc] = run + inc;
+      if (t < tiles) s_tpre[t] = carry + inc - v;
+      carry += __shfl_sync(kFull, inc, 31);
+    }
+    if (lane == 0) s_tpre[tiles] = carry;
+  }
+  __syncthreads();
+  const int G = tile_count ? s_tpre[tiles] : ground_count[k];
+  for (int base = 0; base < G; base += kBinThreads * kBinItems) {
+    for (int i = threadIdx.x; i < kBinItems * kBinWarps * B; i += kBinThreads) s_wc[i] = 0;
+    __syncthreads();
+    int idx[kBinItems], cel[kBinItems], rank[kBinItems];
+    uint32_t zk[kBinItems];
+#pragma unroll
+    for (int q = 0; q < kBinItems; ++q) {  // item order: q-major, then warp, then lane = input order
+      const int v = base + q * kBinThreads + threadIdx.x;
+      int i = v;
+      if (tile_count && v < G) {
+        int lo = 0, hi = tiles - 1;  // last tile with pre[t] <= v
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (s_tpre[mid] <= v) lo = mid; else hi = mid - 1;
+        }
+        i = lo * kSplitTile + (v - s_tpre[lo]);
+      }
+      const int c = v < G ? (int)ck[i] : 255;
+      const bool valid = c < B;
+      idx[q] = i; cel[q] = valid ? c : -1;
+      zk[q] = valid ? float_key(gk[i].z) : 0u;
+      // lanes of this warp in the same cell (invalid lanes get a private key)
+      const unsigned same = __match_any_sync(kFull, valid ? c : 256 + lane);
+      rank[q] = __popc(same & ((1u << lane) - 1u));
+      if (valid && rank[q] == 0) s_wc[(q * kBinWarps + warp) * B + c] = __popc(same);
     }
     __syncthreads();
-    if (valid) {
-      SelKey e; e.z = zk; e.j = (uint32_t)i;
-      mk[s_wc[warp * B + c] + rank] = e;
+    // per cell: exclusive scan of the counts over (item, warp) (one warp per cell, lane = warp
+    // index), turned into absolute output slots; the running offset advances by the total
+    for (int cc = warp; cc < B; cc += kBinWarps) {
+      int run = s_run[cc];
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < kBinItems; ++q) {
+        const int v = s_wc[(q * kBinWarps + lane) * B + cc];
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(kFull, inc, o);
+          if (lane >= o) inc += t;
+        }
+        s_wc[(q * kBinWarps + lane) * B + cc] = run + inc - v;
+        run += __shfl_sync(kFull, inc, 31);
+      }
+      if (lane == 0) s_run[cc] = run;
     }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kBinItems; ++q)
+      if (cel[q] >= 0) {
+        SelKey e; e.z = zk[q]; e.j = (uint32_t)idx[q];
+        mk[s_wc[(q * kBinWarps + warp) * B + cel[q]] + rank[q]] = e;
+      }
     __syncthreads();
   }
 }
@@ -474,12 +513,20 @@ int launch_planes_compact(sloam_ctx *c, int K, const sloam_cell_plane *cells) {
 
 int launch_ground_planes(sloam_ctx *c, int K, const sloam_point *ground, const int32_t *ground_count,
                          int stride, const sloam_pose *pose_est, sloam_cell_plane *cells,
-                         sloam_point *cell_features, sloam_point *kept_points, int32_t *kept_offsets) {
+                         sloam_point *cell_features, sloam_point *kept_points, int32_t *kept_offsets,
+                         bool strided) {
   Workspace &w = c->ws;
   dim3 grid((unsigned)c->hp.B, (unsigned)K);
-  const size_t bin_smem = sizeof(int) * (size_t)(kBinWarps + 1) * c->hp.B;
+  const int k1_tiles = (c->hp.N + kSplitTile - 1) / kSplitTile;
+  const size_t bin_smem = sizeof(int) * ((size_t)(kBinItems * kBinWarps + 1) * c->hp.B + k1_tiles + 1);
+  static bool bin_attr = false;
+  if (!bin_attr && bin_smem > 48 * 1024) {
+    SB_CUDA(c, cudaFuncSetAttribute(ground_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    bin_attr = true;
+  }
   ground_bin_kernel<<<K, kBinThreads, bin_smem, c->stream>>>(c->dp, ground, ground_count, stride, w.ground_cell,
-                                                             w.cell_count, reinterpret_cast<SelKey *>(w.gscratch));
+                                                             w.cell_count, strided ? w.tile_count : nullptr,
+                                                             reinterpret_cast<SelKey *>(w.gscratch));
   SB_LAUNCH_CHECK(c);
   ground_cells_kernel<<<grid, kGThreads, 0, c->stream>>>(
       c->dp, ground, ground_count, stride, reinterpret_cast<SelKey *>(w.gscratch), w.cell_count, pose_est,
@@ -506,5 +553,5 @@ extern "C" int sloam_b200_ground_planes_dev(sloam_ctx *c, int K, const sloam_poi
   int rc = launch_ground_tag(c, K, ground, ground_count, ground_stride);
   if (rc != SLOAM_OK) return rc;
   return launch_ground_planes(c, K, ground, ground_count, ground_stride, pose_est, cells, cell_features,
-                              kept_points, kept_offsets);
+                              kept_points, kept_offsets, false);
 }

@@ -11,10 +11,12 @@ int launch_project_split(sloam_ctx *c, int K, bool do_project, bool do_split, co
                          sloam_point *ground, int32_t *ground_count, uint32_t *tree_bits, bool sparse_tree);
 int launch_ground_planes(sloam_ctx *c, int K, const sloam_point *ground, const int32_t *ground_count,
                          int stride, const sloam_pose *pose_est, sloam_cell_plane *cells,
-                         sloam_point *cell_features, sloam_point *kept_points, int32_t *kept_offsets);
+                         sloam_point *cell_features, sloam_point *kept_points, int32_t *kept_offsets,
+                         bool strided);
 int launch_compute_graph(sloam_ctx *c, int K, const sloam_point *tree, sloam_tree *trees, int32_t *n_trees,
                          sloam_vertex *vertices, sloam_point *vertex_points, bool bits_ready);
 int launch_tree_fill(sloam_ctx *c, int K);
+int launch_ground_compact(sloam_ctx *c, int K, sloam_point *dst);
 int launch_cylinders(sloam_ctx *c, int K, const sloam_tree *trees, const int32_t *n_trees,
                      const sloam_vertex *vertices, const sloam_point *vpoints, const sloam_plane *planes_acc,
                      const int32_t *n_planes_acc, sloam_tree_model *models, sloam_point *features);
@@ -43,6 +45,7 @@ static int run_dev(sloam_ctx *c, int K, const sloam_batch_in *in, const sloam_ba
   int rc = launch_project_split(c, K, true, true, in->points, in->mask, w.pix, range, w.tree, w.ground,
                                 w.ground_count, w.tree_bits, true);
   c->tree_sparse = true;
+  c->ground_strided = true;
   if (rc != SLOAM_OK) return rc;
   // fork: ground cells + plane fits (K2, main stream) and the tree detector (K3, side
   // stream) both depend only on K1 and are latency-bound, so they run concurrently
@@ -55,7 +58,7 @@ static int run_dev(sloam_ctx *c, int K, const sloam_batch_in *in, const sloam_ba
   if (rc != SLOAM_OK) return rc;
   SB_CUDA(c, cudaEventRecord(c->ev_join, c->side));
   rc = launch_ground_planes(c, K, w.ground, w.ground_count, c->hp.N, in->pose_est, w.cells,
-                            w.cell_features, nullptr, nullptr);
+                            w.cell_features, nullptr, nullptr, true);
   if (rc != SLOAM_OK) return rc;
   SB_CUDA(c, cudaStreamWaitEvent(main_stream, c->ev_join, 0));  // join
   rc = launch_cylinders(c, K, w.trees, w.n_trees, w.vertices, w.vertex_points, w.planes_acc,
@@ -161,7 +164,7 @@ int sloam_b200_run_sloam_dev(sloam_ctx *c, int K, const sloam_point *ground, con
   int rc = launch_ground_tag(c, K, ground, ground_count, ground_stride);
   if (rc != SLOAM_OK) return rc;
   rc = launch_ground_planes(c, K, ground, ground_count, ground_stride, in->pose_est, w.cells,
-                            w.cell_features, nullptr, nullptr);
+                            w.cell_features, nullptr, nullptr, false);
   if (rc != SLOAM_OK) return rc;
   rc = launch_cylinders_strided(c, K, trees, n_trees, vertices, vertex_stride, vertex_points, point_stride,
                                 w.planes_acc, w.n_planes_acc, w.tree_models, w.tree_features);
@@ -207,7 +210,13 @@ int sloam_b200_get_intermediates(sloam_ctx *c, sloam_intermediates *o) {
     if (rc != SLOAM_OK) return rc;
     c->tree_sparse = false;
   }
-  o->pix = w.pix; o->tree = w.tree; o->ground = w.ground; o->ground_count = w.ground_count;
+  const sloam_point *ground_dense = w.ground;
+  if (c->ground_strided && c->last_k > 0) {  // contiguous ground cloud of stage a2, into scratch
+    const int rc = launch_ground_compact(c, c->last_k, reinterpret_cast<sloam_point *>(w.qscratch));
+    if (rc != SLOAM_OK) return rc;
+  }
+  if (c->ground_strided) ground_dense = reinterpret_cast<const sloam_point *>(w.qscratch);
+  o->pix = w.pix; o->tree = w.tree; o->ground = const_cast<sloam_point *>(ground_dense); o->ground_count = w.ground_count;
   o->cells = w.cells; o->cell_features = w.cell_features; o->trees = w.trees; o->n_trees = w.n_trees;
   o->vertices = w.vertices; o->vertex_points = w.vertex_points; o->tree_models = w.tree_models;
   o->tree_features = w.tree_features;
