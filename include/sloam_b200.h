@@ -211,6 +211,15 @@ const char *sloam_b200_last_error(const sloam_ctx *ctx);
 int64_t sloam_b200_kernel_launches(const sloam_ctx *ctx);
 /* Bytes of device scratch owned by the context. */
 int64_t sloam_b200_workspace_bytes(const sloam_ctx *ctx);
+/* Device-side timing of the projection / label-split kernel (stage a1 + a2) inside
+ * sloam_b200_run_keyframes_*: with profiling on, every fused run brackets that kernel
+ * with CUDA events on the context's stream (no synchronisation is added).
+ * sloam_b200_profile_read synchronises the stream, returns the summed kernel time in
+ * milliseconds and the number of launches since the last enable/read, and resets both.
+ * No counterpart in the reference (its timing is the wall clock of SLOAMNode::run,
+ * sloamNode.cpp:200-233). */
+int sloam_b200_profile_enable(sloam_ctx *ctx, int on);
+int sloam_b200_profile_read(sloam_ctx *ctx, double *split_kernel_ms, int32_t *launches);
 const char *sloam_b200_version(void);
 
 /* ------------------------------------------------ stage entries (device) */

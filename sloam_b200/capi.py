@@ -17,7 +17,8 @@ _lib = None
 EXPORTS = [
     "sloam_b200_default_params", "sloam_b200_create", "sloam_b200_destroy", "sloam_b200_set_params",
     "sloam_b200_get_params", "sloam_b200_set_stream", "sloam_b200_sync", "sloam_b200_last_error",
-    "sloam_b200_kernel_launches", "sloam_b200_workspace_bytes", "sloam_b200_version",
+    "sloam_b200_kernel_launches", "sloam_b200_workspace_bytes", "sloam_b200_profile_enable",
+    "sloam_b200_profile_read", "sloam_b200_version",
     "sloam_b200_project_dev", "sloam_b200_mask_cloud_dev", "sloam_b200_project_split_dev",
     "sloam_b200_ground_planes_dev", "sloam_b200_find_clusters_dev", "sloam_b200_compute_graph_dev",
     "sloam_b200_cylinders_dev", "sloam_b200_associate_dev", "sloam_b200_optimize_pose_dev",
@@ -150,6 +151,15 @@ class Context:
 
     def launches(self):
         return lib().sloam_b200_kernel_launches(self.h)
+
+    def profile_enable(self, on=True):
+        self.check(lib().sloam_b200_profile_enable(self.h, int(on)))
+
+    def profile_read(self):
+        """-> (summed split-kernel milliseconds, launches) since the last enable/read"""
+        ms, n = C.c_double(), C.c_int32()
+        self.check(lib().sloam_b200_profile_read(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def workspace_bytes(self):
         return lib().sloam_b200_workspace_bytes(self.h)

@@ -149,6 +149,15 @@ struct sloam_ctx {
   // likewise ws.ground is tile-strided after a fused run; ground_dense (ws.qscratch) receives
   // the contiguous cloud on demand
   bool ground_strided = false;
+  // optional event pairs around the split kernel of fused runs (sloam_b200_profile_*)
+  // run_keyframes_host: copy stream + per-chunk events (H2D of chunk j+1 overlaps compute of j)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_chunk[8] = {};
+  cudaEvent_t ev_stage_free = nullptr;
+  bool prof_on = false;
+  int prof_n = 0;
+  static constexpr int kProfPairs = 256;
+  cudaEvent_t prof_ev[2 * kProfPairs] = {};
   // partial results of split association (large maps), grown on demand
   int32_t *assoc_part_i = nullptr;
   double *assoc_part_d = nullptr;

@@ -286,6 +286,10 @@ void sloam_b200_destroy(sloam_ctx *c) {
   if (c->assoc_part_d) cudaFree(c->assoc_part_d);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   if (c->side) cudaStreamDestroy(c->side);
+  for (cudaEvent_t e : c->prof_ev) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->ev_chunk) if (e) cudaEventDestroy(e);
+  if (c->ev_stage_free) cudaEventDestroy(c->ev_stage_free);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   delete c;
@@ -337,5 +341,32 @@ int sloam_b200_sync(sloam_ctx *c) {
 const char *sloam_b200_last_error(const sloam_ctx *c) { return c ? c->err.c_str() : "null context"; }
 int64_t sloam_b200_kernel_launches(const sloam_ctx *c) { return c ? c->launches : 0; }
 int64_t sloam_b200_workspace_bytes(const sloam_ctx *c) { return c ? (int64_t)c->arena_bytes : 0; }
+
+int sloam_b200_profile_enable(sloam_ctx *c, int on) {
+  if (!c) return SLOAM_E_INVALID;
+  cudaSetDevice(c->device);
+  if (on)
+    for (cudaEvent_t &e : c->prof_ev)
+      if (!e) SB_CUDA(c, cudaEventCreate(&e));
+  c->prof_on = on != 0;
+  c->prof_n = 0;
+  return SLOAM_OK;
+}
+
+int sloam_b200_profile_read(sloam_ctx *c, double *split_kernel_ms, int32_t *launches) {
+  if (!c || !split_kernel_ms || !launches) return SLOAM_E_INVALID;
+  SB_CUDA(c, cudaStreamSynchronize(c->stream));
+  double total = 0.0;
+  const int n = c->prof_n < sloam_ctx::kProfPairs ? c->prof_n : sloam_ctx::kProfPairs;
+  for (int i = 0; i < n; ++i) {
+    float ms = 0.f;
+    SB_CUDA(c, cudaEventElapsedTime(&ms, c->prof_ev[2 * i], c->prof_ev[2 * i + 1]));
+    total += ms;
+  }
+  *split_kernel_ms = total;
+  *launches = n;
+  c->prof_n = 0;
+  return SLOAM_OK;
+}
 
 }  // extern "C"

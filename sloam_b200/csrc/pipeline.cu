@@ -106,45 +106,79 @@ int sloam_b200_run_keyframes_host(sloam_ctx *c, int K, const sloam_batch_in *in,
   }
   char *base = (char *)c->stage_dev;
   cudaStream_t s = c->stream;
-  const size_t Ks = (size_t)K;
-#define H2D(partv, src, bytes) SB_CUDA(c, cudaMemcpyAsync(base + partv.off, src, bytes, cudaMemcpyHostToDevice, s))
-  H2D(d_points, in->points, Ks * N * sizeof(sloam_point));
-  H2D(d_mask, in->mask, Ks * N);
-  H2D(d_pose, in->pose_est, Ks * sizeof(sloam_pose));
-  H2D(d_first, in->first_scan, Ks);
-  H2D(d_map, in->map_models, (in->map_shared ? 1 : Ks) * M * sizeof(sloam_cylinder));
-  H2D(d_nmap, in->n_map_models, (in->map_shared ? 1 : Ks) * 4);
-  H2D(d_prev, in->prev_planes, Ks * PP * sizeof(sloam_plane));
-  H2D(d_nprev, in->n_prev_planes, Ks * 4);
+  // The batch is cut into chunks: the host->device copies of all chunks are queued on a copy
+  // stream up front, the compute stream runs chunk j as soon as its inputs have landed, so
+  // the PCIe transfer of chunk j+1.. overlaps the kernels of chunk j (pinned host buffers).
+  constexpr int kMaxChunks = 8;
+  if (!c->copy_stream) {
+    SB_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int j = 0; j < kMaxChunks; ++j) SB_CUDA(c, cudaEventCreateWithFlags(&c->ev_chunk[j], cudaEventDisableTiming));
+    SB_CUDA(c, cudaEventCreateWithFlags(&c->ev_stage_free, cudaEventDisableTiming));
+  }
+  int n_chunks = K / 96;
+  n_chunks = n_chunks < 1 ? 1 : (n_chunks > kMaxChunks ? kMaxChunks : n_chunks);
+  const int per = (K + n_chunks - 1) / n_chunks;
+  const bool shared = in->map_shared != 0;
+  // the copy stream must not overwrite the staging area while earlier work still reads it
+  SB_CUDA(c, cudaEventRecord(c->ev_stage_free, s));
+  SB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_stage_free, 0));
+#define H2D(partv, src, elem, k0, n)                                                                        \
+  SB_CUDA(c, cudaMemcpyAsync(base + partv.off + (size_t)(k0) * (elem), (const char *)(src) + (size_t)(k0) * (elem), \
+                             (size_t)(n) * (elem), cudaMemcpyHostToDevice, c->copy_stream))
+  if (shared) {
+    H2D(d_map, in->map_models, M * sizeof(sloam_cylinder), 0, 1);
+    H2D(d_nmap, in->n_map_models, 4, 0, 1);
+  }
+  for (int j = 0; j < n_chunks; ++j) {
+    const int k0 = j * per, n = (K - k0 < per) ? K - k0 : per;
+    if (n <= 0) { n_chunks = j; break; }
+    H2D(d_points, in->points, N * sizeof(sloam_point), k0, n);
+    H2D(d_mask, in->mask, N, k0, n);
+    H2D(d_pose, in->pose_est, sizeof(sloam_pose), k0, n);
+    H2D(d_first, in->first_scan, 1, k0, n);
+    if (!shared) {
+      H2D(d_map, in->map_models, M * sizeof(sloam_cylinder), k0, n);
+      H2D(d_nmap, in->n_map_models, 4, k0, n);
+    }
+    H2D(d_prev, in->prev_planes, PP * sizeof(sloam_plane), k0, n);
+    H2D(d_nprev, in->n_prev_planes, 4, k0, n);
+    SB_CUDA(c, cudaEventRecord(c->ev_chunk[j], c->copy_stream));
+  }
 #undef H2D
-  sloam_batch_in din = *in;
-  din.points = (const sloam_point *)(base + d_points.off);
-  din.mask = (const uint8_t *)(base + d_mask.off);
-  din.pose_est = (const sloam_pose *)(base + d_pose.off);
-  din.first_scan = (const uint8_t *)(base + d_first.off);
-  din.map_models = (const sloam_cylinder *)(base + d_map.off);
-  din.n_map_models = (const int32_t *)(base + d_nmap.off);
-  din.prev_planes = (const sloam_plane *)(base + d_prev.off);
-  din.n_prev_planes = (const int32_t *)(base + d_nprev.off);
-  sloam_batch_out dout;
-  dout.results = (sloam_kf_result *)(base + d_res.off);
-  dout.matches = (int32_t *)(base + d_match.off);
-  dout.tm = (sloam_cylinder *)(base + d_tm.off);
-  dout.tm_id = (int32_t *)(base + d_tmid.off);
-  dout.planes = (sloam_plane *)(base + d_planes.off);
-  dout.n_planes = (int32_t *)(base + d_npl.off);
-  dout.range_image = out->range_image ? (float *)(base + d_range.off) : nullptr;
-  rc = run_dev(c, K, &din, &dout);
-  if (rc != SLOAM_OK) return rc;
-#define D2H(dst, partv, bytes) SB_CUDA(c, cudaMemcpyAsync(dst, base + partv.off, bytes, cudaMemcpyDeviceToHost, s))
-  D2H(out->results, d_res, Ks * sizeof(sloam_kf_result));
-  D2H(out->matches, d_match, Ks * T * 4);
-  D2H(out->tm, d_tm, Ks * T * sizeof(sloam_cylinder));
-  D2H(out->tm_id, d_tmid, Ks * T * 4);
-  D2H(out->planes, d_planes, Ks * PP * sizeof(sloam_plane));
-  D2H(out->n_planes, d_npl, Ks * 4);
-  if (out->range_image) D2H(out->range_image, d_range, Ks * N * 4);
+  for (int j = 0; j < n_chunks; ++j) {
+    const int k0 = j * per, n = (K - k0 < per) ? K - k0 : per;
+    const size_t k0s = (size_t)k0, ns = (size_t)n;
+    SB_CUDA(c, cudaStreamWaitEvent(s, c->ev_chunk[j], 0));
+    sloam_batch_in din = *in;
+    din.points = (const sloam_point *)(base + d_points.off) + k0s * N;
+    din.mask = (const uint8_t *)(base + d_mask.off) + k0s * N;
+    din.pose_est = (const sloam_pose *)(base + d_pose.off) + k0s;
+    din.first_scan = (const uint8_t *)(base + d_first.off) + k0s;
+    din.map_models = (const sloam_cylinder *)(base + d_map.off) + (shared ? 0 : k0s * M);
+    din.n_map_models = (const int32_t *)(base + d_nmap.off) + (shared ? 0 : k0s);
+    din.prev_planes = (const sloam_plane *)(base + d_prev.off) + k0s * PP;
+    din.n_prev_planes = (const int32_t *)(base + d_nprev.off) + k0s;
+    sloam_batch_out dout;
+    dout.results = (sloam_kf_result *)(base + d_res.off) + k0s;
+    dout.matches = (int32_t *)(base + d_match.off) + k0s * T;
+    dout.tm = (sloam_cylinder *)(base + d_tm.off) + k0s * T;
+    dout.tm_id = (int32_t *)(base + d_tmid.off) + k0s * T;
+    dout.planes = (sloam_plane *)(base + d_planes.off) + k0s * PP;
+    dout.n_planes = (int32_t *)(base + d_npl.off) + k0s;
+    dout.range_image = out->range_image ? (float *)(base + d_range.off) + k0s * N : nullptr;
+    rc = run_dev(c, n, &din, &dout);
+    if (rc != SLOAM_OK) return rc;
+#define D2H(dst, partv, elem) \
+  SB_CUDA(c, cudaMemcpyAsync((char *)(dst) + k0s * (elem), base + partv.off + k0s * (elem), ns * (elem), cudaMemcpyDeviceToHost, s))
+    D2H(out->results, d_res, sizeof(sloam_kf_result));
+    D2H(out->matches, d_match, T * 4);
+    D2H(out->tm, d_tm, T * sizeof(sloam_cylinder));
+    D2H(out->tm_id, d_tmid, T * 4);
+    D2H(out->planes, d_planes, PP * sizeof(sloam_plane));
+    D2H(out->n_planes, d_npl, 4);
+    if (out->range_image) D2H(out->range_image, d_range, N * 4);
 #undef D2H
+  }
   SB_CUDA(c, cudaStreamSynchronize(s));
   return SLOAM_OK;
 }
