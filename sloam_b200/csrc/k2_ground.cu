@@ -24,8 +24,13 @@ namespace sb {
 // shared memory) to have many cells resident per SM.  Larger cells spill their
 // member list / fit workspace to global scratch (L2-resident).
 constexpr int kGThreads = 64;
-constexpr int kSelCap = 1024;   // members kept in shared memory (else global scratch)
-constexpr int kQrCap = 192;     // retained points whose fit lives in shared memory
+#ifndef SLOAM_K2_SELCAP
+#define SLOAM_K2_SELCAP 256
+#define SLOAM_K2_QRCAP 64
+#define SLOAM_K2_MINCTAS 20  // measured (1000 VLP-16 kf): 1024/192/1 -> 483 us, 256/96/20 -> 387, 256/64/20 -> 377, 32/64/28 -> 359
+#endif
+constexpr int kSelCap = SLOAM_K2_SELCAP;   // members kept in shared memory (else global scratch)
+constexpr int kQrCap = SLOAM_K2_QRCAP;     // retained points whose fit lives in shared memory
 
 struct SelKey { uint32_t z; uint32_t j; };
 
@@ -169,7 +174,7 @@ ground_bin_kernel(const DevParams *__restrict__ dp, const sloam_point *__restric
   }
 }
 
-__global__ void __launch_bounds__(kGThreads)
+__global__ void __launch_bounds__(kGThreads, SLOAM_K2_MINCTAS)
 ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ ground,
                     const int32_t *__restrict__ ground_count, int stride,
                     SelKey *__restrict__ members, const int32_t *__restrict__ cell_count,

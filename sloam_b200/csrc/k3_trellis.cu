@@ -334,32 +334,66 @@ __device__ void build_vertex(const DevParams *dp, VtxSmem &s, int n, int row, sl
                              sloam_point *pool, int32_t *pool_count) {
   const int lane = threadIdx.x & 31;
   const int middle = (int)(n / 2.0);  // trellis.cpp:66
-  // order statistics by ranking: every member counts the members before it
+  // Order statistics by counting: member m counts the members strictly below it on each
+  // axis.  Without ties that count is the rank: the member whose count equals `middle` holds
+  // the median, and the z counts are the z order.  Exact ties are rare (float coordinates):
+  // a z tie is detected by counting equal members and handled by the full-key pass below; a
+  // tie group straddling the median leaves no member with count == middle, which is caught
+  // after the loop and redone with the stable (value, index) ranks.
+  // The member arrays are padded to a multiple of 4 with +inf and read as float4.
   float med[3] = {0.f, 0.f, 0.f};
-  unsigned any_ztie = 0;
+  unsigned any_ztie = 0, found = 0;
+  const int n4 = (n + 3) & ~3;
+  if (lane < n4 - n) {
+    const float inf = __int_as_float(0x7f800000);
+    s.x[n + lane] = inf; s.y[n + lane] = inf; s.z[n + lane] = inf;
+  }
+  __syncwarp();
+  const float4 *X4 = reinterpret_cast<const float4 *>(s.x), *Y4 = reinterpret_cast<const float4 *>(s.y),
+               *Z4 = reinterpret_cast<const float4 *>(s.z);
   for (int m = lane; m < ((n + 31) & ~31); m += 32) {
-    int rx = 0, ry = 0, rz = 0;
-    bool ztie = false;
+    int lx = 0, ly = 0, lz = 0, ez = 0;
     float xm = 0.f, ym = 0.f, zm = 0.f;
     if (m < n) {
       xm = s.x[m]; ym = s.y[m]; zm = s.z[m];
-      for (int j = 0; j < n; ++j) {
-        const float xj = s.x[j], yj = s.y[j], zj = s.z[j];
-        rx += (xj < xm) || (xj == xm && j < m);
-        ry += (yj < ym) || (yj == ym && j < m);
-        rz += (zj < zm) || (zj == zm && j < m);
-        ztie |= (zj == zm) && (j != m);
+      for (int j4 = 0; j4 < (n4 >> 2); ++j4) {
+        const float4 xv = X4[j4], yv = Y4[j4], zv = Z4[j4];
+        lx += (xv.x < xm) + (xv.y < xm) + (xv.z < xm) + (xv.w < xm);
+        ly += (yv.x < ym) + (yv.y < ym) + (yv.z < ym) + (yv.w < ym);
+        lz += (zv.x < zm) + (zv.y < zm) + (zv.z < zm) + (zv.w < zm);
+        ez += (zv.x == zm) + (zv.y == zm) + (zv.z == zm) + (zv.w == zm);
       }
-      s.order[rz] = (int16_t)m;  // final order when z has no ties (the common case)
     }
-    any_ztie |= __ballot_sync(kFull, ztie);
-    // the member whose rank is `middle` holds the median of that axis
-    const unsigned bx = __ballot_sync(kFull, m < n && rx == middle);
-    const unsigned by = __ballot_sync(kFull, m < n && ry == middle);
-    const unsigned bz = __ballot_sync(kFull, m < n && rz == middle);
-    if (bx) med[0] = __shfl_sync(kFull, xm, __ffs(bx) - 1);
-    if (by) med[1] = __shfl_sync(kFull, ym, __ffs(by) - 1);
-    if (bz) med[2] = __shfl_sync(kFull, zm, __ffs(bz) - 1);
+    any_ztie |= __ballot_sync(kFull, m < n && ez > 1);
+    const unsigned bx = __ballot_sync(kFull, m < n && lx == middle);
+    const unsigned by = __ballot_sync(kFull, m < n && ly == middle);
+    const unsigned bz = __ballot_sync(kFull, m < n && lz == middle);
+    if (bx) { med[0] = __shfl_sync(kFull, xm, __ffs(bx) - 1); found |= 1u; }
+    if (by) { med[1] = __shfl_sync(kFull, ym, __ffs(by) - 1); found |= 2u; }
+    if (bz) { med[2] = __shfl_sync(kFull, zm, __ffs(bz) - 1); found |= 4u; }
+    __syncwarp();
+    if (m < n) s.order[lz] = (int16_t)m;  // final order when z has no ties (the common case)
+  }
+  if (found != 7u) {  // ties around a median: stable ranks (value, then index)
+    for (int m = lane; m < ((n + 31) & ~31); m += 32) {
+      int rx = 0, ry = 0, rz = 0;
+      float xm = 0.f, ym = 0.f, zm = 0.f;
+      if (m < n) {
+        xm = s.x[m]; ym = s.y[m]; zm = s.z[m];
+        for (int j = 0; j < n; ++j) {
+          const float xj = s.x[j], yj = s.y[j], zj = s.z[j];
+          rx += (xj < xm) || (xj == xm && j < m);
+          ry += (yj < ym) || (yj == ym && j < m);
+          rz += (zj < zm) || (zj == zm && j < m);
+        }
+      }
+      const unsigned bx = __ballot_sync(kFull, m < n && rx == middle);
+      const unsigned by = __ballot_sync(kFull, m < n && ry == middle);
+      const unsigned bz = __ballot_sync(kFull, m < n && rz == middle);
+      if (bx) med[0] = __shfl_sync(kFull, xm, __ffs(bx) - 1);
+      if (by) med[1] = __shfl_sync(kFull, ym, __ffs(by) - 1);
+      if (bz) med[2] = __shfl_sync(kFull, zm, __ffs(bz) - 1);
+    }
   }
   __syncwarp();
   if (any_ztie) {  // exact z ties: full (z, y, x, column) key
@@ -413,7 +447,7 @@ vertex_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ 
               const int32_t *__restrict__ n_vwork, sloam_vertex *__restrict__ slot_vertices,
               sloam_point *__restrict__ pool, int32_t *__restrict__ pool_count,
               int32_t *__restrict__ overflow, int32_t *__restrict__ n_overflow) {
-  __shared__ VtxSmem sm[kVtxWarps];
+  __shared__ __align__(16) VtxSmem sm[kVtxWarps];
   const int N = dp->N, W = dp->p.img_w, H = dp->p.img_h, T = dp->p.max_trees;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   VtxSmem &s = sm[warp];
@@ -684,7 +718,7 @@ int launch_compute_graph(sloam_ctx *c, int K, const sloam_point *tree, sloam_tre
       c->dp, w.tree_bits, w.parent, w.ccol_min, w.ccol_max, w.crow_max, w.row_roots, w.big_roots, w.n_big,
       w.big_rank, w.bbox, w.vwork, w.n_overflow + 1);
   SB_LAUNCH_CHECK(c);
-  const int vgrid = c->sm_count * 4;
+  const int vgrid = c->sm_count * 5;
   vertex_kernel<<<vgrid, kVtxWarps * 32, 0, c->stream>>>(c->dp, tree, w.tree_bits, w.parent, w.big_roots, w.bbox,
                                                          w.vwork, w.n_overflow + 1, w.slot_vertices,
                                                          vertex_points, w.vpool_count, w.overflow_list,
