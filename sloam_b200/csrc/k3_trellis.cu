@@ -440,7 +440,7 @@ __device__ void build_vertex(const DevParams *dp, VtxSmem &s, int n, int row, sl
   if (lane == 0) *out = v;
 }
 
-__global__ void __launch_bounds__(kVtxWarps * 32)
+__global__ void __launch_bounds__(kVtxWarps * 32, 5)
 vertex_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ tree,
               const uint32_t *__restrict__ bits, const int32_t *__restrict__ parent, const int32_t *__restrict__ big_roots,
               const int32_t *__restrict__ bbox, const int32_t *__restrict__ vwork,
@@ -718,7 +718,14 @@ int launch_compute_graph(sloam_ctx *c, int K, const sloam_point *tree, sloam_tre
       c->dp, w.tree_bits, w.parent, w.ccol_min, w.ccol_max, w.crow_max, w.row_roots, w.big_roots, w.n_big,
       w.big_rank, w.bbox, w.vwork, w.n_overflow + 1);
   SB_LAUNCH_CHECK(c);
-  const int vgrid = c->sm_count * 5;
+  // persistent grid: exactly the CTAs that are resident at once (a partial second wave would
+  // double the time of its work items)
+  static int vtx_occ = 0;
+  if (vtx_occ == 0) {
+    SB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&vtx_occ, vertex_kernel, kVtxWarps * 32, 0));
+    if (vtx_occ < 1) vtx_occ = 1;
+  }
+  const int vgrid = c->sm_count * vtx_occ;
   vertex_kernel<<<vgrid, kVtxWarps * 32, 0, c->stream>>>(c->dp, tree, w.tree_bits, w.parent, w.big_roots, w.bbox,
                                                          w.vwork, w.n_overflow + 1, w.slot_vertices,
                                                          vertex_points, w.vpool_count, w.overflow_list,
