@@ -30,6 +30,11 @@ struct DevParams {
   float fov_up, fov_down, fov;  // radians, float like the reference members
   ProjGeom pg;
   GroundGeom gg;
+  // sqrtf(s) < t  <=>  s < sq_cut(t): the smallest float whose correctly rounded square
+  // root reaches t (sqrtf is monotone), so distance tests need no square root
+  float cluster_sq_cut;   // t = cluster_dist_thresh (trellis.cpp clustering tolerance)
+  float centroid_sq_cut;  // t = max_dist_to_centroid
+  unsigned magic_w;       // floor(2^32 / img_w) + 1: i / img_w == umulhi(i, magic_w) for i < 2^21
 };
 
 // hand-over record between the per-cell QR (one CTA per cell) and the per-cell
@@ -203,6 +208,10 @@ __device__ __forceinline__ void st_point(sloam_point *p, const sloam_point &v) {
 // ---- float helpers with the reference's operation order -----------------
 // Eigen Vector3f::norm / squaredNorm: x^2 + (y^2 + z^2)  (Redux.h unroller)
 SLOAM_HD_FN float sqnorm3f(float dx, float dy, float dz) { return dx * dx + (dy * dy + dz * dz); }
+// i / W and i % W without an integer division (i < 2^21, W <= 2^11: the error term
+// i * (magic * W - 2^32) stays below 2^32, so the high word is the exact quotient)
+__device__ __forceinline__ int fast_div_w(int i, unsigned magic_w) { return (int)__umulhi((unsigned)i, magic_w); }
+
 SLOAM_HD_FN float dist3f(float ax, float ay, float az, float bx, float by, float bz) {
   return sqrtf(sqnorm3f(ax - bx, ay - by, az - bz));
 }

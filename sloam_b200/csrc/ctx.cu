@@ -163,6 +163,16 @@ static void derive(DevParams &d) {
   d.gg.TB = p.groundThetaBins;
   d.gg.inv_radial_step_f = (float)(1.0 / d.gg.radial_step);
   d.gg.inv_theta_step_f = (float)(1.0 / d.gg.theta_step);
+  auto sq_cut = [](float t) {
+    if (!(t > 0.f)) return 0.f;  // sqrtf(s) < t never holds for s >= 0
+    float s = t * t;
+    while (s > 0.f && sqrtf(s) >= t) s = nextafterf(s, 0.f);
+    while (sqrtf(s) < t) s = nextafterf(s, INFINITY);
+    return s;
+  };
+  d.cluster_sq_cut = sq_cut(p.cluster_dist_thresh);
+  d.centroid_sq_cut = sq_cut(p.max_dist_to_centroid);
+  d.magic_w = (unsigned)((1ull << 32) / (unsigned)p.img_w) + 1u;
 }
 
 static int upload_tables(sloam_ctx *c) {
@@ -225,7 +235,7 @@ void sloam_b200_default_params(sloam_params *p) {
 int sloam_b200_create(const sloam_params *p, int device, int max_keyframes, sloam_ctx **out) {
   // batch keyframe index and 32-pixel word index are packed 16 + 16 bits (k3_trellis.cu)
   if (!p || !out || max_keyframes <= 0 || max_keyframes > 65535) return SLOAM_E_INVALID;
-  if ((long long)p->img_h * p->img_w > (1ll << 21)) return SLOAM_E_INVALID;
+  if ((long long)p->img_h * p->img_w > (1ll << 21) || p->img_w > 2048) return SLOAM_E_INVALID;
   *out = nullptr;
   int n_dev = 0;
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || device < 0 || device >= n_dev)

@@ -107,6 +107,7 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
   const size_t kbase = (size_t)k * N;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float qnan = __int_as_float(0x7fc00000);
+  uint32_t *tree_bits_k = tree_bits ? tree_bits + (size_t)k * ((N + 31) >> 5) : nullptr;
 
   // ---- phase A: load the tile (8 float4 per thread stay in registers) and project.
   // The pixel index is an integer derived from atan2f/asinf; the bit-exact evaluation
@@ -150,11 +151,12 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
       if (i < N) {
         if (pixr[j] < 0) pixr[j] = s_pix[j * kThreads + threadIdx.x];
         pix_io[kbase + i] = pixr[j];
-        // closest point wins (inference.cpp:135,160-162): minimum over the
-        // bit pattern of the non-negative range; NaN ranges never write
-        const float range = sqrtf(pts[j].x * pts[j].x + pts[j].y * pts[j].y + pts[j].z * pts[j].z);
-        if (range_bits != nullptr && range == range)
-          atomicMin(&range_bits[kbase + pixr[j]], __float_as_uint(range));
+        // closest point wins (inference.cpp:135,160-162): minimum over the bit pattern of the
+        // non-negative SQUARED range (sqrtf is monotone, so the same point wins); the one
+        // square root per pixel is taken by range_finalize_kernel.  NaN ranges never write.
+        const float range_sq = pts[j].x * pts[j].x + pts[j].y * pts[j].y + pts[j].z * pts[j].z;
+        if (range_bits != nullptr && range_sq == range_sq)
+          atomicMin(&range_bits[kbase + pixr[j]], __float_as_uint(range_sq));
       }
     }
   }
@@ -183,7 +185,7 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
     }
     if (tree_bits != nullptr) {
       const unsigned tb = __ballot_sync(kFull, is_t);
-      if (lane == 0 && in) tree_bits[(size_t)k * ((N + 31) >> 5) + (i >> 5)] = tb;
+      if (lane == 0 && in) tree_bits_k[i >> 5] = tb;
     }
     const bool is_g = in && (m == 1);
     bal[j] = __ballot_sync(kFull, is_g);
@@ -256,22 +258,19 @@ __global__ void ground_compact_kernel(const DevParams *__restrict__ dp, const sl
   for (int i = threadIdx.x; i < n; i += blockDim.x) st_point(d + i, ld_point(s + i));
 }
 
-// empty pixels (still 0xFFFFFFFF) become 0 (inference.cpp:150-158)
+// squared range of the closest point -> range; empty pixels (still 0xFFFFFFFF) become 0
+// (inference.cpp:135,150-158)
+__device__ __forceinline__ unsigned range_final(unsigned v) {
+  return v == 0xFFFFFFFFu ? 0u : __float_as_uint(sqrtf(__uint_as_float(v)));
+}
 __global__ void range_finalize_kernel(unsigned *__restrict__ range_bits, long long n) {
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     uint4 v = *reinterpret_cast<uint4 *>(range_bits + i);
-    const bool any = (v.x == 0xFFFFFFFFu) | (v.y == 0xFFFFFFFFu) | (v.z == 0xFFFFFFFFu) | (v.w == 0xFFFFFFFFu);
-    if (any) {
-      if (v.x == 0xFFFFFFFFu) v.x = 0;
-      if (v.y == 0xFFFFFFFFu) v.y = 0;
-      if (v.z == 0xFFFFFFFFu) v.z = 0;
-      if (v.w == 0xFFFFFFFFu) v.w = 0;
-      *reinterpret_cast<uint4 *>(range_bits + i) = v;
-    }
+    v.x = range_final(v.x); v.y = range_final(v.y); v.z = range_final(v.z); v.w = range_final(v.w);
+    *reinterpret_cast<uint4 *>(range_bits + i) = v;
   } else {
-    for (long long j = i; j < n; ++j)
-      if (range_bits[j] == 0xFFFFFFFFu) range_bits[j] = 0;
+    for (long long j = i; j < n; ++j) range_bits[j] = range_final(range_bits[j]);
   }
 }
 

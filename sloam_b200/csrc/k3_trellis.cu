@@ -125,12 +125,13 @@ cc_init_kernel(const DevParams *__restrict__ dp, int K, const sloam_point *__res
                int32_t *__restrict__ csize, int32_t *__restrict__ cmin, int32_t *__restrict__ cmax,
                int32_t *__restrict__ rmax) {
   const int N = dp->N, W = dp->p.img_w, Nw = (N + 31) >> 5;
-  const float thr = dp->p.cluster_dist_thresh;
+  const float cut = dp->cluster_sq_cut;  // dist < cluster_dist_thresh  <=>  squared dist < cut
+  const unsigned magic_w = dp->magic_w;
   const int lane = threadIdx.x & 31;
   for_each_tree_word(wlist, n_wlist, [&](int k, int i, uint32_t word, int idx) {
     const uint32_t *bk = bits + (size_t)k * Nw;
     const size_t g = (size_t)k * N + i;
-    const int row = i / W, col = i - row * W;
+    const int row = fast_div_w(i, magic_w), col = i - row * W;
     const bool bit = (word >> lane) & 1u;  // clear for the padding lanes of the last word
     sloam_point p{0.f, 0.f, 0.f, 0.f};
     if (bit) p = ld_point(tree + g);
@@ -139,16 +140,21 @@ cc_init_kernel(const DevParams *__restrict__ dp, int K, const sloam_point *__res
     const bool valid = bit && isfinite(p.x);
     bool left_ok = false, up_ok = false, upleft_ok = false;  // upleft_ok: (i-W) -- (i-W-1)
     if (valid) {
-      if (col > 0 && tree_bit(bk, i - 1)) {
+      // left neighbour: its bit is in this word (lane 0: the previous word)
+      if (col > 0 && (lane > 0 ? ((word >> (lane - 1)) & 1u) != 0u : tree_bit(bk, i - 1))) {
         const sloam_point q = ld_point(tree + g - 1);
-        left_ok = dist3f(p.x, p.y, p.z, q.x, q.y, q.z) < thr;
+        left_ok = sqnorm3f(p.x - q.x, p.y - q.y, p.z - q.z) < cut;
       }
-      if (row > 0 && tree_bit(bk, i - W)) {
-        const sloam_point q = ld_point(tree + g - W);
-        up_ok = dist3f(p.x, p.y, p.z, q.x, q.y, q.z) < thr;
-        if (up_ok && left_ok && tree_bit(bk, i - W - 1)) {
-          const sloam_point ql = ld_point(tree + g - W - 1);
-          upleft_ok = dist3f(q.x, q.y, q.z, ql.x, ql.y, ql.z) < thr;
+      if (row > 0) {
+        const int u = i - W;
+        const uint32_t wu = bk[u >> 5];
+        if ((wu >> (u & 31)) & 1u) {
+          const sloam_point q = ld_point(tree + g - W);
+          up_ok = sqnorm3f(p.x - q.x, p.y - q.y, p.z - q.z) < cut;
+          if (up_ok && left_ok && ((u & 31) ? ((wu >> ((u & 31) - 1)) & 1u) != 0u : tree_bit(bk, u - 1))) {
+            const sloam_point ql = ld_point(tree + g - W - 1);
+            upleft_ok = sqnorm3f(q.x - ql.x, q.y - ql.y, q.z - ql.z) < cut;
+          }
         }
       }
     }
@@ -158,7 +164,7 @@ cc_init_kernel(const DevParams *__restrict__ dp, int K, const sloam_point *__res
       left_up = 0;
       if (left_ok && row > 0 && tree_bit(bk, i - 1 - W)) {
         const sloam_point a = ld_point(tree + g - 1), b = ld_point(tree + g - 1 - W);
-        left_up = dist3f(a.x, a.y, a.z, b.x, b.y, b.z) < thr;
+        left_up = sqnorm3f(a.x - b.x, a.y - b.y, a.z - b.z) < cut;
       }
     }
     // run starts inside the word: link to the start of the row run (short find chains)
@@ -219,6 +225,7 @@ cc_flatten_kernel(const DevParams *__restrict__ dp, int K, const uint32_t *__res
                   int32_t *__restrict__ n_big, int32_t *__restrict__ kf_flags) {
   const int N = dp->N, W = dp->p.img_w, H = dp->p.img_h;
   const int min_pts = dp->p.min_cluster_points, T = dp->p.max_trees;
+  const unsigned magic_w = dp->magic_w;
   const int lane = threadIdx.x & 31;
   for_each_tree_word(wlist, n_wlist, [&](int k, int i, uint32_t word, int) {
     const size_t g = (size_t)k * N + i;
@@ -228,7 +235,7 @@ cc_flatten_kernel(const DevParams *__restrict__ dp, int K, const uint32_t *__res
       root = par0 == i ? i : uf_find(parent + (size_t)k * N, par0);
       parent[g] = root;
     }
-    const int row = i / W, col = i - row * W;
+    const int row = fast_div_w(i, magic_w), col = i - row * W;
     // Consecutive lanes are consecutive pixels of a row, so the members of a component come
     // in runs: a run = maximal stretch of lanes with the same (root, row).  One lane per run
     // (its head) issues the atomics for the whole run.
@@ -407,14 +414,14 @@ __device__ void build_vertex(const DevParams *dp, VtxSmem &s, int n, int row, sl
     __syncwarp();
   }
   // keep points within max_dist_to_centroid of the median, in z order (trellis.cpp:89-93)
-  const float maxd = dp->p.max_dist_to_centroid;
+  const float cut = dp->centroid_sq_cut;  // dist < max_dist_to_centroid  <=>  squared dist < cut
   int kept = 0;
   for (int sidx = lane; sidx < ((n + 31) & ~31); sidx += 32) {
     bool keep = false;
     int m = 0;
     if (sidx < n) {
       m = s.order[sidx];
-      keep = dist3f(s.x[m], s.y[m], s.z[m], med[0], med[1], med[2]) < maxd;
+      keep = sqnorm3f(s.x[m] - med[0], s.y[m] - med[1], s.z[m] - med[2]) < cut;
     }
     const unsigned b = __ballot_sync(kFull, keep);
     if (keep) s.order[kept + __popc(b & ((1u << lane) - 1u))] = (int16_t)m;  // in-place: kept+pos <= sidx
