@@ -77,27 +77,52 @@ SLOAM_HD_FN void transform_joint(const double x[7], const double cp[3], double l
 
 // lp = AngleAxisRotatePoint(aa, cp) + t (ceres/rotation.h) with x = [t | aa];
 // D = d lp / d x (3x6), exact derivative of whichever branch is taken.
-SLOAM_HD_FN void transform_aa(const double x[6], const double cp[3], double lp[3], double D[3][6]) {
+// Everything that depends on the pose only (theta, sin, cos, the unit axis and its
+// derivatives) is prepared once per evaluation (aa_prepare), not once per residual row;
+// `jmask` selects the angle-axis columns that the parameter subset actually uses.
+struct AaPre {
+  bool big;          // theta^2 > eps branch of AngleAxisRotatePoint
+  double ct, st, ti;
+  double w[3];       // unit axis
+  double dw[3][3];   // dw[j][i] = d w_i / d aa_j
+};
+
+SLOAM_HD_FN void aa_prepare(const double x[6], AaPre &P) {
   const double *aa = x + 3;
   const double theta2 = aa[0] * aa[0] + aa[1] * aa[1] + aa[2] * aa[2];
+  P.big = theta2 > DBL_EPSILON;
+  P.ct = 1.0; P.st = 0.0; P.ti = 0.0;
+  for (int i = 0; i < 3; ++i) { P.w[i] = 0.0; for (int j = 0; j < 3; ++j) P.dw[j][i] = 0.0; }
+  if (P.big) {
+    const double theta = sqrt(theta2);
+    P.ct = cos(theta); P.st = sin(theta); P.ti = 1.0 / theta;
+    for (int i = 0; i < 3; ++i) P.w[i] = aa[i] * P.ti;
+    //   d theta / d aa_j = w_j ;  d w_i / d aa_j = (delta_ij - w_i w_j) / theta
+    for (int j = 0; j < 3; ++j)
+      for (int i = 0; i < 3; ++i) P.dw[j][i] = ((i == j ? 1.0 : 0.0) - P.w[i] * P.w[j]) * P.ti;
+  }
+}
+
+SLOAM_HD_FN void transform_aa(const double x[6], const AaPre &P, const double cp[3], double lp[3],
+                              double D[3][6], unsigned jmask) {
+  const double *aa = x + 3;
   if (D)
     for (int i = 0; i < 3; ++i)
       for (int c = 0; c < 3; ++c) D[i][c] = (i == c) ? 1.0 : 0.0;
-  if (theta2 > DBL_EPSILON) {
-    const double theta = sqrt(theta2), ct = cos(theta), st = sin(theta), ti = 1.0 / theta;
-    const double w[3] = {aa[0] * ti, aa[1] * ti, aa[2] * ti};
+  if (P.big) {
+    const double ct = P.ct, st = P.st;
+    const double *w = P.w;
     double wxp[3];
     cross3(w, cp, wxp);
     const double wp = w[0] * cp[0] + w[1] * cp[1] + w[2] * cp[2];
     const double tmp = wp * (1.0 - ct);
     for (int i = 0; i < 3; ++i) lp[i] = cp[i] * ct + wxp[i] * st + w[i] * tmp + x[i];
     if (!D) return;
-    // chain rule through theta(aa) and w(aa):
-    //   d theta / d aa_j = w_j ;  d w_i / d aa_j = (delta_ij - w_i w_j) / theta
+    // chain rule through theta(aa) and w(aa)
     for (int j = 0; j < 3; ++j) {
+      if (!((jmask >> j) & 1u)) { D[0][3 + j] = D[1][3 + j] = D[2][3 + j] = 0.0; continue; }
       const double dth = w[j];
-      double dw[3];
-      for (int i = 0; i < 3; ++i) dw[i] = ((i == j ? 1.0 : 0.0) - w[i] * w[j]) * ti;
+      const double *dw = P.dw[j];
       double dwxp[3];
       cross3(dw, cp, dwxp);
       const double dwp = dw[0] * cp[0] + dw[1] * cp[1] + dw[2] * cp[2];
@@ -126,7 +151,7 @@ SLOAM_HD_FN double cylinder_res(const double lp[3], const sloam_cylinder &m, dou
   const double s = (d[0] * m.ray[0] + (d[1] * m.ray[1] + d[2] * m.ray[2])) / aa;
   const double e[3] = {d[0] - s * m.ray[0], d[1] - s * m.ray[1], d[2] - s * m.ray[2]};
   const double ne = sqrt(e[0] * e[0] + (e[1] * e[1] + e[2] * e[2]));
-  if (g) { g[0] = e[0] / ne; g[1] = e[1] / ne; g[2] = e[2] / ne; }
+  if (g) { const double inv = 1.0 / ne; g[0] = e[0] * inv; g[1] = e[1] * inv; g[2] = e[2] * inv; }
   return ne - m.radius;
 }
 
@@ -135,16 +160,18 @@ SLOAM_HD_FN double plane_res(const double lp[3], const sloam_plane &m, double g[
   const double nn = sqrt(m.plane[0] * m.plane[0] + (m.plane[1] * m.plane[1] + m.plane[2] * m.plane[2]));
   const double v = m.plane[0] * lp[0] + m.plane[1] * lp[1] + m.plane[2] * lp[2] + m.plane[3];
   const double sg = v < 0.0 ? -1.0 : 1.0;
-  if (g) { g[0] = sg * m.plane[0] / nn; g[1] = sg * m.plane[1] / nn; g[2] = sg * m.plane[2] / nn; }
-  return fabs(v) / nn;
+  const double inv = 1.0 / nn;
+  if (g) { g[0] = sg * m.plane[0] * inv; g[1] = sg * m.plane[1] * inv; g[2] = sg * m.plane[2] * inv; }
+  return fabs(v) * inv;
 }
 
 // One residual: raw value and tangent-space Jacobian row J[n] (n = 6 joint, 3 subset).
-SLOAM_HD_FN double residual_row(int mode, const double *x, const double feat[3], const sloam_cylinder *cyl,
-                                const sloam_plane *pl, double *J) {
+// `pre` = aa_prepare(x) for the angle-axis modes (unused for LM_JOINT).
+SLOAM_HD_FN double residual_row(int mode, const double *x, const AaPre &pre, const double feat[3],
+                                const sloam_cylinder *cyl, const sloam_plane *pl, double *J) {
   double lp[3], D[3][6], g[3];
   if (mode == LM_JOINT) transform_joint(x, feat, lp, J ? D : nullptr);
-  else transform_aa(x, feat, lp, J ? D : nullptr);
+  else transform_aa(x, pre, feat, lp, J ? D : nullptr, mode == LM_XYYAW ? 4u : 3u);  // aa_z | aa_x, aa_y
   const double r = cyl ? cylinder_res(lp, *cyl, J ? g : nullptr) : plane_res(lp, *pl, J ? g : nullptr);
   if (J) {
     if (mode == LM_JOINT) {

@@ -167,6 +167,8 @@ struct WarpEval {
     double x[7];
 #pragma unroll
     for (int i = 0; i < 7; ++i) x[i] = xs[i];
+    AaPre pre;
+    if (N == 3) aa_prepare(x, pre);  // pose-only terms: once per evaluation, not per row
     double acc[NP], accg[N], accc = 0.0;
 #pragma unroll
     for (int i = 0; i < NP; ++i) acc[i] = 0.0;
@@ -176,8 +178,8 @@ struct WarpEval {
     for (int r = lane; r < total; r += 32) {
       double J[6];
       double res;
-      if (r < n_tree) res = residual_row(mode, x, tree_feat + 3 * (size_t)r, tree_obj + r, nullptr, J);
-      else { const int q = r - n_tree; res = residual_row(mode, x, plane_feat + 3 * (size_t)q, nullptr, plane_obj + q, J); }
+      if (r < n_tree) res = residual_row(mode, x, pre, tree_feat + 3 * (size_t)r, tree_obj + r, nullptr, J);
+      else { const int q = r - n_tree; res = residual_row(mode, x, pre, plane_feat + 3 * (size_t)q, nullptr, plane_obj + q, J); }
       double sc;
       accc += huber(res, huber_a, &sc);
       const double rr = res * sc;

@@ -18,10 +18,12 @@ struct SerialEval {
     const int n = mode == LM_JOINT ? 6 : 3, npk = n * (n + 1) / 2;
     double acc[28];
     for (double &a : acc) a = 0.0;
+    AaPre pre;
+    if (mode != LM_JOINT) aa_prepare(x, pre);
     for (int r = 0; r < nt + np_; ++r) {
       double J[6], res;
-      if (r < nt) res = residual_row(mode, x, tf + 3 * r, to + r, nullptr, want_jac ? J : nullptr);
-      else res = residual_row(mode, x, pf + 3 * (r - nt), nullptr, po + (r - nt), want_jac ? J : nullptr);
+      if (r < nt) res = residual_row(mode, x, pre, tf + 3 * r, to + r, nullptr, want_jac ? J : nullptr);
+      else res = residual_row(mode, x, pre, pf + 3 * (r - nt), nullptr, po + (r - nt), want_jac ? J : nullptr);
       double sc;
       acc[27] += huber(res, huber_a, &sc);
       if (want_jac) {
@@ -59,7 +61,9 @@ int hd_lm_solve(int mode, double *x, const double *tf, const sloam_cylinder *to,
 // one residual row: value + tangent-space Jacobian (for finite-difference checks)
 double hd_residual_row(int mode, const double *x, const double *feat, const sloam_cylinder *cyl,
                        const sloam_plane *pl, double *J) {
-  return residual_row(mode, x, feat, cyl, pl, J);
+  AaPre pre;
+  if (mode != LM_JOINT) aa_prepare(x, pre);
+  return residual_row(mode, x, pre, feat, cyl, pl, J);
 }
 void hd_plus(int mode, const double *x, const double *d, double *out) { lm_plus(mode, x, d, out); }
 }
