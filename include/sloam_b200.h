@@ -218,6 +218,15 @@ int64_t sloam_b200_workspace_bytes(const sloam_ctx *ctx);
  * milliseconds and the number of launches since the last enable/read, and resets both.
  * No counterpart in the reference (its timing is the wall clock of SLOAMNode::run,
  * sloamNode.cpp:200-233). */
+/* Lanes: with n > 1 a fused run over K keyframes is cut into n sub-batches that run
+ * concurrently, each on its own stream with its own scratch, so that the latency-bound tail
+ * kernels of one sub-batch (pose optimiser, cylinder fits, per-cell plane fits) overlap the
+ * issue-bound head kernels of another.  Results are identical to n = 1 (keyframes are
+ * independent).  n = 1..4; each lane owns scratch for ceil(max_keyframes / n) keyframes in
+ * addition to the context's own.  With n > 1 sloam_b200_get_intermediates describes the
+ * first sub-batch.  Batches smaller than 64 keyframes per lane are not split.
+ * No counterpart in the reference (one keyframe at a time, sloamNode.cpp:186). */
+int sloam_b200_set_lanes(sloam_ctx *ctx, int n);
 int sloam_b200_profile_enable(sloam_ctx *ctx, int on);
 int sloam_b200_profile_read(sloam_ctx *ctx, double *split_kernel_ms, int32_t *launches);
 const char *sloam_b200_version(void);

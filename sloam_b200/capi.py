@@ -17,7 +17,7 @@ _lib = None
 EXPORTS = [
     "sloam_b200_default_params", "sloam_b200_create", "sloam_b200_destroy", "sloam_b200_set_params",
     "sloam_b200_get_params", "sloam_b200_set_stream", "sloam_b200_sync", "sloam_b200_last_error",
-    "sloam_b200_kernel_launches", "sloam_b200_workspace_bytes", "sloam_b200_profile_enable",
+    "sloam_b200_kernel_launches", "sloam_b200_workspace_bytes", "sloam_b200_profile_enable", "sloam_b200_set_lanes",
     "sloam_b200_profile_read", "sloam_b200_version",
     "sloam_b200_project_dev", "sloam_b200_mask_cloud_dev", "sloam_b200_project_split_dev",
     "sloam_b200_ground_planes_dev", "sloam_b200_find_clusters_dev", "sloam_b200_compute_graph_dev",
@@ -151,6 +151,10 @@ class Context:
 
     def launches(self):
         return lib().sloam_b200_kernel_launches(self.h)
+
+    def set_lanes(self, n):
+        """Cut fused runs into n concurrent sub-batches (1..4); results do not change."""
+        self.check(lib().sloam_b200_set_lanes(self.h, int(n)))
 
     def profile_enable(self, on=True):
         self.check(lib().sloam_b200_profile_enable(self.h, int(on)))

@@ -159,6 +159,10 @@ struct sloam_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_chunk[8] = {};
   cudaEvent_t ev_stage_free = nullptr;
+  // lanes: sub-contexts that run sub-batches of a fused run concurrently (sloam_b200_set_lanes)
+  int n_lanes = 1;
+  sloam_ctx *lane[4] = {};
+  cudaEvent_t ev_lane_start = nullptr, ev_lane_done[4] = {};
   bool prof_on = false;
   int prof_n = 0;
   static constexpr int kProfPairs = 256;

@@ -286,6 +286,9 @@ void sloam_b200_map_free(sloam_ctx *c);
 void sloam_b200_destroy(sloam_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  for (sloam_ctx *&l : c->lane) { if (l) sloam_b200_destroy(l); l = nullptr; }
+  if (c->ev_lane_start) cudaEventDestroy(c->ev_lane_start);
+  for (cudaEvent_t e : c->ev_lane_done) if (e) cudaEventDestroy(e);
   sloam_b200_map_free(c);
   cudaDeviceSynchronize();
   if (c->arena) cudaFree(c->arena);
@@ -322,6 +325,8 @@ int sloam_b200_set_params(sloam_ctx *c, const sloam_params *p) {
   sloam_params np = *p;
   c->hp.p = np;
   derive(c->hp);
+  for (sloam_ctx *l : c->lane)
+    if (l) { const int rc = sloam_b200_set_params(l, p); if (rc != SLOAM_OK) return set_err(c, rc, "set_params: lane"); }
   return upload_tables(c);
 }
 
@@ -349,7 +354,35 @@ int sloam_b200_sync(sloam_ctx *c) {
 }
 
 const char *sloam_b200_last_error(const sloam_ctx *c) { return c ? c->err.c_str() : "null context"; }
-int64_t sloam_b200_kernel_launches(const sloam_ctx *c) { return c ? c->launches : 0; }
+int64_t sloam_b200_kernel_launches(const sloam_ctx *c) {
+  if (!c) return 0;
+  int64_t n = c->launches;
+  for (const sloam_ctx *l : c->lane) if (l) n += l->launches;
+  return n;
+}
+
+int sloam_b200_set_lanes(sloam_ctx *c, int n) {
+  if (!c || n < 1 || n > 4) return SLOAM_E_INVALID;
+  cudaSetDevice(c->device);
+  SB_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (sloam_ctx *&l : c->lane) { if (l) sloam_b200_destroy(l); l = nullptr; }
+  c->n_lanes = 1;
+  if (n == 1) return SLOAM_OK;
+  if (!c->ev_lane_start) {
+    SB_CUDA(c, cudaEventCreateWithFlags(&c->ev_lane_start, cudaEventDisableTiming));
+    for (cudaEvent_t &e : c->ev_lane_done) SB_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  const int per = (c->max_k + n - 1) / n;
+  for (int l = 0; l < n; ++l) {
+    const int rc = sloam_b200_create(&c->hp.p, c->device, per, &c->lane[l]);
+    if (rc != SLOAM_OK) {
+      for (sloam_ctx *&q : c->lane) { if (q) sloam_b200_destroy(q); q = nullptr; }
+      return set_err(c, rc, "set_lanes: could not create a lane context");
+    }
+  }
+  c->n_lanes = n;
+  return SLOAM_OK;
+}
 int64_t sloam_b200_workspace_bytes(const sloam_ctx *c) { return c ? (int64_t)c->arena_bytes : 0; }
 
 int sloam_b200_profile_enable(sloam_ctx *c, int on) {
@@ -360,12 +393,37 @@ int sloam_b200_profile_enable(sloam_ctx *c, int on) {
       if (!e) SB_CUDA(c, cudaEventCreate(&e));
   c->prof_on = on != 0;
   c->prof_n = 0;
+  for (sloam_ctx *l : c->lane)
+    if (l) { const int rc = sloam_b200_profile_enable(l, on); if (rc != SLOAM_OK) return rc; }
   return SLOAM_OK;
 }
 
 int sloam_b200_profile_read(sloam_ctx *c, double *split_kernel_ms, int32_t *launches) {
   if (!c || !split_kernel_ms || !launches) return SLOAM_E_INVALID;
   SB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->n_lanes > 1 && c->lane[0] && c->lane[0]->prof_n > 0) {
+    // split runs: the split kernels of the lanes overlap, so a run counts from the earliest
+    // start to the latest end of its lanes' kernels (event timestamps are device-wide)
+    for (int l = 0; l < c->n_lanes; ++l) SB_CUDA(c, cudaStreamSynchronize(c->lane[l]->stream));
+    const int runs = c->lane[0]->prof_n;
+    double total_ms = 0.0;
+    for (int i = 0; i < runs; ++i) {
+      float span = 0.f;
+      for (int a = 0; a < c->n_lanes; ++a)
+        for (int b = 0; b < c->n_lanes; ++b) {
+          if (c->lane[a]->prof_n <= i || c->lane[b]->prof_n <= i) continue;
+          float ms = 0.f;
+          SB_CUDA(c, cudaEventElapsedTime(&ms, c->lane[a]->prof_ev[2 * i], c->lane[b]->prof_ev[2 * i + 1]));
+          if (ms > span) span = ms;
+        }
+      total_ms += span;
+    }
+    *split_kernel_ms = total_ms;
+    *launches = runs;
+    for (int l = 0; l < c->n_lanes; ++l) c->lane[l]->prof_n = 0;
+    c->prof_n = 0;
+    return SLOAM_OK;
+  }
   double total = 0.0;
   const int n = c->prof_n < sloam_ctx::kProfPairs ? c->prof_n : sloam_ctx::kProfPairs;
   for (int i = 0; i < n; ++i) {

@@ -37,7 +37,57 @@ static int check_batch(sloam_ctx *c, int K, const sloam_batch_in *in, const sloa
   return SLOAM_OK;
 }
 
-static int run_dev(sloam_ctx *c, int K, const sloam_batch_in *in, const sloam_batch_out *out) {
+static int run_dev(sloam_ctx *c, int K, const sloam_batch_in *in, const sloam_batch_out *out, bool allow_split = true);
+
+// sub-batch [k0, k0 + n) of a device batch
+static void slice_batch(const sloam_ctx *c, const sloam_batch_in *in, const sloam_batch_out *out, int k0,
+                        sloam_batch_in *din, sloam_batch_out *dout) {
+  const sloam_params &p = c->hp.p;
+  const size_t N = (size_t)c->hp.N, T = (size_t)p.max_trees, M = (size_t)p.max_map_models,
+               PP = (size_t)p.max_prev_planes, k = (size_t)k0;
+  const bool shared = in->map_shared != 0;
+  *din = *in;
+  din->points = in->points + k * N;
+  din->mask = in->mask + k * N;
+  din->pose_est = in->pose_est + k;
+  din->first_scan = in->first_scan + k;
+  din->map_models = in->map_models + (shared ? 0 : k * M);
+  din->n_map_models = in->n_map_models + (shared ? 0 : k);
+  din->prev_planes = in->prev_planes + k * PP;
+  din->n_prev_planes = in->n_prev_planes + k;
+  *dout = *out;
+  dout->results = out->results + k;
+  dout->matches = out->matches + k * T;
+  dout->tm = out->tm + k * T;
+  dout->tm_id = out->tm_id + k * T;
+  dout->planes = out->planes + k * PP;
+  dout->n_planes = out->n_planes + k;
+  dout->range_image = out->range_image ? out->range_image + k * N : nullptr;
+}
+
+// fused run cut into sub-batches that run concurrently on the lanes' streams
+static int run_lanes(sloam_ctx *c, int K, const sloam_batch_in *in, const sloam_batch_out *out) {
+  const int n = c->n_lanes, per = (K + n - 1) / n;
+  SB_CUDA(c, cudaEventRecord(c->ev_lane_start, c->stream));
+  for (int l = 0; l < n; ++l) {
+    const int k0 = l * per, kn = K - k0 < per ? K - k0 : per;
+    if (kn <= 0) break;
+    sloam_ctx *lc = c->lane[l];
+    SB_CUDA(c, cudaStreamWaitEvent(lc->stream, c->ev_lane_start, 0));
+    sloam_batch_in din;
+    sloam_batch_out dout;
+    slice_batch(c, in, out, k0, &din, &dout);
+    const int rc = run_dev(lc, kn, &din, &dout, false);
+    if (rc != SLOAM_OK) return set_err(c, rc, lc->err);
+    SB_CUDA(c, cudaEventRecord(c->ev_lane_done[l], lc->stream));
+    SB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_lane_done[l], 0));
+  }
+  c->last_k = c->lane[0]->last_k;
+  return SLOAM_OK;
+}
+
+static int run_dev(sloam_ctx *c, int K, const sloam_batch_in *in, const sloam_batch_out *out, bool allow_split) {
+  if (allow_split && c->n_lanes > 1 && K >= 64 * c->n_lanes) return run_lanes(c, K, in, out);
   Workspace &w = c->ws;
   float *range = out->range_image;  // optional output
   // sparse tree cloud: only the tree-labelled points and the bit mask are written (the NaN
@@ -166,7 +216,7 @@ int sloam_b200_run_keyframes_host(sloam_ctx *c, int K, const sloam_batch_in *in,
     dout.planes = (sloam_plane *)(base + d_planes.off) + k0s * PP;
     dout.n_planes = (int32_t *)(base + d_npl.off) + k0s;
     dout.range_image = out->range_image ? (float *)(base + d_range.off) + k0s * N : nullptr;
-    rc = run_dev(c, n, &din, &dout);
+    rc = run_dev(c, n, &din, &dout, false);
     if (rc != SLOAM_OK) return rc;
 #define D2H(dst, partv, elem) \
   SB_CUDA(c, cudaMemcpyAsync((char *)(dst) + k0s * (elem), base + partv.off + k0s * (elem), ns * (elem), cudaMemcpyDeviceToHost, s))
@@ -238,6 +288,12 @@ int sloam_b200_copy_d2h(sloam_ctx *c, void *dst, const void *src, uint64_t bytes
 
 int sloam_b200_get_intermediates(sloam_ctx *c, sloam_intermediates *o) {
   if (!c || !o) return SLOAM_E_INVALID;
+  if (c->n_lanes > 1 && c->lane[0] && c->lane[0]->last_k > 0 && c->last_k == c->lane[0]->last_k) {
+    SB_CUDA(c, cudaStreamSynchronize(c->stream));
+    const int rc = sloam_b200_get_intermediates(c->lane[0], o);
+    if (rc == SLOAM_OK) SB_CUDA(c, cudaStreamSynchronize(c->lane[0]->stream));
+    return rc;
+  }
   const Workspace &w = c->ws;
   if (c->tree_sparse && c->last_k > 0) {  // make ws.tree the dense organized cloud of stage a2
     const int rc = launch_tree_fill(c, c->last_k);

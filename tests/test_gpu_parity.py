@@ -672,6 +672,43 @@ def test_workspace_reuse_and_dense_tree_cloud(capi, oracle):
     ctx.close()
 
 
+def test_lanes_give_identical_results(capi):
+    """sloam_b200_set_lanes: a fused run cut into concurrent sub-batches (own streams, own
+    scratch) returns byte-identical results, including an uneven split."""
+    from sloam_b200 import configs
+    K = 197
+    p, cfg = configs.make(capi, "vlp-16", max_trees=128, max_map_models=64)
+    pts, mask = capi.synth_generate_host(cfg, 0, K)
+    scene = capi.synth_scene(cfg)
+    T, PP, M = p.max_trees, p.max_prev_planes, p.max_map_models
+    pose = np.array([capi.synth_pose(cfg, k)[1] for k in range(K)])
+    first = np.zeros(K, np.uint8); first[::50] = 1
+    maps = np.zeros((K, M), abi.CYLINDER); maps[:, :len(scene)] = scene
+    nmap = np.full(K, len(scene), np.int32)
+    inp = dict(points=pts, mask=mask, pose_est=pose, first_scan=first, map_models=maps, n_map_models=nmap,
+               prev_planes=np.zeros((K, PP), abi.PLANE), n_prev_planes=np.zeros(K, np.int32))
+    d_in = {k: capi.to_dev(v) for k, v in inp.items()}
+    got = []
+    for lanes in (1, 2, 3):
+        ctx = capi.Context(p, K)
+        ctx.set_lanes(lanes)
+        for _ in range(2):  # the second run reuses the lanes' scratch
+            d_out = ctx.alloc_outputs_dev(K)
+            for v in d_out.values():
+                if v is not None:
+                    v.zero_()  # slots beyond n_landmarks are never written
+            ctx.sync()
+            ctx.run_keyframes_dev(K, d_in, d_out)
+            ctx.sync()
+        got.append({k: capi.to_host(d_out[k], np.uint8, None).copy() for k in ("results", "matches", "tm", "tm_id", "planes", "n_planes")})
+        ctx.close()
+    res = got[0]["results"].view(abi.KF_RESULT)
+    assert (res["n_landmarks"] > 0).sum() > K // 2
+    for other in got[1:]:
+        for k, v in got[0].items():
+            assert np.array_equal(v, other[k]), k
+
+
 def test_large_map_association_config5(capi, oracle):
     """configs[4]: 100 000 map cylinders, 2 000 detections per keyframe (split-map path)."""
     rng = np.random.default_rng(55)
