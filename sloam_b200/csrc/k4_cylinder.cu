@@ -351,40 +351,62 @@ cylinder_kernel(const DevParams *__restrict__ dp, const sloam_tree *__restrict__
     m.model.radius = -1.0;
     m.model.ray[0] = m.model.ray[1] = m.model.ray[2] = 0.0;
   } else {
-    // ---- radius statistic (cylinder.cpp:141-163), lane 0 ----
-    if (lane == 0) {
-      int nr = 0;
-      for (int i = 0; i < V; ++i)
-        if (s.vtx[i].n_points > 3) {  // insertion sort, ascending
-          const float r = s.vtx[i].radius;
-          int j = nr++;
-          while (j > 0 && s.radii[j - 1] > r) { s.radii[j] = s.radii[j - 1]; --j; }
-          s.radii[j] = r;
+    // ---- radius statistic (cylinder.cpp:141-163): ascending radii of the vertices with more
+    // than 3 points, by rank (every lane ranks its vertices against all others; only the
+    // sorted VALUES matter, so ties may land in any order) ----
+    int nr = 0;
+    for (int base = 0; base < V; base += 32) {
+      const int i = base + lane;
+      const bool use = i < V && s.vtx[i].n_points > 3;
+      const float r = use ? s.vtx[i].radius : 0.f;
+      int rank = 0;
+      if (use)
+        for (int j = 0; j < V; ++j) {
+          const float rj = s.vtx[j].radius;
+          rank += (s.vtx[j].n_points > 3) && (rj < r || (rj == r && j < i));
         }
-      double radius = -1.0;
-      if (nr > 0) {
-        int d = 0;
-        while (d < nr && !(s.radii[d] > 0.f)) ++d;
-        int middle = (d + 1) + (nr - d) / 2;
-        if (middle > nr - 1) middle = nr - 1;
-        radius = (double)s.radii[middle];
-        if (radius == 0.0) radius = -1.0;
-        else if (radius < P.defaultTreeRadius) radius = P.defaultTreeRadius;
-      }
-      s.radii[0] = (float)0;  // scratch no longer needed
-      m.model.radius = radius;
+      if (use) s.radii[rank] = r;
+      nr += __popc(__ballot_sync(kFull, use));
     }
-    m.model.radius = __shfl_sync(kFull, m.model.radius, 0);
-    // ---- features: first F_t vertex points bottom-up, intensity = tree id (:87-91,:172) ----
-    if (lane == 0) {
-      int f = 0;
-      for (int i = 0; i < V && f < Ft; ++i) {
-        const sloam_vertex &vx = s.vtx[i];
-        for (int q = 0; q < vx.n_points && f < Ft; ++q) {
-          sloam_point p = psrc[vx.point_begin + q];
-          p.intensity = (float)tr.tree_id;
-          fout[f++] = p;
+    __syncwarp();
+    double radius = -1.0;
+    if (nr > 0) {
+      int d = 0;
+      while (d < nr && !(s.radii[d] > 0.f)) ++d;
+      int middle = (d + 1) + (nr - d) / 2;
+      if (middle > nr - 1) middle = nr - 1;
+      radius = (double)s.radii[middle];
+      if (radius == 0.0) radius = -1.0;
+      else if (radius < P.defaultTreeRadius) radius = P.defaultTreeRadius;
+    }
+    m.model.radius = radius;
+    __syncwarp();
+    // ---- features: first F_t vertex points bottom-up, intensity = tree id (:87-91,:172).
+    // Feature f is point f - start[i] of the vertex i whose running point count covers f;
+    // the running counts go to shared memory (radii scratch), the lanes take f = lane, +32, ...
+    int *start = reinterpret_cast<int *>(s.radii);
+    {
+      int carry = 0;
+      for (int base = 0; base < V; base += 32) {
+        const int i = base + lane;
+        const int v = i < V ? s.vtx[i].n_points : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(kFull, inc, o);
+          if (lane >= o) inc += t;
         }
+        if (i < V) start[i] = carry + inc - v;
+        carry += __shfl_sync(kFull, inc, 31);
+      }
+      __syncwarp();
+      const int total = carry < Ft ? carry : Ft;
+      for (int f = lane; f < total; f += 32) {
+        int i = 0;
+        while (i + 1 < V && start[i + 1] <= f) ++i;  // last vertex with start <= f (empty ones skipped)
+        sloam_point p = psrc[s.vtx[i].point_begin + (f - start[i])];
+        p.intensity = (float)tr.tree_id;
+        fout[f] = p;
       }
     }
   }

@@ -39,6 +39,8 @@ build_matches_kernel(const DevParams *__restrict__ dp, const uint8_t *__restrict
                      const int32_t *__restrict__ ground_count, const int32_t *__restrict__ n_trees) {
   __shared__ int s_warp[4];
   __shared__ int s_best[kMaxCells];
+  __shared__ int16_t s_pslot[kMaxCells];
+  extern __shared__ int16_t s_slot[];  // [max_trees] slot of each landmark's matches, -1 = unmatched
   const sloam_params &P = dp->p;
   const int T = P.max_trees, B = dp->B, Ft = P.featuresPerTree, Fg = P.numGroundFeatures;
   const int k = blockIdx.x;
@@ -60,9 +62,8 @@ build_matches_kernel(const DevParams *__restrict__ dp, const uint8_t *__restrict
     for (int i0 = 0; i0 < nl; i0 += 128) {
       const int i = i0 + threadIdx.x;
       bool m = false;
-      int idx = -1;
       if (i < nl) {
-        idx = assoc_idx[(size_t)k * T + i];
+        const int idx = assoc_idx[(size_t)k * T + i];
         m = idx >= 0 && assoc_dist[(size_t)k * T + i] < P.treeMatchThresh;
       }
       const unsigned b = __ballot_sync(kFull, m);
@@ -70,20 +71,20 @@ build_matches_kernel(const DevParams *__restrict__ dp, const uint8_t *__restrict
       __syncthreads();
       int off = base, tot = 0;
       for (int w = 0; w < 4; ++w) { if (w < warp) off += s_warp[w]; tot += s_warp[w]; }
-      if (m) {
-        const int slot = off + __popc(b & ((1u << lane) - 1u));
-        const sloam_cylinder obj = mk[idx];
-        const sloam_point *f = tree_features + ((size_t)k * T + lm_src[(size_t)k * T + i]) * Ft;
-        for (int q = 0; q < Ft; ++q) {  // addFeatureMatches: one match per feature (:288-296)
-          const size_t r = (size_t)slot * Ft + q;
-          tf[3 * r] = (double)f[q].x; tf[3 * r + 1] = (double)f[q].y; tf[3 * r + 2] = (double)f[q].z;
-          to[r] = obj;
-        }
-      }
+      if (i < nl) s_slot[i] = m ? off + __popc(b & ((1u << lane) - 1u)) : -1;
       base += tot;
       __syncthreads();
     }
     n_tres = base * Ft;
+    // addFeatureMatches: one match per feature (:288-296); all threads share the copies
+    for (int e = threadIdx.x; e < nl * Ft; e += 128) {
+      const int i = e / Ft, q = e - i * Ft, slot = s_slot[i];
+      if (slot < 0) continue;
+      const sloam_point f = tree_features[((size_t)k * T + lm_src[(size_t)k * T + i]) * Ft + q];
+      const size_t r = (size_t)slot * Ft + q;
+      tf[3 * r] = (double)f.x; tf[3 * r + 1] = (double)f.y; tf[3 * r + 2] = (double)f.z;
+      to[r] = mk[assoc_idx[(size_t)k * T + i]];
+    }
     // ---- matchFeatures<Plane>: centroid distance to the previous planes, threshold 1.0 (:490)
     for (int g = threadIdx.x; g < npl; g += 128) {
       double c2[3];
@@ -99,23 +100,31 @@ build_matches_kernel(const DevParams *__restrict__ dp, const uint8_t *__restrict
       s_best[g] = (bi >= 0 && bd < P.plane_match_thresh) ? bi : -1;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      double *pf = res_plane_feat + (size_t)k * B * Fg * 3;
-      sloam_plane *po = res_plane_obj + (size_t)k * B * Fg;
-      int r = 0;
-      for (int g = 0; g < npl; ++g) {
-        if (s_best[g] < 0) continue;
-        const sloam_plane obj = prev_planes[(size_t)k * prev_stride + s_best[g]];
-        const sloam_point *f = cell_features + ((size_t)k * B + planes_acc_cell[(size_t)k * B + g]) * Fg;
-        for (int q = 0; q < Fg; ++q, ++r) {
-          pf[3 * r] = (double)f[q].x; pf[3 * r + 1] = (double)f[q].y; pf[3 * r + 2] = (double)f[q].z;
-          po[r] = obj;
-        }
+    if (warp == 0) {  // slots of the matched planes, in plane order (npl <= kMaxCells)
+      int carry = 0;
+      for (int g0 = 0; g0 < npl; g0 += 32) {
+        const int g = g0 + lane;
+        const bool mm = g < npl && s_best[g] >= 0;
+        const unsigned b = __ballot_sync(kFull, mm);
+        if (g < npl) s_pslot[g] = mm ? carry + __popc(b & ((1u << lane) - 1u)) : -1;
+        carry += __popc(b);
       }
-      s_warp[0] = r;
+      if (lane == 0) s_warp[0] = carry * Fg;
     }
     __syncthreads();
     n_pres = s_warp[0];
+    {
+      double *pf = res_plane_feat + (size_t)k * B * Fg * 3;
+      sloam_plane *po = res_plane_obj + (size_t)k * B * Fg;
+      for (int e = threadIdx.x; e < npl * Fg; e += 128) {
+        const int g = e / Fg, q = e - g * Fg, slot = s_pslot[g];
+        if (slot < 0) continue;
+        const sloam_point f = cell_features[((size_t)k * B + planes_acc_cell[(size_t)k * B + g]) * Fg + q];
+        const size_t r = (size_t)slot * Fg + q;
+        pf[3 * r] = (double)f.x; pf[3 * r + 1] = (double)f.y; pf[3 * r + 2] = (double)f.z;
+        po[r] = prev_planes[(size_t)k * prev_stride + s_best[g]];
+      }
+    }
   }
   if (threadIdx.x == 0) {
     n_tree_res[k] = n_tres;
@@ -402,7 +411,7 @@ int launch_sloam_core(sloam_ctx *c, int K, const sloam_batch_in *in, const sloam
   int rc = launch_associate(c, K, w.lm_cyl, w.n_lm, T, T, in->pose_est, in->map_models, in->n_map_models,
                             p.max_map_models, in->map_shared, p.max_map_models, w.assoc_idx, w.assoc_dist);
   if (rc != SLOAM_OK) return rc;
-  build_matches_kernel<<<K, 128, 0, c->stream>>>(
+  build_matches_kernel<<<K, 128, sizeof(int16_t) * (size_t)p.max_trees, c->stream>>>(
       c->dp, in->first_scan, in->pose_est, in->n_map_models, in->map_shared, in->map_models,
       p.max_map_models, in->prev_planes, in->n_prev_planes, p.max_prev_planes, w.n_lm, w.lm_src,
       w.assoc_idx, w.assoc_dist, w.tree_features, w.planes_acc, w.planes_acc_cell, w.n_planes_acc,
