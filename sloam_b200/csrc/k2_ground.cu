@@ -23,11 +23,14 @@ namespace sb {
 // passes separated by barriers), so the CTA is kept small (2 warps, ~16 KB of
 // shared memory) to have many cells resident per SM.  Larger cells spill their
 // member list / fit workspace to global scratch (L2-resident).
-constexpr int kGThreads = 64;
+#ifndef SLOAM_K2_THREADS
+#define SLOAM_K2_THREADS 32  // one warp per cell: every barrier is warp-local, 32 cells resident per SM (64 -> 32 threads: 381 -> 335 us)
+#endif
+constexpr int kGThreads = SLOAM_K2_THREADS;
 #ifndef SLOAM_K2_SELCAP
 #define SLOAM_K2_SELCAP 256
 #define SLOAM_K2_QRCAP 64
-#define SLOAM_K2_MINCTAS 20  // measured (1000 VLP-16 kf): 1024/192/1 -> 483 us, 256/96/20 -> 387, 256/64/20 -> 377, 32/64/28 -> 359
+#define SLOAM_K2_MINCTAS 32  // measured (1000 VLP-16 kf): 1024/192/1 -> 483 us, 256/96/20 -> 387, 256/64/20 -> 377, 32/64/28 -> 359
 #endif
 constexpr int kSelCap = SLOAM_K2_SELCAP;   // members kept in shared memory (else global scratch)
 constexpr int kQrCap = SLOAM_K2_QRCAP;     // retained points whose fit lives in shared memory
