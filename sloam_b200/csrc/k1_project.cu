@@ -10,8 +10,11 @@
 //
 // HBM-bound streaming kernel.  Algorithmic bytes per keyframe: 16N points +
 // 1N mask + 4N pix + 4N range image + 16T tree points + N/8 tree bits + 17G ground
-// points and cell tags (T tree-labelled, G ground-labelled points).  One CTA = one tile of
-// kSplitTile consecutive points of one keyframe; float4 loads/stores are coalesced.
+// points and cell tags (T tree-labelled, G ground-labelled points).  Persistent CTAs (one per
+// resident slot) walk tiles of kSplitTile consecutive points of one keyframe; the points of
+// the next tile are fetched by one TMA bulk copy (cp.async.bulk + mbarrier) into the other
+// half of a shared-memory double buffer while the current tile is processed; stores are
+// coalesced float4.
 //
 // Ground layout: the ground points of tile t are written, in input order, to slots
 // [t * kSplitTile, t * kSplitTile + tile_count[t]) of the keyframe's ground array
@@ -131,21 +134,64 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
   __shared__ uint16_t s_slow[DO_PROJECT ? kSplitTile : 1];
   __shared__ int s_nslow;
   __shared__ int s_cnt[kRounds * (kThreads / 32)];
+  // input staging: the points of the NEXT tile stream into shared memory (one TMA bulk copy,
+  // completion on an mbarrier) while the current tile is being processed, so the kernel
+  // always has a full tile of loads in flight per CTA
+  __shared__ __align__(128) sloam_point s_in[2][kSplitTile];
+  __shared__ __align__(8) unsigned long long s_mbar[2];
 
   const int N = dp->N;
   const int tiles = (N + kSplitTile - 1) / kSplitTile;
-  if (threadIdx.x == 0) s_nslow = 0;
-  if (DO_SPLIT)
-    for (int c = threadIdx.x; c < kMaxCells; c += kThreads) s_hist[c] = 0;
-  __syncthreads();
-  const int k = blockIdx.x / tiles, tile = blockIdx.x % tiles;
-  if (k >= K) return;
+  const int total_tiles = K * tiles;
   const ProjGeom pg = dp->pg;
   const GroundGeom gg = dp->gg;
-  const size_t kbase = (size_t)k * N;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float qnan = __int_as_float(0x7fc00000);
+  const float mx = pg.Wf * 2.5e-6f + 1e-3f, my = 2e-3f, inv_fov = 1.0f / pg.fov;
+  auto issue_tile = [&](int tile_id, int buf) {  // one thread
+    const int kk = tile_id / tiles, tt = tile_id - kk * tiles;
+    const int n_pts = min(kSplitTile, N - tt * kSplitTile);
+    const unsigned bytes = (unsigned)(n_pts * sizeof(sloam_point));
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_mbar[buf]);
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_in[buf][0]);
+    const sloam_point *src = points + (size_t)kk * N + (size_t)tt * kSplitTile;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+  };
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&s_mbar[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&s_mbar[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if ((int)blockIdx.x < total_tiles) issue_tile((int)blockIdx.x, 0);
+  }
+  __syncthreads();
+
+  int iter = 0;
+  for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, ++iter) {
+  const int buf = iter & 1;
+  const int k = tile_id / tiles, tile = tile_id - k * tiles;
+  const size_t kbase = (size_t)k * N;
   uint32_t *tree_bits_k = tree_bits ? tree_bits + (size_t)k * ((N + 31) >> 5) : nullptr;
+  if (threadIdx.x == 0) {
+    s_nslow = 0;
+    // the other buffer was last read two barriers ago (register loads of the previous tile)
+    if (tile_id + (int)gridDim.x < total_tiles) issue_tile(tile_id + (int)gridDim.x, buf ^ 1);
+  }
+  if (DO_SPLIT)
+    for (int c = threadIdx.x; c < kMaxCells; c += kThreads) s_hist[c] = 0;
+  {  // wait for this tile's points
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_mbar[buf]);
+    const unsigned phase = (unsigned)((iter >> 1) & 1);
+    unsigned done = 0;
+    while (!done) {
+      asm volatile(
+          "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+          : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+    }
+  }
+  __syncthreads();
 
   // ---- phase A: load the tile (8 float4 per thread stay in registers) and project.
   // The pixel index is an integer derived from atan2f/asinf; the bit-exact evaluation
@@ -155,7 +201,6 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
   sloam_point pts[kRounds];
   int pixr[kRounds];
   float yawr[kRounds];
-  const float mx = pg.Wf * 2.5e-6f + 1e-3f, my = 2e-3f, inv_fov = 1.0f / pg.fov;
 #pragma unroll
   for (int j = 0; j < kRounds; ++j) {
     const int i = tile * kSplitTile + j * kThreads + threadIdx.x;
@@ -163,7 +208,7 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
     pixr[j] = 0;
     yawr[j] = qnan;
     if (i < N) {
-      pts[j] = ld_point(points + kbase + i);
+      pts[j] = ld_point(&s_in[buf][j * kThreads + threadIdx.x]);
       if (DO_PROJECT) {
         pixr[j] = project_pixel_fast(pg, pts[j].x, pts[j].y, pts[j].z, mx, my, inv_fov, &yawr[j]);
         if (pixr[j] < 0) s_slow[atomicAdd(&s_nslow, 1)] = j * kThreads + threadIdx.x;
@@ -178,7 +223,7 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
     const int ns = s_nslow;
     for (int q = threadIdx.x; q < ns; q += kThreads) {
       const int idx = s_slow[q];
-      const sloam_point p = ld_point(points + kbase + tile * kSplitTile + idx);
+      const sloam_point p = ld_point(&s_in[buf][idx]);
       float range;
       s_pix[idx] = project_pixel(pg, p.x, p.y, p.z, &range);
     }
@@ -200,7 +245,7 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
   }
 
   // ---- phase C: mask gather, dense tree cloud, order-preserving ground compaction
-  if (!DO_SPLIT) return;
+  if (!DO_SPLIT) { __syncthreads(); continue; }
   // all mask gathers of the thread are issued back to back; one block-wide scan over the
   // (round, warp) ballot counts gives every ground point its slot in input order
   unsigned bal[kRounds];
@@ -272,6 +317,8 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
     const int h = s_hist[c];
     if (h) atomicAdd(&cell_count[(size_t)k * kMaxCells + c], h);
   }
+  __syncthreads();  // s_hist / s_cnt / s_nslow are reset by the next tile
+  }  // tile loop
 }
 
 // Contiguous ground cloud (Segmentation::maskCloud's output) from the tile-strided one:
@@ -361,7 +408,17 @@ int launch_project_split(sloam_ctx *c, int K, bool do_project, bool do_split,
     SB_CUDA(c, cudaMemsetAsync(ground_count, 0, sizeof(int32_t) * (size_t)K, c->stream));
     SB_CUDA(c, cudaMemsetAsync(c->ws.cell_count, 0, sizeof(int32_t) * (size_t)K * kMaxCells, c->stream));
   }
-  const unsigned grid = (unsigned)(K * tiles);
+  // persistent CTAs: exactly the resident ones, each walks tiles blockIdx.x, + gridDim.x, ...
+  static int occ[3] = {0, 0, 0};
+  const int which = (do_project && do_split) ? 0 : (do_project ? 1 : 2);
+  if (occ[which] == 0) {
+    if (which == 0) SB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], project_split_kernel<true, true>, kThreads, 0));
+    else if (which == 1) SB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], project_split_kernel<true, false>, kThreads, 0));
+    else SB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], project_split_kernel<false, true>, kThreads, 0));
+    if (occ[which] < 1) occ[which] = 1;
+  }
+  const long long all_tiles = (long long)K * tiles;
+  const unsigned grid = (unsigned)std::min<long long>(all_tiles, (long long)c->sm_count * occ[which]);
 #define SB_K1_ARGS c->dp, K, points, mask, pix, rb, tree, c->ws.ground, ground_count, c->ws.ground_cell, \
                    c->ws.cell_count, c->ws.tile_count, N, tree_bits, sparse_tree ? 1 : 0
   const bool prof = c->prof_on && sparse_tree && c->prof_n < sloam_ctx::kProfPairs;  // fused runs only
