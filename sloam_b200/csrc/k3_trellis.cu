@@ -133,30 +133,26 @@ cc_init_kernel(const DevParams *__restrict__ dp, int K, const sloam_point *__res
     const size_t g = (size_t)k * N + i;
     const int row = fast_div_w(i, magic_w), col = i - row * W;
     const bool bit = (word >> lane) & 1u;  // clear for the padding lanes of the last word
-    sloam_point p{0.f, 0.f, 0.f, 0.f};
+    // The four points (self, left, up, up-left) are loaded together, guarded by their bits
+    // only, so that the loads are in flight at the same time instead of one after another.
+    const int u = i - W;
+    const uint32_t wu = (bit && row > 0) ? bk[u >> 5] : 0u;
+    const bool bit_l = bit && col > 0 && (lane > 0 ? ((word >> (lane - 1)) & 1u) != 0u : tree_bit(bk, i - 1));
+    const bool bit_u = (wu >> (u & 31)) & 1u;
+    const bool bit_ul = bit_u && bit_l && ((u & 31) ? ((wu >> ((u & 31) - 1)) & 1u) != 0u : tree_bit(bk, u - 1));
+    sloam_point p{0.f, 0.f, 0.f, 0.f}, ql = p, qu = p, qul = p;
     if (bit) p = ld_point(tree + g);
+    if (bit_l) ql = ld_point(tree + g - 1);
+    if (bit_u) qu = ld_point(tree + g - W);
+    if (bit_ul) qul = ld_point(tree + g - W - 1);
     // PCL skips a pixel iff !isfinite(x); EuclideanClusterComparator::compare is
     // dist < threshold in float (NaN compares false)
     const bool valid = bit && isfinite(p.x);
     bool left_ok = false, up_ok = false, upleft_ok = false;  // upleft_ok: (i-W) -- (i-W-1)
     if (valid) {
-      // left neighbour: its bit is in this word (lane 0: the previous word)
-      if (col > 0 && (lane > 0 ? ((word >> (lane - 1)) & 1u) != 0u : tree_bit(bk, i - 1))) {
-        const sloam_point q = ld_point(tree + g - 1);
-        left_ok = sqnorm3f(p.x - q.x, p.y - q.y, p.z - q.z) < cut;
-      }
-      if (row > 0) {
-        const int u = i - W;
-        const uint32_t wu = bk[u >> 5];
-        if ((wu >> (u & 31)) & 1u) {
-          const sloam_point q = ld_point(tree + g - W);
-          up_ok = sqnorm3f(p.x - q.x, p.y - q.y, p.z - q.z) < cut;
-          if (up_ok && left_ok && ((u & 31) ? ((wu >> ((u & 31) - 1)) & 1u) != 0u : tree_bit(bk, u - 1))) {
-            const sloam_point ql = ld_point(tree + g - W - 1);
-            upleft_ok = sqnorm3f(q.x - ql.x, q.y - ql.y, q.z - ql.z) < cut;
-          }
-        }
-      }
+      left_ok = bit_l && sqnorm3f(p.x - ql.x, p.y - ql.y, p.z - ql.z) < cut;
+      up_ok = bit_u && sqnorm3f(p.x - qu.x, p.y - qu.y, p.z - qu.z) < cut;
+      upleft_ok = up_ok && left_ok && bit_ul && sqnorm3f(qu.x - qul.x, qu.y - qul.y, qu.z - qul.z) < cut;
     }
     // is the left neighbour connected to ITS upper neighbour?
     int left_up = __shfl_up_sync(kFull, up_ok ? 1 : 0, 1);
