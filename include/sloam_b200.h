@@ -412,6 +412,20 @@ int sloam_b200_sequence_step_host(sloam_ctx *ctx, const sloam_point *points,
                                   sloam_kf_result *result, int32_t *matches,
                                   sloam_cylinder *tm, int32_t *tm_id);
 
+/* ------------------------------------------------ segmentation network hook
+ * SURVEY 8(f)-4.  The two elementwise passes either side of the (external) RangeNet++
+ * engine.  make_tensor = Segmentation::_makeTensor (inference.cpp:167-198) for the
+ * one-channel configuration: tensor [K][H*W] = (range - mean) / std for valid pixels,
+ * the raw value for invalid ones (|range| < 1: the reference tests the value converted
+ * to int, :183); invalid [K][H*W] flags replace the reference's index list, n_invalid [K]
+ * (optional) counts them.  The reference hard-codes mean 12.97, std 12.35 (:169-170).
+ * mask_from_logits = Segmentation::_mask (:275-300): logits [K][3][H*W] channel-major,
+ * strict-'<' argmax, class 2 -> 255, invalid (optional) -> 0.  Device pointers. */
+int sloam_b200_make_tensor_dev(sloam_ctx *ctx, int K, const float *range_image, float mean,
+                               float stdv, float *tensor, uint8_t *invalid, int32_t *n_invalid);
+int sloam_b200_mask_from_logits_dev(sloam_ctx *ctx, int K, const float *logits,
+                                    const uint8_t *invalid, uint8_t *mask);
+
 /* Device-memory helpers so that a host-language binding (cgo / JNI / the C++
  * classes in sloam_b200/host) needs no CUDA headers.  copy_d2h synchronises
  * the context stream before returning. */

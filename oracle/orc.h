@@ -18,7 +18,7 @@
  * Parity pins (tests/test_oracle_golden.py): the four
  * {still,moving}_tree_{t0,t1}.pcd -> *_landmarks_* fixture pairs of the
  * reference (stage a6/a7) reproduce exactly; the restated gtest assertions
- * of sloam/src/tests/*.cpp pass.  The third-party arithmetic that no
+ * of sloam/src/tests (all .cpp files) pass.  The third-party arithmetic that no
  * reference fixture pins (PCL line RANSAC, Eigen JacobiSVD sign, Ceres LM) is
  * restated from the published algorithms: "parity unpinned" for those.
  */

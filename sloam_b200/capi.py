@@ -17,7 +17,8 @@ _lib = None
 EXPORTS = [
     "sloam_b200_default_params", "sloam_b200_create", "sloam_b200_destroy", "sloam_b200_set_params",
     "sloam_b200_get_params", "sloam_b200_set_stream", "sloam_b200_sync", "sloam_b200_last_error",
-    "sloam_b200_kernel_launches", "sloam_b200_workspace_bytes", "sloam_b200_profile_enable", "sloam_b200_set_lanes",
+    "sloam_b200_kernel_launches", "sloam_b200_workspace_bytes", "sloam_b200_profile_enable", "sloam_b200_set_lanes", "sloam_b200_make_tensor_dev",
+    "sloam_b200_mask_from_logits_dev",
     "sloam_b200_profile_read", "sloam_b200_version",
     "sloam_b200_project_dev", "sloam_b200_mask_cloud_dev", "sloam_b200_project_split_dev",
     "sloam_b200_ground_planes_dev", "sloam_b200_find_clusters_dev", "sloam_b200_compute_graph_dev",
@@ -155,6 +156,20 @@ class Context:
     def set_lanes(self, n):
         """Cut fused runs into n concurrent sub-batches (1..4); results do not change."""
         self.check(lib().sloam_b200_set_lanes(self.h, int(n)))
+
+    def make_tensor(self, K, range_image, mean=12.97, std=12.35):
+        """Segmentation::_makeTensor on device tensors -> (tensor, invalid flags, n_invalid)"""
+        tensor = dev_empty(K * self.N * 4, self.device)
+        invalid = dev_empty(K * self.N, self.device)
+        n_inv = dev_empty(K * 4, self.device)
+        self.check(lib().sloam_b200_make_tensor_dev(self.h, K, dptr(range_image), C.c_float(mean), C.c_float(std),
+                                                    dptr(tensor), dptr(invalid), dptr(n_inv)))
+        return tensor, invalid, n_inv
+
+    def mask_from_logits(self, K, logits, invalid=None):
+        mask = dev_empty(K * self.N, self.device)
+        self.check(lib().sloam_b200_mask_from_logits_dev(self.h, K, dptr(logits), dptr(invalid), dptr(mask)))
+        return mask
 
     def profile_enable(self, on=True):
         self.check(lib().sloam_b200_profile_enable(self.h, int(on)))

@@ -244,3 +244,24 @@ class OracleMap:
         hits = np.zeros(cap, np.int32)
         n = lib().orc_map_dump(self.h, abi.ptr(models), abi.ptr(hits), cap)
         return models[:n].copy(), hits[:n].copy()
+
+
+def make_tensor(range_image, mean=12.97, std=12.35):
+    """Segmentation::_makeTensor restatement -> (tensor, invalid flags, ordered invalid indices)"""
+    r = np.ascontiguousarray(range_image, np.float32).reshape(-1)
+    tensor = np.empty_like(r)
+    invalid = np.empty(r.size, np.uint8)
+    idx = np.empty(r.size, np.int32)
+    n = lib().orc_make_tensor(abi.ptr(r), r.size, C.c_float(mean), C.c_float(std), abi.ptr(tensor), abi.ptr(invalid),
+                              abi.ptr(idx))
+    return tensor, invalid, idx[:n].copy()
+
+
+def mask_from_logits(logits, invalid=None):
+    """Segmentation::_mask restatement; logits [3][n] channel-major"""
+    o = np.ascontiguousarray(logits, np.float32)
+    n = o.size // 3
+    mask = np.empty(n, np.uint8)
+    inv = np.ascontiguousarray(invalid, np.uint8) if invalid is not None else None
+    lib().orc_mask_from_logits(abi.ptr(o), n, abi.ptr(inv) if inv is not None else None, abi.ptr(mask))
+    return mask
