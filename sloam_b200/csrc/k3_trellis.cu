@@ -420,6 +420,7 @@ __device__ void build_vertex(const DevParams *dp, VtxSmem &s, int n, int row, sl
       keep = sqnorm3f(s.x[m] - med[0], s.y[m] - med[1], s.z[m] - med[2]) < cut;
     }
     const unsigned b = __ballot_sync(kFull, keep);
+    __syncwarp();  // every lane has read its order[] entry before any lane overwrites one
     if (keep) s.order[kept + __popc(b & ((1u << lane) - 1u))] = (int16_t)m;  // in-place: kept+pos <= sidx
     kept += __popc(b);
     __syncwarp();
