@@ -53,6 +53,7 @@ struct Workspace {
   sloam_point *ground = nullptr;     // [K][N]
   int32_t *ground_count = nullptr;   // [K]
   uint32_t *tree_bits = nullptr;     // [K][ceil(N/32)] bit i: pixel i may hold a tree point
+  uint32_t *root_bits = nullptr;     // [K][ceil(N/32)] bit i: pixel i is the root of its component
   int32_t *tree_words = nullptr;     // [K * ceil(N/32)] indices of the non-zero words of tree_bits
   int32_t *n_tree_words = nullptr;   // [1]
   uint8_t *ground_cell = nullptr;    // [K][N] polar cell of each ground point (255 = none)

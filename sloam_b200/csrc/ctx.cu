@@ -57,6 +57,7 @@ static void layout(sloam_ctx *c, Bump &b) {
   b.take(w.ground, K * N);
   b.take(w.ground_count, K);
   b.take(w.tree_bits, K * ((N + 31) / 32));
+  b.take(w.root_bits, K * ((N + 31) / 32));
   b.take(w.tree_words, 2 * K * ((N + 31) / 32));
   b.take(w.n_tree_words, 4);
   b.take(w.ground_cell, K * N);

@@ -218,7 +218,7 @@ cc_flatten_kernel(const DevParams *__restrict__ dp, int K, const uint32_t *__res
                   int32_t *__restrict__ parent, int32_t *__restrict__ csize, int32_t *__restrict__ cmin,
                   int32_t *__restrict__ cmax, int32_t *__restrict__ rmax, int32_t *__restrict__ row_roots,
                   int32_t *__restrict__ n_roots, int32_t *__restrict__ big_roots,
-                  int32_t *__restrict__ n_big, int32_t *__restrict__ kf_flags) {
+                  int32_t *__restrict__ n_big, int32_t *__restrict__ kf_flags, uint32_t *__restrict__ root_bits) {
   const int N = dp->N, W = dp->p.img_w, H = dp->p.img_h;
   const int min_pts = dp->p.min_cluster_points, T = dp->p.max_trees;
   const unsigned magic_w = dp->magic_w;
@@ -258,12 +258,15 @@ cc_flatten_kernel(const DevParams *__restrict__ dp, int K, const uint32_t *__res
     if (root == i) {
       atomicAdd(&row_roots[(size_t)k * H + row], 1);
       atomicAdd(&n_roots[k], 1);
+      // one bit per pixel: is a component root (cc_plan counts the roots before a given one);
+      // roots are few, the words were zeroed before the launch
+      atomicOr(&root_bits[(size_t)k * ((N + 31) >> 5) + (i >> 5)], 1u << (i & 31));
     }
   });
 }
 
 // ---- 4. plan: sort big clusters, rank them, emit work items ----------------
-__global__ void cc_plan_kernel(const DevParams *__restrict__ dp, const uint32_t *__restrict__ bits,
+__global__ void cc_plan_kernel(const DevParams *__restrict__ dp, const uint32_t *__restrict__ root_bits,
                                const int32_t *__restrict__ parent,
                                const int32_t *__restrict__ cmin, const int32_t *__restrict__ cmax,
                                const int32_t *__restrict__ rmax, const int32_t *__restrict__ row_roots,
@@ -295,11 +298,17 @@ __global__ void cc_plan_kernel(const DevParams *__restrict__ dp, const uint32_t 
   for (int s = warp; s < nb; s += nwarps) {
     const int root = s_sorted[s];
     const int row = root / W, col = root - row * W;
-    // PCL label = number of component roots before this one in raster order
+    // PCL label = number of component roots before this one in raster order: the roots of
+    // the rows above (s_rowpre) + the set bits of root_bits in [row * W, root)
     int cnt = 0;
-    const int32_t *prow = parent + (size_t)k * N + (size_t)row * W;
-    const uint32_t *bk = bits + (size_t)k * ((N + 31) >> 5);
-    for (int c = lane; c < col; c += 32) cnt += tree_bit(bk, row * W + c) && (prow[c] == row * W + c);
+    const uint32_t *rbk = root_bits + (size_t)k * ((N + 31) >> 5);
+    const int a = row * W, b = root;  // pixel range [a, b)
+    for (int wi = (a >> 5) + lane; wi <= (b >> 5); wi += 32) {
+      uint32_t v = rbk[wi];
+      if (wi == (a >> 5)) v &= 0xFFFFFFFFu << (a & 31);
+      if (wi == (b >> 5)) v &= (b & 31) ? (0xFFFFFFFFu >> (32 - (b & 31))) : 0u;
+      cnt += __popc(v);
+    }
     cnt = warp_sum(cnt);
     if (lane == 0) {
       const size_t r = (size_t)k * N + root;
@@ -692,6 +701,7 @@ static int run_cc(sloam_ctx *c, int K, const sloam_point *tree, bool bits_ready)
   }
   const unsigned wgrid = (unsigned)std::min<long long>((total / 32 / 32 / 8) + 1, (long long)c->sm_count * 8);
   SB_CUDA(c, cudaMemsetAsync(w.n_tree_words, 0, sizeof(int32_t), c->stream));
+  SB_CUDA(c, cudaMemsetAsync(w.root_bits, 0, sizeof(uint32_t) * (size_t)K * ((c->hp.N + 31) / 32), c->stream));
   tree_words_kernel<<<wgrid, 256, 0, c->stream>>>(c->dp, K, w.tree_bits, reinterpret_cast<int2 *>(w.tree_words), w.n_tree_words);
   SB_LAUNCH_CHECK(c);
   const int2 *wl = reinterpret_cast<const int2 *>(w.tree_words);
@@ -703,7 +713,7 @@ static int run_cc(sloam_ctx *c, int K, const sloam_point *tree, bool bits_ready)
   SB_LAUNCH_CHECK(c);
   cc_flatten_kernel<<<wgrid, 256, 0, c->stream>>>(c->dp, K, w.tree_bits, wl, w.n_tree_words, w.parent, w.csize, w.ccol_min, w.ccol_max,
                                                    w.crow_max, w.row_roots, w.n_roots, w.big_roots,
-                                                   w.n_big, w.kf_flags);
+                                                   w.n_big, w.kf_flags, w.root_bits);
   SB_LAUNCH_CHECK(c);
   return SLOAM_OK;
 }
@@ -719,7 +729,7 @@ int launch_compute_graph(sloam_ctx *c, int K, const sloam_point *tree, sloam_tre
   SB_CUDA(c, cudaMemsetAsync(w.n_overflow, 0, sizeof(int32_t) * 4, c->stream));
   SB_CUDA(c, cudaMemsetAsync(w.vpool_count, 0, sizeof(int32_t) * K, c->stream));
   cc_plan_kernel<<<K, 256, sizeof(int32_t) * (2 * T + H + 1), c->stream>>>(
-      c->dp, w.tree_bits, w.parent, w.ccol_min, w.ccol_max, w.crow_max, w.row_roots, w.big_roots, w.n_big,
+      c->dp, w.root_bits, w.parent, w.ccol_min, w.ccol_max, w.crow_max, w.row_roots, w.big_roots, w.n_big,
       w.big_rank, w.bbox, w.vwork, w.n_overflow + 1);
   SB_LAUNCH_CHECK(c);
   // persistent grid: exactly the CTAs that are resident at once (a partial second wave would
