@@ -87,6 +87,7 @@ struct Workspace {
   sloam_vertex *slot_vertices = nullptr; // [K][max_trees][H] one candidate vertex per (cluster,row)
   int32_t *vpool_count = nullptr;    // [K]
   int32_t *vwork = nullptr;          // [K*max_trees*H] (k, slot, row) work items, packed
+  int32_t *tied_list = nullptr;      // [K][T*H] work items with exact z ties among > 16 points
   int32_t *overflow_list = nullptr;  // [K*max_trees*H] work items needing the wide path
   int32_t *n_overflow = nullptr;     // [4] counters: [0] ticket/overflow, [1] n_vwork
   int32_t *kf_flags = nullptr;       // [K] capacity-exceeded flags

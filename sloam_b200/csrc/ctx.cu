@@ -90,6 +90,7 @@ static void layout(sloam_ctx *c, Bump &b) {
   b.take(w.vpool_count, K);
   b.take(w.vwork, K * T * H);
   b.take(w.overflow_list, K * T * H);
+  b.take(w.tied_list, K * T * H);
   b.take(w.n_overflow, 4);
   b.take(w.kf_flags, K);
   b.take(w.trees, K * T);

@@ -19,6 +19,7 @@
 // (cluster, row) work items; one warp per work item builds the vertex with
 // rank-based order statistics in shared memory.
 #include "common.cuh"
+#include "dev_stdsort.h"
 
 namespace sb {
 
@@ -342,8 +343,47 @@ __device__ __forceinline__ bool key_less(float za, float ya, float xa, int ca, f
   return ca < cb;
 }
 
-__device__ void build_vertex(const DevParams *dp, VtxSmem &s, int n, int row, sloam_vertex *out,
-                             sloam_point *pool, int32_t *pool_count) {
+// The rare tie path: computeVertexProperties' std::sort by x, by y, by z on members that
+// start in column order, replayed by ONE thread (the algorithm is sequential).
+template <class Idx>
+__device__ __noinline__ void replay_three_sorts(Idx *order, int n, const float *x, const float *y, const float *z) {
+  for (int m = 0; m < n; ++m) order[m] = (Idx)m;
+  const float *keys[3] = {x, y, z};
+  for (int a = 0; a < 3; ++a) {  // one instance of the sort code
+    StdSort<Idx> srt(order, keys[a]);
+    srt.sort(n);
+  }
+}
+// Same with (key, index) packed in one 64-bit word per element (one shared-memory load per
+// access instead of two dependent ones); `pack` is scratch for n words.  A sort whose keys
+// are all distinct has one possible result, so the replay only has to start at the first axis
+// that has ties after it: `first` = 0 (x: start from column order), 1 (y: `init` = the members
+// in x order) or 2 (z: `init` = the members in y order).
+__device__ __noinline__ void replay_sorts_packed(int16_t *order, unsigned long long *pack, int n, int first,
+                                                 const int16_t *init, const float *x, const float *y,
+                                                 const float *z) {
+  const float *keys[3] = {x, y, z};
+  for (int m = 0; m < n; ++m) {
+    const unsigned idx = first == 0 ? (unsigned)m : (unsigned)init[m];
+    pack[m] = ((unsigned long long)__float_as_uint(keys[first][idx]) << 32) | idx;
+  }
+  for (int a = first; a < 3; ++a) {
+    if (a > first)
+      for (int m = 0; m < n; ++m) {
+        const unsigned idx = (unsigned)(pack[m] & 0xFFFFFFFFull);
+        pack[m] = ((unsigned long long)__float_as_uint(keys[a][idx]) << 32) | idx;
+      }
+    StdSortPacked srt{pack, PackedLess{}};
+    srt.sort(n);
+  }
+  for (int m = 0; m < n; ++m) order[m] = (int16_t)(pack[m] & 0xFFFFFFFFull);
+}
+
+// REPLAY = false: returns true when the item has exact z ties among more than 16 points and
+// must be redone by the REPLAY = true instance (nothing was written)
+template <bool REPLAY>
+__device__ bool build_vertex(const DevParams *dp, VtxSmem &s, unsigned long long *pack, int16_t *perm, int n,
+                             int row, sloam_vertex *out, sloam_point *pool, int32_t *pool_count) {
   const int lane = threadIdx.x & 31;
   const int middle = (int)(n / 2.0);  // trellis.cpp:66
   // Order statistics by counting: member m counts the members strictly below it on each
@@ -354,7 +394,7 @@ __device__ void build_vertex(const DevParams *dp, VtxSmem &s, int n, int row, sl
   // after the loop and redone with the stable (value, index) ranks.
   // The member arrays are padded to a multiple of 4 with +inf and read as float4.
   float med[3] = {0.f, 0.f, 0.f};
-  unsigned any_ztie = 0, found = 0;
+  unsigned any_ztie = 0, any_xtie = 0, any_ytie = 0, found = 0;
   const int n4 = (n + 3) & ~3;
   if (lane < n4 - n) {
     const float inf = __int_as_float(0x7f800000);
@@ -364,12 +404,16 @@ __device__ void build_vertex(const DevParams *dp, VtxSmem &s, int n, int row, sl
   const float4 *X4 = reinterpret_cast<const float4 *>(s.x), *Y4 = reinterpret_cast<const float4 *>(s.y),
                *Z4 = reinterpret_cast<const float4 *>(s.z);
   for (int m = lane; m < ((n + 31) & ~31); m += 32) {
-    int lx = 0, ly = 0, lz = 0, ez = 0;
+    int lx = 0, ly = 0, lz = 0, ez = 0, ex = 0, ey = 0;
     float xm = 0.f, ym = 0.f, zm = 0.f;
     if (m < n) {
       xm = s.x[m]; ym = s.y[m]; zm = s.z[m];
       for (int j4 = 0; j4 < (n4 >> 2); ++j4) {
         const float4 xv = X4[j4], yv = Y4[j4], zv = Z4[j4];
+        if (REPLAY) {
+          ex += (xv.x == xm) + (xv.y == xm) + (xv.z == xm) + (xv.w == xm);
+          ey += (yv.x == ym) + (yv.y == ym) + (yv.z == ym) + (yv.w == ym);
+        }
         lx += (xv.x < xm) + (xv.y < xm) + (xv.z < xm) + (xv.w < xm);
         ly += (yv.x < ym) + (yv.y < ym) + (yv.z < ym) + (yv.w < ym);
         lz += (zv.x < zm) + (zv.y < zm) + (zv.z < zm) + (zv.w < zm);
@@ -377,6 +421,11 @@ __device__ void build_vertex(const DevParams *dp, VtxSmem &s, int n, int row, sl
       }
     }
     any_ztie |= __ballot_sync(kFull, m < n && ez > 1);
+    if (REPLAY) {
+      any_xtie |= __ballot_sync(kFull, m < n && ex > 1);
+      any_ytie |= __ballot_sync(kFull, m < n && ey > 1);
+      if (m < n) { perm[lx] = (int16_t)m; perm[kVtxCap + ly] = (int16_t)m; }  // x / y order if tie-free
+    }
     const unsigned bx = __ballot_sync(kFull, m < n && lx == middle);
     const unsigned by = __ballot_sync(kFull, m < n && ly == middle);
     const unsigned bz = __ballot_sync(kFull, m < n && lz == middle);
@@ -408,7 +457,19 @@ __device__ void build_vertex(const DevParams *dp, VtxSmem &s, int n, int row, sl
     }
   }
   __syncwarp();
-  if (any_ztie) {  // exact z ties: full (z, y, x, column) key
+  if (any_ztie) {
+    // Exact z ties: the order of the tied points is whatever the reference's three std::sort
+    // calls (by x, by y, by z; trellis.cpp:71-82) leave behind.  Up to 16 points libstdc++
+    // sorts by insertion (stable), so the result is the lexicographic (z, y, x, column) order.
+    // Beyond that its introsort is not stable and one lane replays it (dev_stdsort.h).  That
+    // code lives in a second instance of the kernel that only sees the (rare) tied items: with
+    // it inside the main instance every item ran 25 % slower.
+    if (n > 16) {
+      if (!REPLAY) return true;
+      __syncwarp();
+      const int first = any_ytie ? (any_xtie ? 0 : 1) : 2;
+      if (lane == 0) replay_sorts_packed(s.order, pack, n, first, first == 1 ? perm : perm + kVtxCap, s.x, s.y, s.z);
+    } else
     for (int m = lane; m < n; m += 32) {
       const float xm = s.x[m], ym = s.y[m], zm = s.z[m];
       const int cm = s.col[m];
@@ -451,19 +512,26 @@ __device__ void build_vertex(const DevParams *dp, VtxSmem &s, int n, int row, sl
     v.n_points = kept; v.point_begin = base; v.is_valid = 1;
   }
   if (lane == 0) *out = v;
+  return false;
 }
 
+template <bool REPLAY>
 __global__ void __launch_bounds__(kVtxWarps * 32, 5)
 vertex_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ tree,
               const uint32_t *__restrict__ bits, const int32_t *__restrict__ parent, const int32_t *__restrict__ big_roots,
               const int32_t *__restrict__ bbox, const int32_t *__restrict__ vwork,
               const int32_t *__restrict__ n_vwork, sloam_vertex *__restrict__ slot_vertices,
               sloam_point *__restrict__ pool, int32_t *__restrict__ pool_count,
-              int32_t *__restrict__ overflow, int32_t *__restrict__ n_overflow) {
+              int32_t *__restrict__ overflow, int32_t *__restrict__ n_overflow,
+              int32_t *__restrict__ tied, int32_t *__restrict__ n_tied) {
   __shared__ __align__(16) VtxSmem sm[kVtxWarps];
+  __shared__ unsigned long long s_pack[REPLAY ? kVtxWarps * kVtxCap : 1];  // replay scratch
+  __shared__ int16_t s_perm[REPLAY ? kVtxWarps * 2 * kVtxCap : 1];        // members in x and in y order
   const int N = dp->N, W = dp->p.img_w, H = dp->p.img_h, T = dp->p.max_trees;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   VtxSmem &s = sm[warp];
+  unsigned long long *pack = REPLAY ? s_pack + warp * kVtxCap : s_pack;
+  int16_t *perm = REPLAY ? s_perm + warp * 2 * kVtxCap : s_perm;
   const int total = *n_vwork;
   for (int item = blockIdx.x * kVtxWarps + warp; item < total; item += gridDim.x * kVtxWarps) {
     const int w = vwork[item];
@@ -499,7 +567,8 @@ vertex_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ 
       continue;
     }
     if (n > dp->p.min_vertex_points) {  // trellis.cpp:119
-      build_vertex(dp, s, n, row, out, pool + (size_t)k * N, pool_count + k);
+      if (build_vertex<REPLAY>(dp, s, pack, perm, n, row, out, pool + (size_t)k * N, pool_count + k) && lane == 0)
+        tied[atomicAdd(n_tied, 1)] = w;
     } else if (lane == 0) {
       sloam_vertex v;
       v.cx = v.cy = v.cz = 0.f; v.radius = 0.f; v.n_points = 0; v.point_begin = 0; v.row = row; v.is_valid = 0;
@@ -559,6 +628,14 @@ __global__ void vertex_wide_kernel(const DevParams *__restrict__ dp, const sloam
       if (rx == middle) s_med[0] = xm;
       if (ry == middle) s_med[1] = ym;
       if (rz == middle) s_med[2] = zm;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {  // exact z ties among > 16 points: replay the three std::sort calls
+      bool tie = false;
+      for (int q = 0; q + 1 < n && !tie; ++q) tie = sz[sorder[q]] == sz[sorder[q + 1]];
+      if (tie) {
+        replay_three_sorts(sorder, n, sx, sy, sz);
+      }
     }
     __syncthreads();
     const float maxd = dp->p.max_dist_to_centroid;
@@ -736,14 +813,19 @@ int launch_compute_graph(sloam_ctx *c, int K, const sloam_point *tree, sloam_tre
   // double the time of its work items)
   static int vtx_occ = 0;
   if (vtx_occ == 0) {
-    SB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&vtx_occ, vertex_kernel, kVtxWarps * 32, 0));
+    SB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&vtx_occ, vertex_kernel<false>, kVtxWarps * 32, 0));
     if (vtx_occ < 1) vtx_occ = 1;
   }
   const int vgrid = c->sm_count * vtx_occ;
-  vertex_kernel<<<vgrid, kVtxWarps * 32, 0, c->stream>>>(c->dp, tree, w.tree_bits, w.parent, w.big_roots, w.bbox,
-                                                         w.vwork, w.n_overflow + 1, w.slot_vertices,
-                                                         vertex_points, w.vpool_count, w.overflow_list,
-                                                         w.n_overflow);
+  // n_overflow[0] rows wider than the warp path, [1] work items, [2] items with exact z ties
+  vertex_kernel<false><<<vgrid, kVtxWarps * 32, 0, c->stream>>>(
+      c->dp, tree, w.tree_bits, w.parent, w.big_roots, w.bbox, w.vwork, w.n_overflow + 1, w.slot_vertices,
+      vertex_points, w.vpool_count, w.overflow_list, w.n_overflow, w.tied_list, w.n_overflow + 2);
+  SB_LAUNCH_CHECK(c);
+  // the tied items again, with the std::sort replay (usually an empty list: the CTAs exit)
+  vertex_kernel<true><<<c->sm_count, kVtxWarps * 32, 0, c->stream>>>(
+      c->dp, tree, w.tree_bits, w.parent, w.big_roots, w.bbox, w.tied_list, w.n_overflow + 2, w.slot_vertices,
+      vertex_points, w.vpool_count, w.overflow_list, w.n_overflow, nullptr, nullptr);
   SB_LAUNCH_CHECK(c);
   const size_t wide_smem = sizeof(float) * 4 * W + sizeof(int) * 3 * W;
   static bool attr_set = false;

@@ -709,6 +709,44 @@ def test_lanes_give_identical_results(capi):
             assert np.array_equal(v, other[k]), k
 
 
+def test_odd_image_size_fused_path(capi, oracle):
+    """H x W = 21 x 1031 = 21651 pixels: not a multiple of 32 (bit-mask words), of 256 (CTA) or
+    of 1024 (split tiles: the last tile is partial and its TMA copy is short), rows that
+    straddle the 32-pixel words everywhere.  Fused path against the oracle, plus the pixel
+    indices and the dense tree / ground clouds of stage a1 + a2 bit for bit."""
+    K = 4
+    H, W = 21, 1031
+    p = capi.default_params(img_h=H, img_w=W, fov_up_deg=15.0, fov_down_deg=-15.0, min_tree_vertices=8,
+                            min_cluster_points=30, minTreeModels=3)
+    cfg = capi.synth_config(H, W, 40, fov_up_deg=15.0, fov_down_deg=-15.0, sensor_height=1.5, tree_r_max=9.0,
+                            max_tilt_deg=1.5)
+    N, T, PP = H * W, p.max_trees, p.max_prev_planes
+    inp, exp = run_sequence(capi, oracle, p, cfg, K, True)
+    ctx = capi.Context(p, K)
+    out = dict(results=np.zeros(K, abi.KF_RESULT), matches=np.zeros((K, T), np.int32),
+               tm=np.zeros((K, T), abi.CYLINDER), tm_id=np.zeros((K, T), np.int32),
+               planes=np.zeros((K, PP), abi.PLANE), n_planes=np.zeros(K, np.int32),
+               range_image=np.zeros((K, N), np.float32))
+    ctx.run_keyframes_host(K, inp, out)
+    assert sum(int(e.result["n_landmarks"]) for e in exp) > 0
+    for k in range(K):
+        compare_keyframe(out["results"][k], out["matches"][k], out["tm"][k], out["tm_id"][k], out["planes"][k],
+                         out["n_planes"][k], exp[k])
+        assert np.array_equal(out["range_image"][k].view(np.uint32), exp[k].range_image.view(np.uint32))
+    it = ctx.intermediates()
+    tree = capi.read_dev(it.tree, K * N * 16, ctx.device).view(np.uint32).reshape(K, N, 4)
+    ground = capi.read_dev(it.ground, K * N * 16, ctx.device).view(np.uint32).reshape(K, N, 4)
+    gcount = capi.read_dev(it.ground_count, K * 4, ctx.device).view(np.int32)
+    pix = capi.read_dev(it.pix, K * N * 4, ctx.device).view(np.int32).reshape(K, N)
+    for k in range(K):
+        e_tree, e_ground = oracle.mask_cloud(p, inp["points"][k], exp[k].pix, inp["mask"][k])
+        assert np.array_equal(pix[k], exp[k].pix)
+        assert np.array_equal(tree[k], e_tree.view(np.uint32).reshape(N, 4))
+        assert gcount[k] == len(e_ground)
+        assert np.array_equal(ground[k][:gcount[k]], e_ground.view(np.uint32).reshape(-1, 4))
+    ctx.close()
+
+
 def test_large_map_association_config5(capi, oracle):
     """configs[4]: 100 000 map cylinders, 2 000 detections per keyframe (split-map path)."""
     rng = np.random.default_rng(55)
