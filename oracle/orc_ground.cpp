@@ -58,10 +58,10 @@ void bin_ground_points(const Options &o, const V3 &origin_d, const Pt *pts, int 
       int bottomIdx = (int)((double)cell.size() / retainNum);
       /* B-5: thresh > 1 erases past end() in the reference; clamp. */
       bottomIdx = std::min(bottomIdx, (int)cell.size());
-      /* B-3: the reference's std::sort is unstable; the oracle fixes the
-       * total order (z, input order) with a stable sort. */
-      std::stable_sort(cell.begin(), cell.end(),
-                       [](const Pt &a, const Pt &b) { return a.z < b.z; });
+      /* std::sort like the reference (:377-380): not stable, so with exact z ties
+       * libstdc++'s introsort decides which tied points survive and in which order
+       * (SURVEY B-3); the device replays the same algorithm (csrc/dev_stdsort.h). */
+      std::sort(cell.begin(), cell.end(), [](const Pt &a, const Pt &b) { return a.z < b.z; });
       cell.erase(cell.begin() + bottomIdx, cell.end());
     }
   }

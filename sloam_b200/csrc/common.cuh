@@ -66,6 +66,9 @@ struct Workspace {
   sloam_plane *planes_acc = nullptr; // [K][B] accepted planes, compact, sensor frame
   int32_t *planes_acc_cell = nullptr;// [K][B] cell index of each accepted plane
   int32_t *n_planes_acc = nullptr;   // [K]
+  unsigned long long *gscratch2 = nullptr; // [K][N] kept records of oversized cells (gscratch stays intact)
+  int32_t *tied_cells = nullptr;     // [K][kMaxCells] (keyframe << 8 | cell) of cells with exact z ties
+  int32_t *n_tied_cells = nullptr;   // [1]
   unsigned long long *gscratch = nullptr; // [K][N] (z key, index) lists of oversized cells
   double *qscratch = nullptr;        // [K][N][3] QR workspace of oversized cells
   float *pscratch = nullptr;         // [K][N][3] point staging of oversized cells

@@ -70,6 +70,9 @@ static void layout(sloam_ctx *c, Bump &b) {
   b.take(w.planes_acc_cell, K * B);
   b.take(w.n_planes_acc, K);
   b.take(w.gscratch, K * N);
+  b.take(w.gscratch2, K * N);
+  b.take(w.tied_cells, K * kMaxCells);
+  b.take(w.n_tied_cells, 4);
   b.take(w.qscratch, K * N * 3);
   b.take(w.pscratch, K * N * 3);
   b.take(w.fit_rec, K * B);

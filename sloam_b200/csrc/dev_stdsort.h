@@ -151,6 +151,45 @@ struct StdSortT {
       insertion_sort(0, n);
     }
   }
+  // The first r positions of std::sort's result, exactly, without finishing the rest: a
+  // partition step only permutes its own range, so a right-hand range that starts at or
+  // beyond r can be left alone (its elements are >= everything before it and the final
+  // insertion pass never moves them in front of it).  Positions >= the returned bound are
+  // NOT in their final order.
+  SLOAM_HD_FN int sort_prefix(int n, int r) {
+    if (n <= 0) return 0;
+    if (r >= n) { sort(n); return n; }
+    int lg = 0;
+    for (int v = n; v > 1; v >>= 1) ++lg;
+    int stack_first[32], stack_last[32], stack_depth[32], sp = 0;
+    int first = 0, last = n, depth = lg * 2, bound = n;
+    for (;;) {
+      while (last - first > 16) {
+        if (depth == 0) { heap_sort(first, last); break; }
+        --depth;
+        const int mid = first + (last - first) / 2;
+        move_median_to_first(first, first + 1, mid, last - 1);
+        const int cut = unguarded_partition(first + 1, last, first);
+        if (cut >= r) {  // [cut, last) cannot influence positions < r
+          if (cut < bound) bound = cut;
+          last = cut;
+          continue;
+        }
+        stack_first[sp] = first; stack_last[sp] = cut; stack_depth[sp] = depth; ++sp;
+        first = cut;
+      }
+      if (sp == 0) break;
+      --sp;
+      first = stack_first[sp]; last = stack_last[sp]; depth = stack_depth[sp];
+    }
+    if (n > 16) {
+      insertion_sort(0, bound < 16 ? bound : 16);
+      for (int i = 16; i < bound; ++i) unguarded_linear_insert(i);
+    } else {
+      insertion_sort(0, n);
+    }
+    return bound;
+  }
 };
 
 // indices compared through a key array: key[a] < key[b]

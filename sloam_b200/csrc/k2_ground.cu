@@ -16,6 +16,7 @@
 // Algorithmic bytes: 16 G in, B * (72 + 16 F_g) out per keyframe.
 #include "common.cuh"
 #include "dev_plane.h"
+#include "dev_stdsort.h"
 
 namespace sb {
 
@@ -40,6 +41,18 @@ struct SelKey { uint32_t z; uint32_t j; };
 __device__ __forceinline__ bool sel_less(const SelKey &a, const SelKey &b) {
   return a.z < b.z || (a.z == b.z && a.j < b.j);
 }
+
+// z of a member from its order-preserving key (inverse of float_key)
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
+}
+// the reference's comparator p1.z < p2.z (sloam.cpp:378-380) on member records
+// (the replay stores the float's own bits in SelKey::z)
+struct MemberZLess {
+  __device__ __forceinline__ bool operator()(const SelKey &a, const SelKey &b) const {
+    return __uint_as_float(a.z) < __uint_as_float(b.z);
+  }
+};
 
 // exclusive block scan of one int per thread (256 threads); returns total in *total
 __device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int *total) {
@@ -177,6 +190,12 @@ ground_bin_kernel(const DevParams *__restrict__ dp, const sloam_point *__restric
   }
 }
 
+// REPLAY = false: grid (cells, keyframes).  Cells whose retained set involves exact z ties
+// among more than 16 points are also listed in `tied`; the REPLAY = true instance (1-D grid
+// over that list) redoes them with libstdc++'s std::sort replayed by one thread, because the
+// reference's sort (sloam.cpp:377-380) is not stable (SURVEY B-3) and the order of tied points
+// decides which of them are kept and in which order they enter the plane fit.
+template <bool REPLAY>
 __global__ void __launch_bounds__(kGThreads, SLOAM_K2_MINCTAS)
 ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ ground,
                     const int32_t *__restrict__ ground_count, int stride,
@@ -185,8 +204,12 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
                     double *__restrict__ qscratch, float *__restrict__ pscratch,
                     FitRec *__restrict__ fit, sloam_cell_plane *__restrict__ cells,
                     sloam_point *__restrict__ cell_features, sloam_point *__restrict__ kept_points,
-                    int32_t *__restrict__ kept_offsets) {
-  __shared__ SelKey s_list[kSelCap];
+                    int32_t *__restrict__ kept_offsets, SelKey *__restrict__ members2,
+                    int32_t *__restrict__ tied, int32_t *__restrict__ n_tied) {
+  // the replay instance sorts whole cells with one thread: give it room for most cells in
+  // shared memory (a global-memory sort is ~10x slower per access)
+  constexpr int kCap = REPLAY ? 2048 : kSelCap;
+  __shared__ SelKey s_list[kCap];
   __shared__ double s_qr[3 * kQrCap];
   __shared__ float s_pts[3 * kQrCap];
   __shared__ int s_hist[256];
@@ -195,8 +218,7 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
   __shared__ double s_red[4];
 
   const int B = dp->B, Fg = dp->p.numGroundFeatures;
-  const int k = blockIdx.y, cell = blockIdx.x;
-  const int G = ground_count[k];
+  auto body = [&](const int k, const int cell) {
   const int n_c = cell_count[(size_t)k * kMaxCells + cell];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const sloam_point *gk = ground + (size_t)k * stride;
@@ -249,15 +271,33 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
   // ---- the members (z key, input index), in input order: contiguous in `members` ----
   SelKey *src = members + (size_t)k * stride + off_all;
   SelKey *list = src;  // oversized cells are processed in place (L2-resident workspace)
-  if (n_c <= kSelCap) {
+  if (n_c <= kCap) {
     list = s_list;
     for (int i = threadIdx.x; i < n_c; i += kGThreads) s_list[i] = src[i];
   }
   __syncthreads();
 
   // ---- select the r lowest (z, j) keys ----
-  SelKey *keep = list;  // compacted in place
-  if (do_sort) {
+  // kept records: in place in shared memory, or in the second member array for oversized
+  // cells (the first one stays intact for a possible replay)
+  SelKey *keep = list;
+  if (do_sort && n_c > kCap) keep = members2 + (size_t)k * stride + off_all;
+  if (REPLAY && do_sort) {
+    // std::sort(cell, p1.z < p2.z) replayed on the whole cell, then the first r are kept
+    // (only the first r positions of the result are needed: sort_prefix; the z field is turned
+    // back into the float's bits first so that the comparator is a plain float compare)
+    for (int i = threadIdx.x; i < n_c; i += kGThreads) {
+      SelKey e = list[i];
+      e.z = __float_as_uint(key_to_float(e.z));
+      keep[i] = e;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      StdSortT<SelKey, MemberZLess> srt{keep, MemberZLess{}};
+      srt.sort_prefix(n_c, r);
+    }
+    __syncthreads();
+  } else if (do_sort) {
     // 8-bit MSD radix select on z for the r-th smallest (rank r-1)
     uint32_t prefix = 0, pmask = 0;
     int want = r - 1;  // 0-based rank among members matching the prefix
@@ -314,15 +354,25 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
     SelKey *tmp = (r * (int)sizeof(SelKey) <= (int)sizeof(s_qr))
                       ? reinterpret_cast<SelKey *>(s_qr)
                       : reinterpret_cast<SelKey *>(qscratch + ((size_t)k * stride + off_all) * 3);
+    // Exact ties among the kept points or across the cut (more members equal to the pivot than
+    // were taken): with more than 16 points in the cell the reference's result depends on
+    // libstdc++'s unstable sort -> the cell is listed for the replay instance (whose outputs
+    // replace everything this instance writes for the cell).  Detected inside the rank loop.
+    bool tie = ties_seen > tie_quota;
     for (int i = threadIdx.x; i < r; i += kGThreads) {
       const SelKey e = keep[i];
-      int rank = 0;
-      for (int j = 0; j < r; ++j) rank += sel_less(keep[j], e);
+      int rank = 0, same = 0;
+      for (int j = 0; j < r; ++j) {
+        rank += sel_less(keep[j], e);
+        same += keep[j].z == e.z;
+      }
+      tie |= same > 1;  // (keys equal <=> floats equal, -0 / +0 aside)
       tmp[rank] = e;
     }
-    __syncthreads();
+    const int any_tie = __syncthreads_or(tie ? 1 : 0);
     for (int i = threadIdx.x; i < r; i += kGThreads) keep[i] = tmp[i];
     __syncthreads();
+    if (any_tie && n_c > 16 && tied != nullptr && threadIdx.x == 0) tied[atomicAdd(n_tied, 1)] = (k << 8) | cell;
   }
 
   if (kept_points) {
@@ -464,6 +514,16 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
     rec->n_cell = n_c; rec->n_kept = r; rec->valid = 1;
   }
   for (int f = lane; f < Fg; f += 32) st_point(fout + f, ld_point(gk + keep[f].j));  // features.resize(numGroundFeatures)
+  };  // body
+  if (!REPLAY) {
+    body((int)blockIdx.y, (int)blockIdx.x);
+  } else {
+    const int total = *n_tied;
+    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+      body(tied[item] >> 8, tied[item] & 0xFF);
+      __syncthreads();
+    }
+  }
 }
 
 // Steps 2-4 of JacobiSVD on the QR-preconditioned 3x3, plane assembly (plane.cpp:115-127)
@@ -536,10 +596,17 @@ int launch_ground_planes(sloam_ctx *c, int K, const sloam_point *ground, const i
                                                              w.cell_count, strided ? w.tile_count : nullptr,
                                                              reinterpret_cast<SelKey *>(w.gscratch));
   SB_LAUNCH_CHECK(c);
-  ground_cells_kernel<<<grid, kGThreads, 0, c->stream>>>(
+  SB_CUDA(c, cudaMemsetAsync(w.n_tied_cells, 0, sizeof(int32_t), c->stream));
+  ground_cells_kernel<false><<<grid, kGThreads, 0, c->stream>>>(
       c->dp, ground, ground_count, stride, reinterpret_cast<SelKey *>(w.gscratch), w.cell_count, pose_est,
-      w.qscratch, w.pscratch, w.fit_rec, cells, cell_features, kept_points,
-      kept_offsets);
+      w.qscratch, w.pscratch, w.fit_rec, cells, cell_features, kept_points, kept_offsets,
+      reinterpret_cast<SelKey *>(w.gscratch2), w.tied_cells, w.n_tied_cells);
+  SB_LAUNCH_CHECK(c);
+  // cells with exact z ties again, with the std::sort replay (usually an empty list)
+  ground_cells_kernel<true><<<c->sm_count * 4, kGThreads, 0, c->stream>>>(
+      c->dp, ground, ground_count, stride, reinterpret_cast<SelKey *>(w.gscratch), w.cell_count, pose_est,
+      w.qscratch, w.pscratch, w.fit_rec, cells, cell_features, kept_points, kept_offsets,
+      reinterpret_cast<SelKey *>(w.gscratch2), w.tied_cells, w.n_tied_cells);
   SB_LAUNCH_CHECK(c);
   plane_finish_kernel<<<(K * c->hp.B + 127) / 128, 128, 0, c->stream>>>(c->dp, K, w.fit_rec, pose_est, cells);
   SB_LAUNCH_CHECK(c);

@@ -25,6 +25,15 @@ int main() {
       for (int i = 0; i < n; ++i) p[i] = (int16_t)i;
       sb::StdSort<int16_t> s(p.data(), key.data());
       s.sort(n);
+      if (n > 0) {  // prefix variant: the first r positions of std::sort's result
+        const int r = 1 + (int)(rng() % n);
+        std::vector<int16_t> q(n);
+        for (int i = 0; i < n; ++i) q[i] = (int16_t)i;
+        sb::StdSort<int16_t> sq(q.data(), key.data());
+        const int bound = sq.sort_prefix(n, r);
+        if (bound < r) { ++bad; }
+        for (int i = 0; i < r; ++i) if (q[i] != a[i].id) { ++bad; if (bad < 5) std::printf("prefix mismatch n=%d r=%d at %d\n", n, r, i); break; }
+      }
       {  // packed variant must give the same permutation
         std::vector<unsigned long long> e(n);
         for (int i = 0; i < n; ++i) { unsigned u; __builtin_memcpy(&u, &key[i], 4); e[i] = ((unsigned long long)u << 32) | (unsigned)i; }

@@ -152,7 +152,9 @@ def test_ground_planes_synthetic(capi, oracle):
 def test_ground_planes_reference_fixture_and_ties(capi, oracle):
     """The reference's own ground cloud (still_ground_t0.pcd) with the parameters of
     core_test.cpp:94-119 (1 x 18 cells, retain 0.05, 60 features), plus a tie-injected
-    copy (SURVEY B-3: total order (z, input index))."""
+    copy: the reference's std::sort is not stable, so which of the tied points survive and in
+    which order is libstdc++'s introsort artefact (SURVEY B-3) -- the oracle calls std::sort,
+    the device replays it (csrc/dev_stdsort.h)."""
     g0 = golden_io.ground("still", "t0")
     p = capi.default_params(img_h=64, img_w=2048, maxGroundLidarDist=30.0, minGroundLidarDist=0.0,
                             groundRadiiBins=1, groundThetaBins=18, groundRetainThresh=0.05,
@@ -272,16 +274,18 @@ def test_compute_graph_edge_cases(capi, oracle):
     c0 = empty()
     c1 = empty()   # blob: rows 4..27, cols 50..349 on a smooth surface (300 > 128 members per row)
     for r in range(4, 28):
-        zperm = rng.permutation(300)   # distinct z per row: no exact ties (SURVEY B-3)
+        zperm = rng.permutation(300)
         for col in range(50, 350):
-            put(c1, r, col, 5.0 + 0.001 * col + rng.normal(0, 1e-4), 0.01 * col,
-                3.0 - 0.05 * r + 2e-6 * zperm[col - 50])
+            # every third row: exact z ties in groups of 7 among 300 members (wide path + the
+            # std::sort replay, SURVEY B-3); the others have distinct z
+            dz = 2e-6 * (zperm[col - 50] // 7) if r % 3 == 0 else 2e-6 * zperm[col - 50]
+            put(c1, r, col, 5.0 + 0.001 * col + rng.normal(0, 1e-4), 0.01 * col, 3.0 - 0.05 * r + dz)
     c2 = empty()   # S-shaped component + isolated pixels + a finite-x / NaN-y pixel
-    # (z strictly increasing along a row: with exact z ties and n > 16 the reference's
-    # std::sort order is libstdc++'s introsort artefact, SURVEY B-3, not comparable)
+    # row 5: 50 members with ONE z value, row 9: z ties in pairs (n > 16: the order is
+    # libstdc++'s introsort artefact, SURVEY B-3, replayed on the device), row 13: distinct z
     for col in range(10, 60):
-        put(c2, 5, col, 4.0, 0.02 * col, 1.0 + 1e-4 * col)
-        put(c2, 9, col, 4.0, 0.02 * col, 0.6 + 1e-4 * col)
+        put(c2, 5, col, 4.0 + 0.003 * ((col * 7) % 11), 0.02 * ((col * 5) % 13), 1.0)
+        put(c2, 9, col, 4.0, 0.02 * col, 0.6 + 1e-4 * (col // 2))
     for r in range(5, 10):
         put(c2, r, 59, 4.0, 0.02 * 59, 1.0 - 0.1 * (r - 5))
     for r in range(9, 14):
