@@ -5,15 +5,17 @@
 // constructor + computeModel (sloam/src/objects/plane.cpp:3-17,96-128) and the
 // acceptance test in sloam::computeModels (sloam.cpp:394-412).
 //
-// One CTA per (keyframe, cell).  The cell tag of every ground point was written
-// by the split kernel (k1_project.cu), so a cell collects its members with one
-// coalesced pass over G bytes, gathers their z keys, selects the r lowest with
-// an 8-bit radix select (ties by input index: SURVEY B-3 total order
-// (z, input index)), sorts only those r, and fits the plane:
+// ground_bin_kernel sorts the ground points of a keyframe by polar cell (stable multisplit on
+// the cell tags the split kernel wrote, k1_project.cu).  ground_cells_kernel: one warp per
+// (keyframe, cell) reads its members contiguously, selects the r lowest z with an 8-bit radix
+// select (ties by input order), sorts only those r, and fits the plane:
 //   - centroid: float32 sequential sum in sorted order (utils.h:14-28), one lane;
 //   - 3 x n JacobiSVD: column-pivoted Householder QR of the n x 3 adjoint with
-//     warp-shuffle reductions, then the 3x3 two-sided Jacobi of dev_plane.h.
-// Algorithmic bytes: 16 G in, B * (72 + 16 F_g) out per keyframe.
+//     warp-shuffle reductions, then the 3x3 two-sided Jacobi of dev_plane.h
+//     (plane_finish_kernel, one thread per cell).
+// Cells whose result depends on how libstdc++'s unstable std::sort orders exact z ties
+// (SURVEY B-3) are redone by a second instance that replays that sort (dev_stdsort.h).
+// Algorithmic bytes: 17 G in, 8 G member records, B * (72 + 16 F_g) out per keyframe.
 #include "common.cuh"
 #include "dev_plane.h"
 #include "dev_stdsort.h"
