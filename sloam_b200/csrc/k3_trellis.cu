@@ -119,7 +119,10 @@ __device__ __forceinline__ void for_each_tree_word(const int2 *__restrict__ list
 }
 
 // ---- 1. init: link every valid pixel to its left (else up) neighbour ------
-__global__ void __launch_bounds__(256)
+#ifndef SLOAM_CCINIT_MIN
+#define SLOAM_CCINIT_MIN 8  // the persistent grid is 8 CTAs per SM: keep all of them resident (32 registers)
+#endif
+__global__ void __launch_bounds__(256, SLOAM_CCINIT_MIN)
 cc_init_kernel(const DevParams *__restrict__ dp, int K, const sloam_point *__restrict__ tree,
                const uint32_t *__restrict__ bits, const int2 *__restrict__ wlist,
                const int32_t *__restrict__ n_wlist, int32_t *__restrict__ parent, uint32_t *__restrict__ mflags,
