@@ -112,9 +112,13 @@ __device__ __forceinline__ void for_each_tree_word(const int2 *__restrict__ list
   const int n = *n_list;
   const int warp0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int nwarps = gridDim.x * (blockDim.x >> 5);
+  // the next list entry is fetched one iteration ahead: one memory round trip less on the
+  // dependent chain entry -> bits / parents -> points of every word
+  int2 e = warp0 < n ? list[warp0] : make_int2(0, 0);
   for (int idx = warp0; idx < n; idx += nwarps) {
-    const int2 e = list[idx];
-    body((int)((unsigned)e.x >> 16), (e.x & 0xFFFF) * 32 + lane, (uint32_t)e.y, idx);
+    const int2 cur = e;
+    if (idx + nwarps < n) e = list[idx + nwarps];
+    body((int)((unsigned)cur.x >> 16), (cur.x & 0xFFFF) * 32 + lane, (uint32_t)cur.y, idx);
   }
 }
 
