@@ -168,6 +168,7 @@ struct sloam_ctx {
   int n_lanes = 1;
   sloam_ctx *lane[4] = {};
   cudaEvent_t ev_lane_start = nullptr, ev_lane_done[4] = {};
+  int epoch = 0;  // bumped by set_params / set_stream: invalidates captured CUDA graphs
   bool prof_on = false;
   int prof_n = 0;
   static constexpr int kProfPairs = 256;

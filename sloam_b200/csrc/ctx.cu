@@ -329,6 +329,7 @@ int sloam_b200_set_params(sloam_ctx *c, const sloam_params *p) {
   // keep the arena layout of the creation-time parameters: only values change
   sloam_params np = *p;
   c->hp.p = np;
+  ++c->epoch;
   derive(c->hp);
   for (sloam_ctx *l : c->lane)
     if (l) { const int rc = sloam_b200_set_params(l, p); if (rc != SLOAM_OK) return set_err(c, rc, "set_params: lane"); }
@@ -343,6 +344,7 @@ int sloam_b200_get_params(const sloam_ctx *c, sloam_params *p) {
 
 int sloam_b200_set_stream(sloam_ctx *c, void *s) {
   if (!c) return SLOAM_E_INVALID;
+  ++c->epoch;
   if (c->own_stream && c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
   if (s) { c->stream = (cudaStream_t)s; c->own_stream = false; }
   else {

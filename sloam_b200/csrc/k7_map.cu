@@ -12,6 +12,7 @@
 // + 8-bit radix select + rank sort of the <= 100 winners, ties by lower index,
 // then the "last 200 landmarks" filter in neighbour order.  One CTA: the map is
 // at most ~1e5 roots (1.6 MB, L2-resident); this path is sequential by nature.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace sb {
@@ -205,6 +206,13 @@ struct sloam_seq_state {
   sloam_cylinder *submap = nullptr; int32_t *n_submap = nullptr;
   sloam_kf_result *res = nullptr; int32_t *matches = nullptr; sloam_cylinder *tm = nullptr; int32_t *tm_id = nullptr;
   sloam_plane *planes = nullptr; int32_t *n_planes = nullptr;
+  // The device part of a step (submap query, ~25 kernels of the fused path with K = 1, map
+  // update, state copies) is launch-bound: it is captured into a CUDA graph on the second call
+  // (the first one runs eagerly and does every lazy initialisation) and replayed afterwards.
+  cudaGraphExec_t graph = nullptr;
+  int graph_epoch = -1, steps = 0;
+  int64_t graph_launches = 0;  // kernels per replay (for sloam_b200_kernel_launches)
+  bool graph_off = false;      // capture failed once, or SLOAM_B200_NO_GRAPH is set
 };
 
 static sloam_seq_state *seq_of(sloam_ctx *c) { return static_cast<sloam_seq_state *>(c->seq); }
@@ -251,6 +259,7 @@ void sloam_b200_map_free(sloam_ctx *c) {
   if (!c || !c->seq) return;
   sloam_seq_state *s = seq_of(c);
   cudaStreamSynchronize(c->stream);
+  if (s->graph) cudaGraphExecDestroy(s->graph);
   if (s->arena) cudaFree(s->arena);
   delete s;
   c->seq = nullptr;
@@ -304,22 +313,59 @@ int sloam_b200_sequence_step_host(sloam_ctx *c, const sloam_point *points, const
   SB_CUDA(c, cudaMemcpyAsync(s->mask, mask, N, cudaMemcpyHostToDevice, st));
   SB_CUDA(c, cudaMemcpyAsync(s->pose, pose_estimate, sizeof(sloam_pose), cudaMemcpyHostToDevice, st));
   SB_CUDA(c, cudaMemcpyAsync(s->first, &first, 1, cudaMemcpyHostToDevice, st));
-  int rc = sloam_b200_map_get_submap_dev(c, s->pose, s->submap, s->n_submap);  // :197
-  if (rc != SLOAM_OK) return rc;
-  sloam_batch_in in{};
-  in.points = s->points; in.mask = s->mask; in.pose_est = s->pose; in.first_scan = s->first;
-  in.map_models = s->submap; in.n_map_models = s->n_submap; in.map_shared = 0;
-  in.prev_planes = s->prev_planes; in.n_prev_planes = s->n_prev;
-  sloam_batch_out out{};
-  out.results = s->res; out.matches = s->matches; out.tm = s->tm; out.tm_id = s->tm_id;
-  out.planes = s->planes; out.n_planes = s->n_planes; out.range_image = nullptr;
-  rc = sloam_b200_run_keyframes_dev(c, 1, &in, &out);  // :208-235
-  if (rc != SLOAM_OK) return rc;
-  rc = sloam_b200_map_update_dev(c, s->res, s->tm, s->tm_id, s->matches);  // :236, also after a false return
-  if (rc != SLOAM_OK) return rc;
-  // prevGPlanes_ for the next call (unchanged copy when RunSloam bailed out)
-  SB_CUDA(c, cudaMemcpyAsync(s->prev_planes, s->planes, PP * sizeof(sloam_plane), cudaMemcpyDeviceToDevice, st));
-  SB_CUDA(c, cudaMemcpyAsync(s->n_prev, s->n_planes, 4, cudaMemcpyDeviceToDevice, st));
+  // ---- device part: getSubmap -> RunSloam -> updateMap -> state for the next call ----
+  auto device_part = [&]() -> int {
+    int rc = sloam_b200_map_get_submap_dev(c, s->pose, s->submap, s->n_submap);  // :197
+    if (rc != SLOAM_OK) return rc;
+    sloam_batch_in in{};
+    in.points = s->points; in.mask = s->mask; in.pose_est = s->pose; in.first_scan = s->first;
+    in.map_models = s->submap; in.n_map_models = s->n_submap; in.map_shared = 0;
+    in.prev_planes = s->prev_planes; in.n_prev_planes = s->n_prev;
+    sloam_batch_out out{};
+    out.results = s->res; out.matches = s->matches; out.tm = s->tm; out.tm_id = s->tm_id;
+    out.planes = s->planes; out.n_planes = s->n_planes; out.range_image = nullptr;
+    rc = sloam_b200_run_keyframes_dev(c, 1, &in, &out);  // :208-235
+    if (rc != SLOAM_OK) return rc;
+    rc = sloam_b200_map_update_dev(c, s->res, s->tm, s->tm_id, s->matches);  // :236, also after a false return
+    if (rc != SLOAM_OK) return rc;
+    // prevGPlanes_ for the next call (unchanged copy when RunSloam bailed out)
+    SB_CUDA(c, cudaMemcpyAsync(s->prev_planes, s->planes, PP * sizeof(sloam_plane), cudaMemcpyDeviceToDevice, st));
+    SB_CUDA(c, cudaMemcpyAsync(s->n_prev, s->n_planes, 4, cudaMemcpyDeviceToDevice, st));
+    return SLOAM_OK;
+  };
+  static const bool no_graph = getenv("SLOAM_B200_NO_GRAPH") != nullptr;
+  if (s->graph && s->graph_epoch != c->epoch) { cudaGraphExecDestroy(s->graph); s->graph = nullptr; }
+  int rc = SLOAM_OK;
+  if (s->graph) {
+    SB_CUDA(c, cudaGraphLaunch(s->graph, st));
+    c->launches += s->graph_launches;
+  } else if (s->steps == 0 || no_graph || s->graph_off || c->prof_on) {
+    rc = device_part();  // eager: first call (lazy initialisation), or graphs disabled
+    if (rc != SLOAM_OK) return rc;
+  } else {
+    const int64_t l0 = c->launches;
+    cudaGraph_t g = nullptr;
+    bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      rc = device_part();
+      ok = cudaStreamEndCapture(st, &g) == cudaSuccess && rc == SLOAM_OK && g != nullptr;
+    }
+    if (ok) ok = cudaGraphInstantiate(&s->graph, g, 0) == cudaSuccess;
+    if (g) cudaGraphDestroy(g);
+    if (ok) {
+      s->graph_epoch = c->epoch;
+      s->graph_launches = c->launches - l0;
+      SB_CUDA(c, cudaGraphLaunch(s->graph, st));
+    } else {  // not capturable in this configuration: stay eager from now on
+      (void)cudaGetLastError();
+      s->graph = nullptr;
+      s->graph_off = true;
+      c->launches = l0;
+      rc = device_part();
+      if (rc != SLOAM_OK) return rc;
+    }
+  }
+  ++s->steps;
   SB_CUDA(c, cudaMemcpyAsync(result, s->res, sizeof(sloam_kf_result), cudaMemcpyDeviceToHost, st));
   if (matches) SB_CUDA(c, cudaMemcpyAsync(matches, s->matches, T * 4, cudaMemcpyDeviceToHost, st));
   if (tm) SB_CUDA(c, cudaMemcpyAsync(tm, s->tm, T * sizeof(sloam_cylinder), cudaMemcpyDeviceToHost, st));
