@@ -195,7 +195,9 @@ void sloam_b200_default_params(sloam_params *p);
 
 /* Replaces the constructors sloam::sloam() (sloam.cpp:6-12), Instance()
  * (trellis.cpp:13) and Segmentation() (inference.cpp:5-19, minus the ONNX
- * session).  max_keyframes = largest K any later call will pass. */
+ * session).  max_keyframes = largest K any later call will pass; at most 65535, and
+ * bits(img_h) + bits(max_trees) + bits(max_keyframes) <= 31 (packed work items), which
+ * allows e.g. 32768 keyframes at 128 scan lines and 1024 trees.  SLOAM_E_INVALID otherwise. */
 int sloam_b200_create(const sloam_params *p, int device, int max_keyframes,
                       sloam_ctx **out);
 void sloam_b200_destroy(sloam_ctx *ctx);

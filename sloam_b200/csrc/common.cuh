@@ -35,6 +35,10 @@ struct DevParams {
   float cluster_sq_cut;   // t = cluster_dist_thresh (trellis.cpp clustering tolerance)
   float centroid_sq_cut;  // t = max_dist_to_centroid
   unsigned magic_w;       // floor(2^32 / img_w) + 1: i / img_w == umulhi(i, magic_w) for i < 2^21
+  // (keyframe, big-cluster slot, row) work items of the vertex kernels in one int32:
+  // row in the low vw_row_bits, slot in the next vw_slot_bits, keyframe above (create checks
+  // that max_keyframes fits)
+  int vw_row_bits, vw_slot_bits;
 };
 
 // hand-over record between the per-cell QR (one CTA per cell) and the per-cell
@@ -218,6 +222,15 @@ __device__ __forceinline__ void st_point(sloam_point *p, const sloam_point &v) {
 // ---- float helpers with the reference's operation order -----------------
 // Eigen Vector3f::norm / squaredNorm: x^2 + (y^2 + z^2)  (Redux.h unroller)
 SLOAM_HD_FN float sqnorm3f(float dx, float dy, float dz) { return dx * dx + (dy * dy + dz * dz); }
+__device__ __forceinline__ int vw_pack(const DevParams *dp, int k, int slot, int row) {
+  return (k << (dp->vw_row_bits + dp->vw_slot_bits)) | (slot << dp->vw_row_bits) | row;
+}
+__device__ __forceinline__ void vw_unpack(const DevParams *dp, int w, int &k, int &slot, int &row) {
+  row = w & ((1 << dp->vw_row_bits) - 1);
+  slot = (w >> dp->vw_row_bits) & ((1 << dp->vw_slot_bits) - 1);
+  k = w >> (dp->vw_row_bits + dp->vw_slot_bits);
+}
+
 // i / W and i % W without an integer division (i < 2^21, W <= 2^11: the error term
 // i * (magic * W - 2^32) stays below 2^32, so the high word is the exact quotient)
 __device__ __forceinline__ int fast_div_w(int i, unsigned magic_w) { return (int)__umulhi((unsigned)i, magic_w); }

@@ -178,6 +178,9 @@ static void derive(DevParams &d) {
   d.cluster_sq_cut = sq_cut(p.cluster_dist_thresh);
   d.centroid_sq_cut = sq_cut(p.max_dist_to_centroid);
   d.magic_w = (unsigned)((1ull << 32) / (unsigned)p.img_w) + 1u;
+  auto bits_for = [](int n) { int b = 1; while ((1 << b) < n) ++b; return b; };  // values 0..n-1
+  d.vw_row_bits = bits_for(p.img_h);
+  d.vw_slot_bits = bits_for(p.max_trees);
 }
 
 static int upload_tables(sloam_ctx *c) {
@@ -257,6 +260,11 @@ int sloam_b200_create(const sloam_params *p, int device, int max_keyframes, sloa
   c->sm_count = prop.multiProcessorCount;
   c->hp.p = *p;
   derive(c->hp);
+  {  // the packed (keyframe, slot, row) work items must fit 31 bits
+    int kb = 1;
+    while ((1 << kb) < max_keyframes) ++kb;
+    if (c->hp.vw_row_bits + c->hp.vw_slot_bits + kb > 31) { delete c; return SLOAM_E_INVALID; }
+  }
   if (cudaSetDevice(device) != cudaSuccess) { delete c; return SLOAM_E_CUDA; }
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return SLOAM_E_CUDA; }
   c->own_stream = true;

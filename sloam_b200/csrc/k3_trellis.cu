@@ -327,7 +327,7 @@ __global__ void cc_plan_kernel(const DevParams *__restrict__ dp, const uint32_t 
       bb[0] = cmin[r]; bb[1] = cmax[r]; bb[2] = row; bb[3] = r1;
       const int nrows = r1 - row + 1;
       const int base = atomicAdd(n_vwork, nrows);
-      for (int q = 0; q < nrows; ++q) vwork[base + q] = (k << 18) | (s << 8) | (row + q);
+      for (int q = 0; q < nrows; ++q) vwork[base + q] = vw_pack(dp, k, s, row + q);
     }
   }
   if (threadIdx.x == 0) n_big[k] = nb;
@@ -542,7 +542,8 @@ vertex_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ 
   const int total = *n_vwork;
   for (int item = blockIdx.x * kVtxWarps + warp; item < total; item += gridDim.x * kVtxWarps) {
     const int w = vwork[item];
-    const int k = w >> 18, slot = (w >> 8) & 0x3FF, row = w & 0xFF;
+    int k, slot, row;
+    vw_unpack(dp, w, k, slot, row);
     const int root = big_roots[(size_t)k * T + slot];
     const int32_t *bb = bbox + ((size_t)k * T + slot) * 4;
     const int c0 = bb[0], c1 = bb[1];
@@ -604,7 +605,8 @@ __global__ void vertex_wide_kernel(const DevParams *__restrict__ dp, const sloam
   const int total = *n_overflow;
   for (int item = blockIdx.x; item < total; item += gridDim.x) {
     const int w = overflow[item];
-    const int k = w >> 18, slot = (w >> 8) & 0x3FF, row = w & 0xFF;
+    int k, slot, row;
+    vw_unpack(dp, w, k, slot, row);
     const int root = big_roots[(size_t)k * T + slot];
     const size_t rbase = (size_t)k * N + (size_t)row * W;
     sloam_vertex *out = slot_vertices + ((size_t)k * T + slot) * H + row;
