@@ -205,7 +205,8 @@ inline int set_err(sloam_ctx *c, int code, const std::string &m) {
     cudaError_t e__ = cudaGetLastError();                                         \
     if (e__ != cudaSuccess)                                                       \
       return sb::set_err(ctx, SLOAM_E_CUDA,                                       \
-                         std::string("kernel launch: ") + cudaGetErrorString(e__)); \
+                         std::string("kernel launch (") + __FILE__ + ":" + std::to_string(__LINE__) + \
+                             "): " + cudaGetErrorString(e__));                    \
   } while (0)
 
 // 16-byte vector access to points (sloam_point is four floats; every point array

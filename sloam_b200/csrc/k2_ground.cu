@@ -589,10 +589,10 @@ int launch_ground_planes(sloam_ctx *c, int K, const sloam_point *ground, const i
   dim3 grid((unsigned)c->hp.B, (unsigned)K);
   const int k1_tiles = (c->hp.N + kSplitTile - 1) / kSplitTile;
   const size_t bin_smem = sizeof(int) * ((size_t)(kBinItems * kBinWarps + 1) * c->hp.B + k1_tiles + 1);
-  static bool bin_attr = false;
-  if (!bin_attr && bin_smem > 48 * 1024) {
-    SB_CUDA(c, cudaFuncSetAttribute(ground_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    bin_attr = true;
+  static size_t bin_set[64] = {};  // per device, only grows (see vertex_wide_kernel)
+  if (bin_smem > 48 * 1024 && bin_smem > bin_set[c->device & 63]) {
+    SB_CUDA(c, cudaFuncSetAttribute(ground_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem));
+    bin_set[c->device & 63] = bin_smem;
   }
   ground_bin_kernel<<<K, kBinThreads, bin_smem, c->stream>>>(c->dp, ground, ground_count, stride, w.ground_cell,
                                                              w.cell_count, strided ? w.tile_count : nullptr,

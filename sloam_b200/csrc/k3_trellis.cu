@@ -837,10 +837,12 @@ int launch_compute_graph(sloam_ctx *c, int K, const sloam_point *tree, sloam_tre
       vertex_points, w.vpool_count, w.overflow_list, w.n_overflow, nullptr, nullptr);
   SB_LAUNCH_CHECK(c);
   const size_t wide_smem = sizeof(float) * 4 * W + sizeof(int) * 3 * W;
-  static bool attr_set = false;
-  if (!attr_set && wide_smem > 48 * 1024) {
+  // opt-in shared memory: the attribute belongs to (function, device) and must only grow -- a
+  // context with a wider image than an earlier one needs more, a narrower one must not lower it
+  static size_t wide_set[64] = {};
+  if (wide_smem > 48 * 1024 && wide_smem > wide_set[c->device & 63]) {
     SB_CUDA(c, cudaFuncSetAttribute(vertex_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem));
-    attr_set = true;
+    wide_set[c->device & 63] = wide_smem;
   }
   vertex_wide_kernel<<<c->sm_count, 256, wide_smem, c->stream>>>(c->dp, tree, w.tree_bits, w.parent, w.big_roots, w.bbox,
                                                                  w.overflow_list, w.n_overflow,

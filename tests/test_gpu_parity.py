@@ -751,6 +751,28 @@ def test_odd_image_size_fused_path(capi, oracle):
     ctx.close()
 
 
+def test_contexts_of_different_image_width_in_one_process(capi, oracle):
+    """A context for a narrow image followed by one for a wide image in the same process:
+    per-function launch attributes (opt-in shared memory of the wide-row vertex kernel) must
+    follow the widest image, in either order (a process-wide "set once" flag did not)."""
+    from sloam_b200 import configs
+    for order in (("vlp-16", "os1-128"), ("os1-128", "vlp-16", "os1-128")):
+        for preset in order:
+            K = 2
+            p, cfg = configs.make(capi, preset)
+            inp, exp = run_sequence(capi, oracle, p, cfg, K, True)
+            T, PP = p.max_trees, p.max_prev_planes
+            ctx = capi.Context(p, K)
+            out = dict(results=np.zeros(K, abi.KF_RESULT), matches=np.zeros((K, T), np.int32),
+                       tm=np.zeros((K, T), abi.CYLINDER), tm_id=np.zeros((K, T), np.int32),
+                       planes=np.zeros((K, PP), abi.PLANE), n_planes=np.zeros(K, np.int32), range_image=None)
+            ctx.run_keyframes_host(K, inp, out)
+            for k in range(K):
+                compare_keyframe(out["results"][k], out["matches"][k], out["tm"][k], out["tm_id"][k],
+                                 out["planes"][k], out["n_planes"][k], exp[k])
+            ctx.close()
+
+
 def test_large_map_association_config5(capi, oracle):
     """configs[4]: 100 000 map cylinders, 2 000 detections per keyframe (split-map path)."""
     rng = np.random.default_rng(55)
