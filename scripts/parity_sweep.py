@@ -12,13 +12,24 @@ import test_gpu_parity as tg
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 only = sys.argv[2] if len(sys.argv) > 2 else None
 cases = [("vlp-16", True, 11), ("vlp-16", True, 12), ("vlp-16", False, 13), ("os1-64", True, 21), ("os1-64", False, 22),
-         ("os1-128", True, 31)]
+         ("os1-128", True, 31), ("os1-64-dense", True, 41), ("vlp-16", True, 51), ("os1-64", True, 52), ("vlp-16", True, 53),
+         ("os1-64", False, 54)]
+# seeds >= 50 also vary the sensor model and the parameters
+VARIANTS = {
+    51: (dict(nan_no_return=0, range_noise=0.03), dict(groundRetainThresh=0.2, featuresPerTree=12)),
+    52: (dict(nan_no_return=0, ground_noise=0.05, max_tilt_deg=4.0), dict(numGroundFeatures=8, groundRetainThresh=0.05)),
+    53: (dict(step_per_keyframe=0.6, guess_sigma_t=0.15), dict(ransac_fixed_hypotheses=256)),
+    54: (dict(azimuth_offset_cols=17.25, ground_slope_deg=2.5), dict(huber_delta=0.05)),
+}
 if only:
     cases = [c for c in cases if c[0] == only]
 total = bad = 0
 for preset, two_step, seed in cases:
-    kk = K if preset != "os1-128" else max(4, K // 8)
-    p, cfg = configs.make(capi, preset, twoStepOptim=int(two_step))
+    kk = K if preset not in ("os1-128", "os1-64-dense") else max(4, K // 8)
+    cfg_kw, p_kw = VARIANTS.get(seed, ({}, {}))
+    p, cfg = configs.make(capi, preset, twoStepOptim=int(two_step), **p_kw)
+    for name, val in cfg_kw.items():
+        setattr(cfg, name, val)
     if preset == "vlp-16" and not two_step:
         p.minGroundModels = 10
     cfg.seed = seed
