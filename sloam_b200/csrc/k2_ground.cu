@@ -197,6 +197,8 @@ ground_bin_kernel(const DevParams *__restrict__ dp, const sloam_point *__restric
 // over that list) redoes them with libstdc++'s std::sort replayed by one thread, because the
 // reference's sort (sloam.cpp:377-380) is not stable (SURVEY B-3) and the order of tied points
 // decides which of them are kept and in which order they enter the plane fit.
+// a cell's CTA is one warp: its barriers are warp barriers
+#define CELL_SYNC() do { if (kGThreads == 32) __syncwarp(); else __syncthreads(); } while (0)
 template <bool REPLAY>
 __global__ void __launch_bounds__(kGThreads, SLOAM_K2_MINCTAS)
 ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ ground,
@@ -249,7 +251,7 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
       }
     }
   }
-  __syncthreads();
+  CELL_SYNC();
   const int off_all = s_misc[0], off_kept = s_misc[1];
   const bool do_sort = n_c > 0 && retainNum < (double)n_c;
   const int r = kept_of(n_c);
@@ -277,7 +279,7 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
     list = s_list;
     for (int i = threadIdx.x; i < n_c; i += kGThreads) s_list[i] = src[i];
   }
-  __syncthreads();
+  CELL_SYNC();
 
   // ---- select the r lowest (z, j) keys ----
   // kept records: in place in shared memory, or in the second member array for oversized
@@ -293,24 +295,24 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
       e.z = __float_as_uint(key_to_float(e.z));
       keep[i] = e;
     }
-    __syncthreads();
+    CELL_SYNC();
     if (threadIdx.x == 0) {
       StdSortT<SelKey, MemberZLess> srt{keep, MemberZLess{}};
       srt.sort_prefix(n_c, r);
     }
-    __syncthreads();
+    CELL_SYNC();
   } else if (do_sort) {
     // 8-bit MSD radix select on z for the r-th smallest (rank r-1)
     uint32_t prefix = 0, pmask = 0;
     int want = r - 1;  // 0-based rank among members matching the prefix
     for (int shift = 24; shift >= 0; shift -= 8) {
       for (int b = threadIdx.x; b < 256; b += kGThreads) s_hist[b] = 0;
-      __syncthreads();
+      CELL_SYNC();
       for (int i = threadIdx.x; i < n_c; i += kGThreads) {
         const uint32_t z = list[i].z;
         if ((z & pmask) == prefix) atomicAdd(&s_hist[(z >> shift) & 0xFF], 1);
       }
-      __syncthreads();
+      CELL_SYNC();
       if (warp == 0) {  // bin that holds rank `want`: 8 bins per lane + a warp scan
         int loc[8], s = 0;
 #pragma unroll
@@ -328,11 +330,11 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
           s_misc[2] = lane * 8 + d; s_misc[3] = want - acc;
         }
       }
-      __syncthreads();
+      CELL_SYNC();
       prefix |= (uint32_t)s_misc[2] << shift;
       pmask |= 0xFFu << shift;
       want = s_misc[3];
-      __syncthreads();
+      CELL_SYNC();
     }
     const uint32_t pivot = prefix;   // z key of the r-th smallest
     const int tie_quota = want + 1;  // members with z == pivot to keep, lowest j first
@@ -343,13 +345,25 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
       SelKey e = {0, 0};
       bool lt = false, eq = false;
       if (i < n_c) { e = list[i]; lt = e.z < pivot; eq = e.z == pivot; }
-      int tot_eq, tot_keep;
-      const int eq_before = ties_seen + block_excl_scan(eq ? 1 : 0, s_warp, &tot_eq);
-      const bool take = lt || (eq && eq_before < tie_quota);
-      const int pos = kept + block_excl_scan(take ? 1 : 0, s_warp, &tot_keep);
+      int tot_eq, tot_keep, eq_before, pos;
+      bool take;
+      if (kGThreads == 32) {  // one warp: ballots instead of shared-memory scans and barriers
+        const unsigned lt_mask = (1u << lane) - 1u;
+        const unsigned be = __ballot_sync(kFull, eq);
+        eq_before = ties_seen + __popc(be & lt_mask);
+        take = lt || (eq && eq_before < tie_quota);
+        const unsigned bt = __ballot_sync(kFull, take);
+        pos = kept + __popc(bt & lt_mask);
+        tot_eq = __popc(be); tot_keep = __popc(bt);
+        __syncwarp();  // every lane has read its list entry before any slot is overwritten
+      } else {
+        eq_before = ties_seen + block_excl_scan(eq ? 1 : 0, s_warp, &tot_eq);
+        take = lt || (eq && eq_before < tie_quota);
+        pos = kept + block_excl_scan(take ? 1 : 0, s_warp, &tot_keep);
+      }
       if (take) keep[pos] = e;  // pos <= i, and every slot < base is already consumed
       kept += tot_keep; ties_seen += tot_eq;
-      __syncthreads();
+      CELL_SYNC();
     }
     // ---- sort the r kept keys: rank sort in place via shared ranks ----
     // (r is a few hundred; O(r^2 / threads))
@@ -371,9 +385,11 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
       tie |= same > 1;  // (keys equal <=> floats equal, -0 / +0 aside)
       tmp[rank] = e;
     }
-    const int any_tie = __syncthreads_or(tie ? 1 : 0);
+    int any_tie;
+    if (kGThreads == 32) { any_tie = __any_sync(kFull, tie); __syncwarp(); }
+    else any_tie = __syncthreads_or(tie ? 1 : 0);
     for (int i = threadIdx.x; i < r; i += kGThreads) keep[i] = tmp[i];
-    __syncthreads();
+    CELL_SYNC();
     if (any_tie && n_c > 16 && tied != nullptr && threadIdx.x == 0) tied[atomicAdd(n_tied, 1)] = (k << 8) | cell;
   }
 
@@ -391,14 +407,14 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
     const sloam_point p = ld_point(gk + keep[i].j);
     P[i] = p.x; P[n + i] = p.y; P[2 * n + i] = p.z;
   }
-  __syncthreads();
+  CELL_SYNC();
   if (threadIdx.x < 3) {  // computeCentroid: float32 sequential sums (utils.h:14-28)
     const float *a = P + threadIdx.x * n;
     float acc = 0.f;
     for (int i = 0; i < n; ++i) acc += a[i];
     s_red[threadIdx.x] = (double)(float)((double)acc / (double)n);
   }
-  __syncthreads();
+  CELL_SYNC();
   const float cxf = (float)s_red[0], cyf = (float)s_red[1], czf = (float)s_red[2];
   // adjoint matrix A^T (n x 3), column-major in Q; entries (double)(float diff) (plane.cpp:106-108)
   double *Q = n <= kQrCap ? s_qr : qscratch + ((size_t)k * stride + off_all) * 3;
@@ -412,16 +428,16 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(kFull, lmax, o));
   if (lane == 0) reinterpret_cast<double *>(s_hist)[warp] = lmax;
-  __syncthreads();
+  CELL_SYNC();
   if (threadIdx.x == 0) {
     double m = 0.0;
     for (int w = 0; w < kGThreads / 32; ++w) m = fmax(m, reinterpret_cast<double *>(s_hist)[w]);
     s_red[3] = (m == 0.0) ? 1.0 : m;
   }
-  __syncthreads();
+  CELL_SYNC();
   const double scale = s_red[3];
   for (int i = threadIdx.x; i < 3 * n; i += kGThreads) Q[i] = Q[i] / scale;
-  __syncthreads();
+  CELL_SYNC();
 
   if (warp != 0) return;  // the tiny QR + Jacobi runs on one warp
   double Wm[9], U[9];
@@ -523,11 +539,12 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
     const int total = *n_tied;
     for (int item = blockIdx.x; item < total; item += gridDim.x) {
       body(tied[item] >> 8, tied[item] & 0xFF);
-      __syncthreads();
+      CELL_SYNC();
     }
   }
 }
 
+#undef CELL_SYNC
 // Steps 2-4 of JacobiSVD on the QR-preconditioned 3x3, plane assembly (plane.cpp:115-127)
 // and the acceptance test (sloam.cpp:401-409): one thread per (keyframe, cell).
 __global__ void plane_finish_kernel(const DevParams *__restrict__ dp, int K, const FitRec *__restrict__ fit,
