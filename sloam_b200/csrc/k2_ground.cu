@@ -212,8 +212,14 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
                     int32_t *__restrict__ tied, int32_t *__restrict__ n_tied) {
   // the replay instance sorts whole cells with one thread: give it room for most cells in
   // shared memory (a global-memory sort is ~10x slower per access)
-  constexpr int kCap = REPLAY ? 2048 : kSelCap;
+  constexpr int kCap = REPLAY ? 2048 : 1;
   __shared__ SelKey s_list[kCap];
+  // the selecting instance keeps only what its passes re-read in shared memory: the z keys of
+  // the cell (4 radix passes) and the r kept records (rank sort); the member records
+  // themselves are streamed from global memory once, by the compaction
+  constexpr int kZCap = REPLAY ? 1 : 2 * kSelCap, kKeepCap = REPLAY ? 1 : 128;
+  __shared__ uint32_t s_z[kZCap];
+  __shared__ SelKey s_keep[kKeepCap];
   __shared__ double s_qr[3 * kQrCap];
   __shared__ float s_pts[3 * kQrCap];
   __shared__ int s_hist[256];
@@ -274,10 +280,13 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
 
   // ---- the members (z key, input index), in input order: contiguous in `members` ----
   SelKey *src = members + (size_t)k * stride + off_all;
-  SelKey *list = src;  // oversized cells are processed in place (L2-resident workspace)
-  if (n_c <= kCap) {
+  SelKey *list = src;
+  const bool zc = !REPLAY && n_c <= kZCap;  // z keys cached in shared memory
+  if (REPLAY && n_c <= kCap) {
     list = s_list;
     for (int i = threadIdx.x; i < n_c; i += kGThreads) s_list[i] = src[i];
+  } else if (zc) {
+    for (int i = threadIdx.x; i < n_c; i += kGThreads) s_z[i] = src[i].z;
   }
   CELL_SYNC();
 
@@ -285,7 +294,10 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
   // kept records: in place in shared memory, or in the second member array for oversized
   // cells (the first one stays intact for a possible replay)
   SelKey *keep = list;
-  if (do_sort && n_c > kCap) keep = members2 + (size_t)k * stride + off_all;
+  if (do_sort) {
+    if (REPLAY) { if (n_c > kCap) keep = members2 + (size_t)k * stride + off_all; }
+    else keep = r <= kKeepCap ? s_keep : members2 + (size_t)k * stride + off_all;
+  }
   if (REPLAY && do_sort) {
     // std::sort(cell, p1.z < p2.z) replayed on the whole cell, then the first r are kept
     // (only the first r positions of the result are needed: sort_prefix; the z field is turned
@@ -309,7 +321,7 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
       for (int b = threadIdx.x; b < 256; b += kGThreads) s_hist[b] = 0;
       CELL_SYNC();
       for (int i = threadIdx.x; i < n_c; i += kGThreads) {
-        const uint32_t z = list[i].z;
+        const uint32_t z = zc ? s_z[i] : list[i].z;
         if ((z & pmask) == prefix) atomicAdd(&s_hist[(z >> shift) & 0xFF], 1);
       }
       CELL_SYNC();
