@@ -440,7 +440,9 @@ __device__ bool build_vertex(const DevParams *dp, VtxSmem &s, unsigned long long
     if (by) { med[1] = __shfl_sync(kFull, ym, __ffs(by) - 1); found |= 2u; }
     if (bz) { med[2] = __shfl_sync(kFull, zm, __ffs(bz) - 1); found |= 4u; }
     __syncwarp();
-    if (m < n) s.order[lz] = (int16_t)m;  // final order when z has no ties (the common case)
+    // final order when z has no ties (the common case); a member with a tied z skips the
+    // store (two of them would hit one slot) -- the tie paths below rewrite the whole order
+    if (m < n && ez == 1) s.order[lz] = (int16_t)m;
   }
   if (found != 7u) {  // ties around a median: stable ranks (value, then index)
     for (int m = lane; m < ((n + 31) & ~31); m += 32) {
