@@ -52,6 +52,7 @@ struct FitRec {
 // Scratch owned by the context, sized for max_keyframes.
 struct Workspace {
   // K1
+  int32_t *zero_begin = nullptr, *zero_end = nullptr;  // bounds of the block zeroed per fused run
   int32_t *pix = nullptr;            // [K][N]
   sloam_point *tree = nullptr;       // [K][N]
   sloam_point *ground = nullptr;     // [K][N]
@@ -172,6 +173,8 @@ struct sloam_ctx {
   int n_lanes = 1;
   sloam_ctx *lane[4] = {};
   cudaEvent_t ev_lane_start = nullptr, ev_lane_done[4] = {};
+  // set by zero_counters(): the launchers named by the bits may skip their own memsets once
+  unsigned zero_valid = 0;  // 1 split kernel, 2 connected components, 4 vertex stage, 8 ground cells
   int epoch = 0;  // bumped by set_params / set_stream: invalidates captured CUDA graphs
   bool prof_on = false;
   int prof_n = 0;

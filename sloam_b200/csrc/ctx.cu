@@ -52,16 +52,26 @@ static void layout(sloam_ctx *c, Bump &b) {
   const size_t K = (size_t)c->max_k, N = (size_t)c->hp.N, B = (size_t)c->hp.B;
   const size_t T = (size_t)p.max_trees, H = (size_t)p.img_h;
   const size_t tiles = (N + kSplitTile - 1) / kSplitTile;
+  // counters and flags that every fused run starts from zero: contiguous, one memset
+  b.take(w.zero_begin, 64);
+  b.take(w.ground_count, K);
+  b.take(w.cell_count, K * kMaxCells);
+  b.take(w.root_bits, K * ((N + 31) / 32));
+  b.take(w.n_tree_words, 4);
+  b.take(w.n_tied_cells, 4);
+  b.take(w.n_big, K);
+  b.take(w.n_roots, K);
+  b.take(w.row_roots, K * H);
+  b.take(w.vpool_count, K);
+  b.take(w.n_overflow, 4);
+  b.take(w.kf_flags, K);
+  b.take(w.zero_end, 64);
   b.take(w.pix, K * N);
   b.take(w.tree, K * N);
   b.take(w.ground, K * N);
-  b.take(w.ground_count, K);
   b.take(w.tree_bits, K * ((N + 31) / 32));
-  b.take(w.root_bits, K * ((N + 31) / 32));
   b.take(w.tree_words, 2 * K * ((N + 31) / 32));
-  b.take(w.n_tree_words, 4);
   b.take(w.ground_cell, K * N);
-  b.take(w.cell_count, K * kMaxCells);
   b.take(w.tile_count, K * tiles);
   b.take(w.range_image, K * N);
   b.take(w.cells, K * B);
@@ -72,7 +82,6 @@ static void layout(sloam_ctx *c, Bump &b) {
   b.take(w.gscratch, K * N);
   b.take(w.gscratch2, K * N);
   b.take(w.tied_cells, K * kMaxCells);
-  b.take(w.n_tied_cells, 4);
   b.take(w.qscratch, K * N * 3);
   b.take(w.pscratch, K * N * 3);
   b.take(w.fit_rec, K * B);
@@ -80,22 +89,16 @@ static void layout(sloam_ctx *c, Bump &b) {
   b.take(w.cc_flags, K * N);
   b.take(w.csize, K * N);
   b.take(w.big_roots, K * T);
-  b.take(w.n_big, K);
-  b.take(w.n_roots, K);
   b.take(w.big_rank, K * T);
   b.take(w.bbox, K * T * 4);
   b.take(w.ccol_min, K * N);
   b.take(w.ccol_max, K * N);
   b.take(w.crow_max, K * N);
   b.take(w.root_rank, K * N);
-  b.take(w.row_roots, K * H);
   b.take(w.slot_vertices, K * T * H);
-  b.take(w.vpool_count, K);
   b.take(w.vwork, K * T * H);
   b.take(w.overflow_list, K * T * H);
   b.take(w.tied_list, K * T * H);
-  b.take(w.n_overflow, 4);
-  b.take(w.kf_flags, K);
   b.take(w.trees, K * T);
   b.take(w.n_trees, K);
   b.take(w.vertices, K * T * (size_t)p.max_tree_vertices);

@@ -405,8 +405,12 @@ int launch_project_split(sloam_ctx *c, int K, bool do_project, bool do_split,
   // as is (ground == ws.ground); a stage entry gets the contiguous cloud by compaction.
   const bool strided_out = ground == c->ws.ground;
   if (do_split) {
-    SB_CUDA(c, cudaMemsetAsync(ground_count, 0, sizeof(int32_t) * (size_t)K, c->stream));
-    SB_CUDA(c, cudaMemsetAsync(c->ws.cell_count, 0, sizeof(int32_t) * (size_t)K * kMaxCells, c->stream));
+    if ((c->zero_valid & 1u) && ground_count == c->ws.ground_count) {
+      c->zero_valid &= ~1u;  // zeroed with the rest of the counters (pipeline.cu)
+    } else {
+      SB_CUDA(c, cudaMemsetAsync(ground_count, 0, sizeof(int32_t) * (size_t)K, c->stream));
+      SB_CUDA(c, cudaMemsetAsync(c->ws.cell_count, 0, sizeof(int32_t) * (size_t)K * kMaxCells, c->stream));
+    }
   }
   // persistent CTAs: exactly the resident ones, each walks tiles blockIdx.x, + gridDim.x, ...
   static int occ[3] = {0, 0, 0};

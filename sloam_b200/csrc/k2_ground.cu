@@ -627,7 +627,8 @@ int launch_ground_planes(sloam_ctx *c, int K, const sloam_point *ground, const i
                                                              w.cell_count, strided ? w.tile_count : nullptr,
                                                              reinterpret_cast<SelKey *>(w.gscratch));
   SB_LAUNCH_CHECK(c);
-  SB_CUDA(c, cudaMemsetAsync(w.n_tied_cells, 0, sizeof(int32_t), c->stream));
+  if (c->zero_valid & 8u) c->zero_valid &= ~8u;
+  else SB_CUDA(c, cudaMemsetAsync(w.n_tied_cells, 0, sizeof(int32_t), c->stream));
   ground_cells_kernel<false><<<grid, kGThreads, 0, c->stream>>>(
       c->dp, ground, ground_count, stride, reinterpret_cast<SelKey *>(w.gscratch), w.cell_count, pose_est,
       w.qscratch, w.pscratch, w.fit_rec, cells, cell_features, kept_points, kept_offsets,

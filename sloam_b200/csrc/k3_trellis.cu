@@ -778,18 +778,24 @@ static int run_cc(sloam_ctx *c, int K, const sloam_point *tree, bool bits_ready)
   Workspace &w = c->ws;
   const long long total = (long long)K * c->hp.N;
   const int H = c->hp.p.img_h;
-  SB_CUDA(c, cudaMemsetAsync(w.row_roots, 0, sizeof(int32_t) * (size_t)K * H, c->stream));
-  SB_CUDA(c, cudaMemsetAsync(w.n_roots, 0, sizeof(int32_t) * K, c->stream));
-  SB_CUDA(c, cudaMemsetAsync(w.n_big, 0, sizeof(int32_t) * K, c->stream));
-  SB_CUDA(c, cudaMemsetAsync(w.kf_flags, 0, sizeof(int32_t) * K, c->stream));
+  const bool pre_zeroed = (c->zero_valid & 2u) != 0;  // zeroed with the rest of the counters (pipeline.cu)
+  c->zero_valid &= ~2u;
+  if (!pre_zeroed) {
+    SB_CUDA(c, cudaMemsetAsync(w.row_roots, 0, sizeof(int32_t) * (size_t)K * H, c->stream));
+    SB_CUDA(c, cudaMemsetAsync(w.n_roots, 0, sizeof(int32_t) * K, c->stream));
+    SB_CUDA(c, cudaMemsetAsync(w.n_big, 0, sizeof(int32_t) * K, c->stream));
+    SB_CUDA(c, cudaMemsetAsync(w.kf_flags, 0, sizeof(int32_t) * K, c->stream));
+  }
   const dim3 blocks((unsigned)((c->hp.N + 255) / 256), (unsigned)K);
   if (!bits_ready) {  // caller-supplied cloud: derive the bits from the points
     tree_bits_kernel<<<blocks, 256, 0, c->stream>>>(c->dp, tree, w.tree_bits);
     SB_LAUNCH_CHECK(c);
   }
   const unsigned wgrid = (unsigned)std::min<long long>((total / 32 / 32 / 8) + 1, (long long)c->sm_count * 8);
-  SB_CUDA(c, cudaMemsetAsync(w.n_tree_words, 0, sizeof(int32_t), c->stream));
-  SB_CUDA(c, cudaMemsetAsync(w.root_bits, 0, sizeof(uint32_t) * (size_t)K * ((c->hp.N + 31) / 32), c->stream));
+  if (!pre_zeroed) {
+    SB_CUDA(c, cudaMemsetAsync(w.n_tree_words, 0, sizeof(int32_t), c->stream));
+    SB_CUDA(c, cudaMemsetAsync(w.root_bits, 0, sizeof(uint32_t) * (size_t)K * ((c->hp.N + 31) / 32), c->stream));
+  }
   tree_words_kernel<<<wgrid, 256, 0, c->stream>>>(c->dp, K, w.tree_bits, reinterpret_cast<int2 *>(w.tree_words), w.n_tree_words);
   SB_LAUNCH_CHECK(c);
   const int2 *wl = reinterpret_cast<const int2 *>(w.tree_words);
@@ -814,8 +820,12 @@ int launch_compute_graph(sloam_ctx *c, int K, const sloam_point *tree, sloam_tre
   const int T = p.max_trees, H = p.img_h, W = p.img_w;
   int rc = run_cc(c, K, tree, bits_ready);
   if (rc != SLOAM_OK) return rc;
-  SB_CUDA(c, cudaMemsetAsync(w.n_overflow, 0, sizeof(int32_t) * 4, c->stream));
-  SB_CUDA(c, cudaMemsetAsync(w.vpool_count, 0, sizeof(int32_t) * K, c->stream));
+  if (c->zero_valid & 4u) {
+    c->zero_valid &= ~4u;
+  } else {
+    SB_CUDA(c, cudaMemsetAsync(w.n_overflow, 0, sizeof(int32_t) * 4, c->stream));
+    SB_CUDA(c, cudaMemsetAsync(w.vpool_count, 0, sizeof(int32_t) * K, c->stream));
+  }
   cc_plan_kernel<<<K, 256, sizeof(int32_t) * (2 * T + H + 1), c->stream>>>(
       c->dp, w.root_bits, w.parent, w.ccol_min, w.ccol_max, w.crow_max, w.row_roots, w.big_roots, w.n_big,
       w.big_rank, w.bbox, w.vwork, w.n_overflow + 1);

@@ -86,9 +86,20 @@ static int run_lanes(sloam_ctx *c, int K, const sloam_batch_in *in, const sloam_
   return SLOAM_OK;
 }
 
+static int run_dev_body(sloam_ctx *c, int K, const sloam_batch_in *in, const sloam_batch_out *out);
+
 static int run_dev(sloam_ctx *c, int K, const sloam_batch_in *in, const sloam_batch_out *out, bool allow_split) {
   if (allow_split && c->n_lanes > 1 && K >= 64 * c->n_lanes) return run_lanes(c, K, in, out);
+  const int rc = run_dev_body(c, K, in, out);
+  c->zero_valid = 0;  // the pre-zeroed counters belong to this run only (also after an error)
+  return rc;
+}
+
+static int run_dev_body(sloam_ctx *c, int K, const sloam_batch_in *in, const sloam_batch_out *out) {
   Workspace &w = c->ws;
+  // every counter / flag array of the run in one memset (they are contiguous in the arena)
+  SB_CUDA(c, cudaMemsetAsync(w.zero_begin, 0, (size_t)((char *)w.zero_end - (char *)w.zero_begin), c->stream));
+  c->zero_valid = 1u | 2u | 4u | 8u;
   float *range = out->range_image;  // optional output
   // sparse tree cloud: only the tree-labelled points and the bit mask are written (the NaN
   // points of the dense cloud are ~90 % of its bytes and nothing downstream needs them)
