@@ -23,7 +23,10 @@
 
 namespace sb {
 
-constexpr int kVtxWarps = 8;
+#ifndef SLOAM_VTX_WARPS
+#define SLOAM_VTX_WARPS 8
+#endif
+constexpr int kVtxWarps = SLOAM_VTX_WARPS;
 constexpr int kVtxCap = 128;   // members per (cluster,row) handled by the warp path
 constexpr int kInvalid = -1;
 

@@ -162,7 +162,10 @@ __device__ __forceinline__ unsigned long long inlier_mask(const CylSmem &s, int 
   return ((unsigned long long)hi << 32) | lo;
 }
 
-__global__ void __launch_bounds__(kCylWarps * 32)
+#ifndef SLOAM_CYL_MIN
+#define SLOAM_CYL_MIN 8  // 64 registers: 141 -> 123 us per 1000 VLP-16 keyframes (6: 131 us)
+#endif
+__global__ void __launch_bounds__(kCylWarps * 32, SLOAM_CYL_MIN)
 cylinder_kernel(const DevParams *__restrict__ dp, const sloam_tree *__restrict__ trees,
                 const int32_t *__restrict__ n_trees, const sloam_vertex *__restrict__ vertices,
                 const sloam_point *__restrict__ vpoints, int vstride, int pstride,

@@ -19,7 +19,10 @@
 
 namespace sb {
 
-constexpr int kLmThreads = 64;  // 2 problems (warps) per CTA
+#ifndef SLOAM_LM_THREADS
+#define SLOAM_LM_THREADS 64
+#endif
+constexpr int kLmThreads = SLOAM_LM_THREADS;  // 2 problems (warps) per CTA
 
 // ---------------------------------------------------------------- matching --
 __global__ void __launch_bounds__(128)
