@@ -527,8 +527,11 @@ __device__ bool build_vertex(const DevParams *dp, VtxSmem &s, unsigned long long
   return false;
 }
 
+#ifndef SLOAM_VTX_MIN
+#define SLOAM_VTX_MIN 5
+#endif
 template <bool REPLAY>
-__global__ void __launch_bounds__(kVtxWarps * 32, 5)
+__global__ void __launch_bounds__(kVtxWarps * 32, SLOAM_VTX_MIN)
 vertex_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ tree,
               const uint32_t *__restrict__ bits, const int32_t *__restrict__ parent, const int32_t *__restrict__ big_roots,
               const int32_t *__restrict__ bbox, const int32_t *__restrict__ vwork,
