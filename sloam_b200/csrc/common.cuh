@@ -97,7 +97,7 @@ struct Workspace {
   int32_t *vwork = nullptr;          // [K*max_trees*H] (k, slot, row) work items, packed
   int32_t *tied_list = nullptr;      // [K][T*H] work items with exact z ties among > 16 points
   int32_t *overflow_list = nullptr;  // [K*max_trees*H] work items needing the wide path
-  int32_t *n_overflow = nullptr;     // [4] counters: [0] ticket/overflow, [1] n_vwork
+  int32_t *n_overflow = nullptr;     // [4] counters: [0] rows for the wide vertex kernel, [1] vertex work items, [2] tied items
   int32_t *kf_flags = nullptr;       // [K] capacity-exceeded flags
   sloam_tree *trees = nullptr;       // [K][max_trees]
   int32_t *n_trees = nullptr;        // [K]

@@ -193,7 +193,7 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
   }
   __syncthreads();
 
-  // ---- phase A: load the tile (8 float4 per thread stay in registers) and project.
+  // ---- phase A: the tile from shared memory (kRounds float4 per thread stay in registers) and project.
   // The pixel index is an integer derived from atan2f/asinf; the bit-exact evaluation
   // (proj_math.h, fp64) is ~230 DP instructions, so it only runs for the ~1.5 % of points
   // whose fast fp32 estimate lies within a proven error margin of a pixel boundary.
