@@ -28,7 +28,7 @@
 namespace sb {
 
 constexpr int kThreads = 256;
-constexpr int kRounds = kSplitTile / kThreads;  // 8
+constexpr int kRounds = kSplitTile / kThreads;  // points per thread and tile (1024 / 256 = 4)
 
 // Cheap atan2 / asin for the ESTIMATE only (the decision is made exact by the margins
 // below plus the fp64 fallback).  Degree-7 polynomials in t^2 fitted on Chebyshev nodes,
