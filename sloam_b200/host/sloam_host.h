@@ -665,3 +665,140 @@ class Segmentation {  // inference.h:55-110
   Mask labels_;
 };
 }  // namespace seg
+
+// ------------------------------------------------------------------ MapManager
+// sloam/include/core/mapManager.h, sloam/src/core/mapManager.cpp:8-71 with the landmark map
+// (models, hit counts, kNN index) resident on the device.  It lives in the context of the
+// Runtime it is given; one map per context.
+class MapManager {
+ public:
+  explicit MapManager(std::shared_ptr<sloam_b200::Runtime> rt, int capacity = 1 << 16) : rt_(std::move(rt)) {
+    rt_->check(sloam_b200_map_init(rt_->ctx(), capacity));
+    capacity_ = capacity;
+  }
+  ~MapManager() { sloam_b200_map_free(rt_->ctx()); }
+  MapManager(const MapManager &) = delete;
+  MapManager &operator=(const MapManager &) = delete;
+
+  // mapManager.cpp:41-71: kNN(100) around (pose.x, pose.y, 1) + the "last 200 landmarks" filter
+  void getSubmap(const SE3 &pose, std::vector<Cylinder> &submap) {
+    sloam_ctx *c = rt_->ctx();
+    const int M = rt_->params().max_map_models;
+    sloam_b200::DevBuf d_pose(c, sizeof(sloam_pose)), d_sub(c, sizeof(sloam_cylinder) * (size_t)M), d_n(c, 4);
+    d_pose.upload(&pose.abi(), sizeof(sloam_pose));
+    rt_->check(sloam_b200_map_get_submap_dev(c, d_pose.as<sloam_pose>(), d_sub.as<sloam_cylinder>(), d_n.as<int32_t>()));
+    int32_t n = 0;
+    d_n.download(&n, 4);
+    std::vector<sloam_cylinder> flat((size_t)n);
+    if (n > 0) d_sub.download(flat.data(), sizeof(sloam_cylinder) * (size_t)n);
+    for (const sloam_cylinder &m : flat) submap.push_back(from_abi(m));
+  }
+  // mapManager.cpp:8-28: matched observations overwrite their landmark and count a hit, the
+  // others are appended
+  void updateMap(std::vector<Cylinder> &obs_tms, const std::vector<int> &cyl_matches) {
+    sloam_ctx *c = rt_->ctx();
+    const size_t T = (size_t)rt_->params().max_trees, n = obs_tms.size();
+    if (n > T || cyl_matches.size() != n) throw std::runtime_error("MapManager::updateMap: bad sizes");
+    std::vector<sloam_cylinder> tm(T);
+    std::vector<int32_t> ids(T, 0), matches(T, -1);
+    for (size_t i = 0; i < n; ++i) {
+      for (int a = 0; a < 3; ++a) { tm[i].root[a] = obs_tms[i].model.root[a]; tm[i].ray[a] = obs_tms[i].model.ray[a]; }
+      tm[i].radius = obs_tms[i].model.radius;
+      ids[i] = (int32_t)obs_tms[i].id;
+      matches[i] = cyl_matches[i];
+    }
+    sloam_kf_result r{};
+    r.status = SLOAM_KF_OK; r.success = 1; r.n_landmarks = (int32_t)n;
+    sloam_b200::DevBuf d_r(c, sizeof r), d_tm(c, sizeof(sloam_cylinder) * T), d_id(c, 4 * T), d_m(c, 4 * T);
+    d_r.upload(&r, sizeof r); d_tm.upload(tm.data(), sizeof(sloam_cylinder) * T);
+    d_id.upload(ids.data(), 4 * T); d_m.upload(matches.data(), 4 * T);
+    rt_->check(sloam_b200_map_update_dev(c, d_r.as<sloam_kf_result>(), d_tm.as<sloam_cylinder>(), d_id.as<int32_t>(),
+                                         d_m.as<int32_t>()));
+    rt_->check(sloam_b200_sync(c));
+  }
+  // mapManager.cpp:30-39: landmarks seen more than twice
+  std::vector<Cylinder> getMap() {
+    std::vector<sloam_cylinder> models((size_t)capacity_);
+    std::vector<int32_t> hits((size_t)capacity_);
+    const int n = sloam_b200_map_dump_host(rt_->ctx(), models.data(), hits.data(), capacity_);
+    std::vector<Cylinder> map;
+    for (int i = 0; i < n && i < capacity_; ++i)
+      if (hits[i] > 2) map.push_back(from_abi(models[i]));
+    return map;
+  }
+  int size() { return sloam_b200_map_dump_host(rt_->ctx(), nullptr, nullptr, 0); }
+
+  static Cylinder from_abi(const sloam_cylinder &m) {
+    Cylinder cyl;
+    for (int a = 0; a < 3; ++a) { cyl.model.root[a] = m.root[a]; cyl.model.ray[a] = m.ray[a]; }
+    cyl.model.radius = m.radius;
+    cyl.isValid = true;
+    return cyl;
+  }
+
+ private:
+  std::shared_ptr<sloam_b200::Runtime> rt_;
+  int capacity_ = 0;
+};
+
+// ------------------------------------------------------------------ SLOAMNode::run
+// The per-keyframe call sequence of sloamNode.cpp:186-282 without ROS: getSubmap -> segmentation
+// mask (supplied by the caller) -> maskCloud x 2 -> computeGraph -> RunSloam -> updateMap, as ONE
+// device call (sloam_b200_sequence_step_host).  firstScan_, prevGPlanes_ and the map stay on the
+// device between calls.
+class SLOAMNodeCore {
+ public:
+  SLOAMNodeCore(const FeatureModelParams &fm, const sloam_b200::HostConfig &hc, int map_capacity = 1 << 16)
+      : rt_(new sloam_b200::Runtime(fm, hc)) {
+    rt_->check(sloam_b200_map_init(rt_->ctx(), map_capacity));
+    const size_t T = (size_t)rt_->params().max_trees;
+    matches_.assign(T, -1); tm_.resize(T); tm_id_.assign(T, 0);
+  }
+  ~SLOAMNodeCore() { sloam_b200_map_free(rt_->ctx()); }
+  SLOAMNodeCore(const SLOAMNodeCore &) = delete;
+  SLOAMNodeCore &operator=(const SLOAMNodeCore &) = delete;
+
+  // bool SLOAMNode::run(const SE3 initialGuess, const SE3 prevKeyPose, CloudT::Ptr cloud, stamp, SE3 &outPose);
+  // rMask is what segmentator_->run(cloud, rMask) returns (sloamNode.cpp:208-209).
+  bool run(const SE3 &initialGuess, const SE3 &prevKeyPose, const CloudT::Ptr &cloud, const Mask &rMask, SE3 &outPose) {
+    const sloam_params &p = rt_->params();
+    const size_t N = (size_t)p.img_h * p.img_w;
+    if (cloud->points.size() != N || (size_t)rMask.rows * rMask.cols != N)
+      throw std::runtime_error("SLOAMNodeCore::run: cloud and mask must hold H*W entries");
+    const SE3 poseEstimate = compose(prevKeyPose, initialGuess);  // :192
+    rt_->check(sloam_b200_sequence_step_host(rt_->ctx(), reinterpret_cast<const sloam_point *>(cloud->points.data()),
+                                             rMask.data.data(), &poseEstimate.abi(), &last_, matches_.data(), tm_.data(),
+                                             tm_id_.data()));
+    if (last_.success) outPose = SE3(last_.T_Map_Curr);  // :238-244
+    return last_.success != 0;
+  }
+  const sloam_kf_result &lastResult() const { return last_; }
+  // landmarks of the last keyframe in the map frame and their map matches (sloamOut.tm / .matches)
+  std::vector<Cylinder> lastLandmarks() const {
+    std::vector<Cylinder> out;
+    const int n = last_.status == SLOAM_KF_OK || last_.status == SLOAM_KF_NOT_CONVERGED ? last_.n_landmarks : 0;
+    for (int i = 0; i < n; ++i) { Cylinder c = MapManager::from_abi(tm_[(size_t)i]); c.id = (size_t)tm_id_[(size_t)i]; out.push_back(c); }
+    return out;
+  }
+  std::vector<int> lastMatches() const { return std::vector<int>(matches_.begin(), matches_.begin() + std::max(0, (int)lastLandmarks().size())); }
+  int mapSize() { return sloam_b200_map_dump_host(rt_->ctx(), nullptr, nullptr, 0); }
+
+  // Sophus: prevKeyPose * initialGuess
+  static SE3 compose(const SE3 &a, const SE3 &b) {
+    const double *qa = a.unit_quaternion(), *qb = b.unit_quaternion();  // x y z w
+    SE3 r;
+    r.setQuaternion(qa[3] * qb[3] - qa[0] * qb[0] - qa[1] * qb[1] - qa[2] * qb[2],
+                    qa[3] * qb[0] + qa[0] * qb[3] + qa[1] * qb[2] - qa[2] * qb[1],
+                    qa[3] * qb[1] - qa[0] * qb[2] + qa[1] * qb[3] + qa[2] * qb[0],
+                    qa[3] * qb[2] + qa[0] * qb[1] - qa[1] * qb[0] + qa[2] * qb[3]);
+    r.translation() = a * b.translation();
+    return r;
+  }
+
+ private:
+  std::unique_ptr<sloam_b200::Runtime> rt_;
+  sloam_kf_result last_{};
+  std::vector<int32_t> matches_, tm_id_;
+  std::vector<sloam_cylinder> tm_;
+};
+

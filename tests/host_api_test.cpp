@@ -172,6 +172,68 @@ static void core_tests(const Fixture &t0, const Fixture &t1, bool two_step) {
   }
 }
 
+// MapManager (mapManager.cpp) through the mirror.
+static void map_manager_tests() {
+  sloam_b200::HostConfig hc;
+  hc.img_h = 16; hc.img_w = 64;
+  std::shared_ptr<sloam_b200::Runtime> rt(new sloam_b200::Runtime(FeatureModelParams(), hc));
+  MapManager mm(rt, 1024);
+  EXPECT_TRUE(mm.size() == 0);
+  std::vector<Cylinder> obs(5);
+  for (size_t i = 0; i < obs.size(); ++i) {
+    obs[i].model.root[0] = 2.0 * (double)i; obs[i].model.root[1] = 1.0; obs[i].model.root[2] = 1.0;
+    obs[i].model.ray[2] = 1.0; obs[i].model.radius = 0.1 + 0.01 * (double)i; obs[i].isValid = true;
+  }
+  mm.updateMap(obs, std::vector<int>(5, -1));  // all new (:21-27)
+  EXPECT_TRUE(mm.size() == 5);
+  EXPECT_TRUE(mm.getMap().empty());            // hits == 1, getMap wants > 2 (:33)
+  for (int rep = 0; rep < 2; ++rep) {
+    std::vector<Cylinder> sub;
+    mm.getSubmap(SE3(), sub);
+    EXPECT_TRUE(sub.size() == 5);
+    // match every observation to the submap entry with the same root
+    std::vector<int> matches(5, -1);
+    for (size_t i = 0; i < obs.size(); ++i)
+      for (size_t j = 0; j < sub.size(); ++j)
+        if (std::fabs(sub[j].model.root[0] - obs[i].model.root[0]) < 1e-9) matches[i] = (int)j;
+    obs[0].model.radius += 0.05;
+    mm.updateMap(obs, matches);
+    EXPECT_TRUE(mm.size() == 5);
+  }
+  const std::vector<Cylinder> map = mm.getMap();
+  EXPECT_TRUE(map.size() == 5);                // 1 + 2 hits
+  if (map.size() == 5) EXPECT_NEAR(map[0].model.radius, 0.2, 1e-6);  // matched landmarks are overwritten (:14-16)
+}
+
+// SLOAMNode::run on a synthetic sequence; the lines are compared with the oracle
+// by tests/test_host_api.py.
+static void node_sequence(int n_keyframes) {
+  sloam_b200::HostConfig hc;
+  hc.img_h = 64; hc.img_w = 1024;
+  sloam_synth_config cfg;
+  sloam_synth_default_config(&cfg, hc.img_h, hc.img_w, 20);
+  SLOAMNodeCore node(FeatureModelParams(), hc, 4096);
+  const size_t N = (size_t)hc.img_h * hc.img_w;
+  CloudT::Ptr cloud(new CloudT());
+  cloud->width = hc.img_w; cloud->height = hc.img_h;
+  cloud->points.resize(N);
+  Mask mask(hc.img_h, hc.img_w);
+  for (int k = 0; k < n_keyframes; ++k) {
+    sloam_pose gt, guess;
+    sloam_synth_pose(&cfg, k, &gt, &guess);
+    EXPECT_TRUE(sloam_synth_generate_host(&cfg, k, 1, reinterpret_cast<sloam_point *>(cloud->points.data()),
+                                          mask.data.data()) == 0);
+    SE3 out;
+    const bool ok = node.run(SE3(guess), SE3(), cloud, mask, out);
+    const sloam_kf_result &r = node.lastResult();
+    EXPECT_TRUE(ok == (r.success != 0));
+    if (k == 0) EXPECT_TRUE(ok);
+    std::printf("SEQ %d %d %d %d %d %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", k, (int)r.status, (int)ok, (int)r.n_landmarks,
+                node.mapSize(), out.translation()[0], out.translation()[1], out.translation()[2],
+                out.unit_quaternion()[0], out.unit_quaternion()[1], out.unit_quaternion()[2], out.unit_quaternion()[3]);
+  }
+}
+
 int main(int argc, char **argv) {
   if (argc < 2) { std::printf("usage: %s fixtures.bin\n", argv[0]); return 2; }
   std::ifstream f(argv[1], std::ios::binary);
@@ -194,6 +256,8 @@ int main(int argc, char **argv) {
       inst.computeGraph(cloud, cloud, lm);
       EXPECT_TRUE(lm.empty());
     }
+    map_manager_tests();
+    node_sequence(argc > 2 ? std::atoi(argv[2]) : 6);
   } catch (const std::exception &e) {
     std::printf("EXCEPTION %s\n", e.what());
     return 3;

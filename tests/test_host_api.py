@@ -41,13 +41,40 @@ def test_host_mirror_compiles_against_the_c_abi(tmp_path):
 
 
 @pytest.mark.gpu
-def test_reference_gtests_through_the_cpp_mirror(tmp_path):
+def test_reference_gtests_through_the_cpp_mirror(tmp_path, oracle):
     exe = build(str(tmp_path))
     blob = os.path.join(str(tmp_path), "fixtures.bin")
     with open(blob, "wb") as f:
         write_fixture(f, "t0")
         write_fixture(f, "t1")
-    r = subprocess.run([exe, blob], capture_output=True, text=True, timeout=600)
+    K = 6
+    r = subprocess.run([exe, blob, str(K)], capture_output=True, text=True, timeout=600)
     print(r.stdout, r.stderr)
     assert r.returncode == 0, r.stdout + r.stderr
     assert " 0 failed" in r.stdout
+    # SLOAMNodeCore::run (8(f)-2) over a synthetic sequence against the oracle's
+    # getSubmap -> RunSloam -> updateMap loop: status, landmark count and map size exact,
+    # pose within north_star's 1e-5 m / 1e-5 rad
+    seq = [l.split()[1:] for l in r.stdout.splitlines() if l.startswith("SEQ ")]
+    assert len(seq) == K
+    from sloam_b200 import capi, configs
+    p, cfg = configs.make(capi, "os1-64")
+    pts, mask = capi.synth_generate_host(cfg, 0, K)
+    omap = oracle.OracleMap()
+    first, prev = True, np.zeros(0, abi.PLANE)
+    for k in range(K):
+        pose = np.array([capi.synth_pose(cfg, k)[1]])
+        sub, _ = omap.get_submap(pose, p.max_map_models)
+        e = oracle.run_keyframe(p, pts[k], mask[k], pose, first, sub, prev)
+        ran = e.result["status"] in (abi.KF_OK, abi.KF_NOT_CONVERGED)
+        n = int(e.result["n_landmarks"]) if ran else 0
+        omap.update(e.tm[:n], e.tm_id[:n], e.matches[:n])
+        prev, first = e.planes[:e.n_planes].copy(), False
+        g = seq[k]
+        assert [int(v) for v in g[:5]] == [k, int(e.result["status"]), int(e.result["success"]),
+                                           int(e.result["n_landmarks"]), omap.size()], (k, g)
+        if e.result["success"]:
+            t, q = np.array(g[5:8], float), np.array(g[8:12], float)
+            assert np.max(np.abs(t - e.result["T_Map_Curr"]["t"])) <= 1e-5
+            qe = e.result["T_Map_Curr"]["q"]     # small-angle form: arccos(dot) loses half the digits near 1
+            assert 2.0 * min(np.linalg.norm(q - qe), np.linalg.norm(q + qe)) <= 1e-5
