@@ -1,6 +1,6 @@
 """Randomised parity sweep (GPU box): fused path vs the CPU oracle on many keyframes of several
 presets / seeds, full comparison of every result field (tests/test_gpu_parity.compare_keyframe).
-usage: python scripts/parity_sweep.py [keyframes_per_case]"""
+usage: [SLOAM_SWEEP_SEED_OFFSET=n] python scripts/parity_sweep.py [keyframes_per_case]"""
 import os, sys, traceback
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -32,7 +32,7 @@ for preset, two_step, seed in cases:
         setattr(cfg, name, val)
     if preset == "vlp-16" and not two_step:
         p.minGroundModels = 10
-    cfg.seed = seed
+    cfg.seed = seed + 1000 * int(os.environ.get("SLOAM_SWEEP_SEED_OFFSET", "0"))  # new scenes, same case list
     cfg.n_trees = cfg.n_trees + seed % 7
     inp, exp = tg.run_sequence(capi, orc, p, cfg, kk, two_step)
     T, PP = p.max_trees, p.max_prev_planes
