@@ -223,6 +223,19 @@ __device__ __forceinline__ void st_point(sloam_point *p, const sloam_point &v) {
   *reinterpret_cast<float4 *>(p) = make_float4(v.x, v.y, v.z, v.intensity);
 }
 
+// Comparison as 1.0f / 0.0f (PTX set -> one FSET.BF): see the counting loop of k3_trellis.cu.
+// NaN compares false, like `<` and `==`.
+__device__ __forceinline__ float flt(float a, float b) {
+  float d;
+  asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
+}
+__device__ __forceinline__ float feq(float a, float b) {
+  float d;
+  asm("set.eq.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
+}
+
 // ---- float helpers with the reference's operation order -----------------
 // Eigen Vector3f::norm / squaredNorm: x^2 + (y^2 + z^2)  (Redux.h unroller)
 SLOAM_HD_FN float sqnorm3f(float dx, float dy, float dz) { return dx * dx + (dy * dy + dz * dz); }

@@ -418,17 +418,22 @@ __device__ bool build_vertex(const DevParams *dp, VtxSmem &s, unsigned long long
     float xm = 0.f, ym = 0.f, zm = 0.f;
     if (m < n) {
       xm = s.x[m]; ym = s.y[m]; zm = s.z[m];
+      float fx = 0.f, fy = 0.f, fz = 0.f, fe = 0.f;
       for (int j4 = 0; j4 < (n4 >> 2); ++j4) {
         const float4 xv = X4[j4], yv = Y4[j4], zv = Z4[j4];
         if (REPLAY) {
           ex += (xv.x == xm) + (xv.y == xm) + (xv.z == xm) + (xv.w == xm);
           ey += (yv.x == ym) + (yv.y == ym) + (yv.z == ym) + (yv.w == ym);
         }
-        lx += (xv.x < xm) + (xv.y < xm) + (xv.z < xm) + (xv.w < xm);
-        ly += (yv.x < ym) + (yv.y < ym) + (yv.z < ym) + (yv.w < ym);
-        lz += (zv.x < zm) + (zv.y < zm) + (zv.z < zm) + (zv.w < zm);
-        ez += (zv.x == zm) + (zv.y == zm) + (zv.z == zm) + (zv.w == zm);
+        // counts accumulate as floats (exact: n <= kVtxCap): one FSET (1.0f / 0.0f) on the ALU
+        // pipe + one FADD on the FMA pipe per comparison, instead of compare + add + predicated
+        // move (two ALU + one FMA) for an integer count
+        fx += (flt(xv.x, xm) + flt(xv.y, xm)) + (flt(xv.z, xm) + flt(xv.w, xm));
+        fy += (flt(yv.x, ym) + flt(yv.y, ym)) + (flt(yv.z, ym) + flt(yv.w, ym));
+        fz += (flt(zv.x, zm) + flt(zv.y, zm)) + (flt(zv.z, zm) + flt(zv.w, zm));
+        fe += (feq(zv.x, zm) + feq(zv.y, zm)) + (feq(zv.z, zm) + feq(zv.w, zm));
       }
+      lx = (int)fx; ly = (int)fy; lz = (int)fz; ez = (int)fe;
     }
     any_ztie |= __ballot_sync(kFull, m < n && ez > 1);
     if (REPLAY) {
