@@ -212,7 +212,7 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
                     int32_t *__restrict__ tied, int32_t *__restrict__ n_tied) {
   // the replay instance sorts whole cells with one thread: give it room for most cells in
   // shared memory (a global-memory sort is ~10x slower per access)
-  constexpr int kCap = REPLAY ? 2048 : 1;
+  constexpr int kCap = REPLAY ? 5120 : 1;
   __shared__ SelKey s_list[kCap];
   // the selecting instance keeps only what its passes re-read in shared memory: the z keys of
   // the cell (4 radix passes) and the r kept records (rank sort); the member records
