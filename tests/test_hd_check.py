@@ -120,3 +120,28 @@ def test_empty_problem_is_convergence(hd):
     x0 = x.copy()
     t, n_it, _ = _solve(hd, 0, x, pb, use_t=False, use_p=False)
     assert (t, n_it) == (0, 0) and np.array_equal(x, x0)
+
+
+@pytest.mark.parametrize("seed", [0, 3, 8])
+def test_two_step_state_machines_match_the_oracle(hd, oracle, seed):
+    """TwoStepOptimizePose (sloam.cpp:48-152): XYYaw over the tree residuals and ZRollPitch over
+    the plane residuals, both started at the pose estimate, composed like pose_pack_kernel."""
+    from scipy.spatial.transform import Rotation as R
+    pb = sm.make_problem(seed)
+    p = oracle.default_params()
+    out, it, term = oracle.optimize_pose(p, 1, pb["guess"], pb["tree_feat"], pb["tree_obj"],
+                                         pb["plane_feat"], pb["plane_obj"])
+    g = pb["guess"][0]
+    x0 = np.array([*g["t"], *R.from_quat(g["q"]).as_rotvec(), 0.0])
+    x1, x2 = x0.copy(), x0.copy()
+    t1, n1, c1 = _solve(hd, 1, x1, pb)
+    t2, n2, c2 = _solve(hd, 2, x2, pb)
+    assert (t1, n1) == (int(term[0]), int(it[0]))
+    assert (t2, n2) == (int(term[1]), int(it[1]))
+    assert c1[1] < c1[0] and c2[1] < c2[0]
+    # XYYaw moves only x, y, yaw; ZRollPitch only z, roll, pitch (SubsetParameterization)
+    assert np.array_equal(x1[[2, 3, 4]], x0[[2, 3, 4]]) and np.array_equal(x2[[0, 1, 5]], x0[[0, 1, 5]])
+    t = np.array([x1[0], x1[1], x2[2]])
+    q = R.from_rotvec([x2[3], x2[4], x1[5]]).as_quat()
+    assert np.allclose(t, out["t"], atol=1e-5)
+    assert 2.0 * min(np.linalg.norm(q - out["q"]), np.linalg.norm(q + out["q"])) < 1e-5
