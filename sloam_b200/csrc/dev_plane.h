@@ -7,7 +7,9 @@
 
 #include <float.h>
 
-#include "common.cuh"
+#include <math.h>
+
+#include "dev_geom.h"
 
 namespace sb {
 

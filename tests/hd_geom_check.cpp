@@ -1,11 +1,13 @@
 // hd_geom_check.cpp -- host build of the bit-exact per-point arithmetic the kernels fall back
-// to (sloam_b200/csrc/proj_math.h: spherical projection, polar ground cell), so that it can be
-// compared with the oracle without a GPU (tests/test_hd_geom.py).  Test infrastructure: the
+// to (sloam_b200/csrc/proj_math.h: spherical projection, polar ground cell) and of the ground
+// plane acceptance test (sloam_b200/csrc/dev_plane.h), so that they can be compared with the
+// oracle without a GPU (tests/test_hd_geom.py).  Test infrastructure: the
 // product runs this code only inside project_split_kernel / ground_tag_kernel on the device.
 //   g++ -O2 -ffp-contract=off -shared -fPIC tests/hd_geom_check.cpp -o hd_geom_check.so
 #include <cmath>
 
 #include "../include/sloam_b200.h"
+#include "../sloam_b200/csrc/dev_plane.h"
 #include "../sloam_b200/csrc/proj_math.h"
 
 using namespace sb;
@@ -33,5 +35,9 @@ void hd_ground_cells(const sloam_params *p, const sloam_point *pts, int n, int32
   g.inv_radial_step_f = (float)(1.0 / g.radial_step);
   g.inv_theta_step_f = (float)(1.0 / g.theta_step);
   for (int i = 0; i < n; ++i) cell[i] = ground_cell_of(g, pts[i].x, pts[i].y);
+}
+// angleCheck && heightCheck (sloam.cpp:401-409) as plane_finish_kernel evaluates it
+int hd_plane_accept(const sloam_pose *pose, const double *plane, const double *centroid, double tol) {
+  return plane_accept(*pose, plane, centroid, tol) ? 1 : 0;
 }
 }

@@ -85,3 +85,37 @@ def test_ground_cells_match_the_oracle(hg, oracle, RB, TB, dmin, dmax):
         assert np.array_equal(hist, cells["n_cell"]), lo  # bit-exact (north_star: indices)
         total += hist
     assert total.sum() < n and total.min() > 0
+
+
+def test_plane_acceptance_matches_the_oracle(hg, oracle):
+    """The acceptance test (FromTwoVectors -> eulerAngles(0,1,2) -> tolerance, and the height
+    check) decides which cells become planes; tilted grounds around the 0.1 rad tolerance and
+    poses with large yaw exercise both outcomes and both branches of the Euler extraction."""
+    from scipy.spatial.transform import Rotation as R
+    rng = np.random.default_rng(5)
+    p = oracle.default_params(minGroundLidarDist=1.0, numGroundFeatures=5)
+    n_valid = n_acc = 0
+    for trial in range(40):
+        tilt = np.radians(rng.uniform(0.0, 11.0))
+        az = rng.uniform(-np.pi, np.pi)
+        nrm = np.array([np.sin(tilt) * np.cos(az), np.sin(tilt) * np.sin(az), np.cos(tilt)])
+        h = rng.uniform(0.8, 2.5) * (1 if trial % 7 else -1)      # every 7th ground is ABOVE the sensor
+        r = rng.uniform(1.5, 24.0, 6000)
+        th = rng.uniform(-np.pi, np.pi, 6000)
+        x, y = r * np.cos(th), r * np.sin(th)
+        z = (-h - nrm[0] * x - nrm[1] * y) / nrm[2] + rng.normal(0, 0.02, 6000)
+        pts = _points(np.stack([x, y, z], 1).astype(np.float32))
+        pose = oracle.identity_pose()
+        pose["q"][0] = R.from_euler("zyx", [rng.uniform(-np.pi, np.pi), rng.normal(0, 0.03), rng.normal(0, 0.03)]).as_quat()
+        pose["t"][0] = rng.normal(0, 5.0, 3)
+        cells, _, _, _ = oracle.ground_planes(p, pts, pose)
+        for c in cells:
+            if not c["is_valid"]:
+                continue
+            plane = np.ascontiguousarray(c["model"]["plane"], np.float64)
+            cen = np.ascontiguousarray(c["model"]["centroid"], np.float64)
+            got = hg.hd_plane_accept(abi.ptr(pose), abi.ptr(plane), abi.ptr(cen), C.c_double(p.ground_angle_tol))
+            assert got == int(c["accepted"]), (trial, plane, cen)
+            n_valid += 1
+            n_acc += got
+    assert n_valid > 1000 and 0.2 * n_valid < n_acc < 0.8 * n_valid   # both outcomes are well represented
