@@ -46,3 +46,27 @@ def test_models_of_the_first_scan_are_the_scene(oracle, preset, min_landmarks):
     assert np.abs(planes["plane"][:, 2]).min() > 0.99
     cen = planes["centroid"]
     assert np.all(cen[:, 2] < gt["t"][2])                # heightCheck (sloam.cpp:404)
+
+
+def test_plane_fit_is_the_total_least_squares_plane(oracle):
+    """Plane::computeModel (plane.cpp:96-128) through the restated Eigen JacobiSVD against
+    numpy's LAPACK SVD: same normal up to sign, plane through the float32 centroid."""
+    rng = np.random.default_rng(3)
+    for trial in range(50):
+        n = int(rng.integers(5, 400))
+        nrm = rng.normal(size=3)
+        nrm /= np.linalg.norm(nrm)
+        basis = np.linalg.svd(nrm[None, :])[2][1:]                       # two in-plane directions
+        xyz = (rng.uniform(-10, 10, (n, 2)) @ basis + rng.normal(0, 0.03, (n, 1)) * nrm + rng.normal(0, 5, 3)).astype(np.float32)
+        pts = np.zeros(n, abi.POINT)
+        pts["x"], pts["y"], pts["z"] = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+        fit = oracle.plane_fit(pts, 5)
+        assert fit["is_valid"]
+        got = np.array(fit["model"]["plane"][:3])
+        cen = xyz.astype(np.float64).mean(0)
+        want = np.linalg.svd((xyz.astype(np.float64) - cen).T)[0][:, 2]
+        assert abs(abs(float(got @ want)) - 1.0) < 1e-9, trial
+        assert abs(np.linalg.norm(got) - 1.0) < 1e-12
+        assert np.allclose(fit["model"]["centroid"], cen, atol=1e-4)
+        # plane[3] = -n . centroid (plane.cpp:124-126)
+        assert abs(fit["model"]["plane"][3] + float(got @ np.array(fit["model"]["centroid"]))) < 1e-9
