@@ -3,17 +3,26 @@
 
 One step = one pass of the whole hot path (projection/split -> ground cells + plane fits
 -> tree clustering + vertices -> cylinder models -> association -> LM pose -> projection
--> association) over one batch of synthetic keyframes.  Workload at N=1: BASELINE.json
-configs[1] (synthetic VLP-16 sequence, 1000 keyframes, 50-tree submap).
+-> association) over one batch of synthetic keyframes.  Default workload: the one
+BASELINE.json's metric is quoted on, synthetic OS1-64 64x1024 forest scans (configs[0]'s
+scene: 20 trees + ground plane), 512 keyframes per step and GPU so that the inputs (570 MB)
+are far larger than the 126 MB L2.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload vlp-16|os1-64|os1-128|os1-64-dense] [--keyframes B]
+                    [--workload os1-64|vlp-16|os1-64-dense|os1-128|assoc-100k] [--keyframes B]
+
+    os1-64        BASELINE metric workload (default)
+    vlp-16        configs[1]: VLP-16 sequence, 1000 keyframes per step
+    os1-64-dense  configs[2]: 300 trees, 4096 RANSAC hypotheses per tree (fixed-count mode)
+    os1-128       configs[3]: OS1-128 2048 columns (the multi-GPU sequence; here per-GPU batches)
+    assoc-100k    configs[4]: association only, 100k map cylinders x 2k detections per keyframe
 
 Under torchrun (N > 1) every rank processes its own B keyframes (weak scaling, no data-path
-collective); the per-keyframe result records are all-gathered over NCCL inside the timed
-region; time is the max over ranks of CUDA-event time.
-`--impl reference` times the CPU oracle (the restated reference path, oracle/) on all host
-cores -- the reference itself cannot be compiled in this image.
+collective); the per-keyframe result records are gathered over NCCL inside the timed region;
+time is the max over ranks of CUDA-event time.
+`--impl reference` times the CPU oracle (the restated reference path, oracle/) with all host
+cores on the SAME keyframes per step -- the reference itself cannot be compiled in this image
+(DESIGN.md section 3).
 """
 import argparse
 import json
@@ -29,7 +38,19 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-METRIC = "keyframes/sec (synthetic forest, whole per-keyframe hot path)"
+# BASELINE.json "metric", verbatim, for the workload it names
+METRIC_OS1_64 = "keyframes/sec (OS1-64 synthetic forest) at 1/2/4/8 B200; kernel HBM GB/s vs peak"
+WORKLOADS = {
+    # name: (preset in sloam_b200/configs.py, default keyframes per step and GPU, metric, BASELINE config)
+    "os1-64": ("os1-64", 512, METRIC_OS1_64, "metric workload: configs[0]'s OS1-64 64x1024 scene (20 trees + ground), batched"),
+    "vlp-16": ("vlp-16", 1000, "keyframes/sec (VLP-16 synthetic forest)", "configs[1]: VLP-16 sequence, 1000 keyframes, 50-tree scene"),
+    "os1-64-dense": ("os1-64-dense", 64, "keyframes/sec (OS1-64 dense synthetic forest, 4096 RANSAC hypotheses/tree)",
+                     "configs[2]: OS1-64 dense forest, 300 trees, 4096 hypotheses per tree"),
+    "os1-128": ("os1-128", 128, "keyframes/sec (OS1-128 2048-column synthetic forest)", "configs[3]: OS1-128 2048-col sequence (per-GPU batch)"),
+    "assoc-100k": (None, 8, "keyframes/sec (data association only: 100k map cylinders, 2k detections/keyframe)",
+                   "configs[4]: 100k cylinder landmarks, 2k detections per keyframe"),
+}
+FP64_PEAK_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # B200: 64 FP64 FMA lanes per SM and clock
 
 
 def load_peaks():
@@ -72,31 +93,50 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons}
 
 
-def k1_traffic(B, workload):
-    """DRAM bytes of one split-kernel launch from the committed `ncu --set full` capture
-    (profiles/k1_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per keyframe of
-    this workload), scaled to the batch; None when no capture is committed."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "k1_traffic.json")
+def committed_traffic(kernel, B, workload):
+    """DRAM bytes of one launch of `kernel` from the committed `ncu --set full` capture
+    (profiles/kernel_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per keyframe of a
+    workload), scaled to the batch; None when no capture of this workload is committed."""
+    path = os.path.join(ROOT, "profiles", "kernel_traffic.json")
     try:
         with open(path) as f:
             rec = json.load(f)
-        return float(rec["dram_bytes_per_keyframe"]) * B if rec.get("workload") == workload else None
-    except (OSError, KeyError, ValueError):
+        per_kf = rec.get(workload, {}).get(kernel)
+        return float(per_kf) * B if per_kf is not None else None
+    except (OSError, ValueError):
         return None
 
 
-def make_inputs(capi, abi, ctx, p, cfg, B, k0, device):
-    """Device-resident inputs of keyframes [k0, k0+B): generated on the GPU; prevGPlanes_ come
-    from an untimed first-scan pass over the same keyframes (planes of keyframe k-1)."""
-    import torch
-    N, M, PP = p.img_h * p.img_w, p.max_map_models, p.max_prev_planes
-    pts, mask = ctx.synth_generate_dev(cfg, k0, B)
+def workload_config(args, p, n_scene):
+    """The `config` object: identical for both arms (the driver compares them)."""
+    N = p.img_h * p.img_w
+    B = args.keyframes
+    return {"workload": args.workload, "baseline_config": WORKLOADS[args.workload][3],
+            "img_h": p.img_h, "img_w": p.img_w, "keyframes_per_step_per_gpu": B,
+            "submap_cylinders": int(n_scene), "two_step": bool(p.twoStepOptim),
+            "ransac_fixed_hypotheses": int(p.ransac_fixed_hypotheses),
+            "l2": f"inputs {B * N * 17 / 1e6:.0f} MB per step > 126 MB L2, no flush needed"
+                  if B * N * 17 > 2 * 126e6 else "inputs smaller than L2 (short run)"}
+
+
+def host_state(capi, abi, p, cfg, k0, B):
+    """Per-keyframe state inputs that do not need the GPU: pose guesses and the submap."""
+    M = p.max_map_models
     scene = capi.synth_scene(cfg)
     assert len(scene) <= M
     pose = np.array([capi.synth_pose(cfg, k0 + k)[1] for k in range(B)])
     maps = np.zeros((B, M), abi.CYLINDER)
     maps[:, :len(scene)] = scene
     nmap = np.full(B, len(scene), np.int32)
+    return scene, pose, maps, nmap
+
+
+def make_inputs(capi, abi, ctx, p, cfg, B, k0, device):
+    """Device-resident inputs of keyframes [k0, k0+B): generated on the GPU; prevGPlanes_ come
+    from an untimed first-scan pass over the same keyframes (planes of keyframe k-1)."""
+    PP = p.max_prev_planes
+    pts, mask = ctx.synth_generate_dev(cfg, k0, B)
+    scene, pose, maps, nmap = host_state(capi, abi, p, cfg, k0, B)
     inp = dict(points=pts, mask=mask, pose_est=capi.to_dev(pose, device),
                first_scan=capi.to_dev(np.ones(B, np.uint8), device),
                map_models=capi.to_dev(maps, device), n_map_models=capi.to_dev(nmap, device),
@@ -117,73 +157,204 @@ def make_inputs(capi, abi, ctx, p, cfg, B, k0, device):
     inp["first_scan"] = capi.to_dev(first, device)
     host = dict(pose_est=pose, first_scan=first, map_models=maps, n_map_models=nmap, prev_planes=prev,
                 n_prev_planes=nprev)
-    return inp, out, host
+    return inp, out, host, len(scene)
+
+
+def run_threads(fn, bounds):
+    """fn(lo, hi) on one thread per slice (the oracle releases the GIL inside ctypes calls)."""
+    errors = []
+
+    def guarded(lo, hi):
+        try:
+            fn(int(lo), int(hi))
+        except Exception as e:  # a failed thread must not look like a fast one
+            errors.append(repr(e))
+    th = [threading.Thread(target=guarded, args=(bounds[i], bounds[i + 1])) for i in range(len(bounds) - 1)
+          if bounds[i + 1] > bounds[i]]
+    t0 = time.perf_counter()
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    if errors:
+        raise SystemExit(f"oracle thread failed: {errors[:1]}")
+    return time.perf_counter() - t0
 
 
 def cpu_reference_arm(args, p, cfg, capi, abi):
-    """--impl reference: the CPU restatement of the reference path on all host cores."""
+    """--impl reference: the CPU restatement of the reference path on all host cores, on the
+    same B keyframes per step as the GPU arm."""
+    import ctypes as C
     import orc
     cores = os.cpu_count() or 1
-    sample = min(args.keyframes, 32 * cores)
-    N, M, PP = p.img_h * p.img_w, p.max_map_models, p.max_prev_planes
-    pts, mask = capi.synth_generate_host(cfg, 0, sample)
-    scene = capi.synth_scene(cfg)
-    pose = np.array([capi.synth_pose(cfg, k)[1] for k in range(sample)])
-    maps = np.zeros((sample, M), abi.CYLINDER); maps[:, :len(scene)] = scene
-    nmap = np.full(sample, len(scene), np.int32)
-    prev = np.zeros((sample, PP), abi.PLANE); nprev = np.zeros(sample, np.int32)
-    first = np.ones(sample, np.uint8)
-    res = np.zeros(sample, abi.KF_RESULT)
-    import ctypes as C
+    B = args.keyframes
+    M, PP = p.max_map_models, p.max_prev_planes
+    pts, mask = capi.synth_generate_host(cfg, 0, B)
+    scene, pose, maps, nmap = host_state(capi, abi, p, cfg, 0, B)
+    prev = np.zeros((B, PP), abi.PLANE)
+    nprev = np.zeros(B, np.int32)
+    res = np.zeros(B, abi.KF_RESULT)
+    bounds = np.linspace(0, B, cores + 1).astype(int)
 
-    errors = []
+    # prevGPlanes_: planes of the previous keyframe from a first-scan pass (untimed, threaded)
+    planes_of = np.zeros((B, PP), abi.PLANE)
+    nplanes_of = np.zeros(B, np.int32)
 
-    def run_slice(lo, hi, first_arr):
-        lo, hi = int(lo), int(hi)
-        try:
-            _run_slice(lo, hi, first_arr)
-        except Exception as e:  # a failed thread must not look like a fast one
-            errors.append(repr(e))
+    def first_pass(lo, hi):
+        for k in range(lo, hi):
+            o = orc.run_keyframe(p, pts[k], mask[k], pose[k:k + 1], True, maps[k, :0], prev[k, :0])
+            planes_of[k] = o.planes
+            nplanes_of[k] = o.n_planes
+    run_threads(first_pass, bounds)
+    prev[1:], nprev[1:] = planes_of[:-1], nplanes_of[:-1]
+    first = np.zeros(B, np.uint8)
+    first[0] = 1
 
-    def _run_slice(lo, hi, first_arr):
+    def run_slice(lo, hi):
         orc.lib().orc_time_keyframes(C.byref(p), 0, hi - lo, abi.ptr(pts[lo:hi]), abi.ptr(mask[lo:hi]),
-                                     abi.ptr(pose[lo:hi]), abi.ptr(first_arr[lo:hi]), abi.ptr(maps[lo:hi]),
+                                     abi.ptr(pose[lo:hi]), abi.ptr(first[lo:hi]), abi.ptr(maps[lo:hi]),
                                      abi.ptr(nmap[lo:hi]), M, abi.ptr(prev[lo:hi]), abi.ptr(nprev[lo:hi]), PP,
                                      abi.ptr(res[lo:hi]))
-    # prevGPlanes_: planes of the previous keyframe from a first-scan pass (untimed)
-    for k in range(sample):
-        o = orc.run_keyframe(p, pts[k], mask[k], pose[k:k + 1], True, maps[k, :0], prev[k, :0])
-        if k + 1 < sample:
-            prev[k + 1] = o.planes; nprev[k + 1] = o.n_planes
-    first = np.zeros(sample, np.uint8); first[0] = 1
-    bounds = np.linspace(0, sample, cores + 1).astype(int)
-
-    def step():
-        th = [threading.Thread(target=run_slice, args=(bounds[i], bounds[i + 1], first)) for i in range(cores)
-              if bounds[i + 1] > bounds[i]]
-        t0 = time.perf_counter()
-        for t in th:
-            t.start()
-        for t in th:
-            t.join()
-        return time.perf_counter() - t0
     for _ in range(args.warmup):
-        step()
-    times = [step() for _ in range(args.steps)]
-    if errors or int((res["n_trees"] > 0).sum()) == 0:
-        raise SystemExit(f"reference arm failed: {errors[:1]} (keyframes with trees: {int((res['n_trees'] > 0).sum())})")
+        run_threads(run_slice, bounds)
+    times = [run_threads(run_slice, bounds) for _ in range(args.steps)]
+    if int((res["n_trees"] > 0).sum()) == 0:
+        raise SystemExit("reference arm failed: no keyframe produced trees")
     total = sum(times)
-    value = sample * args.steps / total
-    line = {"metric": METRIC, "value": value, "unit": "keyframes/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": args.workload, "keyframes_per_step": int(sample),
-                       "note": "CPU oracle (restated reference path); the reference cannot be compiled here"},
+    value = B * args.steps / total
+    line = {"metric": WORKLOADS[args.workload][2], "value": value, "unit": "keyframes/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64",
+            "data": "synthetic", "impl": "reference",
+            "config": workload_config(args, p, len(scene)),
+            "note": "CPU oracle (restated reference path, oracle/); the reference cannot be compiled here",
             "cpu_baseline": {"value": value, "unit": "keyframes/s", "cores": cores, "kind": "port",
-                             "sample": f"{sample} keyframes of {args.workload} per step, {cores} threads"},
+                             "sample": f"all {B} keyframes of the step, {cores} threads"},
             "e2e": {"value": value, "unit": "keyframes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ per-kernel byte model
+def kernel_model(name, c):
+    """Algorithmic bytes of one launch of a kernel group from the batch
+    counts c = {BN pixels, T tree-labelled points, G ground points, Gc binned ground points,
+    V vertex points, cells, words}; -> (bound, bytes or None, formula)."""
+    BN, T, G = c["BN"], c["T"], c["G"]
+    m = {
+        "project_split_kernel": ("hbm", 25 * BN + BN // 8 + 16 * T + 17 * G,
+                                 "16N pts + 1N mask + 4N pix + 4N range + N/8 tree bits + 16 T + 17 G"),
+        "range_finalize_kernel": ("hbm", 8 * BN, "4N read + 4N write of the range image"),
+        "ground_bin_kernel": ("hbm", 13 * G, "1 G tags + 4 G z + 8 G member records"),
+        "ground_cells_kernel<0>": ("latency", 8 * G + 16 * (G // 20), "8 G member records + 16 B per retained point"),
+        "tree_words_kernel": ("hbm", BN // 8, "N/8 tree bits"),
+        "cc_init_kernel": ("latency", 20 * T, "16 T tree points + 4 T parents"),
+        "cc_flatten_kernel": ("latency", 8 * T, "4 T parents read + written"),
+        "cc_rows_kernel": ("hbm", 16 * T + 3 * BN // 8, "16 T tree points + 3 N/8 bit planes"),
+        "cc_label_kernel": ("latency", 3 * BN // 8, "3 N/8 bit planes"),
+        "vertex_kernel<0>": ("latency", 20 * T + 16 * c.get("V", T), "16 T points + 4 T parents + 16 V vertex points"),
+        "vertex_kernel": ("latency", 16 * T + 16 * c.get("V", T), "16 T points + 16 V vertex points"),
+    }
+    for k, v in m.items():
+        if name.startswith(k):
+            return v
+    return ("latency", None, "kilobyte working set per keyframe: not an HBM kernel")
+
+
+def bench_assoc(args, capi, abi):
+    """configs[4]: association only (a11-a13).  FP64-ALU bound: report DP throughput."""
+    import ctypes as C
+    import torch
+    import orc
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    device = f"cuda:{local_rank}"
+    torch.cuda.set_device(local_rank)
+    M, D, K = 100000, 2000, args.keyframes
+    rng = np.random.default_rng(20260005)
+    mp = np.zeros(M, abi.CYLINDER)
+    mp["root"][:, :2] = rng.uniform(-1000, 1000, (M, 2))
+    mp["root"][:, 2] = rng.normal(0, 0.3, M)
+    tilt = rng.normal(0, 0.04, (M, 2))
+    mp["ray"] = np.stack([tilt[:, 0], tilt[:, 1], np.ones(M)], 1)
+    mp["ray"] /= np.linalg.norm(mp["ray"], axis=1, keepdims=True)
+    mp["radius"] = rng.uniform(0.1, 0.28, M)
+    det = np.zeros((K, D), abi.CYLINDER)
+    for k in range(K):
+        sel = rng.choice(M, D, replace=False)
+        det[k] = mp[sel]
+        det[k]["root"] += rng.normal(0, 0.2, (D, 3))
+        far = rng.random(D) < 0.1  # 10 % unmatched
+        det[k]["root"][far, :2] += 500.0
+    p = capi.default_params(max_trees=D, max_map_models=M)
+    ctx = capi.Context(p, K, device=local_rank)
+    d_det, d_map = capi.to_dev(det, device), capi.to_dev(mp, device)
+    d_nd, d_nm = capi.to_dev(np.full(K, D, np.int32), device), capi.to_dev(np.array([M], np.int32), device)
+
+    def step():
+        return ctx.associate(d_det, d_nd, D, None, d_map, d_nm, M, True, K)
+    with torch.cuda.stream(ctx.stream):
+        for _ in range(max(args.warmup, 3)):
+            bi, bd = step()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        l0 = ctx.launches()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(ctx.stream)
+        for _ in range(args.steps):
+            bi, bd = step()
+        ev1.record(ctx.stream)
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        launches = ctx.launches() - l0
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+        # e2e: host detections in, host indices out (the map stays resident: it is the semantic map)
+        h_det = torch.from_numpy(det.reshape(-1).view(np.uint8)).pin_memory()
+        h_idx = torch.empty(K * D * 4, dtype=torch.uint8).pin_memory()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e2e_steps = max(2, min(args.steps, 5))
+        for _ in range(e2e_steps):
+            d_det.copy_(h_det, non_blocking=True)
+            bi, bd = step()
+            h_idx.copy_(bi, non_blocking=True)
+            torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+    gi = capi.to_host(bi, np.int32, (K, D))
+    # CPU baseline: the oracle on a bounded sample of detections of keyframe 0
+    S = 64
+    t0 = time.perf_counter()
+    ci, cd = orc.associate(det[0, :S], None, mp)
+    cpu_s = time.perf_counter() - t0
+    agree = int((ci == gi[0, :S]).sum())
+    pairs = float(K) * D * M
+    flop = pairs * 48.0  # per pair: 3 x (3 sub + 3 mul + 2 add + sqrt) + 2 add + div  (cylinder.cpp:175-194)
+    peak, peak_src = load_peaks()
+    sec = ms * 1e-3 / args.steps
+    bytes_alg = 56.0 * (K * D + M) + 12.0 * K * D
+    line = {"metric": WORKLOADS[args.workload][2], "value": K / sec, "unit": "keyframes/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "baseline_config": WORKLOADS[args.workload][3], "map_cylinders": M,
+                       "detections_per_keyframe": D, "keyframes_per_step_per_gpu": K,
+                       "l2": "map 5.6 MB is L2-resident by design (SURVEY 8d); compute-bound"},
+            "clocks": sampler.summary(),
+            "e2e": {"value": K * e2e_steps / e2e_s, "unit": "keyframes/s", "h2d_bytes_per_step": int(h_det.numel()),
+                    "d2h_bytes_per_step": int(h_idx.numel())},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "assoc_kernel", "achieved": bytes_alg / sec / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": bytes_alg / sec / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "note": "FP64-ALU bound, not HBM (56 (T + M) bytes in): see fp64"},
+            "fp64": {"pair_distances_per_step": pairs, "flop_per_pair": 48, "achieved_tflops": flop / sec / 1e12,
+                     "peak_tflops": FP64_PEAK_TFLOPS, "frac": flop / sec / 1e12 / FP64_PEAK_TFLOPS,
+                     "note": "3 DSQRT per pair are counted as 1 flop each but cost ~10 issue slots"},
+            "cpu_baseline": {"value": (S / D) / cpu_s, "unit": "keyframes/s", "cores": 1, "kind": "port",
+                             "sample": f"{S} of the {D} detections of keyframe 0 against the 100k map, oracle single thread",
+                             "agree_with_gpu": f"{agree}/{S} association indices"}}
+    if rank == 0:
+        print(json.dumps(line))
 
 
 def main():
@@ -192,12 +363,15 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="vlp-16")
-    ap.add_argument("--keyframes", type=int, default=1000, help="keyframes per step per GPU")
-    ap.add_argument("--cpu-sample", type=int, default=512)
+    ap.add_argument("--workload", default="os1-64", choices=sorted(WORKLOADS))
+    ap.add_argument("--keyframes", type=int, default=0, help="keyframes per step per GPU (0 = the workload's default)")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU time budget of the single-thread oracle baseline")
     ap.add_argument("--lanes", type=int, default=2, help="concurrent sub-batches of a fused run (1..4)")
+    ap.add_argument("--no-kernel-profile", action="store_true", help="no per-kernel event pairs in the timed steps")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.keyframes <= 0:
+        args.keyframes = WORKLOADS[args.workload][1]
 
     # NCCL prints its version banner to stdout at VERSION level: keep stdout to the one JSON line
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
@@ -207,7 +381,13 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     from sloam_b200 import abi, capi, configs
-    p, cfg = configs.make(capi, args.workload, max_trees=128, max_map_models=64)
+    if args.workload == "assoc-100k":
+        if args.impl == "reference":
+            raise SystemExit("assoc-100k: the CPU oracle is timed inside the default arm (cpu_baseline)")
+        if rank == 0:
+            bench_assoc(args, capi, abi)
+        return
+    p, cfg = configs.make(capi, WORKLOADS[args.workload][0], max_trees=128, max_map_models=64)
     if args.workload == "os1-64-dense":
         p.max_trees, p.max_map_models = 512, 512
 
@@ -228,7 +408,7 @@ def main():
     ctx = capi.Context(p, B, device=local_rank)
     N, T, M, PP = p.img_h * p.img_w, p.max_trees, p.max_map_models, p.max_prev_planes
     with torch.cuda.stream(ctx.stream):
-        inp, out, host = make_inputs(capi, abi, ctx, p, cfg, B, rank * B, device)
+        inp, out, host, n_scene = make_inputs(capi, abi, ctx, p, cfg, B, rank * B, device)
     ctx.sync()
     gather_buf = None
     if world > 1:
@@ -257,7 +437,7 @@ def main():
         return float(ms.item())
 
     with torch.cuda.stream(ctx.stream):
-        # label statistics of the batch (for the algorithmic bytes of the split kernel): one
+        # label statistics of the batch (for the algorithmic bytes of the kernels): one
         # untimed un-split run, pixel indices from the intermediates
         ctx.set_lanes(1)
         step()
@@ -267,6 +447,9 @@ def main():
         mk_h = capi.to_host(inp["mask"], np.uint8, (B, N))
         lab = np.take_along_axis(mk_h, pix, axis=1)
         n_tree_pts, n_ground_pts = int((lab == 255).sum()), int((lab == 1).sum())
+        trees_h = capi.read_dev(it.trees, B * T * abi.TREE.itemsize, device).view(abi.TREE).reshape(B, T)
+        ntr_h = capi.read_dev(it.n_trees, B * 4, device).view(np.int32)
+        n_vertex_pts = int(sum(int(trees_h[k, :ntr_h[k]]["n_points"].sum()) for k in range(B)))
         del pix, lab
         ctx.set_lanes(args.lanes)
         for _ in range(args.warmup):
@@ -275,21 +458,14 @@ def main():
         sampler = ClockSampler(local_rank)
         sampler.start()
         l0 = ctx.launches()
-        ctx.profile_enable(True)  # CUDA events around the split kernel of every fused run
+        if not args.no_kernel_profile:
+            ctx.profile_enable(True)  # CUDA event pairs around every kernel group of the fused runs
         ms = timed(step, args.steps)
-        k1_total_ms, k1_n = ctx.profile_read()
+        kernels = [] if args.no_kernel_profile else ctx.profile_read_kernels()
         ctx.profile_enable(False)
         launches = ctx.launches() - l0
         sampler.stop_flag = True
         sampler.join(timeout=2)
-
-        # ---- roofline kernel: the fused project/split pass (K1), timed INSIDE the steps above
-        # by the library's own event pairs on the launching stream (sloam_b200_profile_*).
-        # Algorithmic bytes per launch: every point is read once (16 B +
-        # 1 B mask), its pixel index (4 B) and range-image entry (4 B) are written, plus 16 B per
-        # tree-labelled point, 1 bit per pixel of tree mask, 17 B per ground point (point + cell).
-        k1_ms = k1_total_ms / max(k1_n, 1)
-        k1_bytes = float(B * N * (16 + 1 + 4 + 4) + 16 * n_tree_pts + B * N // 8 + 17 * n_ground_pts)
 
         # ---- end to end through the host-buffer C-ABI entry (pinned host memory) ----
         def pin(a):
@@ -324,47 +500,84 @@ def main():
     res = capi.to_host(out["results"], abi.KF_RESULT, (B,))
     peak, peak_src = load_peaks()
     value = world * B * args.steps / (ms * 1e-3)
+    step_ms = ms / args.steps
+
+    # ---- per-kernel table: event-pair time inside the timed steps, algorithmic bytes, fraction
+    counts = {"BN": B * N, "T": n_tree_pts, "G": n_ground_pts, "V": n_vertex_pts}
+    table, ksum = [], 0.0
+    for name, tot_ms, runs in kernels:
+        k_ms = tot_ms / max(runs, 1)
+        bound, nbytes, formula = kernel_model(name, counts)
+        ksum += k_ms
+        row = {"kernel": name, "ms": k_ms, "bound": bound, "algorithmic_bytes": nbytes, "bytes_model": formula,
+               "GBps": (nbytes / (k_ms * 1e-3) / 1e9) if nbytes and k_ms > 0 else None}
+        row["frac"] = row["GBps"] / peak if row["GBps"] is not None else None
+        table.append(row)
+    for row in table:
+        row["share_of_kernel_sum"] = row["ms"] / ksum if ksum > 0 else None
+    # whole path, unfused = 61 N + 32 G per keyframe; ours = what the kernels above move by design
+    survey_bytes = 61.0 * B * N + 32.0 * n_ground_pts
+    own_bytes = float(sum(r["algorithmic_bytes"] for r in table if r["algorithmic_bytes"]))
+    dominant = max(table, key=lambda r: r["ms"]) if table else None
+    if dominant is not None and dominant["algorithmic_bytes"]:
+        roof = {"bound": "hbm", "kernel": dominant["kernel"], "achieved": dominant["GBps"], "peak": peak, "unit": "GB/s",
+                "frac": dominant["frac"], "traffic": committed_traffic(dominant["kernel"], B, args.workload),
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": dominant["algorithmic_bytes"],
+                "ms_per_launch": dominant["ms"], "share_of_step": dominant["ms"] / step_ms,
+                "timed": "cudaEvent pairs around the kernel inside the timed steps; the kernel with the largest "
+                         "measured time (kernels of the two streams and lanes overlap)"}
+    else:
+        roof = {"bound": "hbm", "kernel": dominant["kernel"] if dominant else None, "achieved": None, "peak": peak,
+                "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src}
+    roof.update({"whole_step_frac": survey_bytes / (step_ms * 1e-3) / 1e9 / peak,
+                 "whole_step_bytes_model": "SURVEY 8(d): 61 N + 32 G per keyframe (unfused path)",
+                 "whole_step_frac_own_bytes": own_bytes / (step_ms * 1e-3) / 1e9 / peak,
+                 "tree_points": n_tree_pts, "ground_points": n_ground_pts, "vertex_points": n_vertex_pts})
+
     line = {
-        "metric": METRIC, "value": value, "unit": "keyframes/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
-        "config": {"workload": args.workload, "img_h": p.img_h, "img_w": p.img_w, "keyframes_per_step_per_gpu": B,
-                   "submap_cylinders": int(capi.to_host(inp["n_map_models"], np.int32, (B,))[0]),
-                   "two_step": bool(p.twoStepOptim), "lanes": args.lanes,
-                   "l2": f"inputs {B * N * 17 / 1e6:.0f} MB per step > 126 MB L2, no flush needed"
-                         if B * N * 17 > 2 * 126e6 else "inputs smaller than L2 (short run)",
-                   "keyframes_ok": int((res["success"] == 1).sum()),
-                   "mean_landmarks": float(res["n_landmarks"].mean()),
-                   "lm_converged": int((res["lm_termination"][:, 0] == 0).sum())},
+        "metric": WORKLOADS[args.workload][2], "value": value, "unit": "keyframes/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
+        "config": workload_config(args, p, n_scene),
+        "run": {"lanes": args.lanes, "keyframes_ok": int((res["success"] == 1).sum()),
+                "mean_landmarks": float(res["n_landmarks"].mean()),
+                "lm_converged": int((res["lm_termination"][:, 0] == 0).sum()),
+                "kernel_profile_in_timed_steps": not args.no_kernel_profile},
         "clocks": sampler.summary(),
         "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": "keyframes/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "project_split_kernel<true,true>",
-                     "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / peak, "traffic": k1_traffic(B, args.workload), "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms,
-                     "launches_timed": k1_n, "timed": "cudaEvent pairs around the kernel inside the timed steps",
-                     "tree_points": n_tree_pts, "ground_points": n_ground_pts,
-                     "share_of_step": k1_ms / (ms / args.steps)},
+        "roofline": roof,
+        "kernels": table,
     }
     if rank == 0 and world == 1:
         # CPU baseline: the oracle, single thread, on a bounded sample of the same keyframes
         import ctypes as C
         import orc
-        S = min(args.cpu_sample, B)
-        pts = np.ascontiguousarray(capi.to_host(inp["points"], abi.POINT, (B, N))[:S])
-        mk = np.ascontiguousarray(capi.to_host(inp["mask"], np.uint8, (B, N))[:S])
-        cres = np.zeros(S, abi.KF_RESULT)
-        secs = orc.lib().orc_time_keyframes(
-            C.byref(p), 0, S, abi.ptr(pts), abi.ptr(mk), abi.ptr(host["pose_est"]), abi.ptr(host["first_scan"]),
-            abi.ptr(host["map_models"]), abi.ptr(host["n_map_models"]), M, abi.ptr(host["prev_planes"]),
-            abi.ptr(host["n_prev_planes"]), PP, abi.ptr(cres))
-        agree = int(sum(int(cres[k]["n_landmarks"] == res[k]["n_landmarks"] and
-                            cres[k]["n_tree_matches"] == res[k]["n_tree_matches"]) for k in range(S)))
+        pts = capi.to_host(inp["points"], abi.POINT, (B, N))
+        cres = np.zeros(B, abi.KF_RESULT)
+
+        def oracle(lo, hi):
+            return orc.lib().orc_time_keyframes(
+                C.byref(p), 0, hi - lo, abi.ptr(pts[lo:hi]), abi.ptr(mk_h[lo:hi]), abi.ptr(host["pose_est"][lo:hi]),
+                abi.ptr(host["first_scan"][lo:hi]), abi.ptr(host["map_models"][lo:hi]),
+                abi.ptr(host["n_map_models"][lo:hi]), M, abi.ptr(host["prev_planes"][lo:hi]),
+                abi.ptr(host["n_prev_planes"][lo:hi]), PP, abi.ptr(cres[lo:hi]))
+        probe = min(8, B)
+        secs = oracle(0, probe)
+        S = int(max(probe, min(B, args.cpu_seconds / max(secs / probe, 1e-9))))
+        secs = oracle(0, S)
+        ints = ("status", "success", "n_ground", "n_planes", "n_trees", "n_landmarks", "n_tree_matches",
+                "n_plane_matches", "lm_iterations", "lm_termination")
+        agree = 0
+        for k in range(S):
+            ok = all(np.array_equal(cres[k][f], res[k][f]) for f in ints)
+            ok = ok and np.max(np.abs(cres[k]["T_Map_Curr"]["t"] - res[k]["T_Map_Curr"]["t"])) <= 1e-5
+            ok = ok and np.max(np.abs(cres[k]["T_Map_Curr"]["q"] - res[k]["T_Map_Curr"]["q"])) <= 1e-5
+            agree += int(ok)
         line["cpu_baseline"] = {"value": S / secs, "unit": "keyframes/s", "cores": 1, "kind": "port",
-                                "sample": f"first {S} keyframes of the same batch, oracle single thread",
-                                "agree_with_gpu": f"{agree}/{S} keyframes (landmark + match counts)"}
+                                "sample": f"first {S} keyframes of the same batch ({secs:.1f} s), oracle single thread",
+                                "agree_with_gpu": f"{agree}/{S} keyframes (all integer result fields + pose within 1e-5)"}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

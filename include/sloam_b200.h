@@ -231,6 +231,17 @@ int64_t sloam_b200_workspace_bytes(const sloam_ctx *ctx);
 int sloam_b200_set_lanes(sloam_ctx *ctx, int n);
 int sloam_b200_profile_enable(sloam_ctx *ctx, int on);
 int sloam_b200_profile_read(sloam_ctx *ctx, double *split_kernel_ms, int32_t *launches);
+/* Same for every kernel group of the fused path: one record per group that ran, `ms` summed
+ * over the fused runs since the last enable/read (at most 64 runs are recorded), `launches` =
+ * runs counted.  Groups on different streams / lanes overlap, so the sum over the groups can
+ * exceed the step time.  Synchronises and resets like profile_read. */
+typedef struct sloam_prof_kernel {
+  char name[48];
+  double ms;
+  int32_t launches;
+  int32_t reserved;
+} sloam_prof_kernel;
+int sloam_b200_profile_read_kernels(sloam_ctx *ctx, sloam_prof_kernel *out, int cap, int32_t *n_out);
 const char *sloam_b200_version(void);
 
 /* ------------------------------------------------ stage entries (device) */

@@ -97,6 +97,11 @@ class SynthConfig(C.Structure):
     ]
 
 
+class ProfKernel(C.Structure):
+    """sloam_prof_kernel"""
+    _fields_ = [("name", C.c_char * 48), ("ms", C.c_double), ("launches", C.c_int32), ("reserved", C.c_int32)]
+
+
 class BatchIn(C.Structure):
     """sloam_batch_in: raw pointers (host or device, depending on the entry)."""
     _fields_ = [

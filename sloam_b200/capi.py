@@ -19,7 +19,7 @@ EXPORTS = [
     "sloam_b200_get_params", "sloam_b200_set_stream", "sloam_b200_sync", "sloam_b200_last_error",
     "sloam_b200_kernel_launches", "sloam_b200_workspace_bytes", "sloam_b200_profile_enable", "sloam_b200_set_lanes", "sloam_b200_make_tensor_dev",
     "sloam_b200_mask_from_logits_dev",
-    "sloam_b200_profile_read", "sloam_b200_version",
+    "sloam_b200_profile_read", "sloam_b200_profile_read_kernels", "sloam_b200_version",
     "sloam_b200_project_dev", "sloam_b200_mask_cloud_dev", "sloam_b200_project_split_dev",
     "sloam_b200_ground_planes_dev", "sloam_b200_find_clusters_dev", "sloam_b200_compute_graph_dev",
     "sloam_b200_cylinders_dev", "sloam_b200_associate_dev", "sloam_b200_optimize_pose_dev",
@@ -179,6 +179,14 @@ class Context:
         ms, n = C.c_double(), C.c_int32()
         self.check(lib().sloam_b200_profile_read(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def profile_read_kernels(self):
+        """-> [(kernel group name, summed milliseconds, runs counted)] since the last enable/read"""
+        cap = 32
+        buf = (abi.ProfKernel * cap)()
+        n = C.c_int32()
+        self.check(lib().sloam_b200_profile_read_kernels(self.h, buf, cap, C.byref(n)))
+        return [(buf[i].name.decode(), buf[i].ms, buf[i].launches) for i in range(n.value)]
 
     def workspace_bytes(self):
         return lib().sloam_b200_workspace_bytes(self.h)

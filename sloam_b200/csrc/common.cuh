@@ -178,10 +178,14 @@ struct sloam_ctx {
   // set by zero_counters(): the launchers named by the bits may skip their own memsets once
   unsigned zero_valid = 0;  // 1 split kernel, 2 connected components, 4 vertex stage, 8 ground cells
   int epoch = 0;  // bumped by set_params / set_stream: invalidates captured CUDA graphs
+  // optional event pairs around every kernel group of the fused runs (sloam_b200_profile_*):
+  // prof_ev[(run * kProfIds + id) * 2 + {0 begin, 1 end}], run = fused run since enable/read
   bool prof_on = false;
   int prof_n = 0;
-  static constexpr int kProfPairs = 256;
-  cudaEvent_t prof_ev[2 * kProfPairs] = {};
+  static constexpr int kProfRuns = 64;
+  static constexpr int kProfIds = 24;
+  cudaEvent_t prof_ev[2 * kProfRuns * kProfIds] = {};
+  unsigned prof_seen[kProfRuns] = {};  // bit id: the pair of that run was recorded
   // partial results of split association (large maps), grown on demand
   int32_t *assoc_part_i = nullptr;
   double *assoc_part_d = nullptr;
@@ -190,6 +194,24 @@ struct sloam_ctx {
 };
 
 namespace sb {
+
+// kernel groups timed by sloam_b200_profile_* (names: ctx.cu kProfNames, same order)
+enum ProfId {
+  P_SPLIT = 0, P_RANGE_FIN, P_GROUND_BIN, P_GROUND_CELLS, P_GROUND_REPLAY, P_PLANE_FIT, P_CC_WORDS, P_CC_INIT,
+  P_CC_MERGE, P_CC_FLATTEN, P_CC_PLAN, P_VERTEX, P_VERTEX_REPLAY, P_TREE_COMPACT, P_CYLINDER, P_ASSOC_1,
+  P_BUILD_MATCHES, P_LM, P_FINISH, P_ASSOC_2, P_COUNT
+};
+static_assert(P_COUNT <= sloam_ctx::kProfIds, "profile id table too small");
+
+// event on the stream the NEXT / PREVIOUS kernel of the group is launched on (c->stream is
+// switched to the side stream for the tree detector); no synchronisation is added
+inline void prof_mark(sloam_ctx *c, int id, int end) {
+  if (!c->prof_on || c->prof_n >= sloam_ctx::kProfRuns) return;
+  cudaEventRecord(c->prof_ev[((size_t)c->prof_n * sloam_ctx::kProfIds + id) * 2 + end], c->stream);
+  if (end) c->prof_seen[c->prof_n] |= 1u << id;
+}
+#define PROF_BEGIN(c, id) sb::prof_mark((c), (id), 0)
+#define PROF_END(c, id) sb::prof_mark((c), (id), 1)
 
 inline int set_err(sloam_ctx *c, int code, const std::string &m) {
   if (c) c->err = m;

@@ -403,6 +403,14 @@ int sloam_b200_set_lanes(sloam_ctx *c, int n) {
 }
 int64_t sloam_b200_workspace_bytes(const sloam_ctx *c) { return c ? (int64_t)c->arena_bytes : 0; }
 
+static const char *const kProfNames[P_COUNT] = {
+    "project_split_kernel", "range_finalize_kernel", "ground_bin_kernel", "ground_cells_kernel<0>",
+    "ground_cells_kernel<1> (tie replay)", "plane_finish+planes_compact", "tree_words_kernel", "cc_init_kernel",
+    "cc_merge_kernel", "cc_flatten_kernel", "cc_plan_kernel", "vertex_kernel<0>",
+    "vertex_kernel<1>+vertex_wide (tie replay)", "tree_compact_kernel", "cylinder_kernel+compact",
+    "assoc_kernel (sensor frame)", "build_matches_kernel", "lm_kernel", "finish_kernel",
+    "assoc_kernel+matches (map frame)"};
+
 int sloam_b200_profile_enable(sloam_ctx *c, int on) {
   if (!c) return SLOAM_E_INVALID;
   cudaSetDevice(c->device);
@@ -411,47 +419,92 @@ int sloam_b200_profile_enable(sloam_ctx *c, int on) {
       if (!e) SB_CUDA(c, cudaEventCreate(&e));
   c->prof_on = on != 0;
   c->prof_n = 0;
+  for (unsigned &m : c->prof_seen) m = 0;
   for (sloam_ctx *l : c->lane)
     if (l) { const int rc = sloam_b200_profile_enable(l, on); if (rc != SLOAM_OK) return rc; }
   return SLOAM_OK;
 }
 
+// Summed time of kernel group `id` over the fused runs since the last enable/read.  With lanes
+// the kernels of the sub-batches overlap: a run counts from the earliest start to the latest
+// end over the lanes (event timestamps are device-wide).
+static int prof_sum(sloam_ctx *c, int id, double *total_ms, int *runs_out) {
+  sloam_ctx *src[4] = {c, nullptr, nullptr, nullptr};
+  int ns = 1;
+  if (c->n_lanes > 1 && c->lane[0] && c->lane[0]->prof_n > 0) {
+    ns = c->n_lanes;
+    for (int l = 0; l < ns; ++l) src[l] = c->lane[l];
+  }
+  int runs = 0;
+  for (int l = 0; l < ns; ++l) runs = std::max(runs, std::min(src[l]->prof_n, (int)sloam_ctx::kProfRuns));
+  double total = 0.0;
+  int counted = 0;
+  for (int i = 0; i < runs; ++i) {
+    float span = -1.f;
+    for (int a = 0; a < ns; ++a)
+      for (int b = 0; b < ns; ++b) {
+        if (src[a]->prof_n <= i || src[b]->prof_n <= i) continue;
+        if (!((src[a]->prof_seen[i] >> id) & 1u) || !((src[b]->prof_seen[i] >> id) & 1u)) continue;
+        float ms = 0.f;
+        SB_CUDA(c, cudaEventElapsedTime(&ms, src[a]->prof_ev[((size_t)i * sloam_ctx::kProfIds + id) * 2],
+                                        src[b]->prof_ev[((size_t)i * sloam_ctx::kProfIds + id) * 2 + 1]));
+        if (ms > span) span = ms;
+      }
+    if (span >= 0.f) { total += span; ++counted; }
+  }
+  *total_ms = total;
+  *runs_out = counted;
+  return SLOAM_OK;
+}
+
+static int prof_sync_all(sloam_ctx *c) {
+  SB_CUDA(c, cudaStreamSynchronize(c->stream));
+  SB_CUDA(c, cudaStreamSynchronize(c->side));
+  for (int l = 0; l < c->n_lanes && c->n_lanes > 1; ++l)
+    if (c->lane[l]) {
+      SB_CUDA(c, cudaStreamSynchronize(c->lane[l]->stream));
+      SB_CUDA(c, cudaStreamSynchronize(c->lane[l]->side));
+    }
+  return SLOAM_OK;
+}
+
+static void prof_reset(sloam_ctx *c) {
+  c->prof_n = 0;
+  for (unsigned &m : c->prof_seen) m = 0;
+  for (sloam_ctx *l : c->lane)
+    if (l) { l->prof_n = 0; for (unsigned &m : l->prof_seen) m = 0; }
+}
+
 int sloam_b200_profile_read(sloam_ctx *c, double *split_kernel_ms, int32_t *launches) {
   if (!c || !split_kernel_ms || !launches) return SLOAM_E_INVALID;
-  SB_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (c->n_lanes > 1 && c->lane[0] && c->lane[0]->prof_n > 0) {
-    // split runs: the split kernels of the lanes overlap, so a run counts from the earliest
-    // start to the latest end of its lanes' kernels (event timestamps are device-wide)
-    for (int l = 0; l < c->n_lanes; ++l) SB_CUDA(c, cudaStreamSynchronize(c->lane[l]->stream));
-    const int runs = c->lane[0]->prof_n;
-    double total_ms = 0.0;
-    for (int i = 0; i < runs; ++i) {
-      float span = 0.f;
-      for (int a = 0; a < c->n_lanes; ++a)
-        for (int b = 0; b < c->n_lanes; ++b) {
-          if (c->lane[a]->prof_n <= i || c->lane[b]->prof_n <= i) continue;
-          float ms = 0.f;
-          SB_CUDA(c, cudaEventElapsedTime(&ms, c->lane[a]->prof_ev[2 * i], c->lane[b]->prof_ev[2 * i + 1]));
-          if (ms > span) span = ms;
-        }
-      total_ms += span;
-    }
-    *split_kernel_ms = total_ms;
-    *launches = runs;
-    for (int l = 0; l < c->n_lanes; ++l) c->lane[l]->prof_n = 0;
-    c->prof_n = 0;
-    return SLOAM_OK;
+  int rc = prof_sync_all(c);
+  if (rc != SLOAM_OK) return rc;
+  int runs = 0;
+  rc = prof_sum(c, P_SPLIT, split_kernel_ms, &runs);
+  *launches = runs;
+  prof_reset(c);
+  return rc;
+}
+
+int sloam_b200_profile_read_kernels(sloam_ctx *c, sloam_prof_kernel *out, int cap, int32_t *n_out) {
+  if (!c || !out || !n_out || cap < 0) return SLOAM_E_INVALID;
+  int rc = prof_sync_all(c);
+  if (rc != SLOAM_OK) return rc;
+  int n = 0;
+  for (int id = 0; id < P_COUNT && n < cap; ++id) {
+    double ms = 0.0;
+    int runs = 0;
+    rc = prof_sum(c, id, &ms, &runs);
+    if (rc != SLOAM_OK) return rc;
+    if (runs == 0) continue;
+    std::memset(&out[n], 0, sizeof out[n]);
+    std::strncpy(out[n].name, kProfNames[id], sizeof(out[n].name) - 1);
+    out[n].ms = ms;
+    out[n].launches = runs;
+    ++n;
   }
-  double total = 0.0;
-  const int n = c->prof_n < sloam_ctx::kProfPairs ? c->prof_n : sloam_ctx::kProfPairs;
-  for (int i = 0; i < n; ++i) {
-    float ms = 0.f;
-    SB_CUDA(c, cudaEventElapsedTime(&ms, c->prof_ev[2 * i], c->prof_ev[2 * i + 1]));
-    total += ms;
-  }
-  *split_kernel_ms = total;
-  *launches = n;
-  c->prof_n = 0;
+  *n_out = n;
+  prof_reset(c);
   return SLOAM_OK;
 }
 

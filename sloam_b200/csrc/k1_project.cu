@@ -425,13 +425,12 @@ int launch_project_split(sloam_ctx *c, int K, bool do_project, bool do_split,
   const unsigned grid = (unsigned)std::min<long long>(all_tiles, (long long)c->sm_count * occ[which]);
 #define SB_K1_ARGS c->dp, K, points, mask, pix, rb, tree, c->ws.ground, ground_count, c->ws.ground_cell, \
                    c->ws.cell_count, c->ws.tile_count, N, tree_bits, sparse_tree ? 1 : 0
-  const bool prof = c->prof_on && sparse_tree && c->prof_n < sloam_ctx::kProfPairs;  // fused runs only
-  if (prof) SB_CUDA(c, cudaEventRecord(c->prof_ev[2 * c->prof_n], c->stream));
+  PROF_BEGIN(c, P_SPLIT);
   if (do_project && do_split) project_split_kernel<true, true><<<grid, kThreads, 0, c->stream>>>(SB_K1_ARGS);
   else if (do_project) project_split_kernel<true, false><<<grid, kThreads, 0, c->stream>>>(SB_K1_ARGS);
   else project_split_kernel<false, true><<<grid, kThreads, 0, c->stream>>>(SB_K1_ARGS);
 #undef SB_K1_ARGS
-  if (prof) { SB_CUDA(c, cudaEventRecord(c->prof_ev[2 * c->prof_n + 1], c->stream)); ++c->prof_n; }
+  PROF_END(c, P_SPLIT);
   SB_LAUNCH_CHECK(c);
   if (do_split && !strided_out) {
     ground_compact_kernel<<<dim3((unsigned)tiles, (unsigned)K), 256, 0, c->stream>>>(
@@ -440,7 +439,9 @@ int launch_project_split(sloam_ctx *c, int K, bool do_project, bool do_split,
   }
   if (do_project && rb) {
     const long long nvec = (total + 3) / 4;
+    PROF_BEGIN(c, P_RANGE_FIN);
     range_finalize_kernel<<<(unsigned)((nvec + 255) / 256), 256, 0, c->stream>>>(rb, total);
+    PROF_END(c, P_RANGE_FIN);
     SB_LAUNCH_CHECK(c);
   }
   return SLOAM_OK;

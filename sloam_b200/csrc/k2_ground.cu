@@ -623,26 +623,35 @@ int launch_ground_planes(sloam_ctx *c, int K, const sloam_point *ground, const i
     SB_CUDA(c, cudaFuncSetAttribute(ground_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem));
     bin_set[c->device & 63] = bin_smem;
   }
+  PROF_BEGIN(c, P_GROUND_BIN);
   ground_bin_kernel<<<K, kBinThreads, bin_smem, c->stream>>>(c->dp, ground, ground_count, stride, w.ground_cell,
                                                              w.cell_count, strided ? w.tile_count : nullptr,
                                                              reinterpret_cast<SelKey *>(w.gscratch));
+  PROF_END(c, P_GROUND_BIN);
   SB_LAUNCH_CHECK(c);
   if (c->zero_valid & 8u) c->zero_valid &= ~8u;
   else SB_CUDA(c, cudaMemsetAsync(w.n_tied_cells, 0, sizeof(int32_t), c->stream));
+  PROF_BEGIN(c, P_GROUND_CELLS);
   ground_cells_kernel<false><<<grid, kGThreads, 0, c->stream>>>(
       c->dp, ground, ground_count, stride, reinterpret_cast<SelKey *>(w.gscratch), w.cell_count, pose_est,
       w.qscratch, w.pscratch, w.fit_rec, cells, cell_features, kept_points, kept_offsets,
       reinterpret_cast<SelKey *>(w.gscratch2), w.tied_cells, w.n_tied_cells);
+  PROF_END(c, P_GROUND_CELLS);
   SB_LAUNCH_CHECK(c);
   // cells with exact z ties again, with the std::sort replay (usually an empty list)
+  PROF_BEGIN(c, P_GROUND_REPLAY);
   ground_cells_kernel<true><<<c->sm_count * 4, kGThreads, 0, c->stream>>>(
       c->dp, ground, ground_count, stride, reinterpret_cast<SelKey *>(w.gscratch), w.cell_count, pose_est,
       w.qscratch, w.pscratch, w.fit_rec, cells, cell_features, kept_points, kept_offsets,
       reinterpret_cast<SelKey *>(w.gscratch2), w.tied_cells, w.n_tied_cells);
+  PROF_END(c, P_GROUND_REPLAY);
   SB_LAUNCH_CHECK(c);
+  PROF_BEGIN(c, P_PLANE_FIT);
   plane_finish_kernel<<<(K * c->hp.B + 127) / 128, 128, 0, c->stream>>>(c->dp, K, w.fit_rec, pose_est, cells);
   SB_LAUNCH_CHECK(c);
-  return launch_planes_compact(c, K, cells);
+  const int rc_pc = launch_planes_compact(c, K, cells);
+  PROF_END(c, P_PLANE_FIT);
+  return rc_pc;
 }
 
 }  // namespace sb

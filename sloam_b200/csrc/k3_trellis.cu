@@ -807,18 +807,26 @@ static int run_cc(sloam_ctx *c, int K, const sloam_point *tree, bool bits_ready)
     SB_CUDA(c, cudaMemsetAsync(w.n_tree_words, 0, sizeof(int32_t), c->stream));
     SB_CUDA(c, cudaMemsetAsync(w.root_bits, 0, sizeof(uint32_t) * (size_t)K * ((c->hp.N + 31) / 32), c->stream));
   }
+  PROF_BEGIN(c, P_CC_WORDS);
   tree_words_kernel<<<wgrid, 256, 0, c->stream>>>(c->dp, K, w.tree_bits, reinterpret_cast<int2 *>(w.tree_words), w.n_tree_words);
+  PROF_END(c, P_CC_WORDS);
   SB_LAUNCH_CHECK(c);
   const int2 *wl = reinterpret_cast<const int2 *>(w.tree_words);
+  PROF_BEGIN(c, P_CC_INIT);
   cc_init_kernel<<<wgrid, 256, 0, c->stream>>>(c->dp, K, tree, w.tree_bits, wl, w.n_tree_words, w.parent,
                                                reinterpret_cast<uint32_t *>(w.cc_flags), w.csize,
                                                 w.ccol_min, w.ccol_max, w.crow_max);
+  PROF_END(c, P_CC_INIT);
   SB_LAUNCH_CHECK(c);
+  PROF_BEGIN(c, P_CC_MERGE);
   cc_merge_kernel<<<wgrid, 256, 0, c->stream>>>(c->dp, K, w.tree_bits, wl, w.n_tree_words, reinterpret_cast<const uint32_t *>(w.cc_flags), w.parent);
+  PROF_END(c, P_CC_MERGE);
   SB_LAUNCH_CHECK(c);
+  PROF_BEGIN(c, P_CC_FLATTEN);
   cc_flatten_kernel<<<wgrid, 256, 0, c->stream>>>(c->dp, K, w.tree_bits, wl, w.n_tree_words, w.parent, w.csize, w.ccol_min, w.ccol_max,
                                                    w.crow_max, w.row_roots, w.n_roots, w.big_roots,
                                                    w.n_big, w.kf_flags, w.root_bits);
+  PROF_END(c, P_CC_FLATTEN);
   SB_LAUNCH_CHECK(c);
   return SLOAM_OK;
 }
@@ -837,9 +845,11 @@ int launch_compute_graph(sloam_ctx *c, int K, const sloam_point *tree, sloam_tre
     SB_CUDA(c, cudaMemsetAsync(w.n_overflow, 0, sizeof(int32_t) * 4, c->stream));
     SB_CUDA(c, cudaMemsetAsync(w.vpool_count, 0, sizeof(int32_t) * K, c->stream));
   }
+  PROF_BEGIN(c, P_CC_PLAN);
   cc_plan_kernel<<<K, 256, sizeof(int32_t) * (2 * T + H + 1), c->stream>>>(
       c->dp, w.root_bits, w.parent, w.ccol_min, w.ccol_max, w.crow_max, w.row_roots, w.big_roots, w.n_big,
       w.big_rank, w.bbox, w.vwork, w.n_overflow + 1);
+  PROF_END(c, P_CC_PLAN);
   SB_LAUNCH_CHECK(c);
   // persistent grid: exactly the CTAs that are resident at once (a partial second wave would
   // double the time of its work items)
@@ -850,14 +860,18 @@ int launch_compute_graph(sloam_ctx *c, int K, const sloam_point *tree, sloam_tre
   }
   const int vgrid = c->sm_count * vtx_occ;
   // n_overflow[0] rows wider than the warp path, [1] work items, [2] items with exact z ties
+  PROF_BEGIN(c, P_VERTEX);
   vertex_kernel<false><<<vgrid, kVtxWarps * 32, 0, c->stream>>>(
       c->dp, tree, w.tree_bits, w.parent, w.big_roots, w.bbox, w.vwork, w.n_overflow + 1, w.slot_vertices,
       vertex_points, w.vpool_count, w.overflow_list, w.n_overflow, w.tied_list, w.n_overflow + 2);
+  PROF_END(c, P_VERTEX);
   SB_LAUNCH_CHECK(c);
+  PROF_BEGIN(c, P_VERTEX_REPLAY);
   // the tied items again, with the std::sort replay (usually an empty list: the CTAs exit)
   vertex_kernel<true><<<c->sm_count, kVtxWarps * 32, 0, c->stream>>>(
       c->dp, tree, w.tree_bits, w.parent, w.big_roots, w.bbox, w.tied_list, w.n_overflow + 2, w.slot_vertices,
       vertex_points, w.vpool_count, w.overflow_list, w.n_overflow, nullptr, nullptr);
+  PROF_END(c, P_VERTEX_REPLAY);
   SB_LAUNCH_CHECK(c);
   const size_t wide_smem = sizeof(float) * 4 * W + sizeof(int) * 3 * W;
   // opt-in shared memory: the attribute belongs to (function, device) and must only grow -- a
@@ -872,9 +886,11 @@ int launch_compute_graph(sloam_ctx *c, int K, const sloam_point *tree, sloam_tre
                                                                  w.slot_vertices, vertex_points,
                                                                  w.vpool_count);
   SB_LAUNCH_CHECK(c);
+  PROF_BEGIN(c, P_TREE_COMPACT);
   tree_compact_kernel<<<K, 256, sizeof(int32_t) * 2 * T, c->stream>>>(c->dp, w.n_big, w.big_rank, w.bbox,
                                                                        w.slot_vertices, trees, n_trees,
                                                                        vertices);
+  PROF_END(c, P_TREE_COMPACT);
   SB_LAUNCH_CHECK(c);
   return SLOAM_OK;
 }

@@ -488,11 +488,13 @@ int launch_cylinders_strided(sloam_ctx *c, int K, const sloam_tree *trees, const
                              sloam_tree_model *models, sloam_point *features) {
   const sloam_params &p = c->hp.p;
   dim3 grid((unsigned)((p.max_trees + kCylWarps - 1) / kCylWarps), (unsigned)K);
+  PROF_BEGIN(c, P_CYLINDER);
   cylinder_kernel<<<grid, kCylWarps * 32, 0, c->stream>>>(
       c->dp, trees, n_trees, vertices, vpoints, vstride, pstride, planes_acc,
       n_planes_acc, c->ws.ransac_pairs, c->ws.ransac_pairs_offset, models, features);
   SB_LAUNCH_CHECK(c);
   cylinders_compact_kernel<<<K, 32, 0, c->stream>>>(c->dp, n_trees, models, c->ws.lm_cyl, c->ws.lm_src, c->ws.n_lm);
+  PROF_END(c, P_CYLINDER);
   SB_LAUNCH_CHECK(c);
   return SLOAM_OK;
 }

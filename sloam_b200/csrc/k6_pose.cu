@@ -411,31 +411,41 @@ int launch_sloam_core(sloam_ctx *c, int K, const sloam_batch_in *in, const sloam
   Workspace &w = c->ws;
   const sloam_params &p = c->hp.p;
   const int T = p.max_trees, two_step = p.twoStepOptim ? 1 : 0;
+  PROF_BEGIN(c, P_ASSOC_1);
   int rc = launch_associate(c, K, w.lm_cyl, w.n_lm, T, T, in->pose_est, in->map_models, in->n_map_models,
                             p.max_map_models, in->map_shared, p.max_map_models, w.assoc_idx, w.assoc_dist);
+  PROF_END(c, P_ASSOC_1);
   if (rc != SLOAM_OK) return rc;
+  PROF_BEGIN(c, P_BUILD_MATCHES);
   build_matches_kernel<<<K, 128, sizeof(int16_t) * (size_t)p.max_trees, c->stream>>>(
       c->dp, in->first_scan, in->pose_est, in->n_map_models, in->map_shared, in->map_models,
       p.max_map_models, in->prev_planes, in->n_prev_planes, p.max_prev_planes, w.n_lm, w.lm_src,
       w.assoc_idx, w.assoc_dist, w.tree_features, w.planes_acc, w.planes_acc_cell, w.n_planes_acc,
       w.cell_features, w.res_tree_feat, w.res_tree_obj, w.res_plane_feat, w.res_plane_obj, w.n_tree_res,
       w.n_plane_res, w.optim_flags, w.kf_mode, out->results, w.ground_count, w.n_trees);
+  PROF_END(c, P_BUILD_MATCHES);
   SB_LAUNCH_CHECK(c);
+  PROF_BEGIN(c, P_LM);
   rc = launch_lm(c, K, two_step, in->pose_est, w.res_tree_feat, w.res_tree_obj, w.n_tree_res,
                  T * p.featuresPerTree, w.res_plane_feat, w.res_plane_obj, w.n_plane_res,
                  c->hp.B * p.numGroundFeatures, w.optim_flags);
+  PROF_END(c, P_LM);
   if (rc != SLOAM_OK) return rc;
+  PROF_BEGIN(c, P_FINISH);
   finish_kernel<<<K, 128, 0, c->stream>>>(c->dp, two_step, in->pose_est, w.kf_mode, w.optim_flags, w.lm_x,
                                           w.lm_info, w.n_lm, w.lm_cyl, w.lm_src, w.tree_models, w.planes_acc,
                                           w.n_planes_acc, in->prev_planes, in->n_prev_planes,
                                           p.max_prev_planes, w.curr_pose, out->results, out->tm, out->tm_id,
                                           out->matches, out->planes, out->n_planes, p.max_prev_planes);
+  PROF_END(c, P_FINISH);
   SB_LAUNCH_CHECK(c);
+  PROF_BEGIN(c, P_ASSOC_2);
   rc = launch_associate(c, K, w.lm_cyl, w.n_lm, T, T, w.curr_pose, in->map_models, in->n_map_models,
                         p.max_map_models, in->map_shared, p.max_map_models, w.assoc_idx, w.assoc_dist);
   if (rc != SLOAM_OK) return rc;
   dim3 g((unsigned)((T + 127) / 128), (unsigned)K);
   matches_kernel<<<g, 128, 0, c->stream>>>(c->dp, w.kf_mode, w.n_lm, w.assoc_idx, w.assoc_dist, out->matches);
+  PROF_END(c, P_ASSOC_2);
   SB_LAUNCH_CHECK(c);
   return SLOAM_OK;
 }

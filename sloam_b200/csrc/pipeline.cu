@@ -127,6 +127,7 @@ static int run_dev_body(sloam_ctx *c, int K, const sloam_batch_in *in, const slo
   if (rc != SLOAM_OK) return rc;
   rc = launch_sloam_core(c, K, in, out);
   c->last_k = K;
+  if (c->prof_on && c->prof_n < sloam_ctx::kProfRuns) ++c->prof_n;  // next fused run -> next event slots
   return rc;
 }
 
