@@ -233,8 +233,9 @@ int sloam_b200_profile_enable(sloam_ctx *ctx, int on);
 int sloam_b200_profile_read(sloam_ctx *ctx, double *split_kernel_ms, int32_t *launches);
 /* Same for every kernel group of the fused path: one record per group that ran, `ms` summed
  * over the fused runs since the last enable/read (at most 64 runs are recorded), `launches` =
- * runs counted.  Groups on different streams / lanes overlap, so the sum over the groups can
- * exceed the step time.  Synchronises and resets like profile_read. */
+ * runs counted.  While profiling is enabled a fused run uses one lane and one stream (the
+ * ground stage and the tree detector run one after the other), so that every pair times its
+ * kernels alone; results are unchanged.  Synchronises and resets like profile_read. */
 typedef struct sloam_prof_kernel {
   char name[48];
   double ms;

@@ -22,7 +22,6 @@ constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr int kMaxCells = 256;        // groundRadiiBins * groundThetaBins upper bound
 constexpr int kSplitTile = 1024;      // points per CTA in the project/split kernel
-constexpr int kMaxBigClusters = 1024; // clusters with > min_cluster_points per keyframe
 
 // Device copy of the parameters plus derived constants.
 struct DevParams {
@@ -60,9 +59,6 @@ struct Workspace {
   sloam_point *ground = nullptr;     // [K][N]
   int32_t *ground_count = nullptr;   // [K]
   uint32_t *tree_bits = nullptr;     // [K][ceil(N/32)] bit i: pixel i may hold a tree point
-  uint32_t *root_bits = nullptr;     // [K][ceil(N/32)] bit i: pixel i is the root of its component
-  int32_t *tree_words = nullptr;     // [K * ceil(N/32)] indices of the non-zero words of tree_bits
-  int32_t *n_tree_words = nullptr;   // [1]
   uint8_t *ground_cell = nullptr;    // [K][N] polar cell of each ground point (255 = none)
   int32_t *cell_count = nullptr;     // [K][kMaxCells]
   int32_t *tile_count = nullptr;     // [K][tiles] ground points of each K1 tile (tile-strided ground layout)
@@ -80,27 +76,25 @@ struct Workspace {
   double *qscratch = nullptr;        // [K][N][3] QR workspace of oversized cells
   float *pscratch = nullptr;         // [K][N][3] point staging of oversized cells
   FitRec *fit_rec = nullptr;         // [K][B]
-  // K3
-  int32_t *parent = nullptr;         // [K][N] union-find
-  uint8_t *cc_flags = nullptr;       // [K][N]
-  int32_t *csize = nullptr;          // [K][N] size at root
-  int32_t *big_roots = nullptr;      // [K][kMaxBigClusters] sorted root pixel of big clusters
-  int32_t *n_big = nullptr;          // [K]
-  int32_t *n_roots = nullptr;        // [K]
-  int32_t *big_rank = nullptr;       // [K][kMaxBigClusters] PCL label of each big cluster
-  int32_t *bbox = nullptr;           // [K][max_trees][4] cmin,cmax,rmin,rmax of each big cluster
-  int32_t *ccol_min = nullptr;       // [K][N] at root pixels: min column of the component
-  int32_t *ccol_max = nullptr;       // [K][N] at root pixels: max column
-  int32_t *crow_max = nullptr;       // [K][N] at root pixels: max row
-  int32_t *root_rank = nullptr;      // [K][N] at root pixels: PCL label (find_clusters entry)
-  int32_t *row_roots = nullptr;      // [K][H] number of component roots per row
-  sloam_vertex *slot_vertices = nullptr; // [K][max_trees][H] one candidate vertex per (cluster,row)
+  // K3 (k3_trellis.cu)
+  uint32_t *cc_planes = nullptr;     // [K][ceil(N/32)] uint4 (valid, run start, connected upwards, 0) bit planes
+  int32_t *cc_wbase = nullptr;       // [K][ceil(N/32)] run id base of each word (find_clusters entry only)
+  int32_t *run_par = nullptr;        // [K][N] union-find over runs: global fallback of the shared-memory arrays
+  int32_t *run_siz = nullptr;        // [K][N]  "
+  int32_t *run_len = nullptr;        // [K][N]  "
+  int32_t *run_pix0 = nullptr;       // [K][N] first pixel of each run
+  int32_t *run_info = nullptr;       // [K][N] length << 11 | slot code of each run
+  int32_t *run_label = nullptr;      // [K][N] PCL label of each run's component
+  int32_t *n_big = nullptr;          // [K] big components kept (<= max_trees)
+  int32_t *n_roots = nullptr;        // [K] components
+  int32_t *big_rank = nullptr;       // [K][max_trees] PCL label of each big component
+  uint32_t *slot_rows = nullptr;     // [K][max_trees][ceil(H/32)] rows of a big component that hold a vertex record
+  sloam_vertex *slot_vertices = nullptr; // [K][max_trees][H] one candidate vertex per (component, row)
   int32_t *vpool_count = nullptr;    // [K]
-  int32_t *vwork = nullptr;          // [K*max_trees*H] (k, slot, row) work items, packed
-  int32_t *tied_list = nullptr;      // [K][T*H] work items with exact z ties among > 16 points
-  int32_t *overflow_list = nullptr;  // [K*max_trees*H] work items needing the wide path
-  int32_t *n_overflow = nullptr;     // [4] counters: [0] rows for the wide vertex kernel, [1] vertex work items, [2] tied items
-  int32_t *kf_flags = nullptr;       // [K] capacity-exceeded flags
+  void *vitems = nullptr;            // [K << (row bits + slot bits)] VItem work items of the vertex stage
+  int32_t *vlists = nullptr;         // [6][K*max_trees*H] item ids by size class (+ wide, tied)
+  int32_t *n_vlists = nullptr;       // [8] lengths of the class lists
+  int32_t *kf_flags = nullptr;       // [K] bit 0: more big components than max_trees (first max_trees kept)
   sloam_tree *trees = nullptr;       // [K][max_trees]
   int32_t *n_trees = nullptr;        // [K]
   sloam_vertex *vertices = nullptr;  // [K][max_trees*max_tree_vertices]
@@ -197,9 +191,9 @@ namespace sb {
 
 // kernel groups timed by sloam_b200_profile_* (names: ctx.cu kProfNames, same order)
 enum ProfId {
-  P_SPLIT = 0, P_RANGE_FIN, P_GROUND_BIN, P_GROUND_CELLS, P_GROUND_REPLAY, P_PLANE_FIT, P_CC_WORDS, P_CC_INIT,
-  P_CC_MERGE, P_CC_FLATTEN, P_CC_PLAN, P_VERTEX, P_VERTEX_REPLAY, P_TREE_COMPACT, P_CYLINDER, P_ASSOC_1,
-  P_BUILD_MATCHES, P_LM, P_FINISH, P_ASSOC_2, P_COUNT
+  P_SPLIT = 0, P_RANGE_FIN, P_GROUND_BIN, P_GROUND_CELLS, P_GROUND_REPLAY, P_PLANE_FIT, P_CC_ROWS, P_CC_LABEL,
+  P_VERTEX, P_VERTEX_REPLAY, P_TREE_COMPACT, P_CYLINDER, P_ASSOC_1, P_BUILD_MATCHES, P_LM, P_FINISH, P_ASSOC_2,
+  P_COUNT
 };
 static_assert(P_COUNT <= sloam_ctx::kProfIds, "profile id table too small");
 

@@ -56,21 +56,15 @@ static void layout(sloam_ctx *c, Bump &b) {
   b.take(w.zero_begin, 64);
   b.take(w.ground_count, K);
   b.take(w.cell_count, K * kMaxCells);
-  b.take(w.root_bits, K * ((N + 31) / 32));
-  b.take(w.n_tree_words, 4);
   b.take(w.n_tied_cells, 4);
-  b.take(w.n_big, K);
-  b.take(w.n_roots, K);
-  b.take(w.row_roots, K * H);
   b.take(w.vpool_count, K);
-  b.take(w.n_overflow, 4);
+  b.take(w.n_vlists, 8);
   b.take(w.kf_flags, K);
   b.take(w.zero_end, 64);
   b.take(w.pix, K * N);
   b.take(w.tree, K * N);
   b.take(w.ground, K * N);
   b.take(w.tree_bits, K * ((N + 31) / 32));
-  b.take(w.tree_words, 2 * K * ((N + 31) / 32));
   b.take(w.ground_cell, K * N);
   b.take(w.tile_count, K * tiles);
   b.take(w.range_image, K * N);
@@ -85,20 +79,25 @@ static void layout(sloam_ctx *c, Bump &b) {
   b.take(w.qscratch, K * N * 3);
   b.take(w.pscratch, K * N * 3);
   b.take(w.fit_rec, K * B);
-  b.take(w.parent, K * N);
-  b.take(w.cc_flags, K * N);
-  b.take(w.csize, K * N);
-  b.take(w.big_roots, K * T);
+  b.take(w.cc_planes, 4 * K * ((N + 31) / 32));
+  b.take(w.cc_wbase, K * ((N + 31) / 32));
+  b.take(w.run_par, K * N);
+  b.take(w.run_siz, K * N);
+  b.take(w.run_len, K * N);
+  b.take(w.run_pix0, K * N);
+  b.take(w.run_info, K * N);
+  b.take(w.run_label, K * N);
+  b.take(w.n_big, K);
+  b.take(w.n_roots, K);
   b.take(w.big_rank, K * T);
-  b.take(w.bbox, K * T * 4);
-  b.take(w.ccol_min, K * N);
-  b.take(w.ccol_max, K * N);
-  b.take(w.crow_max, K * N);
-  b.take(w.root_rank, K * N);
+  b.take(w.slot_rows, K * T * ((H + 31) / 32));
   b.take(w.slot_vertices, K * T * H);
-  b.take(w.vwork, K * T * H);
-  b.take(w.overflow_list, K * T * H);
-  b.take(w.tied_list, K * T * H);
+  {
+    sloam_point *items16 = nullptr;  // 16-byte records
+    b.take(items16, K << (c->hp.vw_row_bits + c->hp.vw_slot_bits));
+    w.vitems = items16;
+  }
+  b.take(w.vlists, 6 * K * T * H);
   b.take(w.trees, K * T);
   b.take(w.n_trees, K);
   b.take(w.vertices, K * T * (size_t)p.max_tree_vertices);
@@ -144,6 +143,7 @@ static int validate(const sloam_params &p, std::string &why) {
   if (p.max_tree_vertices < 3 || p.max_tree_vertices > 64) { why = "max_tree_vertices must be in [3,64]"; return -1; }
   if (p.min_tree_vertices < 2) { why = "min_tree_vertices must be >= 2 (cylinder.cpp:11,78 index vertices[2])"; return -1; }
   if (p.max_trees <= 0 || p.max_map_models <= 0) { why = "capacities must be positive"; return -1; }
+  if (p.max_trees > 2046) { why = "max_trees must be <= 2046 (11-bit slot codes, k3_trellis.cu)"; return -1; }
   if (p.max_prev_planes < p.groundRadiiBins * p.groundThetaBins) { why = "max_prev_planes < number of ground cells"; return -1; }
   if (p.do_destagger) { why = "do_destagger is not implemented (sim.yaml:5 uses false)"; return -1; }
   if (p.ransac_fixed_hypotheses < 0 || p.ransac_max_iterations <= 0) { why = "ransac counts"; return -1; }
@@ -405,9 +405,8 @@ int64_t sloam_b200_workspace_bytes(const sloam_ctx *c) { return c ? (int64_t)c->
 
 static const char *const kProfNames[P_COUNT] = {
     "project_split_kernel", "range_finalize_kernel", "ground_bin_kernel", "ground_cells_kernel<0>",
-    "ground_cells_kernel<1> (tie replay)", "plane_finish+planes_compact", "tree_words_kernel", "cc_init_kernel",
-    "cc_merge_kernel", "cc_flatten_kernel", "cc_plan_kernel", "vertex_kernel<0>",
-    "vertex_kernel<1>+vertex_wide (tie replay)", "tree_compact_kernel", "cylinder_kernel+compact",
+    "ground_cells_kernel<1> (tie replay)", "plane_finish+planes_compact", "cc_rows_kernel", "cc_label_kernel",
+    "vertex_kernel", "vertex_replay+vertex_wide (tie replay)", "tree_compact_kernel", "cylinder_kernel+compact",
     "assoc_kernel (sensor frame)", "build_matches_kernel", "lm_kernel", "finish_kernel",
     "assoc_kernel+matches (map frame)"};
 

@@ -11,13 +11,24 @@
 //   row up, a TreeVertex from the cluster's points of that row
 //   (trellis.cpp:104-132, computeVertexProperties :63-102).
 //
-// GPU formulation: lock-free union-find over pixels (init / merge / flatten),
-// where the smaller raster index always wins a union so that every root IS the
-// first pixel of its component; component size, column extent and last row are
-// accumulated at the root with warp-aggregated atomics; a per-keyframe planning
-// CTA sorts the big components (= PCL label order), ranks them and emits
-// (cluster, row) work items; one warp per work item builds the vertex with
-// rank-based order statistics in shared memory.
+// GPU formulation: run-based connected components.
+//   cc_rows_kernel   one pass over the tree pixels (32-pixel words of the tree bit mask, one
+//                    warp per non-zero word): three bit planes per pixel -- valid (finite
+//                    point), start (not connected to its left neighbour: the pixel starts a
+//                    row RUN), up (connected to the pixel above).
+//   cc_label_kernel  one CTA per keyframe, everything in shared memory: run ids by a prefix
+//                    count of the start bits (raster order), lock-free union-find over RUNS
+//                    (a few thousand per scan instead of 65 k pixels; the smaller id wins, so a
+//                    root is the first run of its component and the PCL label is the number of
+//                    roots before it), component sizes, the big components in label order
+//                    (= tree order, deterministic when there are more than max_trees), and
+//                    one work item per (component, row) with its member count, binned by size.
+//   vertex_kernel    sub-warp groups: 4 / 2 / 1 items per warp for rows of <= 8 / 16 / 32
+//                    members (one member per lane, order statistics by counting), a warp loop
+//                    for 33..128, one CTA per wider row.
+//   tree_compact     > 16 / <= 56 vertex rules, bottom row first.
+#include <type_traits>
+
 #include "common.cuh"
 #include "dev_stdsort.h"
 
@@ -28,7 +39,21 @@ namespace sb {
 #endif
 constexpr int kVtxWarps = SLOAM_VTX_WARPS;
 constexpr int kVtxCap = 128;   // members per (cluster,row) handled by the warp path
-constexpr int kInvalid = -1;
+constexpr int kLblThreads = 512;
+constexpr int kLblWarps = kLblThreads / 32;
+constexpr unsigned kSlotMask = 0x7FFu;  // slot code (slot + 1, 0 = none) in the low 11 bits of packed words
+
+// work item of the vertex stage: the members of one component in one row
+struct __align__(16) VItem {
+  int32_t pix0;       // first pixel of the first run
+  int32_t first_run;  // run id (within the keyframe) of the first run
+  uint16_t n;         // members
+  uint16_t span;      // last run id - first run id (0: one run, members are contiguous pixels)
+  uint16_t slot;      // big-component slot (tree order)
+  uint16_t row;
+};
+// class lists: [0] n <= 8, [1] n <= 16, [2] n <= 32, [3] n <= kVtxCap, [4] wider, [5] exact z ties (replay)
+constexpr int kClsWide = 4, kClsTied = 5;
 
 __device__ __forceinline__ int uf_find(const int32_t *parent, int x) {
   int p = *((volatile const int32_t *)&parent[x]);
@@ -53,11 +78,7 @@ __device__ __forceinline__ void uf_union(int32_t *parent, int a, int b) {
 // tree_bits: one bit per pixel, [K][Nw] words (Nw = ceil(N / 32)).  Bit set = the pixel may
 // hold a tree point (the split kernel sets it for mask == 255; for caller-supplied clouds it
 // is isfinite(x)).  Pixels whose bit is clear are never read by the kernels below -- in the
-// fused pipeline their tree point, parent and flag entries are not even written.
-__device__ __forceinline__ bool tree_bit(const uint32_t *__restrict__ bits_k, int i) {
-  return i >= 0 && ((bits_k[i >> 5] >> (i & 31)) & 1u);
-}
-
+// fused pipeline their tree point is not even written.
 __global__ void tree_bits_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ tree,
                                  uint32_t *__restrict__ bits) {
   const int N = dp->N, Nw = (N + 31) >> 5;
@@ -81,266 +102,308 @@ __global__ void tree_fill_kernel(const DevParams *__restrict__ dp, const uint32_
   }
 }
 
-// The three connected-component passes below walk the NON-ZERO bit words, not the pixels
-// (a forest scan is ~90 % non-tree pixels).  tree_words_kernel lists the non-zero words of
-// the batch once; each pass then hands one listed word to a warp, 32 lanes = its 32 pixels,
-// so the work is balanced no matter how the trees cluster in the image.
-__global__ void tree_words_kernel(const DevParams *__restrict__ dp, int K, const uint32_t *__restrict__ bits,
-                                  int2 *__restrict__ list, int32_t *__restrict__ n_list) {
-  const int Nw = (dp->N + 31) >> 5;
-  const long long total_words = (long long)K * Nw;
-  const int lane = threadIdx.x & 31;
-  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-  for (long long base = warp0 * 32; base < total_words; base += nwarps * 32) {
-    const uint32_t word = base + lane < total_words ? bits[base + lane] : 0u;
-    const bool nz = word != 0u;
-    const unsigned m = __ballot_sync(kFull, nz);
-    if (m == 0u) continue;
-    int at = 0;
-    if (lane == 0) at = atomicAdd(n_list, __popc(m));
-    at = __shfl_sync(kFull, at, 0);
-    if (nz) {  // entry = (keyframe << 16 | word index in the keyframe, the word itself)
-      const long long gw = base + lane;
-      const int k = (int)(gw / Nw);
-      list[at + __popc(m & ((1u << lane) - 1u))] = make_int2((k << 16) | (int)(gw - (long long)k * Nw), (int)word);
-    }
-  }
-}
-
-template <class F>
-__device__ __forceinline__ void for_each_tree_word(const int2 *__restrict__ list,
-                                                   const int32_t *__restrict__ n_list, F body) {
-  const int lane = threadIdx.x & 31;
-  const int n = *n_list;
-  const int warp0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int nwarps = gridDim.x * (blockDim.x >> 5);
-  // the next list entry is fetched one iteration ahead: one memory round trip less on the
-  // dependent chain entry -> bits / parents -> points of every word
-  int2 e = warp0 < n ? list[warp0] : make_int2(0, 0);
-  for (int idx = warp0; idx < n; idx += nwarps) {
-    const int2 cur = e;
-    if (idx + nwarps < n) e = list[idx + nwarps];
-    body((int)((unsigned)cur.x >> 16), (cur.x & 0xFFFF) * 32 + lane, (uint32_t)cur.y, idx);
-  }
-}
-
-// ---- 1. init: link every valid pixel to its left (else up) neighbour ------
-#ifndef SLOAM_CCINIT_MIN
-#define SLOAM_CCINIT_MIN 8  // the persistent grid is 8 CTAs per SM: keep all of them resident (32 registers)
+// ---- 1. bit planes: valid / run start / connected upwards -------------------
+// A warp takes 32 consecutive words of the batch's tree bit mask with one coalesced load and
+// then handles the non-zero ones, 32 lanes = the 32 pixels of a word (a forest scan is ~80 %
+// non-tree pixels: they cost one bit).  planes[k][word] = (valid, start, up, 0), written only
+// for non-zero words (cc_label_kernel looks at the tree bits first).
+#ifndef SLOAM_CCROWS_MIN
+#define SLOAM_CCROWS_MIN 8
 #endif
-__global__ void __launch_bounds__(256, SLOAM_CCINIT_MIN)
-cc_init_kernel(const DevParams *__restrict__ dp, int K, const sloam_point *__restrict__ tree,
-               const uint32_t *__restrict__ bits, const int2 *__restrict__ wlist,
-               const int32_t *__restrict__ n_wlist, int32_t *__restrict__ parent, uint32_t *__restrict__ mflags,
-               int32_t *__restrict__ csize, int32_t *__restrict__ cmin, int32_t *__restrict__ cmax,
-               int32_t *__restrict__ rmax) {
+__global__ void __launch_bounds__(256, SLOAM_CCROWS_MIN)
+cc_rows_kernel(const DevParams *__restrict__ dp, int K, const sloam_point *__restrict__ tree,
+               const uint32_t *__restrict__ bits, uint4 *__restrict__ planes) {
   const int N = dp->N, W = dp->p.img_w, Nw = (N + 31) >> 5;
   const float cut = dp->cluster_sq_cut;  // dist < cluster_dist_thresh  <=>  squared dist < cut
   const unsigned magic_w = dp->magic_w;
   const int lane = threadIdx.x & 31;
-  for_each_tree_word(wlist, n_wlist, [&](int k, int i, uint32_t word, int idx) {
-    const uint32_t *bk = bits + (size_t)k * Nw;
-    const size_t g = (size_t)k * N + i;
-    const int row = fast_div_w(i, magic_w), col = i - row * W;
-    const bool bit = (word >> lane) & 1u;  // clear for the padding lanes of the last word
-    // The four points (self, left, up, up-left) are loaded together, guarded by their bits
-    // only, so that the loads are in flight at the same time instead of one after another.
-    const int u = i - W;
-    const uint32_t wu = (bit && row > 0) ? bk[u >> 5] : 0u;
-    const bool bit_l = bit && col > 0 && (lane > 0 ? ((word >> (lane - 1)) & 1u) != 0u : tree_bit(bk, i - 1));
-    const bool bit_u = (wu >> (u & 31)) & 1u;
-    const bool bit_ul = bit_u && bit_l && ((u & 31) ? ((wu >> ((u & 31) - 1)) & 1u) != 0u : tree_bit(bk, u - 1));
-    sloam_point p{0.f, 0.f, 0.f, 0.f}, ql = p, qu = p, qul = p;
-    if (bit) p = ld_point(tree + g);
-    if (bit_l) ql = ld_point(tree + g - 1);
-    if (bit_u) qu = ld_point(tree + g - W);
-    if (bit_ul) qul = ld_point(tree + g - W - 1);
-    // PCL skips a pixel iff !isfinite(x); EuclideanClusterComparator::compare is
-    // dist < threshold in float (NaN compares false)
-    const bool valid = bit && isfinite(p.x);
-    bool left_ok = false, up_ok = false, upleft_ok = false;  // upleft_ok: (i-W) -- (i-W-1)
-    if (valid) {
-      left_ok = bit_l && sqnorm3f(p.x - ql.x, p.y - ql.y, p.z - ql.z) < cut;
-      up_ok = bit_u && sqnorm3f(p.x - qu.x, p.y - qu.y, p.z - qu.z) < cut;
-      upleft_ok = up_ok && left_ok && bit_ul && sqnorm3f(qu.x - qul.x, qu.y - qul.y, qu.z - qul.z) < cut;
-    }
-    // is the left neighbour connected to ITS upper neighbour?
-    int left_up = __shfl_up_sync(kFull, up_ok ? 1 : 0, 1);
-    if (lane == 0) {
-      left_up = 0;
-      if (left_ok && row > 0 && tree_bit(bk, i - 1 - W)) {
-        const sloam_point a = ld_point(tree + g - 1), b = ld_point(tree + g - 1 - W);
-        left_up = sqnorm3f(a.x - b.x, a.y - b.y, a.z - b.z) < cut;
+  const long long total_words = (long long)K * Nw;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long base = warp0 * 32; base < total_words; base += nwarps * 32) {
+    const uint32_t my_word = base + lane < total_words ? bits[base + lane] : 0u;
+    unsigned nz = __ballot_sync(kFull, my_word != 0u);
+    if (nz == 0u) continue;
+    const int k0 = (int)(base / Nw);
+    const int w0 = (int)(base - (long long)k0 * Nw);
+    while (nz) {
+      const int src = __ffs(nz) - 1;
+      nz &= nz - 1;
+      const uint32_t word = __shfl_sync(kFull, my_word, src);
+      int k = k0, wi = w0 + src;
+      while (wi >= Nw) { wi -= Nw; ++k; }  // the chunk may run into the next keyframe(s)
+      const uint32_t *bk = bits + (size_t)k * Nw;
+      const int i = wi * 32 + lane;
+      const size_t g = (size_t)k * N + i;
+      const int row = fast_div_w(i, magic_w), col = i - row * W;
+      const bool bit = (word >> lane) & 1u;  // clear for the padding lanes of the last word
+      // own point and the point above are loaded together (guarded by their bits only), the
+      // left neighbour comes from the lane below
+      const int u = i - W;
+      const bool bit_u = bit && row > 0 && ((bk[u >> 5] >> (u & 31)) & 1u);
+      sloam_point p{0.f, 0.f, 0.f, 0.f}, qu = p;
+      if (bit) p = ld_point(tree + g);
+      if (bit_u) qu = ld_point(tree + g - W);
+      // PCL skips a pixel iff !isfinite(x); EuclideanClusterComparator::compare is
+      // dist < threshold in float (NaN compares false)
+      const bool valid = bit && isfinite(p.x);
+      float lx = __shfl_up_sync(kFull, p.x, 1), ly = __shfl_up_sync(kFull, p.y, 1), lz = __shfl_up_sync(kFull, p.z, 1);
+      bool bit_l = lane > 0 ? ((word >> (lane - 1)) & 1u) != 0u : false;
+      if (lane == 0 && bit && col > 0 && wi > 0 && (bk[wi - 1] >> 31)) {
+        const sloam_point q = ld_point(tree + g - 1);
+        lx = q.x; ly = q.y; lz = q.z;
+        bit_l = true;
       }
-    }
-    // run starts inside the word: link to the start of the row run (short find chains)
-    const unsigned starts = __ballot_sync(kFull, !left_ok);
-    if (i < N) {
-      if (valid) {
-        int par;
-        if (left_ok) {
-          const unsigned s = starts & ((2u << lane) - 1u);   // starts at or below this lane
-          par = s ? i - (lane - (31 - __clz(s))) : i - (lane + 1);
-        } else {
-          par = up_ok ? i - W : i;
-        }
-        parent[g] = par;
-        if (par == i) {  // only a pixel that starts as its own parent can end up a root
-          csize[g] = 0;
-          cmin[g] = col; cmax[g] = col; rmax[g] = row;
-        }
-      } else {
-        parent[g] = kInvalid;
-      }
-    }
-    // A union with the upper neighbour is only needed when it is not implied by
-    // i ~ i-1 (row link), i-1 ~ i-1-W (left neighbour's own up link) and i-W ~ i-W-1.
-    const unsigned mf = __ballot_sync(kFull, left_ok && up_ok && !(left_up && upleft_ok));
-    if (lane == 0) mflags[idx] = mf;  // one bit per pixel of the word, indexed like the word list
-  });
-}
-
-// ---- 2. merge: pixels linked left that are also connected upwards ---------
-__global__ void __launch_bounds__(256)
-cc_merge_kernel(const DevParams *__restrict__ dp, int K, const uint32_t *__restrict__ bits,
-                const int2 *__restrict__ wlist, const int32_t *__restrict__ n_wlist,
-                const uint32_t *__restrict__ mflags, int32_t *__restrict__ parent) {
-  const int N = dp->N, W = dp->p.img_w;
-  const int n = *n_wlist;
-  // thread per listed word: the few pixels whose flag is set are merged by that thread
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
-    uint32_t mf = mflags[idx];
-    if (mf == 0u) continue;
-    const int2 e = wlist[idx];
-    const int k = (int)((unsigned)e.x >> 16), i0 = (e.x & 0xFFFF) * 32;
-    while (mf) {
-      const int i = i0 + __ffs(mf) - 1;
-      mf &= mf - 1;
-      uf_union(parent + (size_t)k * N, i, i - W);
+      const bool left_ok = valid && col > 0 && bit_l && sqnorm3f(p.x - lx, p.y - ly, p.z - lz) < cut;
+      const bool up_ok = valid && bit_u && sqnorm3f(p.x - qu.x, p.y - qu.y, p.z - qu.z) < cut;
+      const unsigned vb = __ballot_sync(kFull, valid);
+      const unsigned sb_ = __ballot_sync(kFull, valid && !left_ok);
+      const unsigned ub = __ballot_sync(kFull, up_ok);
+      if (lane == 0) planes[(size_t)k * Nw + wi] = make_uint4(vb, sb_, ub, 0u);
     }
   }
 }
 
-// ---- 3. flatten + statistics at the root ----------------------------------
-__global__ void __launch_bounds__(256)
-cc_flatten_kernel(const DevParams *__restrict__ dp, int K, const uint32_t *__restrict__ bits,
-                  const int2 *__restrict__ wlist, const int32_t *__restrict__ n_wlist,
-                  int32_t *__restrict__ parent, int32_t *__restrict__ csize, int32_t *__restrict__ cmin,
-                  int32_t *__restrict__ cmax, int32_t *__restrict__ rmax, int32_t *__restrict__ row_roots,
-                  int32_t *__restrict__ n_roots, int32_t *__restrict__ big_roots,
-                  int32_t *__restrict__ n_big, int32_t *__restrict__ kf_flags, uint32_t *__restrict__ root_bits) {
-  const int N = dp->N, W = dp->p.img_w, H = dp->p.img_h;
-  const int min_pts = dp->p.min_cluster_points, T = dp->p.max_trees;
-  const unsigned magic_w = dp->magic_w;
-  const int lane = threadIdx.x & 31;
-  for_each_tree_word(wlist, n_wlist, [&](int k, int i, uint32_t word, int) {
-    const size_t g = (size_t)k * N + i;
-    int root = kInvalid;
-    const int par0 = ((word >> lane) & 1u) ? parent[g] : kInvalid;
-    if (par0 != kInvalid) {
-      root = par0 == i ? i : uf_find(parent + (size_t)k * N, par0);
-      parent[g] = root;
+// ---- 2. per keyframe: runs, union-find, labels, work items -------------------
+// exclusive scan of one int per thread over the CTA; *total = sum.  s_tmp: kLblWarps + 1 ints
+__device__ __forceinline__ int cta_scan_excl(int v, int *s_tmp, int *total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(kFull, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_tmp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const int t = lane < kLblWarps ? s_tmp[lane] : 0;
+    int ti = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int q = __shfl_up_sync(kFull, ti, o);
+      if (lane >= o) ti += q;
     }
-    const int row = fast_div_w(i, magic_w), col = i - row * W;
-    // Consecutive lanes are consecutive pixels of a row, so the members of a component come
-    // in runs: a run = maximal stretch of lanes with the same (root, row).  One lane per run
-    // (its head) issues the atomics for the whole run.
-    const long long key = root == kInvalid ? -1ll - lane : ((long long)root * 4096ll + row);
-    const long long prev = __shfl_up_sync(kFull, key, 1);
-    const bool head = root != kInvalid && (lane == 0 || prev != key);
-    const unsigned heads = __ballot_sync(kFull, head || root == kInvalid);
-    if (head) {
-      // run length = distance to the next head / invalid lane (or the end of the word)
-      const unsigned above = heads & ~((2u << lane) - 1u);
-      const int len = (above ? __ffs(above) - 1 : 32) - lane;
-      const size_t r = (size_t)k * N + root;
-      const int old = atomicAdd(&csize[r], len);
-      if (old <= min_pts && old + len > min_pts) {  // exactly one run sees the crossing
-        const int slot = atomicAdd(&n_big[k], 1);
-        if (slot < T) big_roots[(size_t)k * T + slot] = root;
-        else atomicOr(&kf_flags[k], 1);
-      }
-      // extents of the component (monotone, so the racy pre-checks are safe)
-      if (col < cmin[r]) atomicMin(&cmin[r], col);
-      if (col + len - 1 > cmax[r]) atomicMax(&cmax[r], col + len - 1);
-      if (row > rmax[r]) atomicMax(&rmax[r], row);
-    }
-    if (root == i) {
-      atomicAdd(&row_roots[(size_t)k * H + row], 1);
-      atomicAdd(&n_roots[k], 1);
-      // one bit per pixel: is a component root (cc_plan counts the roots before a given one);
-      // roots are few, the words were zeroed before the launch
-      atomicOr(&root_bits[(size_t)k * ((N + 31) >> 5) + (i >> 5)], 1u << (i & 31));
-    }
-  });
+    if (lane < kLblWarps) s_tmp[lane] = ti - t;
+    if (lane == kLblWarps - 1) s_tmp[kLblWarps] = ti;
+  }
+  __syncthreads();
+  const int off = s_tmp[warp];
+  *total = s_tmp[kLblWarps];
+  __syncthreads();  // s_tmp may be reused by the next call
+  return off + inc - v;
 }
 
-// ---- 4. plan: sort big clusters, rank them, emit work items ----------------
-__global__ void cc_plan_kernel(const DevParams *__restrict__ dp, const uint32_t *__restrict__ root_bits,
-                               const int32_t *__restrict__ parent,
-                               const int32_t *__restrict__ cmin, const int32_t *__restrict__ cmax,
-                               const int32_t *__restrict__ rmax, const int32_t *__restrict__ row_roots,
-                               int32_t *__restrict__ big_roots, int32_t *__restrict__ n_big,
-                               int32_t *__restrict__ big_rank, int32_t *__restrict__ bbox,
-                               int32_t *__restrict__ vwork, int32_t *__restrict__ n_vwork) {
-  extern __shared__ int32_t sm[];
-  const int N = dp->N, W = dp->p.img_w, H = dp->p.img_h, T = dp->p.max_trees;
+// run id of valid pixel i: number of run starts at or before it, minus one
+__device__ __forceinline__ int run_of(const uint32_t *s_start, const int32_t *s_wbase, int i) {
+  const int w = i >> 5, b = i & 31;
+  return s_wbase[w] + __popc(s_start[w] & ((2u << b) - 1u)) - 1;
+}
+// 32 bits of a bit plane starting at bit position pos (pos may be negative or run past the end)
+__device__ __forceinline__ uint32_t bits_at(const uint32_t *s_plane, int Nw, int pos) {
+  if (pos <= -32) return 0u;
+  const int w = pos >> 5;  // floor division also for negative pos
+  const int b = pos & 31;
+  const uint32_t lo = (w >= 0 && w < Nw) ? s_plane[w] : 0u;
+  const uint32_t hi = (w + 1 >= 0 && w + 1 < Nw) ? s_plane[w + 1] : 0u;
+  return b ? ((lo >> b) | (hi << (32 - b))) : lo;
+}
+
+__global__ void __launch_bounds__(kLblThreads)
+cc_label_kernel(const DevParams *__restrict__ dp, const uint32_t *__restrict__ bits,
+                const uint4 *__restrict__ planes, int Rs, int32_t *__restrict__ g_par,
+                uint32_t *__restrict__ g_siz, int32_t *__restrict__ g_len, int32_t *__restrict__ run_pix0,
+                int32_t *__restrict__ run_info, int32_t *__restrict__ run_label, int32_t *__restrict__ wbase_out,
+                int32_t *__restrict__ n_roots, int32_t *__restrict__ n_big, int32_t *__restrict__ big_rank,
+                int32_t *__restrict__ kf_flags, uint32_t *__restrict__ slot_rows, VItem *__restrict__ items,
+                int32_t *__restrict__ vlists, long long list_cap, int32_t *__restrict__ n_lists) {
+  extern __shared__ __align__(16) unsigned char lbl_smem[];
+  const int N = dp->N, W = dp->p.img_w, H = dp->p.img_h, T = dp->p.max_trees, Nw = (N + 31) >> 5;
+  const int Hw = (H + 31) >> 5;
+  const int min_pts = dp->p.min_cluster_points, min_vtx = dp->p.min_vertex_points;
+  const int item_shift = dp->vw_row_bits + dp->vw_slot_bits;
   const int k = blockIdx.x;
-  int32_t *s_roots = sm;            // [T]
-  int32_t *s_sorted = sm + T;       // [T]
-  int32_t *s_rowpre = sm + 2 * T;   // [H+1]
-  const int nb = min(n_big[k], T);
-  for (int s = threadIdx.x; s < nb; s += blockDim.x) s_roots[s] = big_roots[(size_t)k * T + s];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t *s_start = reinterpret_cast<uint32_t *>(lbl_smem);          // [Nw]
+  int32_t *s_wbase = reinterpret_cast<int32_t *>(s_start + Nw);        // [Nw]
+  uint32_t *s_rows = reinterpret_cast<uint32_t *>(s_wbase + Nw);       // [T * Hw]
+  int32_t *s_runs = reinterpret_cast<int32_t *>(s_rows + (size_t)T * Hw);  // 3 x [Rs]
+  __shared__ int s_tmp[kLblWarps + 1];
+  __shared__ int s_nitems;
+  const uint32_t *bk = bits + (size_t)k * Nw;
+  const uint4 *pk = planes + (size_t)k * Nw;
+
+  // -- run ids: prefix count of the start bits, in raster order
+  int R = 0;
+  for (int w0 = 0; w0 < Nw; w0 += kLblThreads) {
+    const int w = w0 + threadIdx.x;
+    uint32_t s = 0u;
+    if (w < Nw && bk[w] != 0u) s = pk[w].y;
+    if (w < Nw) s_start[w] = s;
+    int tot;
+    const int ex = cta_scan_excl(__popc(s), s_tmp, &tot);
+    if (w < Nw) s_wbase[w] = R + ex;
+    R += tot;
+  }
+  if (wbase_out)
+    for (int w = threadIdx.x; w < Nw; w += kLblThreads) wbase_out[(size_t)k * Nw + w] = s_wbase[w];
+  for (int i = threadIdx.x; i < T * Hw; i += kLblThreads) s_rows[i] = 0u;
+  if (threadIdx.x == 0) s_nitems = 0;
+  // per-run arrays: shared memory, or the keyframe's slice of global scratch for scans with
+  // more runs than fit (correct, slower; a forest scan has a few thousand runs)
+  int32_t *par = s_runs;
+  uint32_t *siz = reinterpret_cast<uint32_t *>(s_runs + Rs);
+  int32_t *len = s_runs + 2 * (size_t)Rs;
+  if (R > Rs) { par = g_par + (size_t)k * N; siz = g_siz + (size_t)k * N; len = g_len + (size_t)k * N; }
+  for (int r = threadIdx.x; r < R; r += kLblThreads) { par[r] = r; siz[r] = 0u; len[r] = 0; }
+  __syncthreads();
+
+  // -- run lengths, first pixels, and the unions of vertically connected runs
+  int32_t *pix0_k = run_pix0 + (size_t)k * N;
+  for (int w = threadIdx.x; w < Nw; w += kLblThreads) {
+    if (bk[w] == 0u) continue;
+    const uint4 pl = pk[w];
+    const uint32_t v = pl.x, s = pl.y, u = pl.z;
+    const int base = s_wbase[w];
+    // segments of runs inside this word: one per start bit, plus a run continuing from the
+    // previous word when bit 0 is valid without being a start
+    uint32_t begins = s | (v & 1u);
+    while (begins) {
+      const int b = __ffs(begins) - 1;
+      begins &= begins - 1;
+      const int rid = base + __popc(s & ((2u << b) - 1u)) - 1;
+      int cnt = __ffs(~(v >> b)) - 1;  // consecutive valid bits from b (zeros are shifted in at the top)
+      if (cnt < 0) cnt = 32;           // b == 0 and the whole word is valid
+      const uint32_t later = s & ~((2u << b) - 1u);
+      if (later) cnt = min(cnt, __ffs(later) - 1 - b);
+      atomicAdd(&len[rid], cnt);
+      if ((s >> b) & 1u) pix0_k[rid] = w * 32 + b;
+    }
+    // a union is needed where an up link is not implied by the previous pixel's: the pixel or
+    // the one above starts a run, or the previous pixel has no up link (bit 0: always)
+    const uint32_t su = bits_at(s_start, Nw, w * 32 - W);
+    uint32_t flagged = u & (s | su | ~(u << 1));
+    while (flagged) {
+      const int b = __ffs(flagged) - 1;
+      flagged &= flagged - 1;
+      const int i = w * 32 + b;
+      uf_union(par, base + __popc(s & ((2u << b) - 1u)) - 1, run_of(s_start, s_wbase, i - W));
+    }
+  }
+  __syncthreads();
+  // -- flatten, component sizes at the root
+  for (int r = threadIdx.x; r < R; r += kLblThreads) par[r] = uf_find(par, r);
+  __syncthreads();
+  for (int r = threadIdx.x; r < R; r += kLblThreads) atomicAdd(&siz[par[r]], (uint32_t)len[r]);
+  __syncthreads();
+  // -- PCL label of every root (number of roots before it) and slot of every big component
+  // (number of big roots before it = tree order); siz[root] := label << 11 | slot code
+  int n_root = 0, n_bigc = 0;
+  for (int r0 = 0; r0 < R; r0 += kLblThreads) {
+    const int r = r0 + threadIdx.x;
+    const bool is_root = r < R && par[r] == r;
+    const bool is_big = is_root && (int)siz[r] > min_pts;
+    int tr, tb;
+    const int er = cta_scan_excl(is_root ? 1 : 0, s_tmp, &tr);
+    const int eb = cta_scan_excl(is_big ? 1 : 0, s_tmp, &tb);
+    if (is_root) {
+      const int label = n_root + er, slot = n_bigc + eb;
+      const bool keep = is_big && slot < T;  // more big components than max_trees: the first T in label order
+      siz[r] = ((uint32_t)label << 11) | (keep ? (uint32_t)(slot + 1) : 0u);
+      if (keep) big_rank[(size_t)k * T + slot] = label;
+    }
+    n_root += tr;
+    n_bigc += tb;
+  }
   if (threadIdx.x == 0) {
-    int acc = 0;
-    for (int r = 0; r < H; ++r) { s_rowpre[r] = acc; acc += row_roots[(size_t)k * H + r]; }
-    s_rowpre[H] = acc;
+    n_roots[k] = n_root;
+    n_big[k] = min(n_bigc, T);
+    if (n_bigc > T) atomicOr(&kf_flags[k], 1);
   }
   __syncthreads();
-  for (int s = threadIdx.x; s < nb; s += blockDim.x) {  // rank sort (roots are distinct)
-    const int v = s_roots[s];
-    int r = 0;
-    for (int j = 0; j < nb; ++j) r += s_roots[j] < v;
-    s_sorted[r] = v;
+  // -- per-run tables: length and slot code (shared + global), label (global)
+  int32_t *info_k = run_info + (size_t)k * N, *label_k = run_label + (size_t)k * N;
+  for (int r = threadIdx.x; r < R; r += kLblThreads) {
+    const uint32_t rootw = siz[par[r]];
+    const int packed = (len[r] << 11) | (int)(rootw & kSlotMask);
+    len[r] = packed;
+    info_k[r] = packed;
+    label_k[r] = (int)(rootw >> 11);
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int s = warp; s < nb; s += nwarps) {
-    const int root = s_sorted[s];
-    const int row = root / W, col = root - row * W;
-    // PCL label = number of component roots before this one in raster order: the roots of
-    // the rows above (s_rowpre) + the set bits of root_bits in [row * W, root)
-    int cnt = 0;
-    const uint32_t *rbk = root_bits + (size_t)k * ((N + 31) >> 5);
-    const int a = row * W, b = root;  // pixel range [a, b)
-    for (int wi = (a >> 5) + lane; wi <= (b >> 5); wi += 32) {
-      uint32_t v = rbk[wi];
-      if (wi == (a >> 5)) v &= 0xFFFFFFFFu << (a & 31);
-      if (wi == (b >> 5)) v &= (b & 31) ? (0xFFFFFFFFu >> (32 - (b & 31))) : 0u;
-      cnt += __popc(v);
-    }
-    cnt = warp_sum(cnt);
-    if (lane == 0) {
-      const size_t r = (size_t)k * N + root;
-      big_roots[(size_t)k * T + s] = root;
-      big_rank[(size_t)k * T + s] = s_rowpre[row] + cnt;
-      int32_t *bb = bbox + ((size_t)k * T + s) * 4;
-      const int r1 = rmax[r];
-      bb[0] = cmin[r]; bb[1] = cmax[r]; bb[2] = row; bb[3] = r1;
-      const int nrows = r1 - row + 1;
-      const int base = atomicAdd(n_vwork, nrows);
-      for (int q = 0; q < nrows; ++q) vwork[base + q] = vw_pack(dp, k, s, row + q);
+  // -- work items: one per (big component, row).  One warp per row; a lane per run of the row
+  // scans the row's runs: it is the head of its (slot, row) group when no earlier run of the
+  // row has the same slot, and then sums the members of the later ones.
+  VItem *items_k = items + ((size_t)k << item_shift);
+  for (int row = warp; row < H; row += kLblWarps) {
+    const int p0 = row * W, p1 = p0 + W;
+    const int rb = s_wbase[p0 >> 5] + __popc(s_start[p0 >> 5] & ((1u << (p0 & 31)) - 1u));
+    const int re = p1 >= N ? R : s_wbase[p1 >> 5] + __popc(s_start[p1 >> 5] & ((1u << (p1 & 31)) - 1u));
+    for (int c0 = rb; c0 < re; c0 += 32) {
+      const int r = c0 + lane;
+      int sc = 0, n_tot = 0, last = r;
+      bool head = false;
+      if (r < re) {
+        const int inf = len[r];
+        sc = inf & (int)kSlotMask;
+        n_tot = inf >> 11;
+        head = sc != 0;
+      }
+      if (__any_sync(kFull, head)) {
+        for (int j = rb; j < re; ++j) {
+          const int infj = len[j];
+          if ((infj & (int)kSlotMask) == sc && j != r) {
+            if (j < r) head = false;
+            else { n_tot += infj >> 11; last = j; }
+          }
+        }
+      }
+      int cls = -1;
+      if (head && n_tot > min_vtx)
+        cls = n_tot <= 8 ? 0 : (n_tot <= 16 ? 1 : (n_tot <= 32 ? 2 : (n_tot <= kVtxCap ? 3 : kClsWide)));
+      const unsigned hb = __ballot_sync(kFull, cls >= 0);
+      if (hb == 0u) continue;
+      int ibase = 0;
+      if (lane == 0) ibase = atomicAdd(&s_nitems, __popc(hb));
+      ibase = __shfl_sync(kFull, ibase, 0);
+      const int idx = ibase + __popc(hb & ((1u << lane) - 1u));
+      if (cls >= 0) {
+        VItem it;
+        it.pix0 = pix0_k[r];
+        it.first_run = r;
+        it.n = (uint16_t)n_tot;
+        it.span = (uint16_t)(last - r);
+        it.slot = (uint16_t)(sc - 1);
+        it.row = (uint16_t)row;
+        items_k[idx] = it;
+        atomicOr(&s_rows[(sc - 1) * Hw + (row >> 5)], 1u << (row & 31));
+      }
+#pragma unroll
+      for (int c = 0; c <= kClsWide; ++c) {
+        const unsigned cb = __ballot_sync(kFull, cls == c);
+        if (cb == 0u) continue;
+        const int leader = __ffs(cb) - 1;
+        int lb = 0;
+        if (lane == leader) lb = atomicAdd(&n_lists[c], __popc(cb));
+        lb = __shfl_sync(kFull, lb, leader);
+        if (cls == c) vlists[(size_t)c * list_cap + lb + __popc(cb & ((1u << lane) - 1u))] = (k << item_shift) | idx;
+      }
     }
   }
-  if (threadIdx.x == 0) n_big[k] = nb;
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * Hw; i += kLblThreads) slot_rows[(size_t)k * T * Hw + i] = s_rows[i];
 }
 
-// ---- 5. one vertex per (cluster, row) --------------------------------------
+// ---- 3. one vertex per (cluster, row) ----------------------------------------
 struct VtxSmem {
   float x[kVtxCap], y[kVtxCap], z[kVtxCap], w[kVtxCap];
   int16_t col[kVtxCap];
   int16_t order[kVtxCap];
+};
+// small rows: one member per lane, the groups of a warp side by side
+struct __align__(16) GrpSmem {
+  float x[32], y[32], z[32], w[32];
+  int8_t ord[32], ord2[32];
 };
 
 // lexicographic (z, y, x, col): the order the reference's three std::sort calls
@@ -387,6 +450,145 @@ __device__ __noinline__ void replay_sorts_packed(int16_t *order, unsigned long l
     srt.sort(n);
   }
   for (int m = 0; m < n; ++m) order[m] = (int16_t)(pack[m] & 0xFFFFFFFFull);
+}
+
+// pixel of member m of an item whose members are spread over several runs (rare: a row of a
+// trunk split by a gap): walk the runs of the row between the first and the last one
+__device__ __forceinline__ int member_pixel(const VItem &it, int m, const int32_t *__restrict__ pix0_k,
+                                            const int32_t *__restrict__ info_k) {
+  int acc = 0;
+  for (int j = it.first_run; j <= it.first_run + (int)it.span; ++j) {
+    const int inf = info_k[j];
+    if ((inf & (int)kSlotMask) != (int)it.slot + 1) continue;
+    const int ln = inf >> 11;
+    if (m < acc + ln) return pix0_k[j] + (m - acc);
+    acc += ln;
+  }
+  return it.pix0;  // not reached: n is the sum of the matching runs' lengths
+}
+
+// G lanes per item (G = 8, 16, 32): the warp handles 32 / G items side by side.  Returns (per
+// lane) true when the lane's item has exact z ties among more than 16 members and must be
+// redone by the replay kernel (nothing was written for it).
+template <int G>
+__device__ __forceinline__ bool vertex_group(const DevParams *dp, GrpSmem &s, bool active, const VItem &it, int k,
+                                             const sloam_point *__restrict__ tree, const int32_t *__restrict__ run_pix0,
+                                             const int32_t *__restrict__ run_info, sloam_vertex *__restrict__ slot_vertices,
+                                             sloam_point *__restrict__ pool, int32_t *__restrict__ pool_count) {
+  const int N = dp->N, H = dp->p.img_h, T = dp->p.max_trees;
+  const int lane = threadIdx.x & 31, gl = lane & (G - 1), g0 = lane & ~(G - 1);
+  const unsigned gmask = G == 32 ? kFull : (((1u << G) - 1u) << g0);
+  const unsigned lt = (1u << lane) - 1u;
+  const int n = active ? (int)it.n : 0;
+  const float inf = __int_as_float(0x7f800000);
+  // -- members: one per lane, in column order (trellis.cpp:113-118)
+  sloam_point p{inf, inf, inf, 0.f};
+  if (gl < n) {
+    const int pixel = it.span == 0 ? it.pix0 + gl
+                                   : member_pixel(it, gl, run_pix0 + (size_t)k * N, run_info + (size_t)k * N);
+    p = ld_point(tree + (size_t)k * N + pixel);
+  }
+  __syncwarp();  // the previous item's readers are done
+  s.x[lane] = p.x; s.y[lane] = p.y; s.z[lane] = p.z; s.w[lane] = p.intensity;  // lanes >= n pad with +inf
+  __syncwarp();
+  // -- order statistics by counting: member m counts the members strictly below it on each
+  // axis; without ties that is its rank (float counts: FSET + FADD per comparison)
+  const int middle = n >> 1;  // (int)(n / 2.0), trellis.cpp:66
+  float fx = 0.f, fy = 0.f, fz = 0.f;
+  {
+    const float4 *X4 = reinterpret_cast<const float4 *>(s.x + g0), *Y4 = reinterpret_cast<const float4 *>(s.y + g0),
+                 *Z4 = reinterpret_cast<const float4 *>(s.z + g0);
+    const int n4 = (n + 3) >> 2;
+#pragma unroll
+    for (int j4 = 0; j4 < G / 4; ++j4) {
+      if (j4 < n4) {
+        const float4 xv = X4[j4], yv = Y4[j4], zv = Z4[j4];
+        fx += (flt(xv.x, p.x) + flt(xv.y, p.x)) + (flt(xv.z, p.x) + flt(xv.w, p.x));
+        fy += (flt(yv.x, p.y) + flt(yv.y, p.y)) + (flt(yv.z, p.y) + flt(yv.w, p.y));
+        fz += (flt(zv.x, p.z) + flt(zv.y, p.z)) + (flt(zv.z, p.z) + flt(zv.w, p.z));
+      }
+    }
+  }
+  const int lx = (int)fx, ly = (int)fy, lz = (int)fz;
+  const bool mem = gl < n;
+  // z order; two members with the same count (an exact tie) collide on one slot: detected below
+  if (mem) s.ord[g0 + lz] = (int8_t)gl;
+  unsigned bx = __ballot_sync(kFull, mem && lx == middle) & gmask;
+  unsigned by = __ballot_sync(kFull, mem && ly == middle) & gmask;
+  unsigned bz = __ballot_sync(kFull, mem && lz == middle) & gmask;
+  __syncwarp();
+  const bool lost = mem && s.ord[g0 + lz] != (int8_t)gl;
+  const bool ztie = (__ballot_sync(kFull, lost) & gmask) != 0u;
+  // a tie group straddling a median leaves no member with count == middle: stable ranks
+  // (value, then index) decide, like a stable sort would (the median VALUE is what matters)
+  if (__any_sync(kFull, active && (bx == 0u || by == 0u || bz == 0u))) {
+    int rx = lx, ry = ly, rz = lz;
+    for (int j = 0; j < G; ++j) {
+      if (j < n && j < gl) {
+        rx += s.x[g0 + j] == p.x; ry += s.y[g0 + j] == p.y; rz += s.z[g0 + j] == p.z;
+      }
+    }
+    const unsigned cx = __ballot_sync(kFull, mem && rx == middle) & gmask;
+    const unsigned cy = __ballot_sync(kFull, mem && ry == middle) & gmask;
+    const unsigned cz = __ballot_sync(kFull, mem && rz == middle) & gmask;
+    if (bx == 0u) bx = cx;
+    if (by == 0u) by = cy;
+    if (bz == 0u) bz = cz;
+  }
+  const float med0 = __shfl_sync(kFull, p.x, bx ? __ffs(bx) - 1 : lane);
+  const float med1 = __shfl_sync(kFull, p.y, by ? __ffs(by) - 1 : lane);
+  const float med2 = __shfl_sync(kFull, p.z, bz ? __ffs(bz) - 1 : lane);
+  bool redo = false;
+  if (__any_sync(kFull, ztie)) {
+    // Exact z ties: the order of the tied points is whatever the reference's three std::sort
+    // calls (by x, by y, by z; trellis.cpp:71-82) leave behind.  Up to 16 points libstdc++
+    // sorts by insertion (stable), so the result is the lexicographic (z, y, x, column) order
+    // (members are in column order, so the column comparison is the member index).  Beyond
+    // that its introsort is not stable: the item goes to the replay kernel.
+    if (ztie && n > 16) redo = true;
+    __syncwarp();
+    if (ztie && n <= 16 && mem) {
+      int rk = 0;
+      for (int j = 0; j < n; ++j) rk += key_less(s.z[g0 + j], s.y[g0 + j], s.x[g0 + j], j, p.z, p.y, p.x, gl);
+      s.ord[g0 + rk] = (int8_t)gl;
+    }
+    __syncwarp();
+  }
+  if (redo) active = false;
+  // -- keep points within max_dist_to_centroid of the median, in z order (trellis.cpp:89-93)
+  const float cut = dp->centroid_sq_cut;  // dist < max_dist_to_centroid  <=>  squared dist < cut
+  bool keep = false;
+  int m = 0;
+  if (active && mem) {
+    m = s.ord[g0 + gl];
+    keep = sqnorm3f(s.x[g0 + m] - med0, s.y[g0 + m] - med1, s.z[g0 + m] - med2) < cut;
+  }
+  const unsigned kb = __ballot_sync(kFull, keep) & gmask;
+  const int kept = __popc(kb);
+  if (keep) s.ord2[g0 + __popc(kb & lt)] = (int8_t)m;
+  __syncwarp();
+  int base = 0;
+  if (active && gl == 0 && kept > 1) base = atomicAdd(pool_count + k, kept);
+  base = __shfl_sync(kFull, base, g0);
+  if (active && kept > 1 && gl < kept) {
+    const int q = s.ord2[g0 + gl];
+    sloam_point o; o.x = s.x[g0 + q]; o.y = s.y[g0 + q]; o.z = s.z[g0 + q]; o.intensity = s.w[g0 + q];
+    st_point(pool + (size_t)k * N + base + gl, o);
+  }
+  if (active && gl == 0) {
+    float radius = 0.f;
+    int n_points = 0, point_begin = 0, is_valid = 0;
+    if (kept > 1) {  // trellis.cpp:95-100
+      const int a = s.ord2[g0], b = s.ord2[g0 + kept - 1];
+      radius = dist3f(s.x[g0 + a], s.y[g0 + a], s.z[g0 + a], s.x[g0 + b], s.y[g0 + b], s.z[g0 + b]);
+      n_points = kept; point_begin = base; is_valid = 1;
+    }
+    float4 *dst = reinterpret_cast<float4 *>(slot_vertices + ((size_t)k * T + it.slot) * H + it.row);
+    dst[0] = make_float4(med0, med1, med2, radius);
+    dst[1] = make_float4(__int_as_float(n_points), __int_as_float(point_begin), __int_as_float((int)it.row),
+                         __int_as_float(is_valid));
+  }
+  return redo;
 }
 
 // REPLAY = false: returns true when the item has exact z ties among more than 16 points and
@@ -475,12 +677,9 @@ __device__ bool build_vertex(const DevParams *dp, VtxSmem &s, unsigned long long
   }
   __syncwarp();
   if (any_ztie) {
-    // Exact z ties: the order of the tied points is whatever the reference's three std::sort
-    // calls (by x, by y, by z; trellis.cpp:71-82) leave behind.  Up to 16 points libstdc++
-    // sorts by insertion (stable), so the result is the lexicographic (z, y, x, column) order.
-    // Beyond that its introsort is not stable and one lane replays it (dev_stdsort.h).  That
-    // code lives in a second instance of the kernel that only sees the (rare) tied items: with
-    // it inside the main instance every item ran 25 % slower.
+    // Exact z ties: see vertex_group.  Beyond 16 points one lane replays libstdc++'s introsort
+    // (dev_stdsort.h).  That code lives in a second kernel that only sees the (rare) tied
+    // items: with it inside the main instance every item ran 25 % slower.
     if (n > 16) {
       if (!REPLAY) return true;
       __syncwarp();
@@ -532,110 +731,176 @@ __device__ bool build_vertex(const DevParams *dp, VtxSmem &s, unsigned long long
   return false;
 }
 
+// members of an item into the warp's arrays (column order); n <= kVtxCap
+__device__ __forceinline__ void gather_members(const DevParams *dp, VtxSmem &s, const VItem &it, int k,
+                                               const sloam_point *__restrict__ tree,
+                                               const int32_t *__restrict__ run_pix0,
+                                               const int32_t *__restrict__ run_info) {
+  const int N = dp->N, W = dp->p.img_w;
+  const int lane = threadIdx.x & 31;
+  const sloam_point *tk = tree + (size_t)k * N;
+  const int rowbase = (int)it.row * W;
+  if (it.span == 0) {
+    for (int m = lane; m < (int)it.n; m += 32) {
+      const sloam_point p = ld_point(tk + it.pix0 + m);
+      s.x[m] = p.x; s.y[m] = p.y; s.z[m] = p.z; s.w[m] = p.intensity;
+      s.col[m] = (int16_t)(it.pix0 + m - rowbase);
+    }
+  } else {
+    const int32_t *pix0_k = run_pix0 + (size_t)k * N, *info_k = run_info + (size_t)k * N;
+    int acc = 0;
+    for (int j = it.first_run; j <= it.first_run + (int)it.span; ++j) {
+      const int inf = info_k[j];
+      if ((inf & (int)kSlotMask) != (int)it.slot + 1) continue;
+      const int ln = inf >> 11, p0 = pix0_k[j];
+      for (int t = lane; t < ln; t += 32) {
+        const sloam_point p = ld_point(tk + p0 + t);
+        const int m = acc + t;
+        s.x[m] = p.x; s.y[m] = p.y; s.z[m] = p.z; s.w[m] = p.intensity;
+        s.col[m] = (int16_t)(p0 + t - rowbase);
+      }
+      acc += ln;
+    }
+  }
+  __syncwarp();
+}
+
 #ifndef SLOAM_VTX_MIN
 #define SLOAM_VTX_MIN 5
 #endif
-template <bool REPLAY>
+// One persistent launch walks the four size classes one after the other (independent lists).
 __global__ void __launch_bounds__(kVtxWarps * 32, SLOAM_VTX_MIN)
 vertex_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ tree,
-              const uint32_t *__restrict__ bits, const int32_t *__restrict__ parent, const int32_t *__restrict__ big_roots,
-              const int32_t *__restrict__ bbox, const int32_t *__restrict__ vwork,
-              const int32_t *__restrict__ n_vwork, sloam_vertex *__restrict__ slot_vertices,
-              sloam_point *__restrict__ pool, int32_t *__restrict__ pool_count,
-              int32_t *__restrict__ overflow, int32_t *__restrict__ n_overflow,
-              int32_t *__restrict__ tied, int32_t *__restrict__ n_tied) {
+              const VItem *__restrict__ items, int32_t *__restrict__ vlists, long long list_cap,
+              int32_t *__restrict__ n_lists, const int32_t *__restrict__ run_pix0,
+              const int32_t *__restrict__ run_info, sloam_vertex *__restrict__ slot_vertices,
+              sloam_point *__restrict__ pool, int32_t *__restrict__ pool_count) {
   __shared__ __align__(16) VtxSmem sm[kVtxWarps];
-  __shared__ unsigned long long s_pack[REPLAY ? kVtxWarps * kVtxCap : 1];  // replay scratch
-  __shared__ int16_t s_perm[REPLAY ? kVtxWarps * 2 * kVtxCap : 1];        // members in x and in y order
-  const int N = dp->N, W = dp->p.img_w, H = dp->p.img_h, T = dp->p.max_trees;
+  const int N = dp->N, H = dp->p.img_h, T = dp->p.max_trees;
+  const int item_shift = dp->vw_row_bits + dp->vw_slot_bits;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  VtxSmem &s = sm[warp];
-  unsigned long long *pack = REPLAY ? s_pack + warp * kVtxCap : s_pack;
-  int16_t *perm = REPLAY ? s_perm + warp * 2 * kVtxCap : s_perm;
-  const int total = *n_vwork;
-  for (int item = blockIdx.x * kVtxWarps + warp; item < total; item += gridDim.x * kVtxWarps) {
-    const int w = vwork[item];
-    int k, slot, row;
-    vw_unpack(dp, w, k, slot, row);
-    const int root = big_roots[(size_t)k * T + slot];
-    const int32_t *bb = bbox + ((size_t)k * T + slot) * 4;
-    const int c0 = bb[0], c1 = bb[1];
-    const size_t rbase = (size_t)k * N + (size_t)row * W;
-    const uint32_t *bk = bits + (size_t)k * ((N + 31) >> 5);
-    sloam_vertex *out = slot_vertices + ((size_t)k * T + slot) * H + row;
-    // members of this cluster in this row, in column order (trellis.cpp:113-118)
-    int n = 0;
-    for (int c = c0 + lane; c < ((c1 - c0 + 32) & ~31) + c0; c += 32) {
-      // both loads are unconditional so that they are in flight together
-      const int cc = c <= c1 ? c : c1;
-      const int pc = parent[rbase + cc];  // stale where the bit is clear: never trusted alone
-      const uint32_t bw = bk[(row * W + cc) >> 5];
-      const bool mem = c <= c1 && ((bw >> ((row * W + cc) & 31)) & 1u) && pc == root;
-      const unsigned b = __ballot_sync(kFull, mem);
-      if (mem) {
-        const int pos = n + __popc(b & ((1u << lane) - 1u));
-        if (pos < kVtxCap) {
-          const sloam_point p = ld_point(tree + rbase + c);
-          s.x[pos] = p.x; s.y[pos] = p.y; s.z[pos] = p.z; s.w[pos] = p.intensity;
-          s.col[pos] = (int16_t)c;
-        }
+  const int gwarp = blockIdx.x * kVtxWarps + warp, nwarps = gridDim.x * kVtxWarps;
+  int32_t *tied = vlists + (size_t)kClsTied * list_cap;
+  GrpSmem &gs = *reinterpret_cast<GrpSmem *>(&sm[warp]);
+  auto run_class = [&](auto gtag, int cls) {
+    constexpr int G = decltype(gtag)::value;
+    constexpr int per = 32 / G;
+    const int32_t *list = vlists + (size_t)cls * list_cap;
+    const int count = n_lists[cls];
+    for (int ws = gwarp; ws * per < count; ws += nwarps) {
+      const int li = ws * per + lane / G;
+      const bool active = li < count;
+      VItem it;
+      int gid = 0;
+      if (active) {
+        gid = list[li];
+        it = items[gid];
+      } else {
+        it.pix0 = 0; it.first_run = 0; it.n = 0; it.span = 0; it.slot = 0; it.row = 0;
       }
-      n += __popc(b);
+      const int k = gid >> item_shift;
+      const bool redo = vertex_group<G>(dp, gs, active, it, k, tree, run_pix0, run_info, slot_vertices, pool, pool_count);
+      const unsigned rb = __ballot_sync(kFull, redo && (lane & (G - 1)) == 0);
+      if (rb) {
+        int tb = 0;
+        if (lane == 0) tb = atomicAdd(&n_lists[kClsTied], __popc(rb));
+        tb = __shfl_sync(kFull, tb, 0);
+        if (redo && (lane & (G - 1)) == 0) tied[tb + __popc(rb & ((1u << lane) - 1u))] = gid;
+      }
     }
+  };
+  run_class(std::integral_constant<int, 8>{}, 0);
+  run_class(std::integral_constant<int, 16>{}, 1);
+  run_class(std::integral_constant<int, 32>{}, 2);
+  {  // 33 .. kVtxCap members: one warp per item, the members in shared memory
+    VtxSmem &s = sm[warp];
+    const int32_t *list = vlists + (size_t)3 * list_cap;
+    const int count = n_lists[3];
+    for (int li = gwarp; li < count; li += nwarps) {
+      const int gid = list[li];
+      const VItem it = items[gid];
+      const int k = gid >> item_shift;
+      __syncwarp();
+      gather_members(dp, s, it, k, tree, run_pix0, run_info);
+      sloam_vertex *out = slot_vertices + ((size_t)k * T + it.slot) * H + it.row;
+      if (build_vertex<false>(dp, s, nullptr, nullptr, it.n, it.row, out, pool + (size_t)k * N, pool_count + k) && lane == 0)
+        tied[atomicAdd(&n_lists[kClsTied], 1)] = gid;
+      __syncwarp();
+    }
+  }
+}
+
+// the items with exact z ties among more than 16 members, with the std::sort replay
+__global__ void __launch_bounds__(kVtxWarps * 32)
+vertex_replay_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ tree,
+                     const VItem *__restrict__ items, const int32_t *__restrict__ vlists, long long list_cap,
+                     const int32_t *__restrict__ n_lists, const int32_t *__restrict__ run_pix0,
+                     const int32_t *__restrict__ run_info, sloam_vertex *__restrict__ slot_vertices,
+                     sloam_point *__restrict__ pool, int32_t *__restrict__ pool_count) {
+  __shared__ __align__(16) VtxSmem sm[kVtxWarps];
+  __shared__ unsigned long long s_pack[kVtxWarps * kVtxCap];  // replay scratch
+  __shared__ int16_t s_perm[kVtxWarps * 2 * kVtxCap];         // members in x and in y order
+  const int N = dp->N, H = dp->p.img_h, T = dp->p.max_trees;
+  const int item_shift = dp->vw_row_bits + dp->vw_slot_bits;
+  const int warp = threadIdx.x >> 5;
+  VtxSmem &s = sm[warp];
+  const int32_t *list = vlists + (size_t)kClsTied * list_cap;
+  const int count = n_lists[kClsTied];
+  for (int li = blockIdx.x * kVtxWarps + warp; li < count; li += gridDim.x * kVtxWarps) {
+    const int gid = list[li];
+    const VItem it = items[gid];
+    const int k = gid >> item_shift;
     __syncwarp();
-    if (n > kVtxCap) {  // rare: very wide cluster, handled by the wide kernel
-      if (lane == 0) overflow[atomicAdd(n_overflow, 1)] = w;
-      continue;
-    }
-    if (n > dp->p.min_vertex_points) {  // trellis.cpp:119
-      if (build_vertex<REPLAY>(dp, s, pack, perm, n, row, out, pool + (size_t)k * N, pool_count + k) && lane == 0)
-        tied[atomicAdd(n_tied, 1)] = w;
-    } else if (lane == 0) {
-      sloam_vertex v;
-      v.cx = v.cy = v.cz = 0.f; v.radius = 0.f; v.n_points = 0; v.point_begin = 0; v.row = row; v.is_valid = 0;
-      *out = v;
-    }
+    gather_members(dp, s, it, k, tree, run_pix0, run_info);
+    sloam_vertex *out = slot_vertices + ((size_t)k * T + it.slot) * H + it.row;
+    build_vertex<true>(dp, s, s_pack + warp * kVtxCap, s_perm + warp * 2 * kVtxCap, it.n, it.row, out,
+                       pool + (size_t)k * N, pool_count + k);
     __syncwarp();
   }
 }
 
-// wide path: one CTA per overflow item, all members in global scratch order --
-// same algorithm with a block-wide rank sort; members live in dynamic smem.
+// wide path: one CTA per item with more than kVtxCap members -- same algorithm with a
+// block-wide rank sort; members live in dynamic smem.
 __global__ void vertex_wide_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ tree,
-                                   const uint32_t *__restrict__ bits, const int32_t *__restrict__ parent, const int32_t *__restrict__ big_roots,
-                                   const int32_t *__restrict__ bbox, const int32_t *__restrict__ overflow,
-                                   const int32_t *__restrict__ n_overflow,
+                                   const VItem *__restrict__ items, const int32_t *__restrict__ vlists,
+                                   long long list_cap, const int32_t *__restrict__ n_lists,
+                                   const int32_t *__restrict__ run_pix0, const int32_t *__restrict__ run_info,
                                    sloam_vertex *__restrict__ slot_vertices, sloam_point *__restrict__ pool,
                                    int32_t *__restrict__ pool_count) {
   extern __shared__ float dsm[];
   const int N = dp->N, W = dp->p.img_w, H = dp->p.img_h, T = dp->p.max_trees;
+  const int item_shift = dp->vw_row_bits + dp->vw_slot_bits;
   float *sx = dsm, *sy = dsm + W, *sz = dsm + 2 * W, *sw = dsm + 3 * W;
   int *scol = (int *)(dsm + 4 * W);
   int *sorder = scol + W;
   int *skeep = sorder + W;
-  __shared__ int s_n, s_kept, s_base;
+  __shared__ int s_kept, s_base;
   __shared__ float s_med[3];
-  const int total = *n_overflow;
-  for (int item = blockIdx.x; item < total; item += gridDim.x) {
-    const int w = overflow[item];
-    int k, slot, row;
-    vw_unpack(dp, w, k, slot, row);
-    const int root = big_roots[(size_t)k * T + slot];
-    const size_t rbase = (size_t)k * N + (size_t)row * W;
-    sloam_vertex *out = slot_vertices + ((size_t)k * T + slot) * H + row;
+  const int32_t *list = vlists + (size_t)kClsWide * list_cap;
+  const int total = n_lists[kClsWide];
+  for (int li = blockIdx.x; li < total; li += gridDim.x) {
+    const int gid = list[li];
+    const VItem it = items[gid];
+    const int k = gid >> item_shift, row = it.row, n = it.n;
+    const sloam_point *tk = tree + (size_t)k * N;
+    const int32_t *pix0_k = run_pix0 + (size_t)k * N, *info_k = run_info + (size_t)k * N;
+    sloam_vertex *out = slot_vertices + ((size_t)k * T + it.slot) * H + row;
     __syncthreads();
-    if (threadIdx.x == 0) {  // serial member collection keeps column order (rare path)
-      int n = 0;
-      const int32_t *bb = bbox + ((size_t)k * T + slot) * 4;
-      for (int c = bb[0]; c <= bb[1]; ++c)
-        if (tree_bit(bits + (size_t)k * ((N + 31) >> 5), row * W + c) && parent[rbase + c] == root) {
-          const sloam_point p = ld_point(tree + rbase + c);
-          sx[n] = p.x; sy[n] = p.y; sz[n] = p.z; sw[n] = p.intensity; scol[n] = c; ++n;
+    {  // members in column order (trellis.cpp:113-118)
+      int acc = 0;
+      for (int j = it.first_run; j <= it.first_run + (int)it.span; ++j) {
+        const int inf = info_k[j];
+        if ((inf & (int)kSlotMask) != (int)it.slot + 1) continue;
+        const int ln = inf >> 11, p0 = pix0_k[j];
+        for (int t = threadIdx.x; t < ln; t += blockDim.x) {
+          const sloam_point p = ld_point(tk + p0 + t);
+          const int m = acc + t;
+          sx[m] = p.x; sy[m] = p.y; sz[m] = p.z; sw[m] = p.intensity; scol[m] = p0 + t - row * W;
         }
-      s_n = n;
+        acc += ln;
+      }
     }
     __syncthreads();
-    const int n = s_n;
     const int middle = (int)(n / 2.0);
     for (int m = threadIdx.x; m < n; m += blockDim.x) {
       int rx = 0, ry = 0, rz = 0, rk = 0;
@@ -691,29 +956,30 @@ __global__ void vertex_wide_kernel(const DevParams *__restrict__ dp, const sloam
   }
 }
 
-// ---- 6. trees: keep clusters with enough vertices, bottom row first --------
+// ---- 4. trees: keep clusters with enough vertices, bottom row first --------
 __global__ void tree_compact_kernel(const DevParams *__restrict__ dp, const int32_t *__restrict__ n_big,
-                                    const int32_t *__restrict__ big_rank, const int32_t *__restrict__ bbox,
+                                    const int32_t *__restrict__ big_rank, const uint32_t *__restrict__ slot_rows,
                                     const sloam_vertex *__restrict__ slot_vertices,
                                     sloam_tree *__restrict__ trees, int32_t *__restrict__ n_trees,
                                     sloam_vertex *__restrict__ vertices) {
   extern __shared__ int32_t sm[];
-  const int H = dp->p.img_h, T = dp->p.max_trees;
+  const int H = dp->p.img_h, T = dp->p.max_trees, Hw = (H + 31) >> 5;
   const int minv = dp->p.min_tree_vertices, maxv = dp->p.max_tree_vertices;
   const int k = blockIdx.x;
   const int nb = n_big[k];
   int32_t *s_nv = sm;        // [T] vertices of the slot (0 when rejected)
   int32_t *s_idx = sm + T;   // [T] tree index
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int top0 = ((H + 31) & ~31) - 1;  // rows from the bottom up (trellis.cpp:111), 32 per step
+  // a row holds a vertex record iff the label kernel emitted a work item for it (row bit)
+  auto has_vertex = [&](const uint32_t *rows, const sloam_vertex *sv, int r) {
+    return r >= 0 && r < H && ((rows[r >> 5] >> (r & 31)) & 1u) && sv[r].is_valid;
+  };
   for (int s = warp; s < nb; s += nwarps) {
-    const int32_t *bb = bbox + ((size_t)k * T + s) * 4;
+    const uint32_t *rows = slot_rows + ((size_t)k * T + s) * Hw;
     const sloam_vertex *sv = slot_vertices + ((size_t)k * T + s) * H;
     int cnt = 0;
-    for (int top = bb[3]; top >= bb[2]; top -= 32) {  // rows from the bottom up (trellis.cpp:111)
-      const int r = top - lane;
-      const bool v = r >= bb[2] && sv[r].is_valid;
-      cnt += __popc(__ballot_sync(kFull, v));
-    }
+    for (int top = top0; top >= 0; top -= 32) cnt += __popc(__ballot_sync(kFull, has_vertex(rows, sv, top - lane)));
     if (lane == 0) s_nv[s] = cnt > minv ? min(cnt, maxv) : 0;  // trellis.cpp:124-127
   }
   __syncthreads();
@@ -727,13 +993,13 @@ __global__ void tree_compact_kernel(const DevParams *__restrict__ dp, const int3
     const int nv = s_nv[s];
     if (nv == 0) continue;
     const int t = s_idx[s];
-    const int32_t *bb = bbox + ((size_t)k * T + s) * 4;
+    const uint32_t *rows = slot_rows + ((size_t)k * T + s) * Hw;
     const sloam_vertex *sv = slot_vertices + ((size_t)k * T + s) * H;
     sloam_vertex *dst = vertices + ((size_t)k * T + t) * maxv;
     int cnt = 0, npts = 0;
-    for (int top = bb[3]; top >= bb[2]; top -= 32) {
+    for (int top = top0; top >= 0; top -= 32) {
       const int r = top - lane;
-      const bool v = r >= bb[2] && sv[r].is_valid;
+      const bool v = has_vertex(rows, sv, r);
       const unsigned b = __ballot_sync(kFull, v);
       const int pos = cnt + __popc(b & ((1u << lane) - 1u));
       int np = 0;
@@ -753,80 +1019,65 @@ __global__ void tree_compact_kernel(const DevParams *__restrict__ dp, const int3
 }
 
 // ---- labels for the find_clusters stage entry -------------------------------
-__global__ void cc_rank_rows_kernel(const DevParams *__restrict__ dp, const uint32_t *__restrict__ bits,
-                                    const int32_t *__restrict__ parent,
-                                    const int32_t *__restrict__ row_roots, int32_t *__restrict__ root_rank) {
-  const int N = dp->N, W = dp->p.img_w, H = dp->p.img_h;
-  const int k = blockIdx.y;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= H) return;
-  const int lane = threadIdx.x & 31;
-  int pre = 0;
-  for (int r = lane; r < row; r += 32) pre += row_roots[(size_t)k * H + r];
-  pre = warp_sum(pre);
-  const size_t rbase = (size_t)k * N + (size_t)row * W;
-  for (int c = lane; c < ((W + 31) & ~31); c += 32) {
-    const bool is_root = c < W && tree_bit(bits + (size_t)k * ((N + 31) >> 5), row * W + c) &&
-                         parent[rbase + c] == row * W + c;
-    const unsigned b = __ballot_sync(kFull, is_root);
-    if (is_root) root_rank[rbase + c] = pre + __popc(b & ((1u << lane) - 1u));
-    pre += __popc(b);
-  }
-}
 __global__ void cc_labels_kernel(const DevParams *__restrict__ dp, int K, const uint32_t *__restrict__ bits,
-                                 const int32_t *__restrict__ parent,
-                                 const int32_t *__restrict__ root_rank, uint32_t *__restrict__ labels) {
-  const int N = dp->N;
+                                 const uint4 *__restrict__ planes, const int32_t *__restrict__ wbase,
+                                 const int32_t *__restrict__ run_label, uint32_t *__restrict__ labels) {
+  const int N = dp->N, Nw = (N + 31) >> 5;
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= (long long)K * N) return;
   const int k = (int)(g / N);
   const int i = (int)(g - (long long)k * N);
-  const int r = tree_bit(bits + (size_t)k * ((N + 31) >> 5), i) ? parent[g] : kInvalid;
-  labels[g] = r == kInvalid ? 0xFFFFFFFFu : (uint32_t)root_rank[(size_t)k * N + r];
+  const size_t w = (size_t)k * Nw + (i >> 5);
+  uint32_t lab = 0xFFFFFFFFu;
+  if ((bits[w] >> (i & 31)) & 1u) {
+    const uint4 pl = planes[w];
+    if ((pl.x >> (i & 31)) & 1u)
+      lab = (uint32_t)run_label[(size_t)k * N + wbase[w] + __popc(pl.y & ((2u << (i & 31)) - 1u)) - 1];
+  }
+  labels[g] = lab;
 }
 
-static int run_cc(sloam_ctx *c, int K, const sloam_point *tree, bool bits_ready) {
+static int label_smem_runs(const sloam_ctx *c) {
+  const int rs = c->hp.N / 16;
+  return rs < 1024 ? 1024 : (rs > 8192 ? 8192 : rs);
+}
+
+static int run_cc(sloam_ctx *c, int K, const sloam_point *tree, bool bits_ready, bool want_labels) {
   Workspace &w = c->ws;
-  const long long total = (long long)K * c->hp.N;
-  const int H = c->hp.p.img_h;
+  const sloam_params &p = c->hp.p;
+  const int N = c->hp.N, Nw = (N + 31) / 32, Hw = (p.img_h + 31) / 32, T = p.max_trees;
+  const long long total_words = (long long)K * Nw;
   const bool pre_zeroed = (c->zero_valid & 2u) != 0;  // zeroed with the rest of the counters (pipeline.cu)
-  c->zero_valid &= ~2u;
+  c->zero_valid &= ~(2u | 4u);
   if (!pre_zeroed) {
-    SB_CUDA(c, cudaMemsetAsync(w.row_roots, 0, sizeof(int32_t) * (size_t)K * H, c->stream));
-    SB_CUDA(c, cudaMemsetAsync(w.n_roots, 0, sizeof(int32_t) * K, c->stream));
-    SB_CUDA(c, cudaMemsetAsync(w.n_big, 0, sizeof(int32_t) * K, c->stream));
     SB_CUDA(c, cudaMemsetAsync(w.kf_flags, 0, sizeof(int32_t) * K, c->stream));
+    SB_CUDA(c, cudaMemsetAsync(w.n_vlists, 0, sizeof(int32_t) * 8, c->stream));
+    SB_CUDA(c, cudaMemsetAsync(w.vpool_count, 0, sizeof(int32_t) * K, c->stream));
   }
-  const dim3 blocks((unsigned)((c->hp.N + 255) / 256), (unsigned)K);
   if (!bits_ready) {  // caller-supplied cloud: derive the bits from the points
+    const dim3 blocks((unsigned)((N + 255) / 256), (unsigned)K);
     tree_bits_kernel<<<blocks, 256, 0, c->stream>>>(c->dp, tree, w.tree_bits);
     SB_LAUNCH_CHECK(c);
   }
-  const unsigned wgrid = (unsigned)std::min<long long>((total / 32 / 32 / 8) + 1, (long long)c->sm_count * 8);
-  if (!pre_zeroed) {
-    SB_CUDA(c, cudaMemsetAsync(w.n_tree_words, 0, sizeof(int32_t), c->stream));
-    SB_CUDA(c, cudaMemsetAsync(w.root_bits, 0, sizeof(uint32_t) * (size_t)K * ((c->hp.N + 31) / 32), c->stream));
+  const unsigned rgrid = (unsigned)std::min<long long>((total_words + 255) / 256, (long long)c->sm_count * 8);
+  PROF_BEGIN(c, P_CC_ROWS);
+  cc_rows_kernel<<<rgrid, 256, 0, c->stream>>>(c->dp, K, tree, w.tree_bits, reinterpret_cast<uint4 *>(w.cc_planes));
+  PROF_END(c, P_CC_ROWS);
+  SB_LAUNCH_CHECK(c);
+  const int Rs = label_smem_runs(c);
+  const size_t smem = sizeof(uint32_t) * 2 * (size_t)Nw + sizeof(uint32_t) * (size_t)T * Hw + sizeof(int32_t) * 3 * (size_t)Rs;
+  static size_t lbl_set[64] = {};  // opt-in shared memory per device, only grows
+  if (smem > 48 * 1024 && smem > lbl_set[c->device & 63]) {
+    SB_CUDA(c, cudaFuncSetAttribute(cc_label_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lbl_set[c->device & 63] = smem;
   }
-  PROF_BEGIN(c, P_CC_WORDS);
-  tree_words_kernel<<<wgrid, 256, 0, c->stream>>>(c->dp, K, w.tree_bits, reinterpret_cast<int2 *>(w.tree_words), w.n_tree_words);
-  PROF_END(c, P_CC_WORDS);
-  SB_LAUNCH_CHECK(c);
-  const int2 *wl = reinterpret_cast<const int2 *>(w.tree_words);
-  PROF_BEGIN(c, P_CC_INIT);
-  cc_init_kernel<<<wgrid, 256, 0, c->stream>>>(c->dp, K, tree, w.tree_bits, wl, w.n_tree_words, w.parent,
-                                               reinterpret_cast<uint32_t *>(w.cc_flags), w.csize,
-                                                w.ccol_min, w.ccol_max, w.crow_max);
-  PROF_END(c, P_CC_INIT);
-  SB_LAUNCH_CHECK(c);
-  PROF_BEGIN(c, P_CC_MERGE);
-  cc_merge_kernel<<<wgrid, 256, 0, c->stream>>>(c->dp, K, w.tree_bits, wl, w.n_tree_words, reinterpret_cast<const uint32_t *>(w.cc_flags), w.parent);
-  PROF_END(c, P_CC_MERGE);
-  SB_LAUNCH_CHECK(c);
-  PROF_BEGIN(c, P_CC_FLATTEN);
-  cc_flatten_kernel<<<wgrid, 256, 0, c->stream>>>(c->dp, K, w.tree_bits, wl, w.n_tree_words, w.parent, w.csize, w.ccol_min, w.ccol_max,
-                                                   w.crow_max, w.row_roots, w.n_roots, w.big_roots,
-                                                   w.n_big, w.kf_flags, w.root_bits);
-  PROF_END(c, P_CC_FLATTEN);
+  const long long list_cap = (long long)c->max_k * T * p.img_h;
+  PROF_BEGIN(c, P_CC_LABEL);
+  cc_label_kernel<<<K, kLblThreads, smem, c->stream>>>(
+      c->dp, w.tree_bits, reinterpret_cast<const uint4 *>(w.cc_planes), Rs, w.run_par, reinterpret_cast<uint32_t *>(w.run_siz),
+      w.run_len, w.run_pix0, w.run_info, w.run_label, want_labels ? w.cc_wbase : nullptr, w.n_roots, w.n_big,
+      w.big_rank, w.kf_flags, w.slot_rows, reinterpret_cast<VItem *>(w.vitems), w.vlists, list_cap, w.n_vlists);
+  PROF_END(c, P_CC_LABEL);
   SB_LAUNCH_CHECK(c);
   return SLOAM_OK;
 }
@@ -836,42 +1087,29 @@ int launch_compute_graph(sloam_ctx *c, int K, const sloam_point *tree, sloam_tre
                          bool bits_ready) {
   Workspace &w = c->ws;
   const sloam_params &p = c->hp.p;
-  const int T = p.max_trees, H = p.img_h, W = p.img_w;
-  int rc = run_cc(c, K, tree, bits_ready);
+  const int T = p.max_trees, W = p.img_w;
+  int rc = run_cc(c, K, tree, bits_ready, false);
   if (rc != SLOAM_OK) return rc;
-  if (c->zero_valid & 4u) {
-    c->zero_valid &= ~4u;
-  } else {
-    SB_CUDA(c, cudaMemsetAsync(w.n_overflow, 0, sizeof(int32_t) * 4, c->stream));
-    SB_CUDA(c, cudaMemsetAsync(w.vpool_count, 0, sizeof(int32_t) * K, c->stream));
-  }
-  PROF_BEGIN(c, P_CC_PLAN);
-  cc_plan_kernel<<<K, 256, sizeof(int32_t) * (2 * T + H + 1), c->stream>>>(
-      c->dp, w.root_bits, w.parent, w.ccol_min, w.ccol_max, w.crow_max, w.row_roots, w.big_roots, w.n_big,
-      w.big_rank, w.bbox, w.vwork, w.n_overflow + 1);
-  PROF_END(c, P_CC_PLAN);
-  SB_LAUNCH_CHECK(c);
+  const long long list_cap = (long long)c->max_k * T * p.img_h;
+  const VItem *items = reinterpret_cast<const VItem *>(w.vitems);
   // persistent grid: exactly the CTAs that are resident at once (a partial second wave would
   // double the time of its work items)
   static int vtx_occ = 0;
   if (vtx_occ == 0) {
-    SB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&vtx_occ, vertex_kernel<false>, kVtxWarps * 32, 0));
+    SB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&vtx_occ, vertex_kernel, kVtxWarps * 32, 0));
     if (vtx_occ < 1) vtx_occ = 1;
   }
   const int vgrid = c->sm_count * vtx_occ;
-  // n_overflow[0] rows wider than the warp path, [1] work items, [2] items with exact z ties
   PROF_BEGIN(c, P_VERTEX);
-  vertex_kernel<false><<<vgrid, kVtxWarps * 32, 0, c->stream>>>(
-      c->dp, tree, w.tree_bits, w.parent, w.big_roots, w.bbox, w.vwork, w.n_overflow + 1, w.slot_vertices,
-      vertex_points, w.vpool_count, w.overflow_list, w.n_overflow, w.tied_list, w.n_overflow + 2);
+  vertex_kernel<<<vgrid, kVtxWarps * 32, 0, c->stream>>>(c->dp, tree, items, w.vlists, list_cap, w.n_vlists, w.run_pix0,
+                                                         w.run_info, w.slot_vertices, vertex_points, w.vpool_count);
   PROF_END(c, P_VERTEX);
   SB_LAUNCH_CHECK(c);
-  PROF_BEGIN(c, P_VERTEX_REPLAY);
   // the tied items again, with the std::sort replay (usually an empty list: the CTAs exit)
-  vertex_kernel<true><<<c->sm_count, kVtxWarps * 32, 0, c->stream>>>(
-      c->dp, tree, w.tree_bits, w.parent, w.big_roots, w.bbox, w.tied_list, w.n_overflow + 2, w.slot_vertices,
-      vertex_points, w.vpool_count, w.overflow_list, w.n_overflow, nullptr, nullptr);
-  PROF_END(c, P_VERTEX_REPLAY);
+  PROF_BEGIN(c, P_VERTEX_REPLAY);
+  vertex_replay_kernel<<<c->sm_count, kVtxWarps * 32, 0, c->stream>>>(c->dp, tree, items, w.vlists, list_cap, w.n_vlists,
+                                                                      w.run_pix0, w.run_info, w.slot_vertices,
+                                                                      vertex_points, w.vpool_count);
   SB_LAUNCH_CHECK(c);
   const size_t wide_smem = sizeof(float) * 4 * W + sizeof(int) * 3 * W;
   // opt-in shared memory: the attribute belongs to (function, device) and must only grow -- a
@@ -881,13 +1119,13 @@ int launch_compute_graph(sloam_ctx *c, int K, const sloam_point *tree, sloam_tre
     SB_CUDA(c, cudaFuncSetAttribute(vertex_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem));
     wide_set[c->device & 63] = wide_smem;
   }
-  vertex_wide_kernel<<<c->sm_count, 256, wide_smem, c->stream>>>(c->dp, tree, w.tree_bits, w.parent, w.big_roots, w.bbox,
-                                                                 w.overflow_list, w.n_overflow,
-                                                                 w.slot_vertices, vertex_points,
-                                                                 w.vpool_count);
+  vertex_wide_kernel<<<c->sm_count, 256, wide_smem, c->stream>>>(c->dp, tree, items, w.vlists, list_cap, w.n_vlists,
+                                                                 w.run_pix0, w.run_info, w.slot_vertices,
+                                                                 vertex_points, w.vpool_count);
+  PROF_END(c, P_VERTEX_REPLAY);
   SB_LAUNCH_CHECK(c);
   PROF_BEGIN(c, P_TREE_COMPACT);
-  tree_compact_kernel<<<K, 256, sizeof(int32_t) * 2 * T, c->stream>>>(c->dp, w.n_big, w.big_rank, w.bbox,
+  tree_compact_kernel<<<K, 256, sizeof(int32_t) * 2 * T, c->stream>>>(c->dp, w.n_big, w.big_rank, w.slot_rows,
                                                                        w.slot_vertices, trees, n_trees,
                                                                        vertices);
   PROF_END(c, P_TREE_COMPACT);
@@ -912,15 +1150,11 @@ extern "C" {
 int sloam_b200_find_clusters_dev(sloam_ctx *c, int K, const sloam_point *tree, uint32_t *labels,
                                  int32_t *n_clusters) {
   if (!c || K <= 0 || K > c->max_k || !tree || !labels) return set_err(c, SLOAM_E_INVALID, "find_clusters: bad arguments");
-  int rc = run_cc(c, K, tree, false);
+  int rc = run_cc(c, K, tree, false, true);
   if (rc != SLOAM_OK) return rc;
-  const int H = c->hp.p.img_h;
-  dim3 grid((unsigned)((H + 7) / 8), (unsigned)K);
-  cc_rank_rows_kernel<<<grid, 256, 0, c->stream>>>(c->dp, c->ws.tree_bits, c->ws.parent, c->ws.row_roots, c->ws.root_rank);
-  SB_LAUNCH_CHECK(c);
   const long long total = (long long)K * c->hp.N;
-  cc_labels_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(c->dp, K, c->ws.tree_bits, c->ws.parent,
-                                                                          c->ws.root_rank, labels);
+  cc_labels_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(
+      c->dp, K, c->ws.tree_bits, reinterpret_cast<const uint4 *>(c->ws.cc_planes), c->ws.cc_wbase, c->ws.run_label, labels);
   SB_LAUNCH_CHECK(c);
   if (n_clusters)
     SB_CUDA(c, cudaMemcpyAsync(n_clusters, c->ws.n_roots, sizeof(int32_t) * K, cudaMemcpyDeviceToDevice, c->stream));

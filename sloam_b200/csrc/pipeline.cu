@@ -89,7 +89,9 @@ static int run_lanes(sloam_ctx *c, int K, const sloam_batch_in *in, const sloam_
 static int run_dev_body(sloam_ctx *c, int K, const sloam_batch_in *in, const sloam_batch_out *out);
 
 static int run_dev(sloam_ctx *c, int K, const sloam_batch_in *in, const sloam_batch_out *out, bool allow_split) {
-  if (allow_split && c->n_lanes > 1 && K >= 64 * c->n_lanes) return run_lanes(c, K, in, out);
+  // with kernel profiling on, a run is one lane and one stream, so that the event pairs
+  // time each kernel group alone
+  if (allow_split && c->n_lanes > 1 && !c->prof_on && K >= 64 * c->n_lanes) return run_lanes(c, K, in, out);
   const int rc = run_dev_body(c, K, in, out);
   c->zero_valid = 0;  // the pre-zeroed counters belong to this run only (also after an error)
   return rc;
@@ -111,17 +113,20 @@ static int run_dev_body(sloam_ctx *c, int K, const sloam_batch_in *in, const slo
   // fork: ground cells + plane fits (K2, main stream) and the tree detector (K3, side
   // stream) both depend only on K1 and are latency-bound, so they run concurrently
   cudaStream_t main_stream = c->stream;
-  SB_CUDA(c, cudaEventRecord(c->ev_fork, main_stream));
-  SB_CUDA(c, cudaStreamWaitEvent(c->side, c->ev_fork, 0));
-  c->stream = c->side;
+  const bool fork = !c->prof_on;
+  if (fork) {
+    SB_CUDA(c, cudaEventRecord(c->ev_fork, main_stream));
+    SB_CUDA(c, cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+    c->stream = c->side;
+  }
   rc = launch_compute_graph(c, K, w.tree, w.trees, w.n_trees, w.vertices, w.vertex_points, true);
   c->stream = main_stream;
   if (rc != SLOAM_OK) return rc;
-  SB_CUDA(c, cudaEventRecord(c->ev_join, c->side));
+  if (fork) SB_CUDA(c, cudaEventRecord(c->ev_join, c->side));
   rc = launch_ground_planes(c, K, w.ground, w.ground_count, c->hp.N, in->pose_est, w.cells,
                             w.cell_features, nullptr, nullptr, true);
   if (rc != SLOAM_OK) return rc;
-  SB_CUDA(c, cudaStreamWaitEvent(main_stream, c->ev_join, 0));  // join
+  if (fork) SB_CUDA(c, cudaStreamWaitEvent(main_stream, c->ev_join, 0));  // join
   rc = launch_cylinders(c, K, w.trees, w.n_trees, w.vertices, w.vertex_points, w.planes_acc,
                         w.n_planes_acc, w.tree_models, w.tree_features);
   if (rc != SLOAM_OK) return rc;
