@@ -72,7 +72,9 @@ struct Workspace {
   unsigned long long *gscratch2 = nullptr; // [K][N] kept records of oversized cells (gscratch stays intact)
   int32_t *tied_cells = nullptr;     // [K][kMaxCells] (keyframe << 8 | cell) of cells with exact z ties
   int32_t *n_tied_cells = nullptr;   // [1]
-  unsigned long long *gscratch = nullptr; // [K][N] (z key, index) lists of oversized cells
+  unsigned long long *gscratch = nullptr; // [K][N] fused: (z key, point index) records from the split kernel, tile-strided, input order
+  unsigned long long *gscratch3 = nullptr; // [K][N] (z key, index) member lists, contiguous per cell
+  uint32_t *seg_tab = nullptr;       // [K][B][tiles] points of each cell in each K1 tile, then their first member slot
   double *qscratch = nullptr;        // [K][N][3] QR workspace of oversized cells
   float *pscratch = nullptr;         // [K][N][3] point staging of oversized cells
   FitRec *fit_rec = nullptr;         // [K][B]
@@ -160,6 +162,8 @@ struct sloam_ctx {
   // likewise ws.ground is tile-strided after a fused run; ground_dense (ws.qscratch) receives
   // the contiguous cloud on demand
   bool ground_strided = false;
+  const sloam_point *last_points = nullptr;  // inputs of the last fused run (intermediates on demand)
+  const uint8_t *last_mask = nullptr;
   // optional event pairs around the split kernel of fused runs (sloam_b200_profile_*)
   // run_keyframes_host: copy stream + per-chunk events (H2D of chunk j+1 overlaps compute of j)
   cudaStream_t copy_stream = nullptr;

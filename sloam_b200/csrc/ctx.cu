@@ -75,6 +75,8 @@ static void layout(sloam_ctx *c, Bump &b) {
   b.take(w.n_planes_acc, K);
   b.take(w.gscratch, K * N);
   b.take(w.gscratch2, K * N);
+  b.take(w.gscratch3, K * N);
+  b.take(w.seg_tab, K * tiles * B);
   b.take(w.tied_cells, K * kMaxCells);
   b.take(w.qscratch, K * N * 3);
   b.take(w.pscratch, K * N * 3);
@@ -404,7 +406,7 @@ int sloam_b200_set_lanes(sloam_ctx *c, int n) {
 int64_t sloam_b200_workspace_bytes(const sloam_ctx *c) { return c ? (int64_t)c->arena_bytes : 0; }
 
 static const char *const kProfNames[P_COUNT] = {
-    "project_split_kernel", "range_finalize_kernel", "ground_bin_kernel", "ground_cells_kernel<0>",
+    "project_split_kernel", "range_finalize_kernel", "ground_offsets+ground_scatter_kernel", "ground_cells_kernel<0>",
     "ground_cells_kernel<1> (tie replay)", "plane_finish+planes_compact", "cc_rows_kernel", "cc_label_kernel",
     "vertex_kernel", "vertex_replay+vertex_wide (tie replay)", "tree_compact_kernel", "cylinder_kernel+compact",
     "assoc_kernel (sensor frame)", "build_matches_kernel", "lm_kernel", "finish_kernel",

@@ -120,7 +120,12 @@ __device__ __forceinline__ int ground_cell_fast(const GroundGeom &g, float x, fl
 #ifndef SLOAM_K1_MIN_CTAS
 #define SLOAM_K1_MIN_CTAS 5  // measured: 4 -> 427 us, 5 -> 384 us, 6 -> 390 us per 1000 VLP-16 keyframes
 #endif
-template <bool DO_PROJECT, bool DO_SPLIT>
+// FUSED (the production path, with DO_PROJECT and DO_SPLIT): the ground points are not copied.
+// Every ground point becomes one 8-byte record (z key, point index) in the tile-strided layout
+// described above (slot order = input order) next to its cell tag, and seg_tab[k][cell][tile]
+// receives the number of points of each cell in the tile, from which ground_scatter_kernel
+// (k2_ground.cu) bins every tile independently.
+template <bool DO_PROJECT, bool DO_SPLIT, bool FUSED>
 __global__ void __launch_bounds__(kThreads, SLOAM_K1_MIN_CTAS)
 project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point *__restrict__ points,
                      const uint8_t *__restrict__ mask, int32_t *__restrict__ pix_io,
@@ -128,7 +133,8 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
                      sloam_point *__restrict__ ground, int32_t *__restrict__ ground_count,
                      uint8_t *__restrict__ ground_cell, int32_t *__restrict__ cell_count,
                      int32_t *__restrict__ tile_count, int ground_stride,
-                     uint32_t *__restrict__ tree_bits, int sparse_tree) {
+                     uint32_t *__restrict__ tree_bits, int sparse_tree,
+                     uint2 *__restrict__ ground_recs, uint32_t *__restrict__ seg_tab) {
   __shared__ int s_pix[DO_PROJECT ? kSplitTile : 1];  // exact pixel indices of the queued points
   __shared__ int s_hist[DO_SPLIT ? kMaxCells : 1];
   __shared__ uint16_t s_slow[DO_PROJECT ? kSplitTile : 1];
@@ -299,7 +305,8 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
   __syncthreads();
   // ground points go straight from registers to their slots: the ground lanes of a warp
   // own consecutive slots, so the 16-byte stores of a warp form contiguous runs
-  sloam_point *gout = ground + (size_t)k * ground_stride + (size_t)tile * kSplitTile;
+  sloam_point *gout = FUSED ? nullptr : ground + (size_t)k * ground_stride + (size_t)tile * kSplitTile;
+  uint2 *rout = FUSED ? ground_recs + kbase + (size_t)tile * kSplitTile : nullptr;
   uint8_t *cout = ground_cell + (size_t)k * ground_stride + (size_t)tile * kSplitTile;
 #pragma unroll
   for (int j = 0; j < kRounds; ++j) {
@@ -307,7 +314,10 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
       const sloam_point p = pts[j];
       const int slot = s_cnt[j * (kThreads / 32) + warp] + __popc(bal[j] & ((1u << lane) - 1u));
       const int cell = ground_cell_fast(gg, p.x, p.y, yawr[j]);
-      st_point(gout + slot, p);
+      // FUSED: the point itself is not copied -- an 8-byte (z key, point index) record is all the
+      // ground stage sorts; it reads the few retained points from the input cloud
+      if (FUSED) rout[slot] = make_uint2(float_key(p.z), (unsigned)(tile * kSplitTile + j * kThreads + threadIdx.x));
+      else st_point(gout + slot, p);
       cout[slot] = (uint8_t)(cell < 0 ? 255 : cell);
       if (cell >= 0) atomicAdd(&s_hist[cell], 1);
     }
@@ -316,6 +326,8 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
   for (int c = threadIdx.x; c < kMaxCells; c += kThreads) {
     const int h = s_hist[c];
     if (h) atomicAdd(&cell_count[(size_t)k * kMaxCells + c], h);
+    // per-tile cell counts: ground_scatter_kernel (k2_ground.cu) bins every tile independently
+    if (FUSED && c < dp->B) seg_tab[((size_t)k * dp->B + c) * tiles + tile] = (unsigned)h;
   }
   __syncthreads();  // s_hist / s_cnt / s_nslow are reset by the next tile
   }  // tile loop
@@ -396,6 +408,8 @@ int launch_project_split(sloam_ctx *c, int K, bool do_project, bool do_split,
                          const sloam_point *points, const uint8_t *mask, int32_t *pix,
                          float *range_image, sloam_point *tree, sloam_point *ground,
                          int32_t *ground_count, uint32_t *tree_bits, bool sparse_tree) {
+  // fused pipeline: projection + split, sparse tree cloud, ground points as per-tile cell records
+  const bool fused = do_project && do_split && sparse_tree && ground == nullptr;
   const int N = c->hp.N;
   const int tiles = (N + kSplitTile - 1) / kSplitTile;
   const long long total = (long long)K * N;
@@ -403,7 +417,7 @@ int launch_project_split(sloam_ctx *c, int K, bool do_project, bool do_split,
   if (do_project && rb) SB_CUDA(c, cudaMemsetAsync(rb, 0xFF, sizeof(unsigned) * total, c->stream));
   // The kernel always writes the tile-strided ground layout.  The fused pipeline consumes it
   // as is (ground == ws.ground); a stage entry gets the contiguous cloud by compaction.
-  const bool strided_out = ground == c->ws.ground;
+  const bool strided_out = fused;
   if (do_split) {
     if ((c->zero_valid & 1u) && ground_count == c->ws.ground_count) {
       c->zero_valid &= ~1u;  // zeroed with the rest of the counters (pipeline.cu)
@@ -413,22 +427,25 @@ int launch_project_split(sloam_ctx *c, int K, bool do_project, bool do_split,
     }
   }
   // persistent CTAs: exactly the resident ones, each walks tiles blockIdx.x, + gridDim.x, ...
-  static int occ[3] = {0, 0, 0};
-  const int which = (do_project && do_split) ? 0 : (do_project ? 1 : 2);
+  static int occ[4] = {0, 0, 0, 0};
+  const int which = fused ? 3 : ((do_project && do_split) ? 0 : (do_project ? 1 : 2));
   if (occ[which] == 0) {
-    if (which == 0) SB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], project_split_kernel<true, true>, kThreads, 0));
-    else if (which == 1) SB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], project_split_kernel<true, false>, kThreads, 0));
-    else SB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], project_split_kernel<false, true>, kThreads, 0));
+    if (which == 0) SB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], project_split_kernel<true, true, false>, kThreads, 0));
+    else if (which == 1) SB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], project_split_kernel<true, false, false>, kThreads, 0));
+    else if (which == 2) SB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], project_split_kernel<false, true, false>, kThreads, 0));
+    else SB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[3], project_split_kernel<true, true, true>, kThreads, 0));
     if (occ[which] < 1) occ[which] = 1;
   }
   const long long all_tiles = (long long)K * tiles;
   const unsigned grid = (unsigned)std::min<long long>(all_tiles, (long long)c->sm_count * occ[which]);
 #define SB_K1_ARGS c->dp, K, points, mask, pix, rb, tree, c->ws.ground, ground_count, c->ws.ground_cell, \
-                   c->ws.cell_count, c->ws.tile_count, N, tree_bits, sparse_tree ? 1 : 0
+                   c->ws.cell_count, c->ws.tile_count, N, tree_bits, sparse_tree ? 1 : 0,                 \
+                   reinterpret_cast<uint2 *>(c->ws.gscratch), c->ws.seg_tab
   PROF_BEGIN(c, P_SPLIT);
-  if (do_project && do_split) project_split_kernel<true, true><<<grid, kThreads, 0, c->stream>>>(SB_K1_ARGS);
-  else if (do_project) project_split_kernel<true, false><<<grid, kThreads, 0, c->stream>>>(SB_K1_ARGS);
-  else project_split_kernel<false, true><<<grid, kThreads, 0, c->stream>>>(SB_K1_ARGS);
+  if (fused) project_split_kernel<true, true, true><<<grid, kThreads, 0, c->stream>>>(SB_K1_ARGS);
+  else if (do_project && do_split) project_split_kernel<true, true, false><<<grid, kThreads, 0, c->stream>>>(SB_K1_ARGS);
+  else if (do_project) project_split_kernel<true, false, false><<<grid, kThreads, 0, c->stream>>>(SB_K1_ARGS);
+  else project_split_kernel<false, true, false><<<grid, kThreads, 0, c->stream>>>(SB_K1_ARGS);
 #undef SB_K1_ARGS
   PROF_END(c, P_SPLIT);
   SB_LAUNCH_CHECK(c);

@@ -5,10 +5,15 @@
 // constructor + computeModel (sloam/src/objects/plane.cpp:3-17,96-128) and the
 // acceptance test in sloam::computeModels (sloam.cpp:394-412).
 //
-// ground_bin_kernel sorts the ground points of a keyframe by polar cell (stable multisplit on
-// the cell tags the split kernel wrote, k1_project.cu).  ground_cells_kernel: one warp per
-// (keyframe, cell) reads its members contiguously, selects the r lowest z with an 8-bit radix
-// select (ties by input order), sorts only those r, and fits the plane:
+// Binning (stable, by polar cell, (z key, point index) records of cell 0, then cell 1, ... each
+// in input order).  Fused pipeline: the split kernel (k1_project.cu) leaves one record and one
+// cell tag per ground point, tile by tile in input order, plus the number of points of every
+// cell in every tile; ground_offsets_kernel turns the counts into first slots and
+// ground_scatter_kernel moves the records, one WARP per 1024-point tile, no barriers, no
+// atomics.  Caller-supplied clouds (stage entry): ground_bin_kernel, one CTA per keyframe.
+// ground_cells_kernel: one warp per (keyframe, cell) reads its members contiguously, selects
+// the r lowest z with an 8-bit radix select (ties by input order), sorts only those r, and
+// fits the plane:
 //   - centroid: float32 sequential sum in sorted order (utils.h:14-28), one lane;
 //   - 3 x n JacobiSVD: column-pivoted Householder QR of the n x 3 adjoint with
 //     warp-shuffle reductions, then the 3x3 two-sided Jacobi of dev_plane.h
@@ -189,6 +194,92 @@ ground_bin_kernel(const DevParams *__restrict__ dp, const sloam_point *__restric
         mk[s_wc[(q * kBinWarps + warp) * B + cel[q]] + rank[q]] = e;
       }
     __syncthreads();
+  }
+}
+
+// ---- fused pipeline: binning per tile ------------------------------------------------------
+// seg_tab[k][cell][tile]: in = points of the cell in the tile (split kernel); out = first slot
+// of those points in the keyframe's member array = (points of lower cells) + (points of the
+// cell in lower tiles).  One CTA per keyframe, one warp per cell at a time.
+__global__ void __launch_bounds__(256)
+ground_offsets_kernel(const DevParams *__restrict__ dp, const int32_t *__restrict__ cell_count,
+                      uint32_t *__restrict__ seg_tab) {
+  __shared__ int s_start[kMaxCells];
+  const int B = dp->B, tiles = (dp->N + kSplitTile - 1) / kSplitTile;
+  const int k = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp == 0) {  // first slot of every cell: exclusive prefix of the cell counts
+    int carry = 0;
+    for (int base = 0; base < B; base += 32) {
+      const int c = base + lane;
+      const int v = c < B ? cell_count[(size_t)k * kMaxCells + c] : 0;
+      int inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (c < B) s_start[c] = carry + inc - v;
+      carry += __shfl_sync(kFull, inc, 31);
+    }
+  }
+  __syncthreads();
+  for (int c = warp; c < B; c += 8) {
+    uint32_t *row = seg_tab + ((size_t)k * B + c) * tiles;
+    int carry = s_start[c];
+    for (int t0 = 0; t0 < tiles; t0 += 32) {
+      const int t = t0 + lane;
+      const int v = t < tiles ? (int)row[t] : 0;
+      int inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += u;
+      }
+      if (t < tiles) row[t] = (uint32_t)(carry + inc - v);
+      carry += __shfl_sync(kFull, inc, 31);
+    }
+  }
+}
+
+// One warp per (keyframe, tile): the tile's records are in input order, so walking them 32 at
+// a time and handing every cell of a chunk the next slots of its run keeps the binning stable.
+// The running slots of the cells live in shared memory, one row per warp.
+constexpr int kScatWarps = 8;
+__global__ void __launch_bounds__(kScatWarps * 32)
+ground_scatter_kernel(const DevParams *__restrict__ dp, int K, const uint2 *__restrict__ recs,
+                      const uint8_t *__restrict__ ground_cell, const int32_t *__restrict__ tile_count,
+                      const uint32_t *__restrict__ seg_tab, SelKey *__restrict__ members) {
+  __shared__ int s_run[kScatWarps][kMaxCells];
+  const int N = dp->N, B = dp->B, tiles = (N + kSplitTile - 1) / kSplitTile;
+  const int lane = threadIdx.x & 31;
+  const int wid = blockIdx.x * kScatWarps + (threadIdx.x >> 5);
+  if (wid >= K * tiles) return;
+  const int k = wid / tiles, tile = wid - k * tiles;
+  const int n = tile_count[(size_t)k * tiles + tile];
+  if (n == 0) return;
+  int *run = s_run[threadIdx.x >> 5];
+  for (int c = lane; c < B; c += 32) run[c] = (int)seg_tab[((size_t)k * B + c) * tiles + tile];
+  __syncwarp();
+  const size_t base = (size_t)k * N + (size_t)tile * kSplitTile;
+  SelKey *mk = members + (size_t)k * N;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    int cell = 255;
+    uint2 rec = make_uint2(0u, 0u);
+    if (i < n) { cell = ground_cell[base + i]; rec = recs[base + i]; }
+    unsigned todo = __ballot_sync(kFull, cell < B);
+    while (todo) {
+      const int l = __ffs(todo) - 1;
+      const int c0 = __shfl_sync(kFull, cell, l);
+      const unsigned mm = __ballot_sync(kFull, cell == c0);
+      const int r = run[c0];
+      if (cell == c0) { SelKey e; e.z = rec.x; e.j = rec.y; mk[r + __popc(mm & lt)] = e; }
+      __syncwarp();
+      if (lane == l) run[c0] = r + __popc(mm);
+      __syncwarp();
+      todo &= ~mm;
+    }
   }
 }
 
@@ -614,26 +705,37 @@ int launch_ground_planes(sloam_ctx *c, int K, const sloam_point *ground, const i
                          int stride, const sloam_pose *pose_est, sloam_cell_plane *cells,
                          sloam_point *cell_features, sloam_point *kept_points, int32_t *kept_offsets,
                          bool strided) {
+  // strided (fused pipeline): `ground` is the INPUT cloud (the records index it), the split kernel
+  // left records + tags + per-tile cell counts; else `ground` is a ground cloud tagged by
+  // ground_tag_kernel and the records index that cloud
   Workspace &w = c->ws;
   dim3 grid((unsigned)c->hp.B, (unsigned)K);
   const int k1_tiles = (c->hp.N + kSplitTile - 1) / kSplitTile;
-  const size_t bin_smem = sizeof(int) * ((size_t)(kBinItems * kBinWarps + 1) * c->hp.B + k1_tiles + 1);
-  static size_t bin_set[64] = {};  // per device, only grows (see vertex_wide_kernel)
-  if (bin_smem > 48 * 1024 && bin_smem > bin_set[c->device & 63]) {
-    SB_CUDA(c, cudaFuncSetAttribute(ground_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem));
-    bin_set[c->device & 63] = bin_smem;
-  }
+  SelKey *members = reinterpret_cast<SelKey *>(w.gscratch3);
   PROF_BEGIN(c, P_GROUND_BIN);
-  ground_bin_kernel<<<K, kBinThreads, bin_smem, c->stream>>>(c->dp, ground, ground_count, stride, w.ground_cell,
-                                                             w.cell_count, strided ? w.tile_count : nullptr,
-                                                             reinterpret_cast<SelKey *>(w.gscratch));
+  if (strided) {
+    ground_offsets_kernel<<<K, 256, 0, c->stream>>>(c->dp, w.cell_count, w.seg_tab);
+    SB_LAUNCH_CHECK(c);
+    ground_scatter_kernel<<<(K * k1_tiles + kScatWarps - 1) / kScatWarps, kScatWarps * 32, 0, c->stream>>>(
+        c->dp, K, reinterpret_cast<const uint2 *>(w.gscratch), w.ground_cell, w.tile_count, w.seg_tab, members);
+    SB_LAUNCH_CHECK(c);
+  } else {
+    const size_t bin_smem = sizeof(int) * ((size_t)(kBinItems * kBinWarps + 1) * c->hp.B + k1_tiles + 1);
+    static size_t bin_set[64] = {};  // per device, only grows (see vertex_wide_kernel)
+    if (bin_smem > 48 * 1024 && bin_smem > bin_set[c->device & 63]) {
+      SB_CUDA(c, cudaFuncSetAttribute(ground_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem));
+      bin_set[c->device & 63] = bin_smem;
+    }
+    ground_bin_kernel<<<K, kBinThreads, bin_smem, c->stream>>>(c->dp, ground, ground_count, stride, w.ground_cell,
+                                                               w.cell_count, nullptr, members);
+    SB_LAUNCH_CHECK(c);
+  }
   PROF_END(c, P_GROUND_BIN);
-  SB_LAUNCH_CHECK(c);
   if (c->zero_valid & 8u) c->zero_valid &= ~8u;
   else SB_CUDA(c, cudaMemsetAsync(w.n_tied_cells, 0, sizeof(int32_t), c->stream));
   PROF_BEGIN(c, P_GROUND_CELLS);
   ground_cells_kernel<false><<<grid, kGThreads, 0, c->stream>>>(
-      c->dp, ground, ground_count, stride, reinterpret_cast<SelKey *>(w.gscratch), w.cell_count, pose_est,
+      c->dp, ground, ground_count, stride, members, w.cell_count, pose_est,
       w.qscratch, w.pscratch, w.fit_rec, cells, cell_features, kept_points, kept_offsets,
       reinterpret_cast<SelKey *>(w.gscratch2), w.tied_cells, w.n_tied_cells);
   PROF_END(c, P_GROUND_CELLS);
@@ -641,7 +743,7 @@ int launch_ground_planes(sloam_ctx *c, int K, const sloam_point *ground, const i
   // cells with exact z ties again, with the std::sort replay (usually an empty list)
   PROF_BEGIN(c, P_GROUND_REPLAY);
   ground_cells_kernel<true><<<c->sm_count * 4, kGThreads, 0, c->stream>>>(
-      c->dp, ground, ground_count, stride, reinterpret_cast<SelKey *>(w.gscratch), w.cell_count, pose_est,
+      c->dp, ground, ground_count, stride, members, w.cell_count, pose_est,
       w.qscratch, w.pscratch, w.fit_rec, cells, cell_features, kept_points, kept_offsets,
       reinterpret_cast<SelKey *>(w.gscratch2), w.tied_cells, w.n_tied_cells);
   PROF_END(c, P_GROUND_REPLAY);

@@ -105,10 +105,14 @@ static int run_dev_body(sloam_ctx *c, int K, const sloam_batch_in *in, const slo
   float *range = out->range_image;  // optional output
   // sparse tree cloud: only the tree-labelled points and the bit mask are written (the NaN
   // points of the dense cloud are ~90 % of its bytes and nothing downstream needs them)
-  int rc = launch_project_split(c, K, true, true, in->points, in->mask, w.pix, range, w.tree, w.ground,
+  // ... and the ground points are not copied either: ground == nullptr selects the record
+  // layout (k1_project.cu, FUSED), the cell stage reads the retained points from in->points
+  int rc = launch_project_split(c, K, true, true, in->points, in->mask, w.pix, range, w.tree, nullptr,
                                 w.ground_count, w.tree_bits, true);
   c->tree_sparse = true;
   c->ground_strided = true;
+  c->last_points = in->points;
+  c->last_mask = in->mask;
   if (rc != SLOAM_OK) return rc;
   // fork: ground cells + plane fits (K2, main stream) and the tree detector (K3, side
   // stream) both depend only on K1 and are latency-bound, so they run concurrently
@@ -123,7 +127,7 @@ static int run_dev_body(sloam_ctx *c, int K, const sloam_batch_in *in, const slo
   c->stream = main_stream;
   if (rc != SLOAM_OK) return rc;
   if (fork) SB_CUDA(c, cudaEventRecord(c->ev_join, c->side));
-  rc = launch_ground_planes(c, K, w.ground, w.ground_count, c->hp.N, in->pose_est, w.cells,
+  rc = launch_ground_planes(c, K, in->points, w.ground_count, c->hp.N, in->pose_est, w.cells,
                             w.cell_features, nullptr, nullptr, true);
   if (rc != SLOAM_OK) return rc;
   if (fork) SB_CUDA(c, cudaStreamWaitEvent(main_stream, c->ev_join, 0));  // join
@@ -318,9 +322,13 @@ int sloam_b200_get_intermediates(sloam_ctx *c, sloam_intermediates *o) {
     c->tree_sparse = false;
   }
   const sloam_point *ground_dense = w.ground;
-  if (c->ground_strided && c->last_k > 0) {  // contiguous ground cloud of stage a2, into scratch
-    const int rc = launch_ground_compact(c, c->last_k, reinterpret_cast<sloam_point *>(w.qscratch));
+  if (c->ground_strided && c->last_k > 0) {
+    // the fused run kept no ground cloud: redo the label split of stage a2 from the pixel
+    // indices (the input buffers of that run must still be alive); this also makes ws.tree dense
+    const int rc = launch_project_split(c, c->last_k, false, true, c->last_points, c->last_mask, w.pix, nullptr, w.tree,
+                                        reinterpret_cast<sloam_point *>(w.qscratch), w.ground_count, nullptr, false);
     if (rc != SLOAM_OK) return rc;
+    c->tree_sparse = false;
   }
   if (c->ground_strided) ground_dense = reinterpret_cast<const sloam_point *>(w.qscratch);
   o->pix = w.pix; o->tree = w.tree; o->ground = const_cast<sloam_point *>(ground_dense); o->ground_count = w.ground_count;
