@@ -92,8 +92,8 @@ struct Workspace {
   int32_t *big_rank = nullptr;       // [K][max_trees] PCL label of each big component
   uint32_t *slot_rows = nullptr;     // [K][max_trees][ceil(H/32)] rows of a big component that hold a vertex record
   sloam_vertex *slot_vertices = nullptr; // [K][max_trees][H] one candidate vertex per (component, row)
-  int32_t *vpool_count = nullptr;    // [K]
   void *vitems = nullptr;            // [K << (row bits + slot bits)] VItem work items of the vertex stage
+  int32_t *vitem_pool = nullptr;     // [K << (row bits + slot bits)] first vertex-point slot of each item
   int32_t *vlists = nullptr;         // [6][K*max_trees*H] item ids by size class (+ wide, tied)
   int32_t *n_vlists = nullptr;       // [8] lengths of the class lists
   int32_t *kf_flags = nullptr;       // [K] bit 0: more big components than max_trees (first max_trees kept)

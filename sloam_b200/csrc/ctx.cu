@@ -57,7 +57,6 @@ static void layout(sloam_ctx *c, Bump &b) {
   b.take(w.ground_count, K);
   b.take(w.cell_count, K * kMaxCells);
   b.take(w.n_tied_cells, 4);
-  b.take(w.vpool_count, K);
   b.take(w.n_vlists, 8);
   b.take(w.kf_flags, K);
   b.take(w.zero_end, 64);
@@ -99,6 +98,7 @@ static void layout(sloam_ctx *c, Bump &b) {
     b.take(items16, K << (c->hp.vw_row_bits + c->hp.vw_slot_bits));
     w.vitems = items16;
   }
+  b.take(w.vitem_pool, K << (c->hp.vw_row_bits + c->hp.vw_slot_bits));
   b.take(w.vlists, 6 * K * T * H);
   b.take(w.trees, K * T);
   b.take(w.n_trees, K);

@@ -216,7 +216,8 @@ cc_label_kernel(const DevParams *__restrict__ dp, const uint32_t *__restrict__ b
                 int32_t *__restrict__ run_info, int32_t *__restrict__ run_label, int32_t *__restrict__ wbase_out,
                 int32_t *__restrict__ n_roots, int32_t *__restrict__ n_big, int32_t *__restrict__ big_rank,
                 int32_t *__restrict__ kf_flags, uint32_t *__restrict__ slot_rows, VItem *__restrict__ items,
-                int32_t *__restrict__ vlists, long long list_cap, int32_t *__restrict__ n_lists) {
+                int32_t *__restrict__ item_pool, int32_t *__restrict__ vlists, long long list_cap,
+                int32_t *__restrict__ n_lists) {
   extern __shared__ __align__(16) unsigned char lbl_smem[];
   const int N = dp->N, W = dp->p.img_w, H = dp->p.img_h, T = dp->p.max_trees, Nw = (N + 31) >> 5;
   const int Hw = (H + 31) >> 5;
@@ -229,7 +230,8 @@ cc_label_kernel(const DevParams *__restrict__ dp, const uint32_t *__restrict__ b
   uint32_t *s_rows = reinterpret_cast<uint32_t *>(s_wbase + Nw);       // [T * Hw]
   int32_t *s_runs = reinterpret_cast<int32_t *>(s_rows + (size_t)T * Hw);  // 3 x [Rs]
   __shared__ int s_tmp[kLblWarps + 1];
-  __shared__ int s_nitems;
+  __shared__ int s_nitems, s_pool;
+  __shared__ int s_ccnt[kClsWide + 1], s_cbase[kClsWide + 1];
   const uint32_t *bk = bits + (size_t)k * Nw;
   const uint4 *pk = planes + (size_t)k * Nw;
 
@@ -248,7 +250,8 @@ cc_label_kernel(const DevParams *__restrict__ dp, const uint32_t *__restrict__ b
   if (wbase_out)
     for (int w = threadIdx.x; w < Nw; w += kLblThreads) wbase_out[(size_t)k * Nw + w] = s_wbase[w];
   for (int i = threadIdx.x; i < T * Hw; i += kLblThreads) s_rows[i] = 0u;
-  if (threadIdx.x == 0) s_nitems = 0;
+  if (threadIdx.x == 0) { s_nitems = 0; s_pool = 0; }
+  if (threadIdx.x <= kClsWide) s_ccnt[threadIdx.x] = 0;
   // per-run arrays: shared memory, or the keyframe's slice of global scratch for scans with
   // more runs than fit (correct, slower; a forest scan has a few thousand runs)
   int32_t *par = s_runs;
@@ -363,9 +366,18 @@ cc_label_kernel(const DevParams *__restrict__ dp, const uint32_t *__restrict__ b
         cls = n_tot <= 8 ? 0 : (n_tot <= 16 ? 1 : (n_tot <= 32 ? 2 : (n_tot <= kVtxCap ? 3 : kClsWide)));
       const unsigned hb = __ballot_sync(kFull, cls >= 0);
       if (hb == 0u) continue;
-      int ibase = 0;
-      if (lane == 0) ibase = atomicAdd(&s_nitems, __popc(hb));
-      ibase = __shfl_sync(kFull, ibase, 0);
+      // item index and first slot in the keyframe's vertex-point pool (n slots per item: every
+      // member may be kept), both from shared-memory counters: one atomic per chunk
+      int psum = cls >= 0 ? n_tot : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(kFull, psum, o);
+        if (lane >= o) psum += t;
+      }
+      int ibase = 0, pbase = 0;
+      if (lane == 31) { ibase = atomicAdd(&s_nitems, __popc(hb)); pbase = atomicAdd(&s_pool, psum); }
+      ibase = __shfl_sync(kFull, ibase, 31);
+      pbase = __shfl_sync(kFull, pbase, 31);
       const int idx = ibase + __popc(hb & ((1u << lane) - 1u));
       if (cls >= 0) {
         VItem it;
@@ -376,18 +388,38 @@ cc_label_kernel(const DevParams *__restrict__ dp, const uint32_t *__restrict__ b
         it.slot = (uint16_t)(sc - 1);
         it.row = (uint16_t)row;
         items_k[idx] = it;
+        item_pool[((size_t)k << item_shift) + idx] = pbase + psum - n_tot;
         atomicOr(&s_rows[(sc - 1) * Hw + (row >> 5)], 1u << (row & 31));
+        atomicAdd(&s_ccnt[cls], 1);
       }
+    }
+  }
+  __syncthreads();
+  // -- the items of the keyframe join the batch's class lists: one global atomic per class
+  if (threadIdx.x <= kClsWide) {
+    const int cnt = s_ccnt[threadIdx.x];
+    s_cbase[threadIdx.x] = cnt ? atomicAdd(&n_lists[threadIdx.x], cnt) : 0;
+    s_ccnt[threadIdx.x] = 0;
+  }
+  __syncthreads();
+  const int nitems = s_nitems;
+  for (int i0 = 0; i0 < nitems; i0 += kLblThreads) {
+    const int idx = i0 + threadIdx.x;
+    int cls = -1;
+    if (idx < nitems) {
+      const int n_tot = items_k[idx].n;
+      cls = n_tot <= 8 ? 0 : (n_tot <= 16 ? 1 : (n_tot <= 32 ? 2 : (n_tot <= kVtxCap ? 3 : kClsWide)));
+    }
 #pragma unroll
-      for (int c = 0; c <= kClsWide; ++c) {
-        const unsigned cb = __ballot_sync(kFull, cls == c);
-        if (cb == 0u) continue;
-        const int leader = __ffs(cb) - 1;
-        int lb = 0;
-        if (lane == leader) lb = atomicAdd(&n_lists[c], __popc(cb));
-        lb = __shfl_sync(kFull, lb, leader);
-        if (cls == c) vlists[(size_t)c * list_cap + lb + __popc(cb & ((1u << lane) - 1u))] = (k << item_shift) | idx;
-      }
+    for (int c = 0; c <= kClsWide; ++c) {
+      const unsigned cb = __ballot_sync(kFull, cls == c);
+      if (cb == 0u) continue;
+      const int leader = __ffs(cb) - 1;
+      int lb = 0;
+      if (lane == leader) lb = atomicAdd(&s_ccnt[c], __popc(cb));
+      lb = __shfl_sync(kFull, lb, leader);
+      if (cls == c)
+        vlists[(size_t)c * list_cap + s_cbase[c] + lb + __popc(cb & ((1u << lane) - 1u))] = (k << item_shift) | idx;
     }
   }
   __syncthreads();
@@ -474,7 +506,7 @@ template <int G>
 __device__ __forceinline__ bool vertex_group(const DevParams *dp, GrpSmem &s, bool active, const VItem &it, int k,
                                              const sloam_point *__restrict__ tree, const int32_t *__restrict__ run_pix0,
                                              const int32_t *__restrict__ run_info, sloam_vertex *__restrict__ slot_vertices,
-                                             sloam_point *__restrict__ pool, int32_t *__restrict__ pool_count) {
+                                             sloam_point *__restrict__ pool, int base) {
   const int N = dp->N, H = dp->p.img_h, T = dp->p.max_trees;
   const int lane = threadIdx.x & 31, gl = lane & (G - 1), g0 = lane & ~(G - 1);
   const unsigned gmask = G == 32 ? kFull : (((1u << G) - 1u) << g0);
@@ -567,9 +599,6 @@ __device__ __forceinline__ bool vertex_group(const DevParams *dp, GrpSmem &s, bo
   const int kept = __popc(kb);
   if (keep) s.ord2[g0 + __popc(kb & lt)] = (int8_t)m;
   __syncwarp();
-  int base = 0;
-  if (active && gl == 0 && kept > 1) base = atomicAdd(pool_count + k, kept);
-  base = __shfl_sync(kFull, base, g0);
   if (active && kept > 1 && gl < kept) {
     const int q = s.ord2[g0 + gl];
     sloam_point o; o.x = s.x[g0 + q]; o.y = s.y[g0 + q]; o.z = s.z[g0 + q]; o.intensity = s.w[g0 + q];
@@ -595,7 +624,7 @@ __device__ __forceinline__ bool vertex_group(const DevParams *dp, GrpSmem &s, bo
 // must be redone by the REPLAY = true instance (nothing was written)
 template <bool REPLAY>
 __device__ bool build_vertex(const DevParams *dp, VtxSmem &s, unsigned long long *pack, int16_t *perm, int n,
-                             int row, sloam_vertex *out, sloam_point *pool, int32_t *pool_count) {
+                             int row, sloam_vertex *out, sloam_point *pool, int base) {
   const int lane = threadIdx.x & 31;
   const int middle = (int)(n / 2.0);  // trellis.cpp:66
   // Order statistics by counting: member m counts the members strictly below it on each
@@ -717,9 +746,6 @@ __device__ bool build_vertex(const DevParams *dp, VtxSmem &s, unsigned long long
   if (kept > 1) {  // trellis.cpp:95-100
     const int a = s.order[0], b = s.order[kept - 1];
     v.radius = dist3f(s.x[a], s.y[a], s.z[a], s.x[b], s.y[b], s.z[b]);
-    int base = 0;
-    if (lane == 0) base = atomicAdd(pool_count, kept);
-    base = __shfl_sync(kFull, base, 0);
     for (int q = lane; q < kept; q += 32) {
       const int m = s.order[q];
       sloam_point p; p.x = s.x[m]; p.y = s.y[m]; p.z = s.z[m]; p.intensity = s.w[m];
@@ -774,7 +800,7 @@ vertex_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ 
               const VItem *__restrict__ items, int32_t *__restrict__ vlists, long long list_cap,
               int32_t *__restrict__ n_lists, const int32_t *__restrict__ run_pix0,
               const int32_t *__restrict__ run_info, sloam_vertex *__restrict__ slot_vertices,
-              sloam_point *__restrict__ pool, int32_t *__restrict__ pool_count) {
+              sloam_point *__restrict__ pool, const int32_t *__restrict__ item_pool) {
   __shared__ __align__(16) VtxSmem sm[kVtxWarps];
   const int N = dp->N, H = dp->p.img_h, T = dp->p.max_trees;
   const int item_shift = dp->vw_row_bits + dp->vw_slot_bits;
@@ -787,19 +813,29 @@ vertex_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ 
     constexpr int per = 32 / G;
     const int32_t *list = vlists + (size_t)cls * list_cap;
     const int count = n_lists[cls];
-    for (int ws = gwarp; ws * per < count; ws += nwarps) {
+    // the item of the NEXT round is fetched while the current one is processed (list entry ->
+    // item record -> points is a chain of three dependent loads)
+    VItem nit;
+    int ngid = 0, nbase = 0;
+    auto fetch = [&](int ws) {
       const int li = ws * per + lane / G;
-      const bool active = li < count;
-      VItem it;
-      int gid = 0;
-      if (active) {
-        gid = list[li];
-        it = items[gid];
-      } else {
-        it.pix0 = 0; it.first_run = 0; it.n = 0; it.span = 0; it.slot = 0; it.row = 0;
+      nit.pix0 = 0; nit.first_run = 0; nit.n = 0; nit.span = 0; nit.slot = 0; nit.row = 0;
+      ngid = -1;
+      nbase = 0;
+      if (ws * per < count && li < count) {
+        ngid = list[li];
+        nit = items[ngid];
+        nbase = item_pool[ngid];
       }
-      const int k = gid >> item_shift;
-      const bool redo = vertex_group<G>(dp, gs, active, it, k, tree, run_pix0, run_info, slot_vertices, pool, pool_count);
+    };
+    fetch(gwarp);
+    for (int ws = gwarp; ws * per < count; ws += nwarps) {
+      const VItem it = nit;
+      const int gid = ngid, base = nbase;
+      const bool active = gid >= 0;
+      fetch(ws + nwarps);
+      const int k = active ? (gid >> item_shift) : 0;
+      const bool redo = vertex_group<G>(dp, gs, active, it, k, tree, run_pix0, run_info, slot_vertices, pool, base);
       const unsigned rb = __ballot_sync(kFull, redo && (lane & (G - 1)) == 0);
       if (rb) {
         int tb = 0;
@@ -823,7 +859,7 @@ vertex_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ 
       __syncwarp();
       gather_members(dp, s, it, k, tree, run_pix0, run_info);
       sloam_vertex *out = slot_vertices + ((size_t)k * T + it.slot) * H + it.row;
-      if (build_vertex<false>(dp, s, nullptr, nullptr, it.n, it.row, out, pool + (size_t)k * N, pool_count + k) && lane == 0)
+      if (build_vertex<false>(dp, s, nullptr, nullptr, it.n, it.row, out, pool + (size_t)k * N, item_pool[gid]) && lane == 0)
         tied[atomicAdd(&n_lists[kClsTied], 1)] = gid;
       __syncwarp();
     }
@@ -836,7 +872,7 @@ vertex_replay_kernel(const DevParams *__restrict__ dp, const sloam_point *__rest
                      const VItem *__restrict__ items, const int32_t *__restrict__ vlists, long long list_cap,
                      const int32_t *__restrict__ n_lists, const int32_t *__restrict__ run_pix0,
                      const int32_t *__restrict__ run_info, sloam_vertex *__restrict__ slot_vertices,
-                     sloam_point *__restrict__ pool, int32_t *__restrict__ pool_count) {
+                     sloam_point *__restrict__ pool, const int32_t *__restrict__ item_pool) {
   __shared__ __align__(16) VtxSmem sm[kVtxWarps];
   __shared__ unsigned long long s_pack[kVtxWarps * kVtxCap];  // replay scratch
   __shared__ int16_t s_perm[kVtxWarps * 2 * kVtxCap];         // members in x and in y order
@@ -854,7 +890,7 @@ vertex_replay_kernel(const DevParams *__restrict__ dp, const sloam_point *__rest
     gather_members(dp, s, it, k, tree, run_pix0, run_info);
     sloam_vertex *out = slot_vertices + ((size_t)k * T + it.slot) * H + it.row;
     build_vertex<true>(dp, s, s_pack + warp * kVtxCap, s_perm + warp * 2 * kVtxCap, it.n, it.row, out,
-                       pool + (size_t)k * N, pool_count + k);
+                       pool + (size_t)k * N, item_pool[gid]);
     __syncwarp();
   }
 }
@@ -866,7 +902,7 @@ __global__ void vertex_wide_kernel(const DevParams *__restrict__ dp, const sloam
                                    long long list_cap, const int32_t *__restrict__ n_lists,
                                    const int32_t *__restrict__ run_pix0, const int32_t *__restrict__ run_info,
                                    sloam_vertex *__restrict__ slot_vertices, sloam_point *__restrict__ pool,
-                                   int32_t *__restrict__ pool_count) {
+                                   const int32_t *__restrict__ item_pool) {
   extern __shared__ float dsm[];
   const int N = dp->N, W = dp->p.img_w, H = dp->p.img_h, T = dp->p.max_trees;
   const int item_shift = dp->vw_row_bits + dp->vw_slot_bits;
@@ -941,7 +977,7 @@ __global__ void vertex_wide_kernel(const DevParams *__restrict__ dp, const sloam
       if (kept > 1) {
         const int a = sorder[0], b = sorder[kept - 1];
         v.radius = dist3f(sx[a], sy[a], sz[a], sx[b], sy[b], sz[b]);
-        s_base = atomicAdd(pool_count + k, kept);
+        s_base = item_pool[gid];
         v.n_points = kept; v.point_begin = s_base; v.is_valid = 1;
       }
       *out = v;
@@ -1052,7 +1088,6 @@ static int run_cc(sloam_ctx *c, int K, const sloam_point *tree, bool bits_ready,
   if (!pre_zeroed) {
     SB_CUDA(c, cudaMemsetAsync(w.kf_flags, 0, sizeof(int32_t) * K, c->stream));
     SB_CUDA(c, cudaMemsetAsync(w.n_vlists, 0, sizeof(int32_t) * 8, c->stream));
-    SB_CUDA(c, cudaMemsetAsync(w.vpool_count, 0, sizeof(int32_t) * K, c->stream));
   }
   if (!bits_ready) {  // caller-supplied cloud: derive the bits from the points
     const dim3 blocks((unsigned)((N + 255) / 256), (unsigned)K);
@@ -1076,7 +1111,8 @@ static int run_cc(sloam_ctx *c, int K, const sloam_point *tree, bool bits_ready,
   cc_label_kernel<<<K, kLblThreads, smem, c->stream>>>(
       c->dp, w.tree_bits, reinterpret_cast<const uint4 *>(w.cc_planes), Rs, w.run_par, reinterpret_cast<uint32_t *>(w.run_siz),
       w.run_len, w.run_pix0, w.run_info, w.run_label, want_labels ? w.cc_wbase : nullptr, w.n_roots, w.n_big,
-      w.big_rank, w.kf_flags, w.slot_rows, reinterpret_cast<VItem *>(w.vitems), w.vlists, list_cap, w.n_vlists);
+      w.big_rank, w.kf_flags, w.slot_rows, reinterpret_cast<VItem *>(w.vitems), w.vitem_pool, w.vlists, list_cap,
+      w.n_vlists);
   PROF_END(c, P_CC_LABEL);
   SB_LAUNCH_CHECK(c);
   return SLOAM_OK;
@@ -1102,14 +1138,14 @@ int launch_compute_graph(sloam_ctx *c, int K, const sloam_point *tree, sloam_tre
   const int vgrid = c->sm_count * vtx_occ;
   PROF_BEGIN(c, P_VERTEX);
   vertex_kernel<<<vgrid, kVtxWarps * 32, 0, c->stream>>>(c->dp, tree, items, w.vlists, list_cap, w.n_vlists, w.run_pix0,
-                                                         w.run_info, w.slot_vertices, vertex_points, w.vpool_count);
+                                                         w.run_info, w.slot_vertices, vertex_points, w.vitem_pool);
   PROF_END(c, P_VERTEX);
   SB_LAUNCH_CHECK(c);
   // the tied items again, with the std::sort replay (usually an empty list: the CTAs exit)
   PROF_BEGIN(c, P_VERTEX_REPLAY);
   vertex_replay_kernel<<<c->sm_count, kVtxWarps * 32, 0, c->stream>>>(c->dp, tree, items, w.vlists, list_cap, w.n_vlists,
                                                                       w.run_pix0, w.run_info, w.slot_vertices,
-                                                                      vertex_points, w.vpool_count);
+                                                                      vertex_points, w.vitem_pool);
   SB_LAUNCH_CHECK(c);
   const size_t wide_smem = sizeof(float) * 4 * W + sizeof(int) * 3 * W;
   // opt-in shared memory: the attribute belongs to (function, device) and must only grow -- a
@@ -1121,7 +1157,7 @@ int launch_compute_graph(sloam_ctx *c, int K, const sloam_point *tree, sloam_tre
   }
   vertex_wide_kernel<<<c->sm_count, 256, wide_smem, c->stream>>>(c->dp, tree, items, w.vlists, list_cap, w.n_vlists,
                                                                  w.run_pix0, w.run_info, w.slot_vertices,
-                                                                 vertex_points, w.vpool_count);
+                                                                 vertex_points, w.vitem_pool);
   PROF_END(c, P_VERTEX_REPLAY);
   SB_LAUNCH_CHECK(c);
   PROF_BEGIN(c, P_TREE_COMPACT);
