@@ -65,9 +65,39 @@ void project(const Options &o, const Pt *pts, int n, int32_t *pix, float *range_
   for (size_t idx : order) range_image[pix[idx]] = ranges[idx];
 }
 
+/* Segmentation::_destaggerCloud, inference.cpp:200-228, statement for statement.  `out`
+ * starts as a copy of `in` (pcl::copyPointCloud, :255).  The bound test `im_col > W` lets
+ * col + 32 == W through: the write lands on the first pixel of the next row (SURVEY B-12),
+ * which the next row's own pass overwrites; for an odd H the last such write is past the end
+ * of the cloud (undefined behaviour in the reference) and is dropped here. */
+static void destagger_cloud(const Cloud &in, Cloud &out, int H, int W) {
+  bool col_valid = true;
+  for (int irow = 0; irow < H; irow++) {
+    for (int icol = 0; icol < W; icol++) {
+      int im_col = icol;
+      if (irow % 2 == 0) {
+        im_col += 32;
+        if (im_col < 0 || im_col > W) {
+          col_valid = false;
+          im_col = im_col % W;
+        }
+      }
+      if (col_valid) {
+        const Pt &pt = in[(size_t)irow * W + icol];
+        const size_t dst = (size_t)irow * W + im_col;
+        if (dst < out.size()) {
+          out[dst].x = pt.x;
+          out[dst].y = pt.y;
+          out[dst].z = pt.z;
+        }
+      }
+      col_valid = true;
+    }
+  }
+}
+
 void mask_cloud(const Options &o, const Pt *pts, int n, const int32_t *pix,
                 const uint8_t *mask, Cloud &tree, Cloud &ground) {
-  (void)o;
   /* sloamNode.cpp:212: maskCloud(cloud, mask, ground, 1)          -> sparse
    * sloamNode.cpp:215: maskCloud(cloud, mask, tree, 255, dense)  -> organized
    * inference.cpp:241-253 */
@@ -84,6 +114,11 @@ void mask_cloud(const Options &o, const Pt *pts, int n, const int32_t *pix,
       p.x = p.y = p.z = qnan;
       tree[i] = p;
     }
+  }
+  if (o.p.do_destagger && n == o.p.img_h * o.p.img_w) { /* inference.cpp:256-259: the dense cloud only */
+    Cloud out = tree;
+    destagger_cloud(tree, out, o.p.img_h, o.p.img_w);
+    tree.swap(out);
   }
 }
 

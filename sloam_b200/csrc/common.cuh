@@ -59,6 +59,8 @@ struct Workspace {
   sloam_point *ground = nullptr;     // [K][N]
   int32_t *ground_count = nullptr;   // [K]
   uint32_t *tree_bits = nullptr;     // [K][ceil(N/32)] bit i: pixel i may hold a tree point
+  sloam_point *tree2 = nullptr;      // [K][N] masked cloud before the destagger pass (do_destagger only)
+  uint32_t *tree_bits2 = nullptr;    // [K][ceil(N/32)]  "
   uint8_t *ground_cell = nullptr;    // [K][N] polar cell of each ground point (255 = none)
   int32_t *cell_count = nullptr;     // [K][kMaxCells]
   int32_t *tile_count = nullptr;     // [K][tiles] ground points of each K1 tile (tile-strided ground layout)

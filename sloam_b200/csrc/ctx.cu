@@ -64,6 +64,10 @@ static void layout(sloam_ctx *c, Bump &b) {
   b.take(w.tree, K * N);
   b.take(w.ground, K * N);
   b.take(w.tree_bits, K * ((N + 31) / 32));
+  if (p.do_destagger) {
+    b.take(w.tree2, K * N);
+    b.take(w.tree_bits2, K * ((N + 31) / 32));
+  }
   b.take(w.ground_cell, K * N);
   b.take(w.tile_count, K * tiles);
   b.take(w.range_image, K * N);
@@ -147,7 +151,6 @@ static int validate(const sloam_params &p, std::string &why) {
   if (p.max_trees <= 0 || p.max_map_models <= 0) { why = "capacities must be positive"; return -1; }
   if (p.max_trees > 2046) { why = "max_trees must be <= 2046 (11-bit slot codes, k3_trellis.cu)"; return -1; }
   if (p.max_prev_planes < p.groundRadiiBins * p.groundThetaBins) { why = "max_prev_planes < number of ground cells"; return -1; }
-  if (p.do_destagger) { why = "do_destagger is not implemented (sim.yaml:5 uses false)"; return -1; }
   if (p.ransac_fixed_hypotheses < 0 || p.ransac_max_iterations <= 0) { why = "ransac counts"; return -1; }
   return 0;
 }
@@ -336,7 +339,7 @@ int sloam_b200_set_params(sloam_ctx *c, const sloam_params *p) {
       p->groundRadiiBins * p->groundThetaBins > o.groundRadiiBins * o.groundThetaBins ||
       p->numGroundFeatures > o.numGroundFeatures || p->featuresPerTree > o.featuresPerTree ||
       p->max_trees > o.max_trees || p->max_tree_vertices > o.max_tree_vertices ||
-      p->max_prev_planes > o.max_prev_planes ||
+      p->max_prev_planes > o.max_prev_planes || (p->do_destagger && !o.do_destagger && !c->ws.tree2) ||
       ransac_draws_per_tree(*p) > ransac_draws_per_tree(o))
     return set_err(c, SLOAM_E_INVALID, "set_params: capacities/image size must not grow; create a new context");
   // keep the arena layout of the creation-time parameters: only values change

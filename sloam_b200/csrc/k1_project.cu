@@ -371,6 +371,62 @@ __global__ void range_finalize_kernel(unsigned *__restrict__ range_bits, long lo
   }
 }
 
+// Segmentation::_destaggerCloud (inference.cpp:200-228), applied by maskCloud to the organized
+// (dense) cloud only (:256-259): the output starts as a copy of the masked cloud
+// (pcl::copyPointCloud, :255); then, in raster order, x/y/z of pixel (row, col) are copied to
+// (row, col + 32) on EVEN rows (Ouster column stagger) and to itself on odd rows.  The bound
+// test is `im_col > W` (:209), so col + 32 == W passes and lands on pixel (row + 1, 0) -- which
+// the next (odd) row then overwrites with its own point; columns beyond are dropped.  Net
+// effect: out(row, col).xyz = in(row, col - 32).xyz for even rows and col >= 32, everything
+// else unchanged (columns 0..31 of even rows keep their own point, and it also appears at
+// col + 32); intensity is never moved.  For an odd H the reference's last write of the last
+// row is past the end of the cloud (undefined): dropped here and in the oracle.
+__device__ __forceinline__ int destagger_source(int i, int W, unsigned magic_w) {
+  const int row = fast_div_w(i, magic_w), col = i - row * W;
+  return ((row & 1) == 0 && col >= 32) ? i - 32 : i;
+}
+// dense: src = masked organized cloud (NaN points included), dst = destaggered cloud
+__global__ void destagger_dense_kernel(const DevParams *__restrict__ dp, int K, const sloam_point *__restrict__ src,
+                                       sloam_point *__restrict__ dst) {
+  const int N = dp->N;
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)K * N) return;
+  const int k = (int)(g / N), i = (int)(g - (long long)k * N);
+  const int s = destagger_source(i, dp->p.img_w, dp->magic_w);
+  sloam_point p = ld_point(src + (size_t)k * N + s);
+  if (s != i) p.intensity = src[g].intensity;
+  st_point(dst + g, p);
+}
+// sparse (fused pipeline): only the pixels whose bit is set hold a point
+__global__ void destagger_sparse_kernel(const DevParams *__restrict__ dp, int K, const sloam_point *__restrict__ src,
+                                        const uint32_t *__restrict__ sbits, sloam_point *__restrict__ dst,
+                                        uint32_t *__restrict__ dbits) {
+  const int N = dp->N, W = dp->p.img_w, Nw = (N + 31) >> 5;
+  const unsigned magic_w = dp->magic_w;
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)K * Nw;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long gw = warp0; gw < total; gw += nwarps) {
+    const int k = (int)(gw / Nw), wi = (int)(gw - (long long)k * Nw);
+    const uint32_t *bk = sbits + (size_t)k * Nw;
+    const int i = wi * 32 + lane;
+    bool sb = false;
+    int s = i;
+    if (i < N) {
+      s = destagger_source(i, W, magic_w);
+      sb = (bk[s >> 5] >> (s & 31)) & 1u;
+    }
+    const unsigned ob = __ballot_sync(kFull, sb);
+    if (lane == 0) dbits[gw] = ob;
+    if (sb) {
+      sloam_point p = ld_point(src + (size_t)k * N + s);
+      if (s != i) p.intensity = ((bk[i >> 5] >> (i & 31)) & 1u) ? src[(size_t)k * N + i].intensity : 0.f;
+      st_point(dst + (size_t)k * N + i, p);
+    }
+  }
+}
+
 // Polar cell tags for a ground cloud that did not come through the split
 // kernel (stage entry sloam_b200_ground_planes_dev on caller-supplied clouds).
 __global__ void ground_tag_kernel(const DevParams *__restrict__ dp, int K,
@@ -414,6 +470,15 @@ int launch_project_split(sloam_ctx *c, int K, bool do_project, bool do_split,
   const int tiles = (N + kSplitTile - 1) / kSplitTile;
   const long long total = (long long)K * N;
   unsigned *rb = reinterpret_cast<unsigned *>(range_image);
+  // destagger: the kernel writes the masked cloud into scratch, a second pass shifts it
+  const bool destagger = do_split && c->hp.p.do_destagger != 0;
+  sloam_point *tree_final = tree;
+  uint32_t *bits_final = tree_bits;
+  if (destagger) {
+    if (!c->ws.tree2) return set_err(c, SLOAM_E_INVALID, "do_destagger was not enabled when the context was created");
+    tree = c->ws.tree2;
+    if (tree_bits) tree_bits = c->ws.tree_bits2;
+  }
   if (do_project && rb) SB_CUDA(c, cudaMemsetAsync(rb, 0xFF, sizeof(unsigned) * total, c->stream));
   // The kernel always writes the tile-strided ground layout.  The fused pipeline consumes it
   // as is (ground == ws.ground); a stage entry gets the contiguous cloud by compaction.
@@ -449,6 +514,16 @@ int launch_project_split(sloam_ctx *c, int K, bool do_project, bool do_split,
 #undef SB_K1_ARGS
   PROF_END(c, P_SPLIT);
   SB_LAUNCH_CHECK(c);
+  if (destagger) {
+    if (sparse_tree) {
+      const long long words = (long long)K * ((N + 31) / 32);
+      const unsigned dgrid = (unsigned)std::min<long long>((words + 7) / 8, (long long)c->sm_count * 8);
+      destagger_sparse_kernel<<<dgrid, 256, 0, c->stream>>>(c->dp, K, tree, tree_bits, tree_final, bits_final);
+    } else {
+      destagger_dense_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(c->dp, K, tree, tree_final);
+    }
+    SB_LAUNCH_CHECK(c);
+  }
   if (do_split && !strided_out) {
     ground_compact_kernel<<<dim3((unsigned)tiles, (unsigned)K), 256, 0, c->stream>>>(
         c->dp, c->ws.ground, N, c->ws.tile_count, ground, N);

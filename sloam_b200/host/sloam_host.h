@@ -120,6 +120,7 @@ struct HostConfig {
   float fov_up = 22.5f, fov_down = -22.5f;
   float max_dist_to_centroid = 0.2f;
   int max_trees = 512, max_map_models = 512;
+  bool do_destagger = false;  // Segmentation ctor argument (inference.cpp:5-14); sloamNode.cpp:80 defaults to true
 };
 
 inline void fill_params(sloam_params &p, const FeatureModelParams &f, const HostConfig &h) {
@@ -127,6 +128,7 @@ inline void fill_params(sloam_params &p, const FeatureModelParams &f, const Host
   p.img_h = h.img_h; p.img_w = h.img_w; p.fov_up_deg = h.fov_up; p.fov_down_deg = h.fov_down;
   p.max_dist_to_centroid = h.max_dist_to_centroid;
   p.max_trees = h.max_trees; p.max_map_models = h.max_map_models;
+  p.do_destagger = h.do_destagger ? 1 : 0;
   p.scansPerSweep = f.scansPerSweep;
   p.minTreeModels = f.minTreeModels; p.minGroundModels = f.minGroundModels;
   p.maxLidarDist = f.maxLidarDist; p.maxGroundLidarDist = f.maxGroundLidarDist;
@@ -603,9 +605,9 @@ class Segmentation {  // inference.h:55-110
   // its H x W mask is supplied by the caller (setLabelSource) before run().
   Segmentation(const float fov_up, const float fov_down, const int img_w, const int img_h, const int /*img_d*/,
                bool do_destagger) {
-    if (do_destagger) throw std::runtime_error("do_destagger is not supported (sim.yaml:5 uses false)");
     sloam_b200::HostConfig h;
     h.img_h = img_h; h.img_w = img_w; h.fov_up = fov_up; h.fov_down = fov_down;
+    h.do_destagger = do_destagger;  // _destaggerCloud, inference.cpp:200-228
     rt_.reset(new sloam_b200::Runtime(FeatureModelParams(), h));
   }
   Segmentation(const Segmentation &) = delete;
