@@ -40,6 +40,15 @@ extern "C" {
 #define SLOAM_KF_EMPTY_MAP 1     /* sloam.cpp:476-480, returned false              */
 #define SLOAM_KF_NO_MODELS 2     /* sloam.cpp:482-486, returned false              */
 #define SLOAM_KF_NOT_CONVERGED 3 /* joint OptimizePose did not converge (:241,:507)*/
+/* The code above is the low byte of sloam_kf_result::status (SLOAM_KF_CODE).  Capacity
+ * flags are OR-ed on top; the reference has no capacities (its vectors grow), so a set flag
+ * means the result was computed on truncated data:
+ *   TREE_CAPACITY  more clusters above min_cluster_points than max_trees; the first
+ *                  max_trees in PCL label order were kept (deterministic)
+ *   MAP_CAPACITY   sequential mode: the semantic map is full, new landmarks were dropped */
+#define SLOAM_KF_CODE(status) ((status) & 0xFF)
+#define SLOAM_KF_FLAG_TREE_CAPACITY 0x100
+#define SLOAM_KF_FLAG_MAP_CAPACITY 0x200
 
 /* ------------------------------------------------------------------- types */
 
@@ -116,7 +125,7 @@ typedef struct sloam_tree_model {
 
 /* Per-keyframe output record of RunSloam (SloamOutput, sloam.h:48-55). */
 typedef struct sloam_kf_result {
-  int32_t status;  /* SLOAM_KF_*                                   */
+  int32_t status;  /* SLOAM_KF_* code | SLOAM_KF_FLAG_*            */
   int32_t success; /* the bool RunSloam returns                    */
   int32_t n_ground;        /* points in groundCloud                */
   int32_t n_planes;        /* accepted ground planes               */
@@ -410,8 +419,9 @@ void sloam_b200_map_free(sloam_ctx *ctx);
  * device pointers.  The submap-index -> map-index table is kept for update. */
 int sloam_b200_map_get_submap_dev(sloam_ctx *ctx, const sloam_pose *pose,
                                   sloam_cylinder *submap, int32_t *n_submap);
-/* MapManager::updateMap (:8-28) with the outputs of run_keyframes (K = 1): device pointers. */
-int sloam_b200_map_update_dev(sloam_ctx *ctx, const sloam_kf_result *res,
+/* MapManager::updateMap (:8-28) with the outputs of run_keyframes (K = 1): device pointers.
+ * res->status receives SLOAM_KF_FLAG_MAP_CAPACITY when a new landmark did not fit. */
+int sloam_b200_map_update_dev(sloam_ctx *ctx, sloam_kf_result *res,
                               const sloam_cylinder *tm, const int32_t *tm_id,
                               const int32_t *matches);
 /* Whole map to the host (treeModels_, treeHits_); returns the map size (getMap (:30-39) is

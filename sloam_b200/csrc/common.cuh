@@ -164,6 +164,7 @@ struct sloam_ctx {
   // likewise ws.ground is tile-strided after a fused run; ground_dense (ws.qscratch) receives
   // the contiguous cloud on demand
   bool ground_strided = false;
+  bool kf_flags_valid = false;  // ws.kf_flags belongs to the run in flight (set by the tree detector of a fused run)
   const sloam_point *last_points = nullptr;  // inputs of the last fused run (intermediates on demand)
   const uint8_t *last_mask = nullptr;
   // optional event pairs around the split kernel of fused runs (sloam_b200_profile_*)

@@ -181,7 +181,10 @@ cylinder_kernel(const DevParams *__restrict__ dp, const sloam_tree *__restrict__
   CylSmem &s = sm[warp];
   if (t >= n_trees[k]) return;  // warp-uniform
   const sloam_tree tr = trees[(size_t)k * T + t];
-  const int V = tr.n_vertices < kMaxV ? tr.n_vertices : kMaxV;
+  // the draw tables cover up to max_tree_vertices samples (ctx.cu upload_tables); computeGraph never
+  // emits more (trellis.cpp:125-127), caller-supplied trees are cut like it cuts them
+  const int vcap = P.max_tree_vertices < kMaxV ? P.max_tree_vertices : kMaxV;
+  const int V = tr.n_vertices < vcap ? tr.n_vertices : vcap;
   const sloam_vertex *vsrc = vertices + (size_t)k * vstride + tr.vertex_begin;
   const sloam_point *psrc = vpoints + (size_t)k * pstride;
   sloam_tree_model *out = models + (size_t)k * T + t;

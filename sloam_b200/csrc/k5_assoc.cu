@@ -38,8 +38,8 @@ assoc_kernel(int T, const sloam_cylinder *__restrict__ det, const int32_t *__res
              int32_t *__restrict__ best_index, double *__restrict__ best_dist) {
   __shared__ Samples s_map[kMapTile];
   const int k = blockIdx.z, split = blockIdx.y;
-  const int nd = n_det[k];
-  const int nm = map_shared ? n_map[0] : n_map[k];
+  const int nd = min(n_det[k], det_stride);
+  const int nm = min(map_shared ? n_map[0] : n_map[k], map_stride);
   const int i = blockIdx.x * kAssocThreads + threadIdx.x;
   if (blockIdx.x * kAssocThreads >= nd) return;
   const sloam_cylinder *mk = map_shared ? map : map + (size_t)k * map_stride;

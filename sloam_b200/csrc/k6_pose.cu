@@ -39,7 +39,8 @@ build_matches_kernel(const DevParams *__restrict__ dp, const uint8_t *__restrict
                      sloam_plane *__restrict__ res_plane_obj, int32_t *__restrict__ n_tree_res,
                      int32_t *__restrict__ n_plane_res, uint8_t *__restrict__ optim_flags,
                      uint8_t *__restrict__ kf_mode, sloam_kf_result *__restrict__ results,
-                     const int32_t *__restrict__ ground_count, const int32_t *__restrict__ n_trees) {
+                     const int32_t *__restrict__ ground_count, const int32_t *__restrict__ n_trees,
+                     const int32_t *__restrict__ kf_flags) {
   __shared__ int s_warp[4];
   __shared__ int s_best[kMaxCells];
   __shared__ int16_t s_pslot[kMaxCells];
@@ -49,8 +50,9 @@ build_matches_kernel(const DevParams *__restrict__ dp, const uint8_t *__restrict
   const int k = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nl = n_lm[k], npl = n_planes_acc[k];
-  const int nm = map_shared ? n_map[0] : n_map[k];
-  const int npv = n_prev[k];
+  // counts beyond the capacities the buffers were sized for are clamped (the host entries reject them)
+  const int nm = min(map_shared ? n_map[0] : n_map[k], map_stride);
+  const int npv = min(n_prev[k], prev_stride);
   const sloam_cylinder *mk = map_shared ? map : map + (size_t)k * map_stride;
   int mode = 0, status = SLOAM_KF_OK;
   if (first_scan[k]) mode = 1;
@@ -140,7 +142,8 @@ build_matches_kernel(const DevParams *__restrict__ dp, const uint8_t *__restrict
     optim_flags[2 * k + 1] = (mode == 0 && groundCheck) ? 1 : 0;
     kf_mode[k] = (uint8_t)mode;
     sloam_kf_result r;
-    r.status = status; r.success = (mode == 2) ? 0 : 1;
+    r.status = status | ((kf_flags && (kf_flags[k] & 1)) ? SLOAM_KF_FLAG_TREE_CAPACITY : 0);
+    r.success = (mode == 2) ? 0 : 1;
     r.n_ground = ground_count ? ground_count[k] : 0;
     r.n_planes = npl; r.n_trees = n_trees ? n_trees[k] : 0; r.n_landmarks = nl;
     r.n_tree_matches = n_tres; r.n_plane_matches = n_pres;
@@ -336,7 +339,7 @@ finish_kernel(const DevParams *__restrict__ dp, int two_step, const sloam_pose *
           r.success = 1;
         } else {
           r.success = 0;
-          r.status = SLOAM_KF_NOT_CONVERGED;
+          r.status = SLOAM_KF_NOT_CONVERGED | (r.status & ~0xFF);
         }
       }
     }
@@ -349,7 +352,7 @@ finish_kernel(const DevParams *__restrict__ dp, int two_step, const sloam_pose *
   const sloam_pose cur = s_pose;
   if (mode == 2) {
     // RunSloam returned false before touching its state: prevGPlanes_ is unchanged
-    const int np = n_prev[k];
+    const int np = min(n_prev[k], prev_stride);
     for (int g = threadIdx.x; g < np; g += 128) planes_out[(size_t)k * planes_stride + g] = prev_planes[(size_t)k * prev_stride + g];
     if (threadIdx.x == 0) n_planes_out[k] = np;
     return;
@@ -422,7 +425,8 @@ int launch_sloam_core(sloam_ctx *c, int K, const sloam_batch_in *in, const sloam
       p.max_map_models, in->prev_planes, in->n_prev_planes, p.max_prev_planes, w.n_lm, w.lm_src,
       w.assoc_idx, w.assoc_dist, w.tree_features, w.planes_acc, w.planes_acc_cell, w.n_planes_acc,
       w.cell_features, w.res_tree_feat, w.res_tree_obj, w.res_plane_feat, w.res_plane_obj, w.n_tree_res,
-      w.n_plane_res, w.optim_flags, w.kf_mode, out->results, w.ground_count, w.n_trees);
+      w.n_plane_res, w.optim_flags, w.kf_mode, out->results, w.ground_count, w.n_trees,
+      c->kf_flags_valid ? w.kf_flags : nullptr);
   PROF_END(c, P_BUILD_MATCHES);
   SB_LAUNCH_CHECK(c);
   PROF_BEGIN(c, P_LM);

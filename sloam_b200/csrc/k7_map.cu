@@ -142,11 +142,12 @@ map_submap_kernel(MapState m, const sloam_pose *__restrict__ pose, sloam_cylinde
 // updateMap (:8-28).  Appends keep the observation order; overwrites are applied in
 // observation order by one thread (two observations may hit the same landmark).
 __global__ void __launch_bounds__(kMapThreads)
-map_update_kernel(MapState m, const sloam_kf_result *__restrict__ res, const sloam_cylinder *__restrict__ tm,
+map_update_kernel(MapState m, sloam_kf_result *__restrict__ res, const sloam_cylinder *__restrict__ tm,
                   const int32_t *__restrict__ tm_id, const int32_t *__restrict__ matches,
                   int32_t *__restrict__ overflow) {
   __shared__ int s_warp[kMapThreads / 32];
-  const bool ran = res->status == SLOAM_KF_OK || res->status == SLOAM_KF_NOT_CONVERGED;
+  const int code = SLOAM_KF_CODE(res->status);
+  const bool ran = code == SLOAM_KF_OK || code == SLOAM_KF_NOT_CONVERGED;
   const int n_obs = ran ? res->n_landmarks : 0;  // out.tm is empty when RunSloam bailed out
   const int size0 = *m.size;
   const int nmm = *m.n_matches_map;
@@ -185,6 +186,7 @@ map_update_kernel(MapState m, const sloam_kf_result *__restrict__ res, const slo
     }
     *m.size = min(size0 + appended, m.capacity);
     *m.n_matches_map = 0;  // matchesMap.clear()
+    if (size0 + appended > m.capacity) res->status |= SLOAM_KF_FLAG_MAP_CAPACITY;  // reported, not silent
   }
 }
 
@@ -273,7 +275,7 @@ int sloam_b200_map_get_submap_dev(sloam_ctx *c, const sloam_pose *pose, sloam_cy
   return SLOAM_OK;
 }
 
-int sloam_b200_map_update_dev(sloam_ctx *c, const sloam_kf_result *res, const sloam_cylinder *tm, const int32_t *tm_id,
+int sloam_b200_map_update_dev(sloam_ctx *c, sloam_kf_result *res, const sloam_cylinder *tm, const int32_t *tm_id,
                               const int32_t *matches) {
   if (!c || !c->seq || !res || !tm || !tm_id || !matches) return set_err(c, SLOAM_E_INVALID, "map_update: bad arguments");
   sloam_seq_state *s = seq_of(c);

@@ -134,7 +134,9 @@ static int run_dev_body(sloam_ctx *c, int K, const sloam_batch_in *in, const slo
   rc = launch_cylinders(c, K, w.trees, w.n_trees, w.vertices, w.vertex_points, w.planes_acc,
                         w.n_planes_acc, w.tree_models, w.tree_features);
   if (rc != SLOAM_OK) return rc;
+  c->kf_flags_valid = true;  // written by the tree detector of this run
   rc = launch_sloam_core(c, K, in, out);
+  c->kf_flags_valid = false;
   c->last_k = K;
   if (c->prof_on && c->prof_n < sloam_ctx::kProfRuns) ++c->prof_n;  // next fused run -> next event slots
   return rc;
@@ -156,6 +158,12 @@ int sloam_b200_run_keyframes_host(sloam_ctx *c, int K, const sloam_batch_in *in,
   int rc = check_batch(c, K, in, out);
   if (rc != SLOAM_OK) return rc;
   const sloam_params &p = c->hp.p;
+  // host buffers: the counts can be checked against the capacities before anything is copied
+  for (int k = 0; k < K; ++k) {
+    const int nm = in->n_map_models[in->map_shared ? 0 : k], npv = in->n_prev_planes[k];
+    if (nm < 0 || nm > p.max_map_models || npv < 0 || npv > p.max_prev_planes)
+      return set_err(c, SLOAM_E_INVALID, "run_keyframes_host: n_map_models / n_prev_planes exceed max_map_models / max_prev_planes");
+  }
   const size_t N = (size_t)c->hp.N, T = (size_t)p.max_trees, M = (size_t)p.max_map_models,
                PP = (size_t)p.max_prev_planes, Kc = (size_t)c->max_k;
   // device staging for the largest batch, allocated once

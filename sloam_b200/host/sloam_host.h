@@ -401,7 +401,7 @@ class sloam {  // sloam.h:57-107
     d_npl.download(&npl, 4);
     std::vector<sloam_plane> planes(std::max(npl, 1));
     d_planes.download(planes.data(), sizeof(sloam_plane) * npl);
-    if (res.status == SLOAM_KF_EMPTY_MAP || res.status == SLOAM_KF_NO_MODELS) return false;  // :476-486
+    if (SLOAM_KF_CODE(res.status) == SLOAM_KF_EMPTY_MAP || SLOAM_KF_CODE(res.status) == SLOAM_KF_NO_MODELS) return false;  // :476-486
     std::vector<int32_t> matches(std::max(res.n_landmarks, 1)), ids(std::max(res.n_landmarks, 1));
     std::vector<sloam_cylinder> tm(std::max(res.n_landmarks, 1));
     d_match.download(matches.data(), 4 * (size_t)res.n_landmarks);
@@ -778,7 +778,7 @@ class SLOAMNodeCore {
   // landmarks of the last keyframe in the map frame and their map matches (sloamOut.tm / .matches)
   std::vector<Cylinder> lastLandmarks() const {
     std::vector<Cylinder> out;
-    const int n = last_.status == SLOAM_KF_OK || last_.status == SLOAM_KF_NOT_CONVERGED ? last_.n_landmarks : 0;
+    const int n = SLOAM_KF_CODE(last_.status) == SLOAM_KF_OK || SLOAM_KF_CODE(last_.status) == SLOAM_KF_NOT_CONVERGED ? last_.n_landmarks : 0;
     for (int i = 0; i < n; ++i) { Cylinder c = MapManager::from_abi(tm_[(size_t)i]); c.id = (size_t)tm_id_[(size_t)i]; out.push_back(c); }
     return out;
   }

@@ -116,3 +116,57 @@ def test_submap_knn_and_recent_filter(capi, oracle):
             assert gsub.tobytes() == esub.tobytes()
     assert omap.size() == n_total
     ctx.close()
+
+
+def test_capacities_are_reported_not_silent(capi, oracle):
+    """more clusters than max_trees, a full semantic map, and counts beyond the
+    buffer capacities must be visible to the caller (status flags / SLOAM_E_INVALID); the
+    trees that are kept are the first max_trees big clusters in PCL label order."""
+    from sloam_b200 import configs
+    p, cfg = configs.make(capi, "os1-64")
+    full = oracle.compute_graph(p, oracle.mask_cloud(p, *_scan(capi, oracle, p, cfg))[0])[0]
+    assert len(full) >= 8
+    small = p.copy(); small.max_trees = 4; small.max_map_models = 8
+    pts, mask = capi.synth_generate_host(cfg, 0, 1)
+    ctx = capi.Context(small, 1)
+    assert capi.lib().sloam_b200_map_init(ctx.h, 1) == 0          # room for one landmark only
+    T = small.max_trees
+    flags, n_lm = [], []
+    for rep in range(2):                                           # twice: identical (deterministic) truncation
+        res = np.zeros(1, abi.KF_RESULT)
+        matches = np.zeros(T, np.int32); tm = np.zeros(T, abi.CYLINDER); tm_id = np.zeros(T, np.int32)
+        pose = np.array([capi.synth_pose(cfg, 0)[1]])
+        rc = capi.lib().sloam_b200_sequence_step_host(ctx.h, abi.ptr(pts[0]), abi.ptr(mask[0]), abi.ptr(pose),
+                                                      abi.ptr(res), abi.ptr(matches), abi.ptr(tm), abi.ptr(tm_id))
+        assert rc == 0
+        flags.append(int(res[0]["status"]))
+        n_lm.append(int(res[0]["n_landmarks"]))
+        it = ctx.intermediates()
+        trees = capi.read_dev(it.trees, T * abi.TREE.itemsize, ctx.device).view(abi.TREE)
+        ntr = int(capi.read_dev(it.n_trees, 4, ctx.device).view(np.int32)[0])
+        # kept trees = oracle trees of the first clusters, same ids, in order
+        want = [t for t in full["tree_id"]][:ntr]
+        assert ntr >= 1 and list(trees[:ntr]["tree_id"]) == want
+    assert flags[0] & 0x100 and flags[1] & 0x100                   # SLOAM_KF_FLAG_TREE_CAPACITY
+    assert n_lm[0] >= 2 and flags[0] & 0x200                        # SLOAM_KF_FLAG_MAP_CAPACITY: 2+ new landmarks, room for 1
+    assert (flags[0] & 0xFF) == abi.KF_OK
+    ctx.close()
+    # counts beyond the capacities: rejected by the host entry before any copy
+    K = 1
+    ctx = capi.Context(small, K)
+    PP, M = small.max_prev_planes, small.max_map_models
+    inp = dict(points=pts, mask=mask, pose_est=np.array([capi.synth_pose(cfg, 0)[1]]), first_scan=np.zeros(1, np.uint8),
+               map_models=np.zeros((K, M), abi.CYLINDER), n_map_models=np.array([M + 1], np.int32),
+               prev_planes=np.zeros((K, PP), abi.PLANE), n_prev_planes=np.zeros(K, np.int32))
+    out = dict(results=np.zeros(K, abi.KF_RESULT), matches=np.zeros((K, T), np.int32),
+               tm=np.zeros((K, T), abi.CYLINDER), tm_id=np.zeros((K, T), np.int32),
+               planes=np.zeros((K, PP), abi.PLANE), n_planes=np.zeros(K, np.int32), range_image=None)
+    with pytest.raises(RuntimeError, match="exceed"):
+        ctx.run_keyframes_host(K, inp, out)
+    ctx.close()
+
+
+def _scan(capi, oracle, p, cfg):
+    pts, mask = capi.synth_generate_host(cfg, 0, 1)
+    pix, _ = oracle.project(p, pts[0], want_range=False)
+    return pts[0], pix, mask[0]
