@@ -117,11 +117,37 @@ def main():
                 vertex_coords=v_coords, vertex_points=v_points)
             print(prefix, stamp, "trees", len(lm), "vertices", len(verts), "finite", len(finite))
         for stamp in ("t0", "t1"):
-            if prefix != "still":
-                continue  # only the `still` ground clouds are used by the reference tests
+            # the reference's tests only load the `still` ground clouds (core_test.cpp:30-70); the
+            # `moving` pair + poses.txt pin the whole a3..a19 path on data it never exercised
             w, h, ground = read_pcd_ascii(f"{REF}/{prefix}_ground_{stamp}.pcd")
             np.savez_compressed(f"{OUT}/{prefix}_{stamp}_ground.npz", xyzi=ground)
             print(prefix, stamp, "ground", ground.shape)
+    poses = read_poses(f"{REF}/poses.txt")
+    import json
+    with open(f"{OUT}/moving_poses.json", "w") as f:
+        json.dump(poses, f, indent=1)
+    print("poses", poses)
+
+
+def read_poses(path):
+    """poses.txt: two nav_msgs/Odometry dumps (t0, t1) of the `moving` pair -> {stamp: {t, q}}."""
+    out, stamp, sect = {}, None, None
+    for line in open(path):
+        s = line.strip()
+        if s in ("t0", "t1"):
+            stamp = s
+            out[stamp] = {"t": [None] * 3, "q": [None] * 4}
+        elif s in ("position:", "orientation:"):
+            sect = s[:-1]
+        elif stamp and sect and len(s) > 2 and s[0] in "xyzw" and s[1] == ":":
+            v = float(s[2:])
+            if sect == "position":
+                out[stamp]["t"]["xyz".index(s[0])] = v
+            else:
+                out[stamp]["q"]["xyzw".index(s[0])] = v
+            if (sect == "position" and s[0] == "z") or (sect == "orientation" and s[0] == "w"):
+                sect = None
+    return out
 
 
 if __name__ == "__main__":

@@ -476,6 +476,45 @@ def test_pose_optimisation_matches_oracle(capi, oracle, mode):
     ctx.close()
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_pose_optimisation_ill_conditioned(capi, oracle, mode):
+    """lm_kernel on rank-deficient / badly conditioned problems (tests/synth_matches.make_degenerate:
+    collinear trunks, one or two planes, zero-padded features, a single trunk, fewer rows than
+    unknowns): same termination and iteration count as the oracle's QR-based solver."""
+    pbs = [sm.make_degenerate(kind, seed=3) for kind in sm.DEGENERATE]
+    K = len(pbs)
+    nt = np.array([len(pb["tree_obj"]) for pb in pbs], np.int32)
+    npl = np.array([len(pb["plane_obj"]) for pb in pbs], np.int32)
+    ts, ps = int(nt.max()), int(npl.max())
+    tf, to = np.zeros((K, ts, 3)), np.zeros((K, ts), abi.CYLINDER)
+    pf, po = np.zeros((K, ps, 3)), np.zeros((K, ps), abi.PLANE)
+    guess = np.zeros(K, abi.POSE)
+    for k, pb in enumerate(pbs):
+        tf[k, :nt[k]], to[k, :nt[k]] = pb["tree_feat"], pb["tree_obj"]
+        pf[k, :npl[k]], po[k, :npl[k]] = pb["plane_feat"], pb["plane_obj"]
+        guess[k] = pb["guess"][0]
+    ones = np.ones(K, np.uint8)
+    p = capi.default_params()
+    ctx = capi.Context(p, K)
+    out, it, term = ctx.optimize_pose(mode, capi.to_dev(guess), capi.to_dev(tf), capi.to_dev(to), capi.to_dev(nt),
+                                      ts, capi.to_dev(pf), capi.to_dev(po), capi.to_dev(npl), ps,
+                                      capi.to_dev(ones), capi.to_dev(ones), K)
+    ctx.sync()
+    out = capi.to_host(out, abi.POSE, (K,))
+    it = capi.to_host(it, np.int32, (K, 2)); term = capi.to_host(term, np.int32, (K, 2))
+    long_runs = 0
+    for k, pb in enumerate(pbs):
+        e_pose, e_it, e_term = oracle.optimize_pose(p, mode, pb["guess"], pb["tree_feat"], pb["tree_obj"],
+                                                    pb["plane_feat"], pb["plane_obj"], True, True)
+        assert np.array_equal(term[k], e_term), sm.DEGENERATE[k]
+        assert np.array_equal(it[k], e_it), sm.DEGENERATE[k]
+        assert np.max(np.abs(out[k]["t"] - e_pose["t"])) <= POSE_T_TOL, sm.DEGENERATE[k]
+        assert quat_angle(out[k]["q"], e_pose["q"]) <= POSE_R_TOL, sm.DEGENERATE[k]
+        long_runs += int(e_it.max() >= 15)
+    assert long_runs >= 1   # at least one problem wanders along an unobservable direction
+    ctx.close()
+
+
 # ------------------------------------------------------------------ fused path a1..a19
 def run_sequence(capi, oracle, p, cfg, K, two_step, first_all=False):
     """K keyframes: keyframe 0 is a first scan, the others use the GT scene as submap and
