@@ -368,6 +368,10 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU time budget of the single-thread oracle baseline")
     ap.add_argument("--lanes", type=int, default=2, help="concurrent sub-batches of a fused run (1..4)")
     ap.add_argument("--no-kernel-profile", action="store_true", help="no per-kernel event pairs in the timed steps")
+    ap.add_argument("--total-keyframes", type=int, default=0,
+                    help="strong scaling: a fixed sequence of this many keyframes is sharded over the ranks "
+                         "(BASELINE configs[3]: --workload os1-128 --total-keyframes 10000); a step processes "
+                         "the rank's whole share in batches of --keyframes")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.keyframes <= 0:
@@ -376,6 +380,7 @@ def main():
     # NCCL prints its version banner to stdout at VERSION level: keep stdout to the one JSON line
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
         os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # (the banner is printed at WARN too)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -407,17 +412,33 @@ def main():
     B = args.keyframes
     ctx = capi.Context(p, B, device=local_rank)
     N, T, M, PP = p.img_h * p.img_w, p.max_trees, p.max_map_models, p.max_prev_planes
+    # strong scaling: the rank's share of a fixed sequence, resident in HBM, as batches of B keyframes
+    share = (args.total_keyframes // world) if args.total_keyframes > 0 else B
+    n_batches = max(1, share // B)
+    share = n_batches * B
+    batches = []
     with torch.cuda.stream(ctx.stream):
-        inp, out, host, n_scene = make_inputs(capi, abi, ctx, p, cfg, B, rank * B, device)
+        for b in range(n_batches):
+            batches.append(make_inputs(capi, abi, ctx, p, cfg, B, rank * share + b * B, device))
+    inp, out, host, n_scene = batches[0]
     ctx.sync()
-    gather_buf = None
+    # the only exchange of the sharded path: all-gather of the per-keyframe results, inside the
+    # library (comm.cu: ncclAllGather on a side stream that overlaps the next batch)
+    gathered = None
     if world > 1:
-        gather_buf = torch.empty(world * out["results"].numel(), dtype=torch.uint8, device=device)
+        ident = [capi.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        ctx.comm_init(rank, world, ident[0])
+        gathered = dict(results=capi.dev_empty(world * B * abi.KF_RESULT.itemsize, device),
+                        matches=capi.dev_empty(world * B * T * 4, device),
+                        tm=capi.dev_empty(world * B * T * abi.CYLINDER.itemsize, device),
+                        tm_id=capi.dev_empty(world * B * T * 4, device))
 
     def step():
-        ctx.run_keyframes_dev(B, inp, out)
-        if world > 1:  # gather the per-keyframe result records (north star: NCCL only for this)
-            dist.all_gather_into_tensor(gather_buf, out["results"])
+        for b_inp, b_out, _, _ in batches:
+            ctx.run_keyframes_dev(B, b_inp, b_out)
+            if world > 1:
+                ctx.gather_results(B, b_out, gathered)
 
     def timed(fn, steps):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -427,6 +448,8 @@ def main():
         ev0.record(ctx.stream)
         for _ in range(steps):
             fn()
+        if world > 1:
+            ctx.comm_wait()  # the last gather is part of the step
         ev1.record(ctx.stream)
         torch.cuda.synchronize()
         if world > 1:
@@ -440,7 +463,7 @@ def main():
         # label statistics of the batch (for the algorithmic bytes of the kernels): one
         # untimed un-split run, pixel indices from the intermediates
         ctx.set_lanes(1)
-        step()
+        ctx.run_keyframes_dev(B, inp, out)
         ctx.sync()
         it = ctx.intermediates()
         pix = capi.read_dev(it.pix, B * N * 4, device).view(np.int32).reshape(B, N)
@@ -506,7 +529,7 @@ def main():
 
     res = capi.to_host(out["results"], abi.KF_RESULT, (B,))
     peak, peak_src = load_peaks()
-    value = world * B * args.steps / (ms * 1e-3)
+    value = world * share * args.steps / (ms * 1e-3)
     step_ms = ms / args.steps
 
     # ---- per-kernel table: event-pair time inside the timed steps, algorithmic bytes, fraction
@@ -521,16 +544,16 @@ def main():
         row["frac"] = row["GBps"] / peak if row["GBps"] is not None else None
         table.append(row)
     for row in table:
-        row["share_of_serial_step"] = row["ms"] / (ms_serial / args.steps) if ms_serial else None
+        row["share_of_serial_step"] = row["ms"] / (ms_serial / args.steps / n_batches) if ms_serial else None
     # whole path, unfused = 61 N + 32 G per keyframe; ours = what the kernels above move by design
-    survey_bytes = 61.0 * B * N + 32.0 * n_ground_pts
-    own_bytes = float(sum(r["algorithmic_bytes"] for r in table if r["algorithmic_bytes"]))
+    survey_bytes = n_batches * (61.0 * B * N + 32.0 * n_ground_pts)
+    own_bytes = n_batches * float(sum(r["algorithmic_bytes"] for r in table if r["algorithmic_bytes"]))
     dominant = max(table, key=lambda r: r["ms"]) if table else None
     if dominant is not None and dominant["algorithmic_bytes"]:
         roof = {"bound": "hbm", "kernel": dominant["kernel"], "achieved": dominant["GBps"], "peak": peak, "unit": "GB/s",
                 "frac": dominant["frac"], "traffic": committed_traffic(dominant["kernel"], B, args.workload),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": dominant["algorithmic_bytes"],
-                "ms_per_launch": dominant["ms"], "share_of_step": dominant["ms"] / (ms_serial / args.steps),
+                "ms_per_launch": dominant["ms"], "share_of_step": dominant["ms"] / (ms_serial / args.steps / n_batches),
                 "timed": "cudaEvent pairs around each kernel in a second timed region of the same steps run on one "
                          "lane and one stream (serial_ms_per_step); the kernel with the largest time is reported"}
     else:
@@ -544,9 +567,13 @@ def main():
     line = {
         "metric": WORKLOADS[args.workload][2], "value": value, "unit": "keyframes/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
+        "scaling": "strong" if args.total_keyframes > 0 else "weak", "vs_baseline": None, "dtype": "f32/f64",
+        "data": "synthetic",
         "config": workload_config(args, p, n_scene),
-        "run": {"lanes": args.lanes, "keyframes_ok": int((res["success"] == 1).sum()),
+        "run": {"lanes": args.lanes, "keyframes_per_step_per_gpu": share, "batches_per_step": n_batches,
+                "total_keyframes": world * share,
+                "gather": "sloam_b200_gather_results_dev (ncclAllGather, side stream)" if world > 1 else None,
+                "keyframes_ok": int((res["success"] == 1).sum()),
                 "mean_landmarks": float(res["n_landmarks"].mean()),
                 "lm_converged": int((res["lm_termination"][:, 0] == 0).sum()),
                 "serial_ms_per_step": (ms_serial / args.steps) if ms_serial else None,

@@ -406,6 +406,34 @@ int sloam_b200_run_sloam_dev(sloam_ctx *ctx, int K, const sloam_point *ground,
                              const sloam_batch_in *in,
                              const sloam_batch_out *out);
 
+/* ------------------------------------------------------------------ multi-GPU
+ * SURVEY 8(e).  Keyframes are sharded over ranks (one process and one context per GPU);
+ * nothing is exchanged during compute.  The one exchange is the gather of the per-keyframe
+ * SloamOutput records (sloam/include/core/sloam.h:48-55) of every rank, ncclAllGather over
+ * NVLink on a side stream of the context.  The reference has no counterpart (one process,
+ * one keyframe at a time, sloamNode.cpp:186).
+ *   comm_unique_id  rank 0 fills 128 bytes (ncclUniqueId) and hands them to the other ranks by
+ *                   any means (torch.distributed, MPI, a file)
+ *   comm_init       collective: every rank calls it with the same id
+ *   gather_results  all-gather of results [K] (and of matches / tm / tm_id [K][max_trees] when
+ *                   both `local` and `all` hold a pointer for them): all->x is [world][K]...,
+ *                   rank-major.  Asynchronous: it starts when the work queued on the context
+ *                   stream so far is done and overlaps whatever is queued next; a following
+ *                   run_keyframes_* only makes its OUTPUT kernels wait for it, so the `local`
+ *                   buffers may be the output buffers of the next run.
+ *   comm_wait       makes the context stream wait for the last gather (call it before reading
+ *                   `all` through the context stream or sloam_b200_sync)
+ * SLOAM_E_NODEVICE when libnccl.so.2 cannot be loaded. */
+#define SLOAM_COMM_ID_BYTES 128
+int sloam_b200_comm_unique_id(void *id128);
+int sloam_b200_comm_init(sloam_ctx *ctx, int rank, int world, const void *id128);
+int sloam_b200_comm_destroy(sloam_ctx *ctx);
+int sloam_b200_comm_size(const sloam_ctx *ctx);
+int sloam_b200_comm_rank(const sloam_ctx *ctx);
+int sloam_b200_gather_results_dev(sloam_ctx *ctx, int K, const struct sloam_batch_out *local,
+                                  const struct sloam_batch_out *all);
+int sloam_b200_comm_wait(sloam_ctx *ctx);
+
 /* ---------------------------------------------- semantic map + sequential mode
  * SURVEY 8(f)-1/2.  MapManager (sloam/src/core/mapManager.cpp:8-71) and the
  * state-carrying call sequence of SLOAMNode::run (sloamNode.cpp:186-282), both

@@ -27,6 +27,8 @@ EXPORTS = [
     "sloam_b200_run_sloam_dev", "sloam_b200_dev_alloc", "sloam_b200_dev_free", "sloam_b200_copy_h2d",
     "sloam_b200_copy_d2h", "sloam_b200_map_init", "sloam_b200_map_free", "sloam_b200_map_get_submap_dev",
     "sloam_b200_map_update_dev", "sloam_b200_map_dump_host", "sloam_b200_sequence_step_host",
+    "sloam_b200_comm_unique_id", "sloam_b200_comm_init", "sloam_b200_comm_destroy", "sloam_b200_comm_size",
+    "sloam_b200_comm_rank", "sloam_b200_gather_results_dev", "sloam_b200_comm_wait",
     "sloam_synth_default_config", "sloam_synth_scene", "sloam_synth_pose",
     "sloam_synth_generate_host", "sloam_synth_generate_dev",
 ]
@@ -314,6 +316,23 @@ class Context:
                           hp(out["planes"]), hp(out["n_planes"]), hp(out.get("range_image")))
         self.check(lib().sloam_b200_run_keyframes_host(self.h, K, C.byref(bi), C.byref(bo)))
 
+    # ---- multi-GPU gather (comm.cu) ----
+    def comm_init(self, rank, world, id_bytes):
+        buf = (C.c_char * 128).from_buffer_copy(bytes(id_bytes))
+        self.check(lib().sloam_b200_comm_init(self.h, int(rank), int(world), buf))
+
+    def gather_results(self, K, local, gathered):
+        """all-gather of the result arrays of this rank's batch (device tensors) into `gathered`
+        (dict with the same keys, world x larger); asynchronous, see sloam_b200_gather_results_dev"""
+        def bo(o):
+            return abi.BatchOut(dptr(o.get("results")), dptr(o.get("matches")), dptr(o.get("tm")), dptr(o.get("tm_id")),
+                                None, None, None)
+        lo, al = bo(local), bo(gathered)
+        self.check(lib().sloam_b200_gather_results_dev(self.h, K, C.byref(lo), C.byref(al)))
+
+    def comm_wait(self):
+        self.check(lib().sloam_b200_comm_wait(self.h))
+
     def intermediates(self):
         it = abi.Intermediates()
         self.check(lib().sloam_b200_get_intermediates(self.h, C.byref(it)))
@@ -324,6 +343,15 @@ class Context:
         mask = dev_empty(K * self.N, self.device)
         self.check(lib().sloam_synth_generate_dev(self.h, C.byref(cfg), C.c_int64(k0), K, dptr(pts), dptr(mask)))
         return pts, mask
+
+
+def comm_unique_id():
+    """ncclUniqueId (128 bytes) for sloam_b200_comm_init: rank 0 creates it, everyone gets a copy"""
+    buf = (C.c_char * 128)()
+    rc = lib().sloam_b200_comm_unique_id(buf)
+    if rc != 0:
+        raise RuntimeError(f"sloam_b200_comm_unique_id failed with {rc} (-4: libnccl.so.2 not found)")
+    return bytes(buf)
 
 
 def read_dev(ptr_value, nbytes, device="cuda:0"):

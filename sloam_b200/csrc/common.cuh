@@ -192,6 +192,12 @@ struct sloam_ctx {
   double *assoc_part_d = nullptr;
   size_t assoc_part_cap = 0;
   void *seq = nullptr;  // sloam_seq_state (k7_map.cu): semantic map + sequential state
+  // multi-GPU gather (comm.cu): communicator + side stream; the output kernels of a fused run
+  // wait for a gather in flight, which may still be reading the output buffers
+  void *comm = nullptr;
+  cudaEvent_t ev_gather_done = nullptr;
+  bool gather_pending = false;
+  sloam_ctx *parent = nullptr;  // lane contexts: the context that owns them
 };
 
 namespace sb {

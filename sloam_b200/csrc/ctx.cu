@@ -303,6 +303,7 @@ int sloam_b200_create(const sloam_params *p, int device, int max_keyframes, sloa
 }
 
 void sloam_b200_map_free(sloam_ctx *c);
+int sloam_b200_comm_destroy(sloam_ctx *c);
 
 void sloam_b200_destroy(sloam_ctx *c) {
   if (!c) return;
@@ -311,7 +312,9 @@ void sloam_b200_destroy(sloam_ctx *c) {
   if (c->ev_lane_start) cudaEventDestroy(c->ev_lane_start);
   for (cudaEvent_t e : c->ev_lane_done) if (e) cudaEventDestroy(e);
   sloam_b200_map_free(c);
+  sloam_b200_comm_destroy(c);
   cudaDeviceSynchronize();
+  if (c->ev_gather_done) cudaEventDestroy(c->ev_gather_done);
   if (c->arena) cudaFree(c->arena);
   if (c->dp) cudaFree(c->dp);
   if (c->pinned) cudaFreeHost(c->pinned);
@@ -402,6 +405,7 @@ int sloam_b200_set_lanes(sloam_ctx *c, int n) {
       for (sloam_ctx *&q : c->lane) { if (q) sloam_b200_destroy(q); q = nullptr; }
       return set_err(c, rc, "set_lanes: could not create a lane context");
     }
+    c->lane[l]->parent = c;
   }
   c->n_lanes = n;
   return SLOAM_OK;

@@ -135,6 +135,10 @@ static int run_dev_body(sloam_ctx *c, int K, const sloam_batch_in *in, const slo
                         w.n_planes_acc, w.tree_models, w.tree_features);
   if (rc != SLOAM_OK) return rc;
   c->kf_flags_valid = true;  // written by the tree detector of this run
+  {  // a result gather still in flight may be reading the output buffers (comm.cu)
+    sloam_ctx *root = c->parent ? c->parent : c;
+    if (root->gather_pending) SB_CUDA(c, cudaStreamWaitEvent(c->stream, root->ev_gather_done, 0));
+  }
   rc = launch_sloam_core(c, K, in, out);
   c->kf_flags_valid = false;
   c->last_k = K;
