@@ -393,6 +393,14 @@ int sloam_b200_run_keyframes_host(sloam_ctx *ctx, int K,
                                   const sloam_batch_in *in,
                                   const sloam_batch_out *out);
 
+/* Same for a cloud packed as x, y, z (12 bytes per point, [K][H*W][3]); in->points is ignored.
+ * pcl::PointXYZI is 32 bytes in host memory, so a binding repacks the cloud anyway, and no
+ * output of RunSloam depends on the input intensity (tree features carry the tree id,
+ * cylinder.cpp:87-91; the optimiser reads x, y, z): packing only x, y, z moves 25 % fewer
+ * bytes over PCIe, which is what bounds this entry.  Intensities read as 0 in the intermediates. */
+int sloam_b200_run_keyframes_host_xyz(sloam_ctx *ctx, int K, const float *points_xyz,
+                                      const sloam_batch_in *in, const sloam_batch_out *out);
+
 /* sloam::RunSloam (sloam.cpp:453-532) alone, for callers that already hold the
  * SloamInput of the reference: ground clouds [K][ground_stride] with counts,
  * landmarks as produced by compute_graph (trees [K][max_trees], vertices

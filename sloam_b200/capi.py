@@ -23,7 +23,8 @@ EXPORTS = [
     "sloam_b200_project_dev", "sloam_b200_mask_cloud_dev", "sloam_b200_project_split_dev",
     "sloam_b200_ground_planes_dev", "sloam_b200_find_clusters_dev", "sloam_b200_compute_graph_dev",
     "sloam_b200_cylinders_dev", "sloam_b200_associate_dev", "sloam_b200_optimize_pose_dev",
-    "sloam_b200_run_keyframes_dev", "sloam_b200_run_keyframes_host", "sloam_b200_get_intermediates",
+    "sloam_b200_run_keyframes_dev", "sloam_b200_run_keyframes_host", "sloam_b200_run_keyframes_host_xyz",
+    "sloam_b200_get_intermediates",
     "sloam_b200_run_sloam_dev", "sloam_b200_dev_alloc", "sloam_b200_dev_free", "sloam_b200_copy_h2d",
     "sloam_b200_copy_d2h", "sloam_b200_map_init", "sloam_b200_map_free", "sloam_b200_map_get_submap_dev",
     "sloam_b200_map_update_dev", "sloam_b200_map_dump_host", "sloam_b200_sequence_step_host",
@@ -309,12 +310,15 @@ class Context:
             if isinstance(x, np.ndarray):
                 return abi.ptr(x)
             return C.c_void_p(x.data_ptr())
-        bi = abi.BatchIn(hp(inp["points"]), hp(inp["mask"]), hp(inp["pose_est"]), hp(inp["first_scan"]),
+        bi = abi.BatchIn(hp(inp.get("points")), hp(inp["mask"]), hp(inp["pose_est"]), hp(inp["first_scan"]),
                          hp(inp["map_models"]), hp(inp["n_map_models"]), int(map_shared),
                          hp(inp["prev_planes"]), hp(inp["n_prev_planes"]))
         bo = abi.BatchOut(hp(out["results"]), hp(out["matches"]), hp(out["tm"]), hp(out["tm_id"]),
                           hp(out["planes"]), hp(out["n_planes"]), hp(out.get("range_image")))
-        self.check(lib().sloam_b200_run_keyframes_host(self.h, K, C.byref(bi), C.byref(bo)))
+        if inp.get("points_xyz") is not None:  # packed x, y, z cloud
+            self.check(lib().sloam_b200_run_keyframes_host_xyz(self.h, K, hp(inp["points_xyz"]), C.byref(bi), C.byref(bo)))
+        else:
+            self.check(lib().sloam_b200_run_keyframes_host(self.h, K, C.byref(bi), C.byref(bo)))
 
     # ---- multi-GPU gather (comm.cu) ----
     def comm_init(self, rank, world, id_bytes):

@@ -158,8 +158,23 @@ int sloam_b200_run_keyframes_dev(sloam_ctx *c, int K, const sloam_batch_in *in, 
   return run_dev(c, K, in, out);
 }
 
-int sloam_b200_run_keyframes_host(sloam_ctx *c, int K, const sloam_batch_in *in, const sloam_batch_out *out) {
-  int rc = check_batch(c, K, in, out);
+}  // extern "C"
+
+namespace sb {
+// x, y, z packed (12 bytes per point) -> sloam_point with intensity 0
+__global__ void expand_xyz_kernel(const float *__restrict__ xyz, sloam_point *__restrict__ pts, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  st_point(pts + i, sloam_point{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.f});
+}
+}  // namespace sb
+
+// host entry; xyz != nullptr: the cloud comes as packed x, y, z instead of in->points
+static int run_keyframes_host_impl(sloam_ctx *c, int K, const sloam_batch_in *in, const sloam_batch_out *out,
+                                   const float *xyz) {
+  sloam_batch_in in_chk;
+  if (xyz && in) { in_chk = *in; in_chk.points = reinterpret_cast<const sloam_point *>(xyz); }
+  int rc = check_batch(c, K, xyz && in ? &in_chk : in, out);
   if (rc != SLOAM_OK) return rc;
   const sloam_params &p = c->hp.p;
   // host buffers: the counts can be checked against the capacities before anything is copied
@@ -180,7 +195,7 @@ int sloam_b200_run_keyframes_host(sloam_ctx *c, int K, const sloam_batch_in *in,
              d_res = part(Kc * sizeof(sloam_kf_result)), d_match = part(Kc * T * 4),
              d_tm = part(Kc * T * sizeof(sloam_cylinder)), d_tmid = part(Kc * T * 4),
              d_planes = part(Kc * PP * sizeof(sloam_plane)), d_npl = part(Kc * 4),
-             d_range = part(Kc * N * 4);
+             d_range = part(Kc * N * 4), d_xyz = part(xyz ? Kc * N * 12 : 0);
   if (c->stage_dev_bytes < off) {
     if (c->stage_dev) cudaFree(c->stage_dev);
     c->stage_dev = nullptr; c->stage_dev_bytes = 0;
@@ -215,7 +230,8 @@ int sloam_b200_run_keyframes_host(sloam_ctx *c, int K, const sloam_batch_in *in,
   for (int j = 0; j < n_chunks; ++j) {
     const int k0 = j * per, n = (K - k0 < per) ? K - k0 : per;
     if (n <= 0) { n_chunks = j; break; }
-    H2D(d_points, in->points, N * sizeof(sloam_point), k0, n);
+    if (xyz) H2D(d_xyz, xyz, N * 12, k0, n);
+    else H2D(d_points, in->points, N * sizeof(sloam_point), k0, n);
     H2D(d_mask, in->mask, N, k0, n);
     H2D(d_pose, in->pose_est, sizeof(sloam_pose), k0, n);
     H2D(d_first, in->first_scan, 1, k0, n);
@@ -232,6 +248,13 @@ int sloam_b200_run_keyframes_host(sloam_ctx *c, int K, const sloam_batch_in *in,
     const int k0 = j * per, n = (K - k0 < per) ? K - k0 : per;
     const size_t k0s = (size_t)k0, ns = (size_t)n;
     SB_CUDA(c, cudaStreamWaitEvent(s, c->ev_chunk[j], 0));
+    if (xyz) {
+      const long long npts = (long long)n * (long long)N;
+      expand_xyz_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, s>>>(
+          reinterpret_cast<const float *>(base + d_xyz.off) + k0s * N * 3,
+          reinterpret_cast<sloam_point *>(base + d_points.off) + k0s * N, npts);
+      SB_LAUNCH_CHECK(c);
+    }
     sloam_batch_in din = *in;
     din.points = (const sloam_point *)(base + d_points.off) + k0s * N;
     din.mask = (const uint8_t *)(base + d_mask.off) + k0s * N;
@@ -264,6 +287,18 @@ int sloam_b200_run_keyframes_host(sloam_ctx *c, int K, const sloam_batch_in *in,
   }
   SB_CUDA(c, cudaStreamSynchronize(s));
   return SLOAM_OK;
+}
+
+extern "C" {
+
+int sloam_b200_run_keyframes_host(sloam_ctx *c, int K, const sloam_batch_in *in, const sloam_batch_out *out) {
+  return run_keyframes_host_impl(c, K, in, out, nullptr);
+}
+
+int sloam_b200_run_keyframes_host_xyz(sloam_ctx *c, int K, const float *points_xyz, const sloam_batch_in *in,
+                                      const sloam_batch_out *out) {
+  if (!points_xyz) return set_err(c, SLOAM_E_INVALID, "run_keyframes_host_xyz: null cloud");
+  return run_keyframes_host_impl(c, K, in, out, points_xyz);
 }
 
 int sloam_b200_run_sloam_dev(sloam_ctx *c, int K, const sloam_point *ground, const int32_t *ground_count,

@@ -630,6 +630,32 @@ def test_run_keyframes_guards(capi, oracle):
     ctx.close()
 
 
+def test_host_entry_with_packed_xyz_cloud(capi, oracle):
+    """sloam_b200_run_keyframes_host_xyz: the same keyframes as a 12-byte x, y, z cloud give
+    byte-identical results (no output of RunSloam depends on the input intensity)."""
+    H, W, K = 64, 1024, 3
+    p = capi.default_params(img_h=H, img_w=W)
+    cfg = capi.synth_config(H, W, 20)
+    inp, exp = run_sequence(capi, oracle, p, cfg, K, True)
+    T, PP = p.max_trees, p.max_prev_planes
+    ctx = capi.Context(p, K)
+
+    def outputs():
+        return dict(results=np.zeros(K, abi.KF_RESULT), matches=np.zeros((K, T), np.int32),
+                    tm=np.zeros((K, T), abi.CYLINDER), tm_id=np.zeros((K, T), np.int32),
+                    planes=np.zeros((K, PP), abi.PLANE), n_planes=np.zeros(K, np.int32), range_image=None)
+    a, b = outputs(), outputs()
+    ctx.run_keyframes_host(K, inp, a)
+    xyz = np.ascontiguousarray(np.stack([inp["points"]["x"], inp["points"]["y"], inp["points"]["z"]], axis=-1))
+    inp_xyz = dict(inp, points=None, points_xyz=xyz)
+    ctx.run_keyframes_host(K, inp_xyz, b)
+    for key in ("results", "matches", "tm", "tm_id", "planes", "n_planes"):
+        assert a[key].tobytes() == b[key].tobytes(), key
+    for k in range(K):
+        compare_keyframe(b["results"][k], b["matches"][k], b["tm"][k], b["tm_id"][k], b["planes"][k], b["n_planes"][k], exp[k])
+    ctx.close()
+
+
 def test_c_abi_rejects_bad_arguments(capi):
     p = capi.default_params(img_h=16, img_w=64)
     ctx = capi.Context(p, 2)
