@@ -336,6 +336,15 @@ int sloam_b200_associate_dev(sloam_ctx *ctx, int K, const sloam_cylinder *det,
                              int map_shared, int32_t *best_index,
                              double *best_dist);
 
+/* a12 for ground planes: the argmin of matchFeatures<Plane> (sloam.cpp:257-286) --
+ * Plane::project moves the centroid (plane.cpp:174), Plane::distance(model) is the centroid
+ * distance (plane.cpp:131-134).  det [K][det_stride] projected with tf [K] (NULL = identity),
+ * map [K][map_stride]; best_index = first minimum (strict <), -1 without map planes. */
+int sloam_b200_associate_planes_dev(sloam_ctx *ctx, int K, const sloam_plane *det,
+                                    const int32_t *n_det, int det_stride, const sloam_pose *tf,
+                                    const sloam_plane *map, const int32_t *n_map, int map_stride,
+                                    int32_t *best_index, double *best_dist);
+
 /* a14-a17: OptimizePose / TwoStepOptimizePose (sloam.cpp:33-255) on explicit
  * match lists.  tree_feat [K][tf_stride][3] sensor-frame features with their
  * matched cylinder tree_obj [K][tf_stride]; plane_feat/plane_obj likewise.

@@ -22,7 +22,7 @@ EXPORTS = [
     "sloam_b200_profile_read", "sloam_b200_profile_read_kernels", "sloam_b200_version",
     "sloam_b200_project_dev", "sloam_b200_mask_cloud_dev", "sloam_b200_project_split_dev",
     "sloam_b200_ground_planes_dev", "sloam_b200_find_clusters_dev", "sloam_b200_compute_graph_dev",
-    "sloam_b200_cylinders_dev", "sloam_b200_associate_dev", "sloam_b200_optimize_pose_dev",
+    "sloam_b200_cylinders_dev", "sloam_b200_associate_dev", "sloam_b200_associate_planes_dev", "sloam_b200_optimize_pose_dev",
     "sloam_b200_run_keyframes_dev", "sloam_b200_run_keyframes_host", "sloam_b200_run_keyframes_host_xyz",
     "sloam_b200_get_intermediates",
     "sloam_b200_run_sloam_dev", "sloam_b200_dev_alloc", "sloam_b200_dev_free", "sloam_b200_copy_h2d",

@@ -109,6 +109,34 @@ __global__ void assoc_reduce_kernel(int T, const int32_t *__restrict__ n_det, in
   best_dist[(size_t)k * out_stride + i] = bd;
 }
 
+// matchFeatures<Plane> (sloam.cpp:257-286): Plane::project moves the centroid
+// (plane.cpp:174), Plane::distance(model) is the centroid distance (plane.cpp:131-134).
+// One thread per current plane; the few dozen map planes are read through L1.
+__global__ void __launch_bounds__(kAssocThreads)
+assoc_planes_kernel(const sloam_plane *__restrict__ det, const int32_t *__restrict__ n_det, int det_stride,
+                    const sloam_pose *__restrict__ tf, const sloam_plane *__restrict__ map,
+                    const int32_t *__restrict__ n_map, int map_stride, int32_t *__restrict__ best_index,
+                    double *__restrict__ best_dist) {
+  const int k = blockIdx.y;
+  const int i = blockIdx.x * kAssocThreads + threadIdx.x;
+  if (i >= min(n_det[k], det_stride)) return;
+  const int nm = min(n_map[k], map_stride);
+  double c2[3];
+  const double *cen = det[(size_t)k * det_stride + i].centroid;
+  if (tf) pose_apply(tf[k], cen, c2);
+  else { c2[0] = cen[0]; c2[1] = cen[1]; c2[2] = cen[2]; }
+  double bd = INFINITY;
+  int bi = -1;
+  for (int j = 0; j < nm; ++j) {
+    const double *pc = map[(size_t)k * map_stride + j].centroid;
+    const double dx = pc[0] - c2[0], dy = pc[1] - c2[1], dz = pc[2] - c2[2];
+    const double d = sqrt(dx * dx + (dy * dy + dz * dz));
+    if (d < bd) { bd = d; bi = j; }
+  }
+  best_index[(size_t)k * det_stride + i] = bi;
+  best_dist[(size_t)k * det_stride + i] = bd;
+}
+
 int launch_associate(sloam_ctx *c, int K, const sloam_cylinder *det, const int32_t *n_det, int det_stride,
                      int det_cap, const sloam_pose *tf, const sloam_cylinder *map, const int32_t *n_map,
                      int map_stride, int map_shared, int map_cap, int32_t *best_index, double *best_dist) {
@@ -160,4 +188,17 @@ extern "C" int sloam_b200_associate_dev(sloam_ctx *c, int K, const sloam_cylinde
   // outputs are [K][det_stride]
   return launch_associate(c, K, det, n_det, det_stride, det_stride, tf, map, n_map, map_stride, map_shared,
                           map_stride, best_index, best_dist);
+}
+
+extern "C" int sloam_b200_associate_planes_dev(sloam_ctx *c, int K, const sloam_plane *det, const int32_t *n_det,
+                                               int det_stride, const sloam_pose *tf, const sloam_plane *map,
+                                               const int32_t *n_map, int map_stride, int32_t *best_index,
+                                               double *best_dist) {
+  if (!c || K <= 0 || !det || !n_det || !map || !n_map || !best_index || !best_dist || det_stride <= 0 || map_stride <= 0)
+    return set_err(c, SLOAM_E_INVALID, "associate_planes: bad arguments");
+  dim3 grid((unsigned)((det_stride + kAssocThreads - 1) / kAssocThreads), (unsigned)K);
+  assoc_planes_kernel<<<grid, kAssocThreads, 0, c->stream>>>(det, n_det, det_stride, tf, map, n_map, map_stride,
+                                                             best_index, best_dist);
+  SB_LAUNCH_CHECK(c);
+  return SLOAM_OK;
 }

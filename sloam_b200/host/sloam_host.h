@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <map>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -144,13 +145,50 @@ inline void fill_params(sloam_params &p, const FeatureModelParams &f, const Host
     p.max_prev_planes = p.groundRadiiBins * p.groundThetaBins;
 }
 
+// Device staging of the mirror: one arena per context instead of a cudaMalloc per buffer and
+// call.  Buffers are bump-allocated; when the last live buffer of a call is released the arena
+// rewinds, and if the call needed more than the arena holds it is re-created with that size --
+// so from the second call of a given shape on there is no device allocation at all.
+struct Arena {
+  char *base = nullptr;
+  size_t cap = 0, off = 0, want = 0;
+  int live = 0;
+};
+inline std::map<sloam_ctx *, Arena> &arenas() {
+  static std::map<sloam_ctx *, Arena> m;
+  return m;
+}
+
 // RAII device buffer through the C ABI helpers (no CUDA headers on the host side).
 class DevBuf {
  public:
-  DevBuf(sloam_ctx *c, size_t bytes) : c_(c), bytes_(bytes), p_(sloam_b200_dev_alloc(c, bytes)) {
-    if (!p_) throw std::runtime_error("sloam_b200: device allocation failed");
+  DevBuf(sloam_ctx *c, size_t bytes) : c_(c), bytes_(bytes) {
+    Arena &a = arenas()[c];
+    const size_t need = (std::max<size_t>(bytes, 16) + 255) / 256 * 256;
+    a.want += need;
+    if (a.live == 0 && a.cap < std::max(a.want, need)) {  // between calls: grow to what the last call asked for
+      if (a.base) sloam_b200_dev_free(c, a.base);
+      a.cap = std::max(std::max(a.want, need) * 5 / 4, (size_t)1 << 20);
+      a.base = static_cast<char *>(sloam_b200_dev_alloc(c, a.cap));
+      if (!a.base) { a.cap = 0; throw std::runtime_error("sloam_b200: device allocation failed"); }
+      a.off = 0;
+    }
+    if (a.live == 0) a.want = need;
+    if (a.off + need <= a.cap) {
+      p_ = a.base + a.off;
+      a.off += need;
+      ++a.live;
+    } else {  // first call of this shape: beyond the arena, allocated on its own
+      p_ = sloam_b200_dev_alloc(c, bytes);
+      own_ = true;
+      if (!p_) throw std::runtime_error("sloam_b200: device allocation failed");
+    }
   }
-  ~DevBuf() { sloam_b200_dev_free(c_, p_); }
+  ~DevBuf() {
+    if (own_) { sloam_b200_dev_free(c_, p_); return; }
+    Arena &a = arenas()[c_];
+    if (--a.live == 0) a.off = 0;
+  }
   DevBuf(const DevBuf &) = delete;
   DevBuf &operator=(const DevBuf &) = delete;
   template <typename T> T *as() { return static_cast<T *>(p_); }
@@ -163,10 +201,11 @@ class DevBuf {
  private:
   sloam_ctx *c_;
   size_t bytes_;
-  void *p_;
+  void *p_ = nullptr;
+  bool own_ = false;
 };
 
-// One context per parameter set (created lazily, K = 1 like a reference call).
+// One context per parameter set (K = 1 like a reference call).
 class Runtime {
  public:
   Runtime(const FeatureModelParams &f, const HostConfig &h) {
@@ -176,7 +215,14 @@ class Runtime {
       throw std::runtime_error("sloam_b200_create failed (" + std::to_string(rc) +
                                "): no CPU fallback, a B200 is required");
   }
-  ~Runtime() { sloam_b200_destroy(ctx_); }
+  ~Runtime() {
+    auto it = arenas().find(ctx_);
+    if (it != arenas().end()) {
+      if (it->second.base) sloam_b200_dev_free(ctx_, it->second.base);
+      arenas().erase(it);
+    }
+    sloam_b200_destroy(ctx_);
+  }
   Runtime(const Runtime &) = delete;
   Runtime &operator=(const Runtime &) = delete;
   sloam_ctx *ctx() const { return ctx_; }
@@ -189,6 +235,22 @@ class Runtime {
   sloam_params p_{};
   sloam_ctx *ctx_ = nullptr;
 };
+
+// The objects of the reference API are created by the thousand (one Plane per ground cell, one
+// Cylinder per tree): they share one cached context per parameter set instead of owning one.
+inline std::shared_ptr<Runtime> shared_runtime(const FeatureModelParams &f, const HostConfig &h) {
+  arenas();  // constructed before the cache, hence destroyed after the contexts that use it
+  static std::map<std::string, std::shared_ptr<Runtime>> cache;
+  sloam_params p;
+  fill_params(p, f, h);
+  const std::string key(reinterpret_cast<const char *>(&p), sizeof p);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  if (cache.size() >= 8) cache.clear();  // parameter sweeps: bounded
+  auto rt = std::make_shared<Runtime>(f, h);
+  cache.emplace(key, rt);
+  return rt;
+}
 
 // landmarks <-> flattened ABI records
 inline void flatten(const std::vector<std::vector<TreeVertex>> &lm, std::vector<sloam_tree> &trees,
@@ -314,6 +376,14 @@ class Cylinder : public SemanticObject<CylinderParameters> {
 };
 
 // ------------------------------------------------------------------ sloam core
+template <typename T>
+struct ObjectMatch {  // sloam.h:13-27 (`dist = dist` there leaves the member unset; it is set here)
+  ObjectMatch(PointT ft, T obj, Scalar d) : object(obj), dist(d) { feature[0] = ft.x; feature[1] = ft.y; feature[2] = ft.z; }
+  Vector3 feature;
+  T object;
+  double dist;
+};
+
 struct SloamInput {  // sloam.h:32-46
   SloamInput() : groundCloud(new CloudT()) {}
   SE3 poseEstimate;
@@ -329,6 +399,9 @@ struct SloamOutput {  // sloam.h:48-55
   SE3 T_Delta;
 };
 
+// boost::multi_array<VectorType, 2> stand-in: scgf[radial bin][theta bin]
+using GroundGrid = std::vector<std::vector<VectorType>>;
+
 namespace sloam {
 class sloam {  // sloam.h:57-107
  public:
@@ -336,77 +409,306 @@ class sloam {  // sloam.h:57-107
   const FeatureModelParams &fmParams() const { return fmParams_; }
   void setFmParams(const FeatureModelParams &p) { fmParams_ = p; rt_.reset(); }
   std::vector<Plane> getPrevGroundModel() { return prevGPlanes_; }
+  CloudT getPrevGroundFeatures() {  // sloam.h:96: the features of prevGPlanes_, one cloud
+    CloudT c;
+    for (const Plane &pl : prevGPlanes_) c.points.insert(c.points.end(), pl.features.begin(), pl.features.end());
+    c.width = (uint32_t)c.points.size(); c.height = 1;
+    return c;
+  }
+
+  // ---- Pose optimisation (sloam.cpp:33-255): sloam_b200_optimize_pose_dev -------------------
+  // joint 6-DoF; true and tf = the optimum iff Ceres would report CONVERGENCE (:241-246)
+  bool OptimizePose(const SE3 &poseEstimate, const std::vector<ObjectMatch<Cylinder>> &allTMatch,
+                    const std::vector<ObjectMatch<Plane>> &allGMatch, SE3 &tf) {
+    sloam_pose out;
+    int32_t term[2];
+    solve(0, poseEstimate, true, true, allTMatch, allGMatch, out, term);
+    if (term[0] != 0) return false;
+    tf = SE3(out);
+    return true;
+  }
+  // XYYaw over the trees + ZRollPitch over the ground, each falling back to the estimate
+  // unless optimised and converged; always true (:33-53)
+  bool TwoStepOptimizePose(const SE3 &poseEstimate, const bool optimTrees, const bool optimGround,
+                           const std::vector<ObjectMatch<Cylinder>> &allTMatch,
+                           const std::vector<ObjectMatch<Plane>> &allGMatch, SE3 &tf) {
+    sloam_pose out;
+    int32_t term[2];
+    solve(1, poseEstimate, optimTrees, optimGround, allTMatch, allGMatch, out, term);
+    tf = SE3(out);
+    return true;
+  }
+  // out = {x, y, yaw} (:55-114).  The composed pose of the two-step entry with the ground block
+  // switched off is angle-axis (rx0, ry0, yaw) and translation (x, y, z0): its parts are read back.
+  void OptimizeXYYaw(const SE3 &poseEstimate, const bool optimize, const std::vector<ObjectMatch<Cylinder>> &allTMatch,
+                     double *out) {
+    sloam_pose r;
+    int32_t term[2];
+    solve(1, poseEstimate, optimize, false, allTMatch, {}, r, term);
+    double aa[3];
+    quat_to_angle_axis(r.q, aa);
+    out[0] = r.t[0]; out[1] = r.t[1]; out[2] = aa[2];
+  }
+  // out = {z, roll, pitch} (:116-172)
+  void OptimizeZRollPitch(const SE3 &poseEstimate, const bool optimize, const std::vector<ObjectMatch<Plane>> &allGMatch,
+                          double *out) {
+    sloam_pose r;
+    int32_t term[2];
+    solve(1, poseEstimate, false, optimize, {}, allGMatch, r, term);
+    double aa[3];
+    quat_to_angle_axis(r.q, aa);
+    out[0] = r.t[2]; out[1] = aa[0]; out[2] = aa[1];
+  }
+
+  // ---- Model estimation --------------------------------------------------------------------
+  void projectModels(const SE3 &tf, std::vector<Cylinder> &landmarks, std::vector<Plane> &planes) {  // :438-451
+    for (auto &p : planes) p.project(tf);
+    for (auto &l : landmarks) l.project(tf);
+  }
+  // :330-386 through sloam_b200_ground_planes_dev (kept point lists).  The device bins around the
+  // origin, as the reference calls it (:392); for another pose the cloud is shifted on the way in,
+  // and every retained point is mapped back to the caller's point through its index (carried in
+  // the intensity lane), so the lists hold the original points bit for bit.
+  void binGroundPoints(const SE3 pose, const VectorType &points, GroundGrid &scgf) {
+    auto rt = runtime(points.size());
+    sloam_ctx *c = rt->ctx();
+    const sloam_params &p = rt->params();
+    const int N = p.img_h * p.img_w, B = p.groundRadiiBins * p.groundThetaBins, Fg = p.numGroundFeatures;
+    std::vector<sloam_point> in(points.size());
+    const float ox = (float)pose.translation()[0], oy = (float)pose.translation()[1];
+    for (size_t i = 0; i < points.size(); ++i) {
+      in[i] = sloam_point{points[i].x - ox, points[i].y - oy, points[i].z, 0.f};
+      if (ox == 0.f && oy == 0.f) { in[i].x = points[i].x; in[i].y = points[i].y; }
+      const uint32_t idx = (uint32_t)i;
+      std::memcpy(&in[i].intensity, &idx, 4);
+    }
+    const int32_t n = (int32_t)points.size();
+    sloam_pose ident{}; ident.q[3] = 1.0;
+    using sloam_b200::DevBuf;
+    DevBuf d_g(c, sizeof(sloam_point) * (size_t)N), d_n(c, 4), d_pose(c, sizeof ident), d_cells(c, sizeof(sloam_cell_plane) * B),
+        d_feat(c, sizeof(sloam_point) * (size_t)B * Fg), d_kept(c, sizeof(sloam_point) * (size_t)N), d_off(c, 4 * (size_t)(B + 1));
+    d_g.upload(in.data(), sizeof(sloam_point) * in.size());
+    d_n.upload(&n, 4);
+    d_pose.upload(&ident, sizeof ident);
+    rt->check(sloam_b200_ground_planes_dev(c, 1, d_g.as<sloam_point>(), d_n.as<int32_t>(), N, d_pose.as<sloam_pose>(),
+                                           d_cells.as<sloam_cell_plane>(), d_feat.as<sloam_point>(), d_kept.as<sloam_point>(),
+                                           d_off.as<int32_t>()));
+    std::vector<int32_t> off((size_t)B + 1);
+    d_off.download(off.data(), 4 * off.size());
+    std::vector<sloam_point> kept((size_t)std::max(off[B], 1));
+    if (off[B] > 0) d_kept.download(kept.data(), sizeof(sloam_point) * (size_t)off[B]);
+    scgf.assign((size_t)p.groundRadiiBins, std::vector<VectorType>((size_t)p.groundThetaBins));
+    for (int cell = 0; cell < B; ++cell) {
+      VectorType &dst = scgf[(size_t)(cell / p.groundThetaBins)][(size_t)(cell % p.groundThetaBins)];
+      for (int i = off[cell]; i < off[cell + 1]; ++i) {
+        uint32_t idx;
+        std::memcpy(&idx, &kept[(size_t)i].intensity, 4);
+        dst.push_back(points[idx]);
+      }
+    }
+  }
+  // :388-436: ground cells -> accepted planes, then one cylinder per landmark on its nearest plane
+  void computeModels(SloamInput &in, std::vector<Cylinder> &landmarks, std::vector<Plane> &planes) {
+    auto rt = runtime(in.groundCloud->points.size());
+    sloam_ctx *c = rt->ctx();
+    const sloam_params &p = rt->params();
+    const int N = p.img_h * p.img_w, B = p.groundRadiiBins * p.groundThetaBins, Fg = p.numGroundFeatures,
+              Ft = p.featuresPerTree, T = p.max_trees;
+    std::vector<sloam_tree> trees; std::vector<sloam_vertex> verts; std::vector<sloam_point> vpts;
+    sloam_b200::flatten(in.landmarks, trees, verts, vpts);
+    if ((int)trees.size() > T) throw std::runtime_error("sloam_b200: more landmarks than max_trees");
+    for (const sloam_tree &t : trees)
+      if (t.n_vertices > p.max_tree_vertices) throw std::runtime_error("sloam_b200: a landmark has more vertices than max_tree_vertices");
+    const int32_t n_ground = (int32_t)in.groundCloud->points.size(), n_trees = (int32_t)trees.size();
+    const sloam_pose pose = in.poseEstimate.abi();
+    using sloam_b200::DevBuf;
+    DevBuf d_g(c, sizeof(sloam_point) * (size_t)N), d_n(c, 4), d_pose(c, sizeof pose), d_cells(c, sizeof(sloam_cell_plane) * B),
+        d_feat(c, sizeof(sloam_point) * (size_t)B * Fg), d_trees(c, sizeof(sloam_tree) * T), d_nt(c, 4),
+        d_verts(c, sizeof(sloam_vertex) * (size_t)T * p.max_tree_vertices), d_vpts(c, sizeof(sloam_point) * (size_t)N),
+        d_models(c, sizeof(sloam_tree_model) * T), d_tfeat(c, sizeof(sloam_point) * (size_t)T * Ft);
+    if (vpts.size() > (size_t)N) throw std::runtime_error("sloam_b200: landmark points exceed H*W");
+    d_g.upload(in.groundCloud->points.data(), sizeof(sloam_point) * (size_t)n_ground);
+    d_n.upload(&n_ground, 4);
+    d_pose.upload(&pose, sizeof pose);
+    rt->check(sloam_b200_ground_planes_dev(c, 1, d_g.as<sloam_point>(), d_n.as<int32_t>(), N, d_pose.as<sloam_pose>(),
+                                           d_cells.as<sloam_cell_plane>(), d_feat.as<sloam_point>(), nullptr, nullptr));
+    std::vector<sloam_cell_plane> cells((size_t)B);
+    std::vector<sloam_point> feats((size_t)B * Fg);
+    d_cells.download(cells.data(), sizeof(sloam_cell_plane) * B);
+    d_feat.download(feats.data(), sizeof(sloam_point) * feats.size());
+    for (int cell = 0; cell < B; ++cell) {
+      if (!cells[(size_t)cell].accepted) continue;
+      Plane pl;
+      for (int a = 0; a < 4; ++a) pl.model.plane[a] = cells[(size_t)cell].model.plane[a];
+      for (int a = 0; a < 3; ++a) pl.model.centroid[a] = cells[(size_t)cell].model.centroid[a];
+      pl.isValid = true;
+      for (int f = 0; f < Fg; ++f) { const sloam_point &q = feats[(size_t)cell * Fg + f]; PointT t; t.x = q.x; t.y = q.y; t.z = q.z; t.intensity = q.intensity; pl.features.push_back(t); }
+      planes.push_back(pl);
+    }
+    if (planes.empty() || trees.empty()) return;  // :414
+    // the flattened landmarks are laid out like compute_graph's output: vertex_begin = t * max_tree_vertices
+    std::vector<sloam_vertex> vpad((size_t)T * p.max_tree_vertices);
+    for (size_t t = 0; t < trees.size(); ++t) {
+      for (int k = 0; k < trees[t].n_vertices; ++k) vpad[t * p.max_tree_vertices + k] = verts[(size_t)trees[t].vertex_begin + k];
+      trees[t].vertex_begin = (int)(t * p.max_tree_vertices);
+    }
+    d_trees.upload(trees.data(), sizeof(sloam_tree) * trees.size());
+    d_nt.upload(&n_trees, 4);
+    d_verts.upload(vpad.data(), sizeof(sloam_vertex) * vpad.size());
+    if (!vpts.empty()) d_vpts.upload(vpts.data(), sizeof(sloam_point) * vpts.size());
+    rt->check(sloam_b200_cylinders_dev(c, 1, d_trees.as<sloam_tree>(), d_nt.as<int32_t>(), d_verts.as<sloam_vertex>(),
+                                       d_vpts.as<sloam_point>(), d_cells.as<sloam_cell_plane>(), d_models.as<sloam_tree_model>(),
+                                       d_tfeat.as<sloam_point>()));
+    std::vector<sloam_tree_model> models(trees.size());
+    std::vector<sloam_point> tfeat(trees.size() * (size_t)Ft);
+    d_models.download(models.data(), sizeof(sloam_tree_model) * models.size());
+    d_tfeat.download(tfeat.data(), sizeof(sloam_point) * tfeat.size());
+    for (size_t t = 0; t < trees.size(); ++t) {
+      if (!models[t].is_valid) continue;  // :433-434
+      Cylinder cy;
+      for (int a = 0; a < 3; ++a) { cy.model.root[a] = models[t].model.root[a]; cy.model.ray[a] = models[t].model.ray[a]; }
+      cy.model.radius = models[t].model.radius;
+      cy.model.vertices = in.landmarks[t];
+      for (const auto &v : in.landmarks[t]) cy.model.radii.push_back(v.radius);
+      cy.id = (size_t)models[t].id;
+      cy.isValid = true;
+      for (int f = 0; f < Ft; ++f) { const sloam_point &q = tfeat[t * Ft + f]; PointT pt; pt.x = q.x; pt.y = q.y; pt.z = q.z; pt.intensity = q.intensity; cy.features.push_back(pt); }
+      landmarks.push_back(cy);
+    }
+  }
+
+  // ---- Data association (:257-328) ----------------------------------------------------------
+  // matchIndices[i] = index of the nearest map cylinder when closer than AddNewTreeThreshDist
+  void matchModels(const std::vector<Cylinder> &currObjects, const std::vector<Cylinder> &mapObjects,
+                   std::vector<int> &matchIndices) {
+    std::vector<int32_t> idx; std::vector<double> dist;
+    nearest(currObjects, mapObjects, nullptr, idx, dist);
+    if (matchIndices.size() < currObjects.size()) matchIndices.resize(currObjects.size(), -1);
+    for (size_t i = 0; i < currObjects.size(); ++i)
+      if (idx[i] >= 0 && dist[i] < fmParams_.treeMatchThresh + 100 && dist[i] < fmParams_.AddNewTreeThreshDist) matchIndices[i] = idx[i];
+  }
+  // one ObjectMatch per feature of every current object whose nearest map object (after
+  // projecting the current object with tf) is closer than distThresh
+  std::vector<ObjectMatch<Cylinder>> matchFeatures(const SE3 tf, const std::vector<Cylinder> &currObjects,
+                                                   const std::vector<Cylinder> &mapObjects, const Scalar distThresh) {
+    std::vector<int32_t> idx; std::vector<double> dist;
+    nearest(currObjects, mapObjects, &tf, idx, dist);
+    std::vector<ObjectMatch<Cylinder>> matches;
+    for (size_t i = 0; i < currObjects.size(); ++i)
+      if (idx[i] >= 0 && dist[i] < distThresh)
+        for (const PointT &f : currObjects[i].features) matches.emplace_back(f, mapObjects[(size_t)idx[i]], dist[i]);
+    return matches;
+  }
+  std::vector<ObjectMatch<Plane>> matchFeatures(const SE3 tf, const std::vector<Plane> &currObjects,
+                                                const std::vector<Plane> &mapObjects, const Scalar distThresh) {
+    std::vector<ObjectMatch<Plane>> matches;
+    if (currObjects.empty() || mapObjects.empty()) return matches;
+    auto rt = runtime(0);
+    sloam_ctx *c = rt->ctx();
+    const int32_t nd = (int32_t)currObjects.size(), nm = (int32_t)mapObjects.size();
+    std::vector<sloam_plane> det((size_t)nd), map((size_t)nm);
+    for (int i = 0; i < nd; ++i) to_abi(currObjects[(size_t)i], det[(size_t)i]);
+    for (int i = 0; i < nm; ++i) to_abi(mapObjects[(size_t)i], map[(size_t)i]);
+    const sloam_pose pose = tf.abi();
+    using sloam_b200::DevBuf;
+    DevBuf d_det(c, sizeof(sloam_plane) * nd), d_nd(c, 4), d_map(c, sizeof(sloam_plane) * nm), d_nm(c, 4), d_tf(c, sizeof pose),
+        d_idx(c, 4 * (size_t)nd), d_dist(c, 8 * (size_t)nd);
+    d_det.upload(det.data(), sizeof(sloam_plane) * nd); d_nd.upload(&nd, 4);
+    d_map.upload(map.data(), sizeof(sloam_plane) * nm); d_nm.upload(&nm, 4);
+    d_tf.upload(&pose, sizeof pose);
+    rt->check(sloam_b200_associate_planes_dev(c, 1, d_det.as<sloam_plane>(), d_nd.as<int32_t>(), nd, d_tf.as<sloam_pose>(),
+                                              d_map.as<sloam_plane>(), d_nm.as<int32_t>(), nm, d_idx.as<int32_t>(),
+                                              d_dist.as<double>()));
+    std::vector<int32_t> idx((size_t)nd); std::vector<double> dist((size_t)nd);
+    d_idx.download(idx.data(), 4 * (size_t)nd);
+    d_dist.download(dist.data(), 8 * (size_t)nd);
+    for (int i = 0; i < nd; ++i)
+      if (idx[(size_t)i] >= 0 && dist[(size_t)i] < distThresh)
+        for (const PointT &f : currObjects[(size_t)i].features) matches.emplace_back(f, mapObjects[(size_t)idx[(size_t)i]], dist[(size_t)i]);
+    return matches;
+  }
 
   // sloam.cpp:453-532, one keyframe.  Returns false exactly when the reference does.
   bool RunSloam(SloamInput &in, SloamOutput &out) {
-    if (!rt_) rt_.reset(new sloam_b200::Runtime(fmParams_, sized_for(in.groundCloud->points.size())));
-    else if ((int)in.groundCloud->points.size() > rt_->params().img_h * rt_->params().img_w)
-      rt_.reset(new sloam_b200::Runtime(fmParams_, sized_for(in.groundCloud->points.size())));
-    sloam_ctx *c = rt_->ctx();
-    const sloam_params &p = rt_->params();
+    auto rt = runtime(in.groundCloud->points.size());
+    sloam_ctx *c = rt->ctx();
+    const sloam_params &p = rt->params();
     const int N = p.img_h * p.img_w, T = p.max_trees, M = p.max_map_models, PP = p.max_prev_planes;
+    const int B = p.groundRadiiBins * p.groundThetaBins, Fg = p.numGroundFeatures;
     std::vector<sloam_tree> trees; std::vector<sloam_vertex> verts; std::vector<sloam_point> vpts;
     sloam_b200::flatten(in.landmarks, trees, verts, vpts);
     if ((int)trees.size() > T || (int)in.mapModels.size() > M || (int)prevGPlanes_.size() > PP)
       throw std::runtime_error("sloam_b200: capacity exceeded (max_trees / max_map_models / max_prev_planes)");
+    for (const sloam_tree &t : trees)
+      if (t.n_vertices > p.max_tree_vertices) throw std::runtime_error("sloam_b200: a landmark has more vertices than max_tree_vertices");
     const int32_t n_ground = (int32_t)in.groundCloud->points.size(), n_trees = (int32_t)trees.size();
+    if (n_ground > N) throw std::runtime_error("sloam_b200: ground cloud larger than the context was sized for");
     std::vector<sloam_cylinder> map(std::max<size_t>(in.mapModels.size(), 1));
-    for (size_t i = 0; i < in.mapModels.size(); ++i) {
-      for (int a = 0; a < 3; ++a) { map[i].root[a] = in.mapModels[i].model.root[a]; map[i].ray[a] = in.mapModels[i].model.ray[a]; }
-      map[i].radius = in.mapModels[i].model.radius;
-    }
+    for (size_t i = 0; i < in.mapModels.size(); ++i) to_abi(in.mapModels[i], map[i]);
     std::vector<sloam_plane> prev(std::max<size_t>(prevGPlanes_.size(), 1));
-    for (size_t i = 0; i < prevGPlanes_.size(); ++i) {
-      for (int a = 0; a < 4; ++a) prev[i].plane[a] = prevGPlanes_[i].model.plane[a];
-      for (int a = 0; a < 3; ++a) prev[i].centroid[a] = prevGPlanes_[i].model.centroid[a];
-    }
+    for (size_t i = 0; i < prevGPlanes_.size(); ++i) to_abi(prevGPlanes_[i], prev[i]);
     const int32_t n_map = (int32_t)in.mapModels.size(), n_prev = (int32_t)prevGPlanes_.size();
     const uint8_t first = firstScan_ ? 1 : 0;
     const sloam_pose pose = in.poseEstimate.abi();
+    // one packed upload and one packed download per call (every copy through the C ABI is a
+    // synchronous round trip): the inputs are laid out in one host block mirroring one device block
     using sloam_b200::DevBuf;
-    DevBuf d_ground(c, sizeof(sloam_point) * (size_t)N), d_ng(c, 4), d_trees(c, sizeof(sloam_tree) * T),
-        d_nt(c, 4), d_verts(c, sizeof(sloam_vertex) * std::max<size_t>(verts.size(), 1)),
-        d_vpts(c, sizeof(sloam_point) * std::max<size_t>(vpts.size(), 1)), d_pose(c, sizeof pose), d_first(c, 1),
-        d_map(c, sizeof(sloam_cylinder) * M), d_nmap(c, 4), d_prev(c, sizeof(sloam_plane) * PP), d_nprev(c, 4),
-        d_res(c, sizeof(sloam_kf_result)), d_match(c, 4 * T), d_tm(c, sizeof(sloam_cylinder) * T),
-        d_tmid(c, 4 * T), d_planes(c, sizeof(sloam_plane) * PP), d_npl(c, 4);
-    d_ground.upload(in.groundCloud->points.data(), sizeof(sloam_point) * (size_t)n_ground);
-    d_ng.upload(&n_ground, 4);
-    d_trees.upload(trees.data(), sizeof(sloam_tree) * trees.size());
-    d_nt.upload(&n_trees, 4);
-    d_verts.upload(verts.data(), sizeof(sloam_vertex) * verts.size());
-    d_vpts.upload(vpts.data(), sizeof(sloam_point) * vpts.size());
-    d_pose.upload(&pose, sizeof pose);
-    d_first.upload(&first, 1);
-    d_map.upload(map.data(), sizeof(sloam_cylinder) * in.mapModels.size());
-    d_nmap.upload(&n_map, 4);
-    d_prev.upload(prev.data(), sizeof(sloam_plane) * prevGPlanes_.size());
-    d_nprev.upload(&n_prev, 4);
+    struct Part { size_t off, bytes; };
+    size_t in_bytes = 0, out_bytes = 0;
+    auto part = [](size_t &total, size_t bytes) { Part q{total, bytes}; total = (total + bytes + 255) / 256 * 256; return q; };
+    const Part i_ground = part(in_bytes, sizeof(sloam_point) * (size_t)n_ground), i_ng = part(in_bytes, 4),
+               i_trees = part(in_bytes, sizeof(sloam_tree) * (size_t)T), i_nt = part(in_bytes, 4),
+               i_verts = part(in_bytes, sizeof(sloam_vertex) * std::max<size_t>(verts.size(), 1)),
+               i_vpts = part(in_bytes, sizeof(sloam_point) * std::max<size_t>(vpts.size(), 1)), i_pose = part(in_bytes, sizeof pose),
+               i_first = part(in_bytes, 1), i_map = part(in_bytes, sizeof(sloam_cylinder) * (size_t)M), i_nmap = part(in_bytes, 4),
+               i_prev = part(in_bytes, sizeof(sloam_plane) * (size_t)PP), i_nprev = part(in_bytes, 4);
+    const Part o_res = part(out_bytes, sizeof(sloam_kf_result)), o_npl = part(out_bytes, 4), o_match = part(out_bytes, 4 * (size_t)T),
+               o_tmid = part(out_bytes, 4 * (size_t)T), o_tm = part(out_bytes, sizeof(sloam_cylinder) * (size_t)T),
+               o_planes = part(out_bytes, sizeof(sloam_plane) * (size_t)PP);
+    stage_.resize(std::max(in_bytes, out_bytes));
+    auto put = [&](const Part &q, const void *src, size_t bytes) { if (bytes) std::memcpy(stage_.data() + q.off, src, bytes); };
+    put(i_ground, in.groundCloud->points.data(), sizeof(sloam_point) * (size_t)n_ground);
+    put(i_ng, &n_ground, 4);
+    put(i_trees, trees.data(), sizeof(sloam_tree) * trees.size());
+    put(i_nt, &n_trees, 4);
+    put(i_verts, verts.data(), sizeof(sloam_vertex) * verts.size());
+    put(i_vpts, vpts.data(), sizeof(sloam_point) * vpts.size());
+    put(i_pose, &pose, sizeof pose);
+    put(i_first, &first, 1);
+    put(i_map, map.data(), sizeof(sloam_cylinder) * in.mapModels.size());
+    put(i_nmap, &n_map, 4);
+    put(i_prev, prev.data(), sizeof(sloam_plane) * prevGPlanes_.size());
+    put(i_nprev, &n_prev, 4);
+    DevBuf d_in(c, in_bytes), d_out(c, out_bytes);
+    d_in.upload(stage_.data(), in_bytes);
+    char *di = d_in.as<char>(), *dout = d_out.as<char>();
     sloam_batch_in bi{};
-    bi.pose_est = d_pose.as<sloam_pose>(); bi.first_scan = d_first.as<uint8_t>();
-    bi.map_models = d_map.as<sloam_cylinder>(); bi.n_map_models = d_nmap.as<int32_t>();
-    bi.prev_planes = d_prev.as<sloam_plane>(); bi.n_prev_planes = d_nprev.as<int32_t>();
+    bi.pose_est = reinterpret_cast<sloam_pose *>(di + i_pose.off); bi.first_scan = reinterpret_cast<uint8_t *>(di + i_first.off);
+    bi.map_models = reinterpret_cast<sloam_cylinder *>(di + i_map.off); bi.n_map_models = reinterpret_cast<int32_t *>(di + i_nmap.off);
+    bi.prev_planes = reinterpret_cast<sloam_plane *>(di + i_prev.off); bi.n_prev_planes = reinterpret_cast<int32_t *>(di + i_nprev.off);
     sloam_batch_out bo{};
-    bo.results = d_res.as<sloam_kf_result>(); bo.matches = d_match.as<int32_t>();
-    bo.tm = d_tm.as<sloam_cylinder>(); bo.tm_id = d_tmid.as<int32_t>();
-    bo.planes = d_planes.as<sloam_plane>(); bo.n_planes = d_npl.as<int32_t>();
-    rt_->check(sloam_b200_run_sloam_dev(c, 1, d_ground.as<sloam_point>(), d_ng.as<int32_t>(), N,
-                                        d_trees.as<sloam_tree>(), d_nt.as<int32_t>(), d_verts.as<sloam_vertex>(),
-                                        (int)std::max<size_t>(verts.size(), 1), d_vpts.as<sloam_point>(),
-                                        (int)std::max<size_t>(vpts.size(), 1), &bi, &bo));
+    bo.results = reinterpret_cast<sloam_kf_result *>(dout + o_res.off); bo.matches = reinterpret_cast<int32_t *>(dout + o_match.off);
+    bo.tm = reinterpret_cast<sloam_cylinder *>(dout + o_tm.off); bo.tm_id = reinterpret_cast<int32_t *>(dout + o_tmid.off);
+    bo.planes = reinterpret_cast<sloam_plane *>(dout + o_planes.off); bo.n_planes = reinterpret_cast<int32_t *>(dout + o_npl.off);
+    rt->check(sloam_b200_run_sloam_dev(c, 1, reinterpret_cast<sloam_point *>(di + i_ground.off),
+                                       reinterpret_cast<int32_t *>(di + i_ng.off), std::max(n_ground, 1),
+                                       reinterpret_cast<sloam_tree *>(di + i_trees.off), reinterpret_cast<int32_t *>(di + i_nt.off),
+                                       reinterpret_cast<sloam_vertex *>(di + i_verts.off), (int)std::max<size_t>(verts.size(), 1),
+                                       reinterpret_cast<sloam_point *>(di + i_vpts.off), (int)std::max<size_t>(vpts.size(), 1), &bi, &bo));
+    d_out.download(stage_.data(), out_bytes);
     sloam_kf_result res;
-    d_res.download(&res, sizeof res);
+    std::memcpy(&res, stage_.data() + o_res.off, sizeof res);
     last_ = res;
     int32_t npl = 0;
-    d_npl.download(&npl, 4);
+    std::memcpy(&npl, stage_.data() + o_npl.off, 4);
     std::vector<sloam_plane> planes(std::max(npl, 1));
-    d_planes.download(planes.data(), sizeof(sloam_plane) * npl);
+    std::memcpy(planes.data(), stage_.data() + o_planes.off, sizeof(sloam_plane) * (size_t)npl);
     if (SLOAM_KF_CODE(res.status) == SLOAM_KF_EMPTY_MAP || SLOAM_KF_CODE(res.status) == SLOAM_KF_NO_MODELS) return false;  // :476-486
     std::vector<int32_t> matches(std::max(res.n_landmarks, 1)), ids(std::max(res.n_landmarks, 1));
     std::vector<sloam_cylinder> tm(std::max(res.n_landmarks, 1));
-    d_match.download(matches.data(), 4 * (size_t)res.n_landmarks);
-    d_tmid.download(ids.data(), 4 * (size_t)res.n_landmarks);
-    d_tm.download(tm.data(), sizeof(sloam_cylinder) * (size_t)res.n_landmarks);
+    std::memcpy(matches.data(), stage_.data() + o_match.off, 4 * (size_t)res.n_landmarks);
+    std::memcpy(ids.data(), stage_.data() + o_tmid.off, 4 * (size_t)res.n_landmarks);
+    std::memcpy(tm.data(), stage_.data() + o_tm.off, sizeof(sloam_cylinder) * (size_t)res.n_landmarks);
     out.matches.assign(matches.begin(), matches.begin() + res.n_landmarks);
     out.tm.clear();
     for (int i = 0; i < res.n_landmarks; ++i) {
@@ -419,13 +721,31 @@ class sloam {  // sloam.h:57-107
     }
     out.T_Map_Curr = SE3(res.T_Map_Curr);
     out.T_Delta = SE3(res.T_Delta);
-    prevGPlanes_.clear();  // :471,:525
-    for (int i = 0; i < npl; ++i) {
+    // prevGPlanes_ = planes (:471,:525): the accepted planes projected with the new pose, with
+    // their features (Plane::project moves them with pcl::transformPoint: float results)
+    sloam_intermediates im{};
+    rt->check(sloam_b200_get_intermediates(c, &im));
+    std::vector<sloam_cell_plane> cells((size_t)B);
+    std::vector<sloam_point> feats((size_t)B * Fg);
+    rt->check(sloam_b200_copy_d2h(c, cells.data(), im.cells, sizeof(sloam_cell_plane) * B));
+    rt->check(sloam_b200_copy_d2h(c, feats.data(), im.cell_features, sizeof(sloam_point) * feats.size()));
+    prevGPlanes_.clear();
+    int acc = 0;
+    for (int cell = 0; cell < B && acc < npl; ++cell) {
+      if (!cells[(size_t)cell].accepted) continue;
       Plane pl;
-      for (int a = 0; a < 4; ++a) pl.model.plane[a] = planes[i].plane[a];
-      for (int a = 0; a < 3; ++a) pl.model.centroid[a] = planes[i].centroid[a];
+      for (int a = 0; a < 4; ++a) pl.model.plane[a] = planes[acc].plane[a];
+      for (int a = 0; a < 3; ++a) pl.model.centroid[a] = planes[acc].centroid[a];
       pl.isValid = true;
+      for (int f = 0; f < Fg; ++f) {
+        const sloam_point &q = feats[(size_t)cell * Fg + f];
+        Vector3 v; v[0] = q.x; v[1] = q.y; v[2] = q.z;
+        const Vector3 w = out.T_Map_Curr * v;
+        PointT t; t.x = (float)w[0]; t.y = (float)w[1]; t.z = (float)w[2]; t.intensity = q.intensity;
+        pl.features.push_back(t);
+      }
       prevGPlanes_.push_back(pl);
+      ++acc;
     }
     firstScan_ = false;
     return res.success != 0;
@@ -433,17 +753,95 @@ class sloam {  // sloam.h:57-107
   const sloam_kf_result &lastResult() const { return last_; }
 
  private:
-  sloam_b200::HostConfig sized_for(size_t n_ground) const {
-    sloam_b200::HostConfig h = hc_;
-    while ((size_t)h.img_h * h.img_w < n_ground) h.img_w *= 2;
-    return h;
+  static void to_abi(const Cylinder &cy, sloam_cylinder &o) {
+    for (int a = 0; a < 3; ++a) { o.root[a] = cy.model.root[a]; o.ray[a] = cy.model.ray[a]; }
+    o.radius = cy.model.radius;
+  }
+  static void to_abi(const Plane &pl, sloam_plane &o) {
+    for (int a = 0; a < 4; ++a) o.plane[a] = pl.model.plane[a];
+    for (int a = 0; a < 3; ++a) o.centroid[a] = pl.model.centroid[a];
+  }
+  // ceres::QuaternionToAngleAxis on (x, y, z, w)
+  static void quat_to_angle_axis(const double *q, double *aa) {
+    const double s2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2];
+    if (s2 > 0.0) {
+      const double s = std::sqrt(s2), cw = q[3];
+      const double two_theta = 2.0 * (cw < 0.0 ? std::atan2(-s, -cw) : std::atan2(s, cw));
+      const double k = two_theta / s;
+      aa[0] = q[0] * k; aa[1] = q[1] * k; aa[2] = q[2] * k;
+    } else {
+      aa[0] = q[0] * 2.0; aa[1] = q[1] * 2.0; aa[2] = q[2] * 2.0;
+    }
+  }
+  // nearest map cylinder of every current cylinder (projected with tf when given)
+  void nearest(const std::vector<Cylinder> &curr, const std::vector<Cylinder> &mapObjects, const SE3 *tf,
+               std::vector<int32_t> &idx, std::vector<double> &dist) {
+    idx.assign(curr.size(), -1);
+    dist.assign(curr.size(), std::numeric_limits<double>::infinity());
+    if (curr.empty() || mapObjects.empty()) return;
+    auto rt = runtime(0);
+    sloam_ctx *c = rt->ctx();
+    const int32_t nd = (int32_t)curr.size(), nm = (int32_t)mapObjects.size();
+    std::vector<sloam_cylinder> det((size_t)nd), map((size_t)nm);
+    for (int i = 0; i < nd; ++i) to_abi(curr[(size_t)i], det[(size_t)i]);
+    for (int i = 0; i < nm; ++i) to_abi(mapObjects[(size_t)i], map[(size_t)i]);
+    using sloam_b200::DevBuf;
+    DevBuf d_det(c, sizeof(sloam_cylinder) * nd), d_nd(c, 4), d_map(c, sizeof(sloam_cylinder) * nm), d_nm(c, 4),
+        d_tf(c, sizeof(sloam_pose)), d_idx(c, 4 * (size_t)nd), d_dist(c, 8 * (size_t)nd);
+    d_det.upload(det.data(), sizeof(sloam_cylinder) * nd); d_nd.upload(&nd, 4);
+    d_map.upload(map.data(), sizeof(sloam_cylinder) * nm); d_nm.upload(&nm, 4);
+    if (tf) d_tf.upload(&tf->abi(), sizeof(sloam_pose));
+    rt->check(sloam_b200_associate_dev(c, 1, d_det.as<sloam_cylinder>(), d_nd.as<int32_t>(), nd,
+                                       tf ? d_tf.as<sloam_pose>() : nullptr, d_map.as<sloam_cylinder>(), d_nm.as<int32_t>(),
+                                       nm, 0, d_idx.as<int32_t>(), d_dist.as<double>()));
+    d_idx.download(idx.data(), 4 * (size_t)nd);
+    d_dist.download(dist.data(), 8 * (size_t)nd);
+  }
+  // OptimizePose / TwoStepOptimizePose on explicit match lists
+  void solve(int mode, const SE3 &est, bool optimTrees, bool optimGround, const std::vector<ObjectMatch<Cylinder>> &tm,
+             const std::vector<ObjectMatch<Plane>> &gm, sloam_pose &out, int32_t term[2]) {
+    auto rt = runtime(0);
+    sloam_ctx *c = rt->ctx();
+    const int32_t nt = (int32_t)tm.size(), ng = (int32_t)gm.size();
+    const int ts = std::max(nt, 1), gs = std::max(ng, 1);
+    std::vector<double> tf((size_t)ts * 3, 0.0), gf((size_t)gs * 3, 0.0);
+    std::vector<sloam_cylinder> to((size_t)ts);
+    std::vector<sloam_plane> go((size_t)gs);
+    for (int i = 0; i < nt; ++i) { for (int a = 0; a < 3; ++a) tf[(size_t)i * 3 + a] = tm[(size_t)i].feature[a]; to_abi(tm[(size_t)i].object, to[(size_t)i]); }
+    for (int i = 0; i < ng; ++i) { for (int a = 0; a < 3; ++a) gf[(size_t)i * 3 + a] = gm[(size_t)i].feature[a]; to_abi(gm[(size_t)i].object, go[(size_t)i]); }
+    const sloam_pose pose = est.abi();
+    const uint8_t ot = optimTrees ? 1 : 0, og = optimGround ? 1 : 0;
+    using sloam_b200::DevBuf;
+    DevBuf d_pose(c, sizeof pose), d_tf(c, 8 * tf.size()), d_to(c, sizeof(sloam_cylinder) * to.size()), d_nt(c, 4),
+        d_gf(c, 8 * gf.size()), d_go(c, sizeof(sloam_plane) * go.size()), d_ng(c, 4), d_ot(c, 1), d_og(c, 1),
+        d_out(c, sizeof(sloam_pose)), d_it(c, 8), d_term(c, 8);
+    d_pose.upload(&pose, sizeof pose);
+    d_tf.upload(tf.data(), 8 * tf.size()); d_to.upload(to.data(), sizeof(sloam_cylinder) * to.size()); d_nt.upload(&nt, 4);
+    d_gf.upload(gf.data(), 8 * gf.size()); d_go.upload(go.data(), sizeof(sloam_plane) * go.size()); d_ng.upload(&ng, 4);
+    d_ot.upload(&ot, 1); d_og.upload(&og, 1);
+    rt->check(sloam_b200_optimize_pose_dev(c, 1, mode, d_pose.as<sloam_pose>(), d_tf.as<double>(), d_to.as<sloam_cylinder>(),
+                                           d_nt.as<int32_t>(), ts, d_gf.as<double>(), d_go.as<sloam_plane>(), d_ng.as<int32_t>(), gs,
+                                           d_ot.as<uint8_t>(), d_og.as<uint8_t>(), d_out.as<sloam_pose>(), d_it.as<int32_t>(),
+                                           d_term.as<int32_t>()));
+    d_out.download(&out, sizeof out);
+    d_term.download(term, 8);
+  }
+  // the shared context for this parameter set, wide enough for n_ground points
+  std::shared_ptr<sloam_b200::Runtime> runtime(size_t n_ground) {
+    if (!rt_ || (size_t)rt_->params().img_h * rt_->params().img_w < n_ground) {
+      sloam_b200::HostConfig h = hc_;
+      while ((size_t)h.img_h * h.img_w < n_ground) h.img_w *= 2;
+      rt_ = sloam_b200::shared_runtime(fmParams_, h);
+    }
+    return rt_;
   }
   sloam_b200::HostConfig hc_;
   FeatureModelParams fmParams_;
-  std::unique_ptr<sloam_b200::Runtime> rt_;
+  std::shared_ptr<sloam_b200::Runtime> rt_;
   std::vector<Plane> prevGPlanes_;
   bool firstScan_ = true;
   sloam_kf_result last_{};
+  std::vector<char> stage_;  // host side of the packed copies, kept between calls
 };
 }  // namespace sloam
 
@@ -458,10 +856,11 @@ inline Plane::Plane(const VectorType &points, const FeatureModelParams &fmParams
   FeatureModelParams f = fmParams;
   f.groundRadiiBins = 1; f.groundThetaBins = 1;
   f.minGroundLidarDist = -1.0; f.maxGroundLidarDist = 1e30;
-  f.groundRetainThresh = std::min(1.0, 1.0 / (double)(features.size() + 1));
+  f.groundRetainThresh = 1.0 / 1073741824.0;  // 1/thresh >= any size: never sorted (and one cache key for all sizes)
   sloam_b200::HostConfig h = hc;
   while ((size_t)h.img_h * h.img_w < features.size()) h.img_w *= 2;
-  sloam_b200::Runtime rt(f, h);
+  const auto rtp = sloam_b200::shared_runtime(f, h);  // one cached context, not one per object
+  sloam_b200::Runtime &rt = *rtp;
   sloam_ctx *c = rt.ctx();
   const int N = rt.params().img_h * rt.params().img_w, Fg = f.numGroundFeatures;
   const int32_t n = (int32_t)features.size();
@@ -483,11 +882,14 @@ inline Plane::Plane(const VectorType &points, const FeatureModelParams &fmParams
 
 inline Cylinder::Cylinder(const std::vector<TreeVertex> vertices, const Plane &gplane,
                           const FeatureModelParams &fmParams, const sloam_b200::HostConfig &hc) {
-  sloam_b200::Runtime rt(fmParams, hc);
+  const auto rtp = sloam_b200::shared_runtime(fmParams, hc);  // one cached context, not one per object
+  sloam_b200::Runtime &rt = *rtp;
   sloam_ctx *c = rt.ctx();
   const sloam_params &p = rt.params();
   std::vector<sloam_tree> trees; std::vector<sloam_vertex> verts; std::vector<sloam_point> vpts;
   sloam_b200::flatten({vertices}, trees, verts, vpts);
+  if ((int)vertices.size() > p.max_tree_vertices)
+    throw std::runtime_error("sloam_b200: a landmark has more vertices than max_tree_vertices");
   const int B = p.groundRadiiBins * p.groundThetaBins, Ft = p.featuresPerTree;
   std::vector<sloam_cell_plane> cells(B);
   std::memset(cells.data(), 0, sizeof(sloam_cell_plane) * B);

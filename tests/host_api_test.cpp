@@ -172,6 +172,107 @@ static void core_tests(const Fixture &t0, const Fixture &t1, bool two_step) {
   }
 }
 
+// The public per-stage methods of sloam::sloam (sloam.h:71-96): RunSloam's own body
+// (sloam.cpp:453-532) re-assembled from them must give what RunSloam gives.
+#include <chrono>
+static void stage_method_tests(const Fixture &t0, const Fixture &t1, bool two_step) {
+  const FeatureModelParams params = core_params(two_step);
+  // ---- the fused entry
+  sloam::sloam ref;
+  ref.setFmParams(params);
+  SloamOutput r0, r1;
+  SloamInput a0 = make_input(t0), a1 = make_input(t1);
+  ref.RunSloam(a0, r0);
+  a1.mapModels = r0.tm;
+  const bool ok_ref = ref.RunSloam(a1, r1);
+  // ---- the same from the stage methods
+  sloam::sloam s;
+  s.setFmParams(params);
+  SloamInput in0 = make_input(t0), in1 = make_input(t1);
+  std::vector<Cylinder> lm0, lm1;
+  std::vector<Plane> pl0, pl1;
+  s.computeModels(in0, lm0, pl0);                      // :487 (first scan: :463-473)
+  EXPECT_EQ(lm0.size(), r0.tm.size());
+  EXPECT_TRUE(pl0.size() > 0 && pl0[0].features.size() == (size_t)params.numGroundFeatures);
+  s.projectModels(in0.poseEstimate, lm0, pl0);
+  in1.mapModels = lm0;
+  s.computeModels(in1, lm1, pl1);
+  EXPECT_EQ(lm1.size(), r1.tm.size());
+  const SE3 currPose = in1.poseEstimate;
+  auto treeMatches = s.matchFeatures(currPose, lm1, in1.mapModels, params.treeMatchThresh);   // :489
+  auto planeMatches = s.matchFeatures(currPose, pl1, pl0, 1.0);                               // :490
+  EXPECT_EQ((int)treeMatches.size(), ref.lastResult().n_tree_matches);
+  EXPECT_EQ((int)planeMatches.size(), ref.lastResult().n_plane_matches);
+  const double minPlanes = params.groundRadiiBins * params.groundThetaBins * 0.1;
+  const bool treeCheck = lm1.size() > params.minTreeModels && treeMatches.size() > 5.0 * params.featuresPerTree;   // :499
+  const bool groundCheck = planeMatches.size() > params.minGroundModels && pl1.size() > minPlanes;                 // :500
+  SE3 tf = currPose;
+  bool success = true;
+  if (two_step) success = s.TwoStepOptimizePose(currPose, treeCheck, groundCheck, treeMatches, planeMatches, tf);
+  else if (treeCheck && groundCheck) success = s.OptimizePose(currPose, treeMatches, planeMatches, tf);
+  EXPECT_EQ(success, ok_ref);
+  for (int a = 0; a < 3; ++a) EXPECT_NEAR(tf.translation()[a], r1.T_Map_Curr.translation()[a], 1e-9);
+  for (int a = 0; a < 4; ++a) EXPECT_NEAR(tf.unit_quaternion()[a], r1.T_Map_Curr.unit_quaternion()[a], 1e-9);
+  s.projectModels(tf, lm1, pl1);                        // :511
+  std::vector<int> matches(lm1.size(), -1);
+  s.matchModels(lm1, in1.mapModels, matches);           // :516
+  EXPECT_TRUE(matches == r1.matches);
+  for (size_t i = 0; i < lm1.size() && i < r1.tm.size(); ++i) {
+    for (int a = 0; a < 3; ++a) EXPECT_NEAR(lm1[i].model.root[a], r1.tm[i].model.root[a], 1e-9);
+    EXPECT_EQ(lm1[i].id, r1.tm[i].id);
+  }
+  // the two half problems on their own: the pieces TwoStepOptimizePose composes (:33-53)
+  if (two_step) {
+    double treeOut[3], groundOut[3];
+    s.OptimizeXYYaw(currPose, treeCheck, treeMatches, treeOut);
+    s.OptimizeZRollPitch(currPose, groundCheck, planeMatches, groundOut);
+    EXPECT_NEAR(treeOut[0], tf.translation()[0], 1e-9);
+    EXPECT_NEAR(treeOut[1], tf.translation()[1], 1e-9);
+    EXPECT_NEAR(groundOut[0], tf.translation()[2], 1e-9);
+  }
+  // getPrevGroundFeatures: numGroundFeatures points per remembered plane, in the map frame
+  EXPECT_EQ(ref.getPrevGroundFeatures().points.size(), ref.getPrevGroundModel().size() * (size_t)params.numGroundFeatures);
+  // binGroundPoints: the retained lists are the lowest points of their cells, z ascending
+  GroundGrid scgf;
+  s.binGroundPoints(SE3(), in1.groundCloud->points, scgf);
+  EXPECT_EQ((int)scgf.size(), params.groundRadiiBins);
+  size_t kept = 0;
+  bool sorted = true;
+  for (auto &row : scgf)
+    for (auto &cell : row) {
+      kept += cell.size();
+      for (size_t i = 1; i < cell.size(); ++i) sorted = sorted && !(cell[i].z < cell[i - 1].z);
+    }
+  EXPECT_TRUE(sorted && kept > 100 && kept < in1.groundCloud->points.size() / 10);
+  {  // about another origin: shifting cloud and pose together selects the same number of points
+    SE3 shifted;
+    shifted.translation()[0] = 2.0; shifted.translation()[1] = -1.0;
+    VectorType moved = in1.groundCloud->points;
+    for (auto &q : moved) { q.x += 2.0f; q.y -= 1.0f; }
+    GroundGrid g2;
+    s.binGroundPoints(shifted, moved, g2);
+    size_t kept2 = 0;
+    for (auto &row : g2) for (auto &cell : row) kept2 += cell.size();
+    EXPECT_TRUE(kept2 + 20 > kept && kept2 < kept + 20);
+  }
+  // cost of one RunSloam through the mirror once its staging arena is warm
+  sloam::sloam timed;
+  timed.setFmParams(params);
+  SloamOutput o;
+  SloamInput w0 = make_input(t0);
+  timed.RunSloam(w0, o);
+  double best = 1e9;
+  for (int rep = 0; rep < 5; ++rep) {
+    SloamInput w1 = make_input(t1);
+    w1.mapModels = r0.tm;
+    const auto c0 = std::chrono::steady_clock::now();
+    timed.RunSloam(w1, o);
+    best = std::min(best, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - c0).count());
+  }
+  std::printf("  two_step=%d  RunSloam through the C++ mirror: %.3f ms (best of 5, %zu ground points, %zu landmarks)\n",
+              (int)two_step, best, t1.ground.size(), t1.landmarks.size());
+}
+
 // MapManager (mapManager.cpp) through the mirror.
 static void map_manager_tests() {
   sloam_b200::HostConfig hc;
@@ -235,6 +336,7 @@ static void node_sequence(int n_keyframes) {
 }
 
 int main(int argc, char **argv) {
+  std::setvbuf(stdout, nullptr, _IOLBF, 0);
   if (argc < 2) { std::printf("usage: %s fixtures.bin\n", argv[0]); return 2; }
   std::ifstream f(argv[1], std::ios::binary);
   Fixture t0, t1;
@@ -246,6 +348,8 @@ int main(int argc, char **argv) {
     cylinder_tests(t0);
     core_tests(t0, t1, false);
     core_tests(t0, t1, true);
+    stage_method_tests(t0, t1, false);
+    stage_method_tests(t0, t1, true);
     {  // Instance::computeGraph on an empty organized cloud: no landmarks, no crash
       Instance inst;
       CloudT::Ptr cloud(new CloudT());
