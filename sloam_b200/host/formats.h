@@ -8,7 +8,9 @@
 //    sloam/include/helpers/serialization.h:13-33 (the *_landmarks_t{0,1} fixtures that
 //    sloam/src/tests/core_test.cpp:79 loads).
 //  * ROS1 wire encoding of sloam_msgs/ROSCylinder and of a ROSCylinder[] field
-//    (sloam_msgs/msg/ROSCylinder.msg; filled from a Cylinder in sloamNode.cpp:140-146).
+//    (sloam_msgs/msg/ROSCylinder.msg; filled from a Cylinder in sloamNode.cpp:140-146), of
+//    sloam_msgs/ROSGround and of sloam_msgs/ROSObservation (the message SLOAMNode advertises,
+//    sloamNode.cpp:45) with the std_msgs / geometry_msgs / sensor_msgs messages they embed.
 //
 // Header-only, host-only; uses the stand-in types of sloam_host.h.
 #ifndef SLOAM_B200_FORMATS_H
@@ -277,6 +279,164 @@ inline ROSCylinder ros_from_cylinder(const sloam_cylinder &m, int64_t id, const 
   c.radii = radii;
   c.id = id;
   return c;
+}
+
+// ------------------------------------- ROS1 wire: ROSGround, ROSObservation ----
+// sloam_msgs/msg/ROSGround.msg and ROSObservation.msg (the message SLOAMNode advertises on
+// "observation", sloamNode.cpp:45,132) with the standard messages they embed: std_msgs/Header,
+// geometry_msgs/PoseStamped, sensor_msgs/PointCloud2.  ROS1 serialisation: little-endian,
+// fields in declaration order, strings and variable arrays behind a uint32 length.
+struct ROSHeader {  // std_msgs/Header
+  uint32_t seq = 0, secs = 0, nsecs = 0;
+  std::string frame_id;
+};
+struct ROSPoseStamped {  // geometry_msgs/PoseStamped
+  ROSHeader header;
+  double position[3] = {0, 0, 0}, orientation[4] = {0, 0, 0, 1};  // x y z w
+};
+struct ROSPointField {  // sensor_msgs/PointField
+  std::string name;
+  uint32_t offset = 0;
+  uint8_t datatype = 7;  // FLOAT32
+  uint32_t count = 1;
+};
+struct ROSPointCloud2 {  // sensor_msgs/PointCloud2
+  ROSHeader header;
+  uint32_t height = 1, width = 0;
+  std::vector<ROSPointField> fields;
+  uint8_t is_bigendian = 0;
+  uint32_t point_step = 0, row_step = 0;
+  std::string data;
+  uint8_t is_dense = 0;
+};
+struct ROSGround {  // float32[4] coefs, PointCloud2 features, int64 id
+  float coefs[4] = {0, 0, 0, 0};
+  ROSPointCloud2 features;
+  int64_t id = 0;
+};
+struct ROSObservation {
+  ROSHeader header;
+  ROSPoseStamped pose, initialGuess;
+  ROSPointCloud2 pc;
+  std::vector<ROSCylinder> treeModels;
+  ROSGround ground;
+  std::vector<int32_t> matches;
+  uint8_t success = 0;
+};
+
+inline void put_str(std::string &o, const std::string &v) { put(o, (uint32_t)v.size()); o.append(v); }
+inline std::string get_str(const std::string &s, size_t &pos) {
+  const uint32_t n = get<uint32_t>(s, pos);
+  if (pos + n > s.size()) throw std::runtime_error("ros: truncated message");
+  std::string v = s.substr(pos, n);
+  pos += n;
+  return v;
+}
+inline void ros_encode(std::string &o, const ROSHeader &h) { put(o, h.seq); put(o, h.secs); put(o, h.nsecs); put_str(o, h.frame_id); }
+inline void ros_decode(const std::string &s, size_t &pos, ROSHeader &h) {
+  h.seq = get<uint32_t>(s, pos); h.secs = get<uint32_t>(s, pos); h.nsecs = get<uint32_t>(s, pos); h.frame_id = get_str(s, pos);
+}
+inline void ros_encode(std::string &o, const ROSPoseStamped &p) {
+  ros_encode(o, p.header);
+  for (double v : p.position) put(o, v);
+  for (double v : p.orientation) put(o, v);
+}
+inline void ros_decode(const std::string &s, size_t &pos, ROSPoseStamped &p) {
+  ros_decode(s, pos, p.header);
+  for (double &v : p.position) v = get<double>(s, pos);
+  for (double &v : p.orientation) v = get<double>(s, pos);
+}
+inline void ros_encode(std::string &o, const ROSPointCloud2 &c) {
+  ros_encode(o, c.header);
+  put(o, c.height); put(o, c.width);
+  put(o, (uint32_t)c.fields.size());
+  for (const ROSPointField &f : c.fields) { put_str(o, f.name); put(o, f.offset); put(o, f.datatype); put(o, f.count); }
+  put(o, c.is_bigendian); put(o, c.point_step); put(o, c.row_step);
+  put_str(o, c.data);
+  put(o, c.is_dense);
+}
+inline void ros_decode(const std::string &s, size_t &pos, ROSPointCloud2 &c) {
+  ros_decode(s, pos, c.header);
+  c.height = get<uint32_t>(s, pos); c.width = get<uint32_t>(s, pos);
+  c.fields.resize(get<uint32_t>(s, pos));
+  for (ROSPointField &f : c.fields) { f.name = get_str(s, pos); f.offset = get<uint32_t>(s, pos); f.datatype = get<uint8_t>(s, pos); f.count = get<uint32_t>(s, pos); }
+  c.is_bigendian = get<uint8_t>(s, pos); c.point_step = get<uint32_t>(s, pos); c.row_step = get<uint32_t>(s, pos);
+  c.data = get_str(s, pos);
+  c.is_dense = get<uint8_t>(s, pos);
+}
+inline void ros_encode(std::string &o, const ROSGround &g) {
+  for (float v : g.coefs) put(o, v);
+  ros_encode(o, g.features);
+  put(o, g.id);
+}
+inline void ros_decode(const std::string &s, size_t &pos, ROSGround &g) {
+  for (float &v : g.coefs) v = get<float>(s, pos);
+  ros_decode(s, pos, g.features);
+  g.id = get<int64_t>(s, pos);
+}
+inline std::string ros_encode(const ROSObservation &m) {
+  std::string o;
+  ros_encode(o, m.header);
+  ros_encode(o, m.pose);
+  ros_encode(o, m.initialGuess);
+  ros_encode(o, m.pc);
+  put(o, (uint32_t)m.treeModels.size());
+  for (const ROSCylinder &c : m.treeModels) ros_encode(o, c);
+  ros_encode(o, m.ground);
+  put(o, (uint32_t)m.matches.size());
+  for (int32_t v : m.matches) put(o, v);
+  put(o, m.success);
+  return o;
+}
+inline ROSObservation ros_decode_observation(const std::string &s) {
+  ROSObservation m;
+  size_t pos = 0;
+  ros_decode(s, pos, m.header);
+  ros_decode(s, pos, m.pose);
+  ros_decode(s, pos, m.initialGuess);
+  ros_decode(s, pos, m.pc);
+  m.treeModels.resize(get<uint32_t>(s, pos));
+  for (ROSCylinder &c : m.treeModels) c = ros_decode_cylinder(s, pos);
+  ros_decode(s, pos, m.ground);
+  m.matches.resize(get<uint32_t>(s, pos));
+  for (int32_t &v : m.matches) v = get<int32_t>(s, pos);
+  m.success = get<uint8_t>(s, pos);
+  if (pos != s.size()) throw std::runtime_error("ros: trailing bytes");
+  return m;
+}
+// pcl::toROSMsg of a PointXYZI cloud as the node publishes its feature clouds: fields x, y, z,
+// intensity (FLOAT32) at offsets 0, 4, 8, 16 of PCL's 32-byte point
+inline ROSPointCloud2 ros_cloud_xyzi(const std::vector<sloam_point> &pts, const std::string &frame) {
+  ROSPointCloud2 c;
+  c.header.frame_id = frame;
+  c.width = (uint32_t)pts.size();
+  const char *names[4] = {"x", "y", "z", "intensity"};
+  const uint32_t offs[4] = {0, 4, 8, 16};
+  for (int i = 0; i < 4; ++i) { ROSPointField f; f.name = names[i]; f.offset = offs[i]; c.fields.push_back(f); }
+  c.point_step = 32;
+  c.row_step = 32 * c.width;
+  c.data.assign((size_t)32 * pts.size(), '\0');
+  for (size_t i = 0; i < pts.size(); ++i) {
+    const float one = 1.0f;
+    std::memcpy(&c.data[32 * i], &pts[i].x, 12);
+    std::memcpy(&c.data[32 * i + 12], &one, 4);          // PCL's padding lane holds 1.0f
+    std::memcpy(&c.data[32 * i + 16], &pts[i].intensity, 4);
+  }
+  return c;
+}
+// SloamOutput + the accepted ground plane of a keyframe -> the observation message
+inline ROSObservation ros_observation(const sloam_kf_result &res, const sloam_cylinder *tm, const int32_t *tm_id,
+                                      const int32_t *matches, const sloam_pose &guess, const sloam_plane *ground,
+                                      const std::string &frame) {
+  ROSObservation m;
+  m.header.frame_id = m.pose.header.frame_id = m.initialGuess.header.frame_id = frame;
+  for (int i = 0; i < 3; ++i) { m.pose.position[i] = res.T_Map_Curr.t[i]; m.initialGuess.position[i] = guess.t[i]; }
+  for (int i = 0; i < 4; ++i) { m.pose.orientation[i] = res.T_Map_Curr.q[i]; m.initialGuess.orientation[i] = guess.q[i]; }
+  for (int i = 0; i < res.n_landmarks; ++i) { m.treeModels.push_back(ros_from_cylinder(tm[i], tm_id[i])); m.matches.push_back(matches[i]); }
+  if (ground) for (int i = 0; i < 4; ++i) m.ground.coefs[i] = (float)ground->plane[i];
+  m.pc.header.frame_id = m.ground.features.header.frame_id = frame;
+  m.success = res.success ? 1 : 0;
+  return m;
 }
 
 }  // namespace sloam_formats

@@ -59,6 +59,37 @@ int main(int argc, char **argv) {
   bool threw = false;
   try { ros_decode_cylinders(wire.substr(0, wire.size() - 3)); } catch (const std::runtime_error &) { threw = true; }
   CHECK(threw);
+  {  // ROSGround / ROSObservation: known bytes of the fixed part, round trip of the whole
+    ROSHeader h; h.seq = 7; h.secs = 1630612694u; h.nsecs = 758621199u; h.frame_id = "map";
+    std::string hb; ros_encode(hb, h);
+    const unsigned char want[] = {7, 0, 0, 0, 0xd6, 0x2c, 0x31, 0x61, 0x0f, 0xa4, 0x37, 0x2d, 3, 0, 0, 0, 'm', 'a', 'p'};
+    CHECK(hb.size() == sizeof want && std::memcmp(hb.data(), want, sizeof want) == 0);
+    sloam_kf_result res{};
+    res.success = 1; res.n_landmarks = 2;
+    res.T_Map_Curr.t[0] = 0.625; res.T_Map_Curr.q[3] = 1.0;
+    sloam_cylinder tm[2] = {};
+    tm[0].root[0] = 1.5; tm[0].ray[2] = 1.0; tm[0].radius = 0.2; tm[1].root[1] = -2.0; tm[1].ray[2] = 1.0; tm[1].radius = 0.1;
+    const int32_t ids[2] = {4, 9}, matches[2] = {3, -1};
+    sloam_pose guess{}; guess.q[3] = 1.0; guess.t[0] = 0.6;
+    sloam_plane gp{}; gp.plane[2] = 1.0; gp.plane[3] = 3.4;
+    ROSObservation m = ros_observation(res, tm, ids, matches, guess, &gp, "map");
+    std::vector<sloam_point> feat = {{1.f, 2.f, 3.f, 4.f}, {5.f, 6.f, 7.f, 8.f}};
+    m.ground.features = ros_cloud_xyzi(feat, "map");
+    m.ground.id = 11;
+    const std::string wire = ros_encode(m);
+    const ROSObservation b = ros_decode_observation(wire);
+    CHECK(ros_encode(b) == wire);
+    CHECK(b.treeModels.size() == 2 && b.treeModels[1].id == 9 && b.matches.size() == 2 && b.matches[1] == -1 && b.success == 1);
+    CHECK(b.pose.position[0] == 0.625 && b.initialGuess.position[0] == 0.6 && b.ground.coefs[3] == 3.4f && b.ground.id == 11);
+    CHECK(b.ground.features.width == 2 && b.ground.features.point_step == 32 && b.ground.features.data.size() == 64 &&
+          b.ground.features.fields.size() == 4 && b.ground.features.fields[3].name == "intensity" && b.ground.features.fields[3].offset == 16);
+    float back = 0.f;
+    std::memcpy(&back, &b.ground.features.data[32 + 16], 4);
+    CHECK(back == 8.f);
+    bool threw2 = false;
+    try { ros_decode_observation(wire.substr(0, wire.size() - 1)); } catch (const std::runtime_error &) { threw2 = true; }
+    CHECK(threw2);
+  }
   // the reference's own fixtures, byte for byte
   if (argc > 1) {
     const std::string dir = argv[1];
