@@ -48,6 +48,7 @@ struct FitRec {
   double W[9], U[9];
   float c[3];
   int32_t n_cell, n_kept, valid;
+  int32_t off_all;  // first member slot of the cell (select kernel -> fit kernel)
 };
 
 // Scratch owned by the context, sized for max_keyframes.

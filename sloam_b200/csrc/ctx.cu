@@ -414,7 +414,7 @@ int64_t sloam_b200_workspace_bytes(const sloam_ctx *c) { return c ? (int64_t)c->
 
 static const char *const kProfNames[P_COUNT] = {
     "project_split_kernel", "range_finalize_kernel", "ground_offsets+ground_scatter_kernel", "ground_cells_kernel<0>",
-    "ground_cells_kernel<1> (tie replay)", "plane_finish+planes_compact", "cc_rows_kernel", "cc_label_kernel",
+    "ground_cells_kernel<1> (tie replay)", "ground_fit+plane_finish+planes_compact", "cc_rows_kernel", "cc_label_kernel",
     "vertex_kernel", "vertex_replay+vertex_wide (tie replay)", "tree_compact_kernel", "cylinder_kernel+compact",
     "assoc_kernel (sensor frame)", "build_matches_kernel", "lm_kernel", "finish_kernel",
     "assoc_kernel+matches (map frame)"};

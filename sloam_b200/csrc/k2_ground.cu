@@ -35,10 +35,14 @@ namespace sb {
 #define SLOAM_K2_THREADS 32  // one warp per cell: every barrier is warp-local, 32 cells resident per SM (64 -> 32 threads: 381 -> 335 us)
 #endif
 constexpr int kGThreads = SLOAM_K2_THREADS;
+#ifndef SLOAM_K2_CELLS_PER_CTA
+#define SLOAM_K2_CELLS_PER_CTA 2
+#endif
+constexpr int kCellsPerCta = SLOAM_K2_CELLS_PER_CTA;
 #ifndef SLOAM_K2_SELCAP
 #define SLOAM_K2_SELCAP 256
 #define SLOAM_K2_QRCAP 64
-#define SLOAM_K2_MINCTAS 32  // measured (1000 VLP-16 kf): 1024/192/1 -> 483 us, 256/96/20 -> 387, 256/64/20 -> 377, 32/64/28 -> 359
+#define SLOAM_K2_MINCTAS 24  // measured (1000 VLP-16 kf): 1024/192/1 -> 483 us, 256/96/20 -> 387, 256/64/20 -> 377, 32/64/28 -> 359
 #endif
 constexpr int kSelCap = SLOAM_K2_SELCAP;   // members kept in shared memory (else global scratch)
 constexpr int kQrCap = SLOAM_K2_QRCAP;     // retained points whose fit lives in shared memory
@@ -291,7 +295,7 @@ ground_scatter_kernel(const DevParams *__restrict__ dp, int K, const uint2 *__re
 // a cell's CTA is one warp: its barriers are warp barriers
 #define CELL_SYNC() do { if (kGThreads == 32) __syncwarp(); else __syncthreads(); } while (0)
 template <bool REPLAY>
-__global__ void __launch_bounds__(kGThreads, SLOAM_K2_MINCTAS)
+__global__ void __launch_bounds__(REPLAY ? 32 : 32 * kCellsPerCta, REPLAY ? 16 : SLOAM_K2_MINCTAS)
 ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ ground,
                     const int32_t *__restrict__ ground_count, int stride,
                     SelKey *__restrict__ members, const int32_t *__restrict__ cell_count,
@@ -304,24 +308,30 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
   // the replay instance sorts whole cells with one thread: give it room for most cells in
   // shared memory (a global-memory sort is ~10x slower per access)
   constexpr int kCap = REPLAY ? 5120 : 1;
+  // the selecting instance packs kCellsPerCta independent cells (warps) into a CTA: the SM holds
+  // at most 32 CTAs, and with one-warp CTAs that would cap it at 32 of its 64 warp slots
+  constexpr int kW = REPLAY ? 1 : kCellsPerCta;
+  const int wslot = REPLAY ? 0 : (int)(threadIdx.x >> 5);
+  const int tid = threadIdx.x & 31;
   __shared__ SelKey s_list[kCap];
   // the selecting instance keeps only what its passes re-read in shared memory: the z keys of
   // the cell (4 radix passes) and the r kept records (rank sort); the member records
   // themselves are streamed from global memory once, by the compaction
   constexpr int kZCap = REPLAY ? 1 : 2 * kSelCap, kKeepCap = REPLAY ? 1 : 128;
-  __shared__ uint32_t s_z[kZCap];
-  __shared__ SelKey s_keep[kKeepCap];
-  __shared__ double s_qr[3 * kQrCap];
-  __shared__ float s_pts[3 * kQrCap];
-  __shared__ int s_hist[256];
-  __shared__ int s_warp[kGThreads / 32];
-  __shared__ int s_misc[8];
-  __shared__ double s_red[4];
+  __shared__ uint32_t s_z_[kW][kZCap];
+  __shared__ SelKey s_keep_[kW][kKeepCap];
+  __shared__ SelKey s_tmp_[kW][kKeepCap];  // rank-sort target
+  __shared__ int s_hist_[kW][256];
+  __shared__ int s_warp_[kW][1];
+  __shared__ int s_misc_[kW][8];
+  uint32_t *s_z = s_z_[wslot];
+  SelKey *s_keep = s_keep_[wslot], *s_tmp = s_tmp_[wslot];
+  int *s_hist = s_hist_[wslot], *s_warp = s_warp_[wslot], *s_misc = s_misc_[wslot];
 
   const int B = dp->B, Fg = dp->p.numGroundFeatures;
   auto body = [&](const int k, const int cell) {
   const int n_c = cell_count[(size_t)k * kMaxCells + cell];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = tid, warp = 0;
   const sloam_point *gk = ground + (size_t)k * stride;
   sloam_cell_plane *out = cells + (size_t)k * B + cell;
   sloam_point *fout = cell_features + ((size_t)k * B + cell) * Fg;
@@ -357,7 +367,7 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
     // Plane::Plane: features.size() < numGroundFeatures -> invalid (plane.cpp:7-10);
     // n < 3 is out-of-range in the reference's ThinU access: declared invalid.
     // (kept point lists of such cells are still emitted below when requested.)
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
       sloam_cell_plane c;
       for (int i = 0; i < 4; ++i) c.model.plane[i] = 0.0;
       for (int i = 0; i < 3; ++i) c.model.centroid[i] = 0.0;
@@ -365,7 +375,7 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
       *out = c;
       fit[(size_t)k * B + cell].valid = 0;
     }
-    for (int f = threadIdx.x; f < Fg; f += kGThreads) fout[f] = sloam_point{0.f, 0.f, 0.f, 0.f};
+    for (int f = tid; f < Fg; f += kGThreads) fout[f] = sloam_point{0.f, 0.f, 0.f, 0.f};
     if (kept_points == nullptr || n_c == 0) return;
   }
 
@@ -375,9 +385,9 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
   const bool zc = !REPLAY && n_c <= kZCap;  // z keys cached in shared memory
   if (REPLAY && n_c <= kCap) {
     list = s_list;
-    for (int i = threadIdx.x; i < n_c; i += kGThreads) s_list[i] = src[i];
+    for (int i = tid; i < n_c; i += kGThreads) s_list[i] = src[i];
   } else if (zc) {
-    for (int i = threadIdx.x; i < n_c; i += kGThreads) s_z[i] = src[i].z;
+    for (int i = tid; i < n_c; i += kGThreads) s_z[i] = src[i].z;
   }
   CELL_SYNC();
 
@@ -393,13 +403,13 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
     // std::sort(cell, p1.z < p2.z) replayed on the whole cell, then the first r are kept
     // (only the first r positions of the result are needed: sort_prefix; the z field is turned
     // back into the float's bits first so that the comparator is a plain float compare)
-    for (int i = threadIdx.x; i < n_c; i += kGThreads) {
+    for (int i = tid; i < n_c; i += kGThreads) {
       SelKey e = list[i];
       e.z = __float_as_uint(key_to_float(e.z));
       keep[i] = e;
     }
     CELL_SYNC();
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
       StdSortT<SelKey, MemberZLess> srt{keep, MemberZLess{}};
       srt.sort_prefix(n_c, r);
     }
@@ -409,9 +419,9 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
     uint32_t prefix = 0, pmask = 0;
     int want = r - 1;  // 0-based rank among members matching the prefix
     for (int shift = 24; shift >= 0; shift -= 8) {
-      for (int b = threadIdx.x; b < 256; b += kGThreads) s_hist[b] = 0;
+      for (int b = tid; b < 256; b += kGThreads) s_hist[b] = 0;
       CELL_SYNC();
-      for (int i = threadIdx.x; i < n_c; i += kGThreads) {
+      for (int i = tid; i < n_c; i += kGThreads) {
         const uint32_t z = zc ? s_z[i] : list[i].z;
         if ((z & pmask) == prefix) atomicAdd(&s_hist[(z >> shift) & 0xFF], 1);
       }
@@ -444,7 +454,7 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
     // order-preserving compaction (the list is in j order, so ties come lowest j first)
     int kept = 0, ties_seen = 0;
     for (int base = 0; base < n_c; base += kGThreads) {
-      const int i = base + threadIdx.x;
+      const int i = base + tid;
       SelKey e = {0, 0};
       bool lt = false, eq = false;
       if (i < n_c) { e = list[i]; lt = e.z < pivot; eq = e.z == pivot; }
@@ -470,15 +480,13 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
     }
     // ---- sort the r kept keys: rank sort in place via shared ranks ----
     // (r is a few hundred; O(r^2 / threads))
-    SelKey *tmp = (r * (int)sizeof(SelKey) <= (int)sizeof(s_qr))
-                      ? reinterpret_cast<SelKey *>(s_qr)
-                      : reinterpret_cast<SelKey *>(qscratch + ((size_t)k * stride + off_all) * 3);
+    SelKey *tmp = r <= kKeepCap ? s_tmp : reinterpret_cast<SelKey *>(qscratch + ((size_t)k * stride + off_all) * 3);
     // Exact ties among the kept points or across the cut (more members equal to the pivot than
     // were taken): with more than 16 points in the cell the reference's result depends on
     // libstdc++'s unstable sort -> the cell is listed for the replay instance (whose outputs
     // replace everything this instance writes for the cell).  Detected inside the rank loop.
     bool tie = ties_seen > tie_quota;
-    for (int i = threadIdx.x; i < r; i += kGThreads) {
+    for (int i = tid; i < r; i += kGThreads) {
       const SelKey e = keep[i];
       int rank = 0, same = 0;
       for (int j = 0; j < r; ++j) {
@@ -491,17 +499,68 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
     int any_tie;
     if (kGThreads == 32) { any_tie = __any_sync(kFull, tie); __syncwarp(); }
     else any_tie = __syncthreads_or(tie ? 1 : 0);
-    for (int i = threadIdx.x; i < r; i += kGThreads) keep[i] = tmp[i];
+    for (int i = tid; i < r; i += kGThreads) keep[i] = tmp[i];
     CELL_SYNC();
-    if (any_tie && n_c > 16 && tied != nullptr && threadIdx.x == 0) tied[atomicAdd(n_tied, 1)] = (k << 8) | cell;
+    if (any_tie && n_c > 16 && tied != nullptr && tid == 0) tied[atomicAdd(n_tied, 1)] = (k << 8) | cell;
   }
 
   if (kept_points) {
     sloam_point *kp = kept_points + (size_t)k * stride + off_kept;
-    for (int i = threadIdx.x; i < r; i += kGThreads) st_point(kp + i, ld_point(gk + keep[i].j));
+    for (int i = tid; i < r; i += kGThreads) st_point(kp + i, ld_point(gk + keep[i].j));
   }
   if (n_c == 0 || r < Fg || r < 3) return;
+  // ---- hand the r retained records, in order, to ground_fit_kernel (members2, the cell's region)
+  {
+    SelKey *kout = members2 + (size_t)k * stride + off_all;
+    if (keep != kout)
+      for (int i = tid; i < r; i += kGThreads) kout[i] = keep[i];
+    if (tid == 0) {
+      FitRec *rec = fit + (size_t)k * B + cell;
+      rec->n_cell = n_c; rec->n_kept = r; rec->off_all = off_all; rec->valid = 1;
+    }
+  }
+  };  // body
+  if (!REPLAY) {
+    const int cell = (int)blockIdx.x * kCellsPerCta + wslot;
+    if (cell < B) body((int)blockIdx.y, cell);
+  } else {
+    const int total = *n_tied;
+    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+      body(tied[item] >> 8, tied[item] & 0xFF);
+      CELL_SYNC();
+    }
+  }
+}
 
+#undef CELL_SYNC
+
+// ---- plane fit of every cell with enough retained points: one warp per (keyframe, cell) ----
+// Reads the r retained records of the cell (members2, written by the select / replay
+// instances of ground_cells_kernel), gathers the points, and runs Plane::computeModel up to the
+// QR preconditioner; plane_finish_kernel finishes the 3 x 3 SVD.  Kept apart from the selection
+// so that the selection runs without the fit's registers and shared memory (twice the warps
+// per SM), and so that cells redone by the replay instance are fitted here like all others.
+__global__ void __launch_bounds__(32, 24)
+ground_fit_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ ground, int stride,
+                  const SelKey *__restrict__ members2, double *__restrict__ qscratch, float *__restrict__ pscratch,
+                  FitRec *__restrict__ fit, sloam_point *__restrict__ cell_features) {
+  __shared__ double s_qr[3 * kQrCap];
+  __shared__ float s_pts[3 * kQrCap];
+  __shared__ double s_red[4];
+  const int B = dp->B, Fg = dp->p.numGroundFeatures;
+  const int k = blockIdx.y, cell = blockIdx.x;
+  const int lane = threadIdx.x;
+  FitRec *rec = fit + (size_t)k * B + cell;
+  if (!rec->valid) return;
+  const int n_c = rec->n_cell, r = rec->n_kept, off_all = rec->off_all;
+  const sloam_point *gk = ground + (size_t)k * stride;
+  const SelKey *keep = members2 + (size_t)k * stride + off_all;
+  sloam_point *fout = cell_features + ((size_t)k * B + cell) * Fg;
+  (void)n_c;
+#define CELL_SYNC() __syncwarp()
+  constexpr int kGThreads = 32;
+  const int warp = 0;
+  double *s_hist = s_red;  // scratch of the scale reduction (one warp: one entry)
   // ---- Plane::computeModel on the r retained points, in order ----
   const int n = r;
   // stage the retained points (x | y | z planes) so the serial float sum reads shared memory
@@ -530,11 +589,11 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
   // scale = max |coeff| (JacobiSVD::compute)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(kFull, lmax, o));
-  if (lane == 0) reinterpret_cast<double *>(s_hist)[warp] = lmax;
+  if (lane == 0) s_hist[3] = lmax;
   CELL_SYNC();
   if (threadIdx.x == 0) {
     double m = 0.0;
-    for (int w = 0; w < kGThreads / 32; ++w) m = fmax(m, reinterpret_cast<double *>(s_hist)[w]);
+    for (int w = 0; w < kGThreads / 32; ++w) m = fmax(m, s_hist[3]);
     s_red[3] = (m == 0.0) ? 1.0 : m;
   }
   CELL_SYNC();
@@ -628,26 +687,12 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
   }
   // hand the 3x3 problem to plane_finish_kernel (one thread per cell: the Jacobi sweeps and
   // the acceptance test are scalar fp64 code, 32 cells per warp instead of one)
-  FitRec *rec = fit + (size_t)k * B + cell;
   if (lane < 9) { rec->W[lane] = Wm[lane]; rec->U[lane] = U[lane]; }
-  if (lane == 0) {
-    rec->c[0] = cxf; rec->c[1] = cyf; rec->c[2] = czf;
-    rec->n_cell = n_c; rec->n_kept = r; rec->valid = 1;
-  }
+  if (lane == 0) { rec->c[0] = cxf; rec->c[1] = cyf; rec->c[2] = czf; }
   for (int f = lane; f < Fg; f += 32) st_point(fout + f, ld_point(gk + keep[f].j));  // features.resize(numGroundFeatures)
-  };  // body
-  if (!REPLAY) {
-    body((int)blockIdx.y, (int)blockIdx.x);
-  } else {
-    const int total = *n_tied;
-    for (int item = blockIdx.x; item < total; item += gridDim.x) {
-      body(tied[item] >> 8, tied[item] & 0xFF);
-      CELL_SYNC();
-    }
-  }
+#undef CELL_SYNC
 }
 
-#undef CELL_SYNC
 // Steps 2-4 of JacobiSVD on the QR-preconditioned 3x3, plane assembly (plane.cpp:115-127)
 // and the acceptance test (sloam.cpp:401-409): one thread per (keyframe, cell).
 __global__ void plane_finish_kernel(const DevParams *__restrict__ dp, int K, const FitRec *__restrict__ fit,
@@ -734,7 +779,8 @@ int launch_ground_planes(sloam_ctx *c, int K, const sloam_point *ground, const i
   if (c->zero_valid & 8u) c->zero_valid &= ~8u;
   else SB_CUDA(c, cudaMemsetAsync(w.n_tied_cells, 0, sizeof(int32_t), c->stream));
   PROF_BEGIN(c, P_GROUND_CELLS);
-  ground_cells_kernel<false><<<grid, kGThreads, 0, c->stream>>>(
+  const dim3 sgrid((unsigned)((c->hp.B + kCellsPerCta - 1) / kCellsPerCta), (unsigned)K);
+  ground_cells_kernel<false><<<sgrid, 32 * kCellsPerCta, 0, c->stream>>>(
       c->dp, ground, ground_count, stride, members, w.cell_count, pose_est,
       w.qscratch, w.pscratch, w.fit_rec, cells, cell_features, kept_points, kept_offsets,
       reinterpret_cast<SelKey *>(w.gscratch2), w.tied_cells, w.n_tied_cells);
@@ -749,6 +795,9 @@ int launch_ground_planes(sloam_ctx *c, int K, const sloam_point *ground, const i
   PROF_END(c, P_GROUND_REPLAY);
   SB_LAUNCH_CHECK(c);
   PROF_BEGIN(c, P_PLANE_FIT);
+  ground_fit_kernel<<<grid, 32, 0, c->stream>>>(c->dp, ground, stride, reinterpret_cast<const SelKey *>(w.gscratch2), w.qscratch,
+                                                w.pscratch, w.fit_rec, cell_features);
+  SB_LAUNCH_CHECK(c);
   plane_finish_kernel<<<(K * c->hp.B + 127) / 128, 128, 0, c->stream>>>(c->dp, K, w.fit_rec, pose_est, cells);
   SB_LAUNCH_CHECK(c);
   const int rc_pc = launch_planes_compact(c, K, cells);
