@@ -166,6 +166,36 @@ def test_ground_planes_reference_fixture_and_ties(capi, oracle):
     assert check_ground(capi, oracle, p, [g0, ties], poses) >= 20
 
 
+def test_ground_tie_replay_stress(capi, oracle):
+    """Exact z ties at every density and cell size (SURVEY B-3): the warp-cooperative replay of
+    libstdc++'s std::sort (k2_ground.cu: warp_sort_prefix) against the oracle's real std::sort --
+    retained sets in order, centroids bit-equal.  Includes cells that are ONE z value (quicksort's
+    worst case: the depth limit and the heapsort fallback), cells larger than the replay's
+    shared-memory list, and different retain fractions."""
+    rng = np.random.default_rng(77)
+    H, W = 64, 1024
+    clouds = []
+    for n_pts, quant in [(3000, 0.05), (9000, 0.01), (20000, 0.002), (40000, 0.1), (60000, 0.0005), (5000, 1000.0)]:
+        ang = rng.uniform(-np.pi, np.pi, n_pts)
+        rad = rng.uniform(5.5, 24.0, n_pts)
+        g = np.zeros(n_pts, abi.POINT)
+        g["x"], g["y"] = (rad * np.cos(ang)).astype(np.float32), (rad * np.sin(ang)).astype(np.float32)
+        z = -3.4 + 0.02 * rad * np.cos(ang) + rng.normal(0, 0.03, n_pts)
+        g["z"] = (np.round(z / quant) * quant).astype(np.float32)     # quant = 1000: every z is 0
+        g["intensity"] = rng.uniform(0, 1, n_pts).astype(np.float32)
+        clouds.append(g)
+    # one cell of 12 000 points (more than the replay keeps in shared memory) with heavy ties
+    big = clouds[3][:12000].copy()
+    big["x"], big["y"] = rng.uniform(8, 9, 12000).astype(np.float32), rng.uniform(0.5, 1.0, 12000).astype(np.float32)
+    clouds.append(big)
+    poses = np.zeros(len(clouds), abi.POSE)
+    poses["q"][:, 3] = 1
+    poses["t"][:, 2] = 5.0
+    for retain, fg in [(0.05, 5), (0.3, 12)]:
+        p = capi.default_params(img_h=H, img_w=W, groundRetainThresh=retain, numGroundFeatures=fg)
+        assert check_ground(capi, oracle, p, clouds, poses) >= 30
+
+
 def test_ground_small_cells_and_empty(capi, oracle):
     """Cells below 1/retain points keep input order; empty cloud; fewer points than features."""
     rng = np.random.default_rng(5)
