@@ -103,42 +103,81 @@ __global__ void tree_fill_kernel(const DevParams *__restrict__ dp, const uint32_
 }
 
 // ---- 1. bit planes: valid / run start / connected upwards -------------------
-// A warp takes 32 consecutive words of the batch's tree bit mask with one coalesced load and
-// then handles the non-zero ones, 32 lanes = the 32 pixels of a word (a forest scan is ~80 %
-// non-tree pixels: they cost one bit).  planes[k][word] = (valid, start, up, 0), written only
-// for non-zero words (cc_label_kernel looks at the tree bits first).
+// A warp takes 32 consecutive words of the batch's tree bit mask (1024 pixels) with one
+// coalesced load and then works on the SET bits only, 32 tree pixels per step, one per lane:
+// the j-th set bit of the chunk is found through the prefix popcounts of the words (binary
+// search with shuffles, then the bit inside the word).  A forest scan has 10-20 % tree pixels
+// scattered over most words, so walking words with one lane per pixel left two thirds of the
+// lanes idle.  The three result bits of a pixel are OR-ed into per-word accumulators in shared
+// memory (the pixels of a word are neighbours in the lane order: one warp-reduce per word) and
+// written as planes[k][word] = (valid, start, up, 0) for the non-zero words at the end.
 #ifndef SLOAM_CCROWS_MIN
 #define SLOAM_CCROWS_MIN 8
 #endif
-__global__ void __launch_bounds__(256, SLOAM_CCROWS_MIN)
+constexpr int kRowsWarps = 8;
+// position of the (n + 1)-th set bit of a non-zero word (n < popc(word))
+__device__ __forceinline__ int nth_set_bit(uint32_t word, int n) {
+  int pos = 0;
+#pragma unroll
+  for (int width = 16; width >= 1; width >>= 1) {
+    const int c = __popc((word >> pos) & ((1u << width) - 1u));
+    if (n >= c) { n -= c; pos += width; }
+  }
+  return pos;
+}
+__global__ void __launch_bounds__(kRowsWarps * 32, SLOAM_CCROWS_MIN)
 cc_rows_kernel(const DevParams *__restrict__ dp, int K, const sloam_point *__restrict__ tree,
                const uint32_t *__restrict__ bits, uint4 *__restrict__ planes) {
+  __shared__ uint32_t s_acc[kRowsWarps][3][32];
   const int N = dp->N, W = dp->p.img_w, Nw = (N + 31) >> 5;
   const float cut = dp->cluster_sq_cut;  // dist < cluster_dist_thresh  <=>  squared dist < cut
   const unsigned magic_w = dp->magic_w;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t(*acc)[32] = s_acc[warp];
   const long long total_words = (long long)K * Nw;
-  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long warp0 = (long long)blockIdx.x * kRowsWarps + warp;
+  const long long nwarps = (long long)gridDim.x * kRowsWarps;
   for (long long base = warp0 * 32; base < total_words; base += nwarps * 32) {
-    const uint32_t my_word = base + lane < total_words ? bits[base + lane] : 0u;
-    unsigned nz = __ballot_sync(kFull, my_word != 0u);
-    if (nz == 0u) continue;
-    const int k0 = (int)(base / Nw);
-    const int w0 = (int)(base - (long long)k0 * Nw);
-    while (nz) {
-      const int src = __ffs(nz) - 1;
-      nz &= nz - 1;
-      const uint32_t word = __shfl_sync(kFull, my_word, src);
-      int k = k0, wi = w0 + src;
-      while (wi >= Nw) { wi -= Nw; ++k; }  // the chunk may run into the next keyframe(s)
+    const long long gw = base + lane;
+    const uint32_t my_word = gw < total_words ? bits[gw] : 0u;
+    if (__ballot_sync(kFull, my_word != 0u) == 0u) continue;
+    // keyframe / word index of this lane's word, prefix popcounts of the chunk
+    const int my_k = (int)(gw / Nw), my_wi = (int)(gw - (long long)my_k * Nw);
+    const int cnt = __popc(my_word);
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(kFull, inc, o);
+      if (lane >= o) inc += t;
+    }
+    const int pre = inc - cnt;
+    const int total = __shfl_sync(kFull, inc, 31);
+    acc[0][lane] = 0u; acc[1][lane] = 0u; acc[2][lane] = 0u;
+    __syncwarp();
+    // point of the last pixel of the previous step (left neighbour of this step's first pixel)
+    float carry_x = 0.f, carry_y = 0.f, carry_z = 0.f;
+    int carry_pix = -2, carry_k = -1;
+    for (int j0 = 0; j0 < total; j0 += 32) {
+      const int j = j0 + lane;
+      const bool act = j < total;
+      // word holding the j-th set bit: the last word whose prefix is <= j
+      int w = 0;
+#pragma unroll
+      for (int step = 16; step >= 1; step >>= 1) {
+        const int cand = w + step;
+        const int pc = __shfl_sync(kFull, pre, cand & 31);
+        if (cand < 32 && pc <= j) w = cand;
+      }
+      const uint32_t word = __shfl_sync(kFull, my_word, w);
+      const int pre_w = __shfl_sync(kFull, pre, w);
+      const int k = __shfl_sync(kFull, my_k, w), wi = __shfl_sync(kFull, my_wi, w);
+      const int b = act ? nth_set_bit(word, j - pre_w) : 0;
+      const int i = wi * 32 + b;
+      const bool bit = act && i < N;
       const uint32_t *bk = bits + (size_t)k * Nw;
-      const int i = wi * 32 + lane;
       const size_t g = (size_t)k * N + i;
       const int row = fast_div_w(i, magic_w), col = i - row * W;
-      const bool bit = (word >> lane) & 1u;  // clear for the padding lanes of the last word
-      // own point and the point above are loaded together (guarded by their bits only), the
-      // left neighbour comes from the lane below
+      // own point and the point above are loaded together (guarded by their bits only)
       const int u = i - W;
       const bool bit_u = bit && row > 0 && ((bk[u >> 5] >> (u & 31)) & 1u);
       sloam_point p{0.f, 0.f, 0.f, 0.f}, qu = p;
@@ -147,20 +186,31 @@ cc_rows_kernel(const DevParams *__restrict__ dp, int K, const sloam_point *__res
       // PCL skips a pixel iff !isfinite(x); EuclideanClusterComparator::compare is
       // dist < threshold in float (NaN compares false)
       const bool valid = bit && isfinite(p.x);
+      // left neighbour = the previous set bit when it is pixel i - 1 of the same keyframe
       float lx = __shfl_up_sync(kFull, p.x, 1), ly = __shfl_up_sync(kFull, p.y, 1), lz = __shfl_up_sync(kFull, p.z, 1);
-      bool bit_l = lane > 0 ? ((word >> (lane - 1)) & 1u) != 0u : false;
-      if (lane == 0 && bit && col > 0 && wi > 0 && (bk[wi - 1] >> 31)) {
+      int lpix = __shfl_up_sync(kFull, i, 1), lk = __shfl_up_sync(kFull, k, 1);
+      if (lane == 0) { lx = carry_x; ly = carry_y; lz = carry_z; lpix = carry_pix; lk = carry_k; }
+      bool bit_l = bit && col > 0 && lpix == i - 1 && lk == k;
+      if (bit && col > 0 && !bit_l && j == 0 && wi > 0 && b == 0 && (bk[wi - 1] >> 31)) {
+        // first set bit of the chunk: its left neighbour belongs to the previous chunk
         const sloam_point q = ld_point(tree + g - 1);
         lx = q.x; ly = q.y; lz = q.z;
         bit_l = true;
       }
-      const bool left_ok = valid && col > 0 && bit_l && sqnorm3f(p.x - lx, p.y - ly, p.z - lz) < cut;
+      const bool left_ok = valid && bit_l && sqnorm3f(p.x - lx, p.y - ly, p.z - lz) < cut;
       const bool up_ok = valid && bit_u && sqnorm3f(p.x - qu.x, p.y - qu.y, p.z - qu.z) < cut;
-      const unsigned vb = __ballot_sync(kFull, valid);
-      const unsigned sb_ = __ballot_sync(kFull, valid && !left_ok);
-      const unsigned ub = __ballot_sync(kFull, up_ok);
-      if (lane == 0) planes[(size_t)k * Nw + wi] = make_uint4(vb, sb_, ub, 0u);
+      // OR the three bits of the pixels of each word (contiguous lanes) into the accumulators
+      const unsigned grp = __match_any_sync(kFull, act ? w : 32 + lane);
+      const uint32_t vb = __reduce_or_sync(grp, valid ? (1u << b) : 0u);
+      const uint32_t sb_ = __reduce_or_sync(grp, (valid && !left_ok) ? (1u << b) : 0u);
+      const uint32_t ub = __reduce_or_sync(grp, up_ok ? (1u << b) : 0u);
+      if (act && lane == __ffs(grp) - 1) { acc[0][w] |= vb; acc[1][w] |= sb_; acc[2][w] |= ub; }
+      carry_x = __shfl_sync(kFull, p.x, 31); carry_y = __shfl_sync(kFull, p.y, 31); carry_z = __shfl_sync(kFull, p.z, 31);
+      carry_pix = __shfl_sync(kFull, bit ? i : -2, 31); carry_k = __shfl_sync(kFull, k, 31);
+      __syncwarp();
     }
+    if (my_word != 0u) planes[gw] = make_uint4(acc[0][lane], acc[1][lane], acc[2][lane], 0u);
+    __syncwarp();
   }
 }
 
@@ -1096,7 +1146,7 @@ static int run_cc(sloam_ctx *c, int K, const sloam_point *tree, bool bits_ready,
   }
   const unsigned rgrid = (unsigned)std::min<long long>((total_words + 255) / 256, (long long)c->sm_count * 8);
   PROF_BEGIN(c, P_CC_ROWS);
-  cc_rows_kernel<<<rgrid, 256, 0, c->stream>>>(c->dp, K, tree, w.tree_bits, reinterpret_cast<uint4 *>(w.cc_planes));
+  cc_rows_kernel<<<rgrid, kRowsWarps * 32, 0, c->stream>>>(c->dp, K, tree, w.tree_bits, reinterpret_cast<uint4 *>(w.cc_planes));
   PROF_END(c, P_CC_ROWS);
   SB_LAUNCH_CHECK(c);
   const int Rs = label_smem_runs(c);
