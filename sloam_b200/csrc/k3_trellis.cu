@@ -108,9 +108,8 @@ __global__ void tree_fill_kernel(const DevParams *__restrict__ dp, const uint32_
 // the j-th set bit of the chunk is found through the prefix popcounts of the words (binary
 // search with shuffles, then the bit inside the word).  A forest scan has 10-20 % tree pixels
 // scattered over most words, so walking words with one lane per pixel left two thirds of the
-// lanes idle.  The three result bits of a pixel are OR-ed into per-word accumulators in shared
-// memory (the pixels of a word are neighbours in the lane order: one warp-reduce per word) and
-// written as planes[k][word] = (valid, start, up, 0) for the non-zero words at the end.
+// lanes idle.  The result planes live in per-word accumulators in shared memory and are written
+// as planes[k][word] = (valid, start, up, 0) for the non-zero words at the end.
 #ifndef SLOAM_CCROWS_MIN
 #define SLOAM_CCROWS_MIN 8
 #endif
@@ -152,7 +151,7 @@ cc_rows_kernel(const DevParams *__restrict__ dp, int K, const sloam_point *__res
     }
     const int pre = inc - cnt;
     const int total = __shfl_sync(kFull, inc, 31);
-    acc[0][lane] = 0u; acc[1][lane] = 0u; acc[2][lane] = 0u;
+    acc[0][lane] = my_word; acc[1][lane] = 0u; acc[2][lane] = my_word;
     __syncwarp();
     // point of the last pixel of the previous step (left neighbour of this step's first pixel)
     float carry_x = 0.f, carry_y = 0.f, carry_z = 0.f;
@@ -200,11 +199,18 @@ cc_rows_kernel(const DevParams *__restrict__ dp, int K, const sloam_point *__res
       const bool left_ok = valid && bit_l && sqnorm3f(p.x - lx, p.y - ly, p.z - lz) < cut;
       const bool up_ok = valid && bit_u && sqnorm3f(p.x - qu.x, p.y - qu.y, p.z - qu.z) < cut;
       // OR the three bits of the pixels of each word (contiguous lanes) into the accumulators
-      const unsigned grp = __match_any_sync(kFull, act ? w : 32 + lane);
-      const uint32_t vb = __reduce_or_sync(grp, valid ? (1u << b) : 0u);
-      const uint32_t sb_ = __reduce_or_sync(grp, (valid && !left_ok) ? (1u << b) : 0u);
-      const uint32_t ub = __reduce_or_sync(grp, up_ok ? (1u << b) : 0u);
-      if (act && lane == __ffs(grp) - 1) { acc[0][w] |= vb; acc[1][w] |= sb_; acc[2][w] |= ub; }
+      // The planes start from the tree bits themselves (valid and up: nearly all of them stay
+      // set; start: clear) and only the exceptions touch shared memory: a non-finite point, a
+      // pixel that starts a run, a pixel without an upward link.
+      if (bit) {
+        if (!valid) {
+          atomicAnd(&acc[0][w], ~(1u << b));
+          atomicAnd(&acc[2][w], ~(1u << b));
+        } else {
+          if (!left_ok) atomicOr(&acc[1][w], 1u << b);
+          if (!up_ok) atomicAnd(&acc[2][w], ~(1u << b));
+        }
+      }
       carry_x = __shfl_sync(kFull, p.x, 31); carry_y = __shfl_sync(kFull, p.y, 31); carry_z = __shfl_sync(kFull, p.z, 31);
       carry_pix = __shfl_sync(kFull, bit ? i : -2, 31); carry_k = __shfl_sync(kFull, k, 31);
       __syncwarp();
@@ -403,11 +409,28 @@ cc_label_kernel(const DevParams *__restrict__ dp, const uint32_t *__restrict__ b
         head = sc != 0;
       }
       if (__any_sync(kFull, head)) {
-        for (int j = rb; j < re; ++j) {
-          const int infj = len[j];
-          if ((infj & (int)kSlotMask) == sc && j != r) {
-            if (j < r) head = false;
-            else { n_tot += infj >> 11; last = j; }
+        // inside the chunk: lanes with the same slot find each other with match_any; the lowest
+        // one is the head and sums the others' lengths (a handful of shuffles)
+        const int own = n_tot;
+        const unsigned grp = __match_any_sync(kFull, sc != 0 ? sc : -(lane + 1));
+        head = head && lane == __ffs(grp) - 1;
+        const int gsize = __popc(grp);
+        const int gmax = __reduce_max_sync(kFull, gsize);
+        unsigned rest = grp & ~(1u << lane);
+        for (int it = 1; it < gmax; ++it) {
+          const int src = rest ? __ffs(rest) - 1 : lane;
+          const int v = __shfl_sync(kFull, own, src);
+          if (rest) { n_tot += v; last = max(last, c0 + src); rest &= rest - 1; }
+        }
+        // rows with more than 32 runs: the same slot may also sit in another chunk
+        if (re - rb > 32) {
+          for (int j = rb; j < re; ++j) {
+            if (j >= c0 && j < c0 + 32) continue;
+            const int infj = len[j];
+            if ((infj & (int)kSlotMask) == sc) {
+              if (j < r) head = false;
+              else { n_tot += infj >> 11; last = max(last, j); }
+            }
           }
         }
       }
