@@ -118,7 +118,10 @@ __device__ __forceinline__ int ground_cell_fast(const GroundGeom &g, float x, fl
 }
 
 #ifndef SLOAM_K1_MIN_CTAS
-#define SLOAM_K1_MIN_CTAS 5  // measured: 4 -> 427 us, 5 -> 384 us, 6 -> 390 us per 1000 VLP-16 keyframes
+// round 1 (separate scan + flush barriers): 4 -> 427 us, 5 -> 384 us, 6 -> 390 us per 1000 VLP-16 keyframes.
+// round 2 (double-buffered counts, 4 barriers per tile): 5 CTAs / 48 registers spill 120 bytes -> 400 us,
+// 4 CTAs / 64 registers no spill -> 367 us per 512 OS1-64 keyframes
+#define SLOAM_K1_MIN_CTAS 4
 #endif
 // FUSED (the production path, with DO_PROJECT and DO_SPLIT): the ground points are not copied.
 // Every ground point becomes one 8-byte record (z key, point index) in the tile-strided layout
@@ -136,10 +139,14 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
                      uint32_t *__restrict__ tree_bits, int sparse_tree,
                      uint2 *__restrict__ ground_recs, uint32_t *__restrict__ seg_tab) {
   __shared__ int s_pix[DO_PROJECT ? kSplitTile : 1];  // exact pixel indices of the queued points
-  __shared__ int s_hist[DO_SPLIT ? kMaxCells : 1];
+  // per-tile cell counts and (round, warp) ground counts, double-buffered by tile parity: a
+  // tile's counts are flushed / read while the next tile already fills the other buffer, which
+  // saves the two block barriers that would otherwise fence their reuse
+  __shared__ int s_hist2[DO_SPLIT ? 2 * kMaxCells : 1];
   __shared__ uint16_t s_slow[DO_PROJECT ? kSplitTile : 1];
   __shared__ int s_nslow;
-  __shared__ int s_cnt[kRounds * (kThreads / 32)];
+  static_assert(kRounds * (kThreads / 32) == 32, "one (round, warp) count per lane");
+  __shared__ int s_cnt2[2][32];
   // input staging: the points of the NEXT tile stream into shared memory (one TMA bulk copy,
   // completion on an mbarrier) while the current tile is being processed, so the kernel
   // always has a full tile of loads in flight per CTA
@@ -174,11 +181,22 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
   }
   __syncthreads();
 
-  int iter = 0;
+  // cell counts of a finished tile -> global (ground stage input)
+  auto flush_hist = [&](const int *hist, int fk, int ftile) {
+    for (int c = threadIdx.x; c < kMaxCells; c += kThreads) {
+      const int h = hist[c];
+      if (h) atomicAdd(&cell_count[(size_t)fk * kMaxCells + c], h);
+      // per-tile cell counts: ground_scatter_kernel (k2_ground.cu) bins every tile independently
+      if (FUSED && c < dp->B) seg_tab[((size_t)fk * dp->B + c) * tiles + ftile] = (unsigned)h;
+    }
+  };
+  int iter = 0, prev_k = -1, prev_tile = 0;
   for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, ++iter) {
   const int buf = iter & 1;
   const int k = tile_id / tiles, tile = tile_id - k * tiles;
   const size_t kbase = (size_t)k * N;
+  int *const s_hist = s_hist2 + (DO_SPLIT ? buf * kMaxCells : 0);
+  int *const s_cnt = s_cnt2[buf];
   uint32_t *tree_bits_k = tree_bits ? tree_bits + (size_t)k * ((N + 31) >> 5) : nullptr;
   if (threadIdx.x == 0) {
     s_nslow = 0;
@@ -198,6 +216,9 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
     }
   }
   __syncthreads();
+  // the previous tile of this CTA is complete behind that barrier: hand over its cell counts
+  if (DO_SPLIT && prev_k >= 0) flush_hist(s_hist2 + (buf ^ 1) * kMaxCells, prev_k, prev_tile);
+  prev_k = k; prev_tile = tile;
 
   // ---- phase A: the tile from shared memory (kRounds float4 per thread stay in registers) and project.
   // The pixel index is an integer derived from atan2f/asinf; the bit-exact evaluation
@@ -252,8 +273,8 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
 
   // ---- phase C: mask gather, dense tree cloud, order-preserving ground compaction
   if (!DO_SPLIT) { __syncthreads(); continue; }
-  // all mask gathers of the thread are issued back to back; one block-wide scan over the
-  // (round, warp) ballot counts gives every ground point its slot in input order
+  // all mask gathers of the thread are issued back to back; the (round, warp) ballot counts
+  // give every ground point its slot in input order
   unsigned bal[kRounds];
   unsigned gmask = 0;  // bit j: point j of this thread is ground
 #pragma unroll
@@ -282,27 +303,21 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
     if (lane == 0) s_cnt[j * (kThreads / 32) + warp] = __popc(bal[j]);
   }
   __syncthreads();
-  if (warp == 0) {  // exclusive scan of the kRounds * 8 counts, round-major
-    constexpr int kEnt = kRounds * (kThreads / 32);
-    constexpr int kPer = (kEnt + 31) / 32;
-    int v[kPer], s = 0;
+  // every warp sums the counts of the units before its own (one count per lane, one REDUX per
+  // round) instead of waiting for a scan by one warp behind a second barrier
+  int unit_base[kRounds];
+  {
+    const int cnt_l = s_cnt[lane];
 #pragma unroll
-    for (int q = 0; q < kPer; ++q) { const int e = lane * kPer + q; v[q] = e < kEnt ? s_cnt[e] : 0; s += v[q]; }
-    int inc = s;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(kFull, inc, o);
-      if (lane >= o) inc += t;
-    }
-    int run = inc - s;
-#pragma unroll
-    for (int q = 0; q < kPer; ++q) { const int e = lane * kPer + q; if (e < kEnt) s_cnt[e] = run; run += v[q]; }
-    if (lane == 31) {  // inc = ground points of this tile
-      tile_count[(size_t)k * tiles + tile] = inc;
-      if (inc) atomicAdd(&ground_count[k], inc);
+    for (int j = 0; j < kRounds; ++j) unit_base[j] = __reduce_add_sync(kFull, lane < j * (kThreads / 32) + warp ? cnt_l : 0);
+    if (warp == 0) {
+      const int tot = __reduce_add_sync(kFull, cnt_l);
+      if (lane == 0) {  // ground points of this tile
+        tile_count[(size_t)k * tiles + tile] = tot;
+        if (tot) atomicAdd(&ground_count[k], tot);
+      }
     }
   }
-  __syncthreads();
   // ground points go straight from registers to their slots: the ground lanes of a warp
   // own consecutive slots, so the 16-byte stores of a warp form contiguous runs
   sloam_point *gout = FUSED ? nullptr : ground + (size_t)k * ground_stride + (size_t)tile * kSplitTile;
@@ -312,7 +327,7 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
   for (int j = 0; j < kRounds; ++j) {
     if ((gmask >> j) & 1u) {
       const sloam_point p = pts[j];
-      const int slot = s_cnt[j * (kThreads / 32) + warp] + __popc(bal[j] & ((1u << lane) - 1u));
+      const int slot = unit_base[j] + __popc(bal[j] & ((1u << lane) - 1u));
       const int cell = ground_cell_fast(gg, p.x, p.y, yawr[j]);
       // FUSED: the point itself is not copied -- an 8-byte (z key, point index) record is all the
       // ground stage sorts; it reads the few retained points from the input cloud
@@ -322,15 +337,11 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
       if (cell >= 0) atomicAdd(&s_hist[cell], 1);
     }
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < kMaxCells; c += kThreads) {
-    const int h = s_hist[c];
-    if (h) atomicAdd(&cell_count[(size_t)k * kMaxCells + c], h);
-    // per-tile cell counts: ground_scatter_kernel (k2_ground.cu) bins every tile independently
-    if (FUSED && c < dp->B) seg_tab[((size_t)k * dp->B + c) * tiles + tile] = (unsigned)h;
-  }
-  __syncthreads();  // s_hist / s_cnt / s_nslow are reset by the next tile
   }  // tile loop
+  if (DO_SPLIT && prev_k >= 0) {  // the last tile of this CTA
+    __syncthreads();
+    flush_hist(s_hist2 + ((iter - 1) & 1) * kMaxCells, prev_k, prev_tile);
+  }
 }
 
 // Contiguous ground cloud (Segmentation::maskCloud's output) from the tile-strided one:
