@@ -242,11 +242,12 @@ def kernel_model(name, c):
     V vertex points, cells, words}; -> (bound, bytes or None, formula)."""
     BN, T, G = c["BN"], c["T"], c["G"]
     m = {
-        "project_split_kernel": ("hbm", 25 * BN + BN // 8 + 16 * T + 17 * G,
-                                 "16N pts + 1N mask + 4N pix + 4N range + N/8 tree bits + 16 T + 17 G"),
+        "project_split_kernel": ("hbm", 21 * BN + BN // 8 + 16 * T + 9 * G,
+                                 "16N pts + 1N mask + 4N range + N/8 tree bits + 16 T tree points + 9 G ground records and tags"),
         "range_finalize_kernel": ("hbm", 8 * BN, "4N read + 4N write of the range image"),
-        "ground_bin_kernel": ("hbm", 13 * G, "1 G tags + 4 G z + 8 G member records"),
-        "ground_cells_kernel<0>": ("latency", 8 * G + 16 * (G // 20), "8 G member records + 16 B per retained point"),
+        "ground_offsets+ground_scatter_kernel": ("hbm", 17 * G, "9 G records and tags in + 8 G member records out"),
+        "ground_cells_kernel<0>": ("latency", 8 * G + 8 * (G // 20), "8 G member records in + 8 B per retained record out"),
+        "ground_fit": ("latency", 24 * (G // 20), "8 B record + 16 B point per retained point"),
         "tree_words_kernel": ("hbm", BN // 8, "N/8 tree bits"),
         "cc_init_kernel": ("latency", 20 * T, "16 T tree points + 4 T parents"),
         "cc_flatten_kernel": ("latency", 8 * T, "4 T parents read + written"),

@@ -156,6 +156,9 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
   const int N = dp->N;
   const int tiles = (N + kSplitTile - 1) / kSplitTile;
   const int total_tiles = K * tiles;
+  // floor(2^32 / tiles) + 1 gives the exact quotient while tile_id * tiles < 2^32; else divide
+  const unsigned magic_tiles = (tiles > 1 && (unsigned long long)total_tiles * (unsigned)tiles < 0x100000000ull)
+                                   ? (unsigned)(0x100000000ull / (unsigned)tiles) + 1u : 0u;
   const ProjGeom pg = dp->pg;
   const GroundGeom gg = dp->gg;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -193,7 +196,7 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
   int iter = 0, prev_k = -1, prev_tile = 0;
   for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, ++iter) {
   const int buf = iter & 1;
-  const int k = tile_id / tiles, tile = tile_id - k * tiles;
+  const int k = magic_tiles ? (int)__umulhi((unsigned)tile_id, magic_tiles) : tile_id / tiles, tile = tile_id - k * tiles;
   const size_t kbase = (size_t)k * N;
   int *const s_hist = s_hist2 + (DO_SPLIT ? buf * kMaxCells : 0);
   int *const s_cnt = s_cnt2[buf];
@@ -260,7 +263,10 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
       const int i = tile * kSplitTile + j * kThreads + threadIdx.x;
       if (i < N) {
         if (pixr[j] < 0) pixr[j] = s_pix[j * kThreads + threadIdx.x];
-        pix_io[kbase + i] = pixr[j];
+        // FUSED: the pixel indices (proj_xs / proj_ys, which the reference keeps only for
+        // maskCloud, inference.cpp:131-132) feed the mask gather below and are not stored;
+        // sloam_b200_get_intermediates recomputes them on demand
+        if (!FUSED) pix_io[kbase + i] = pixr[j];
         // closest point wins (inference.cpp:135,160-162): minimum over the bit pattern of the
         // non-negative SQUARED range (sqrtf is monotone, so the same point wins); the one
         // square root per pixel is taken by range_finalize_kernel.  NaN ranges never write.

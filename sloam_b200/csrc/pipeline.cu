@@ -370,10 +370,14 @@ int sloam_b200_get_intermediates(sloam_ctx *c, sloam_intermediates *o) {
   }
   const sloam_point *ground_dense = w.ground;
   if (c->ground_strided && c->last_k > 0) {
-    // the fused run kept no ground cloud: redo the label split of stage a2 from the pixel
-    // indices (the input buffers of that run must still be alive); this also makes ws.tree dense
-    const int rc = launch_project_split(c, c->last_k, false, true, c->last_points, c->last_mask, w.pix, nullptr, w.tree,
-                                        reinterpret_cast<sloam_point *>(w.qscratch), w.ground_count, nullptr, false);
+    // the fused run kept neither the pixel indices nor a ground cloud: redo the projection and
+    // the label split of stages a1 + a2 (the input buffers of that run must still be alive);
+    // this also makes ws.tree dense
+    int rc = launch_project_split(c, c->last_k, true, false, c->last_points, nullptr, w.pix, nullptr, nullptr, nullptr,
+                                  nullptr, nullptr, false);
+    if (rc != SLOAM_OK) return rc;
+    rc = launch_project_split(c, c->last_k, false, true, c->last_points, c->last_mask, w.pix, nullptr, w.tree,
+                              reinterpret_cast<sloam_point *>(w.qscratch), w.ground_count, nullptr, false);
     if (rc != SLOAM_OK) return rc;
     c->tree_sparse = false;
   }
