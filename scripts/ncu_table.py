@@ -10,7 +10,13 @@ cols = [("Kernel Name", "kernel"), ("gpu__time_duration.sum", "time"), ("launch_
         ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "DRAM %peak"),
         ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue active %"),
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"),
-        ("lts__t_sector_hit_rate.pct", "L2 hit %")]
+        ("lts__t_sector_hit_rate.pct", "L2 hit %"),
+        ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "ALU %"),
+        ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "FMA %"),
+        ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "FP64 %"),
+        ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU %"),
+        ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "XU %"),
+        ("smsp__inst_executed.sum", "warp instructions")]
 idx = [(h.index(k), n) for k, n in cols if k in h]
 print("| " + " | ".join(f"{n} [{u[i]}]" if u[i] else n for i, n in idx) + " |")
 print("|" + "---|" * len(idx))

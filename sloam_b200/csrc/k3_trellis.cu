@@ -292,17 +292,25 @@ cc_label_kernel(const DevParams *__restrict__ dp, const uint32_t *__restrict__ b
   const uint4 *pk = planes + (size_t)k * Nw;
 
   // -- run ids: prefix count of the start bits, in raster order
+  // (every thread takes a block of consecutive words and scans it serially: one CTA-wide scan,
+  // three barriers, whatever the image size)
   int R = 0;
-  for (int w0 = 0; w0 < Nw; w0 += kLblThreads) {
-    const int w = w0 + threadIdx.x;
-    uint32_t s = 0u;
-    if (w < Nw && bk[w] != 0u) s = pk[w].y;
-    if (w < Nw) s_start[w] = s;
-    int tot;
-    const int ex = cta_scan_excl(__popc(s), s_tmp, &tot);
-    if (w < Nw) s_wbase[w] = R + ex;
-    R += tot;
+  {
+    const int per = (Nw + kLblThreads - 1) / kLblThreads;
+    const int w_lo = min((int)threadIdx.x * per, Nw), w_hi = min(w_lo + per, Nw);
+    int mine = 0;
+    for (int w = w_lo; w < w_hi; ++w) {
+      const uint32_t s = bk[w] != 0u ? pk[w].y : 0u;
+      s_start[w] = s;
+      mine += __popc(s);
+    }
+    int run = cta_scan_excl(mine, s_tmp, &R);
+    for (int w = w_lo; w < w_hi; ++w) {
+      s_wbase[w] = run;
+      run += __popc(s_start[w]);
+    }
   }
+  __syncthreads();
   if (wbase_out)
     for (int w = threadIdx.x; w < Nw; w += kLblThreads) wbase_out[(size_t)k * Nw + w] = s_wbase[w];
   for (int i = threadIdx.x; i < T * Hw; i += kLblThreads) s_rows[i] = 0u;
@@ -357,22 +365,28 @@ cc_label_kernel(const DevParams *__restrict__ dp, const uint32_t *__restrict__ b
   __syncthreads();
   // -- PCL label of every root (number of roots before it) and slot of every big component
   // (number of big roots before it = tree order); siz[root] := label << 11 | slot code
+  // (both counts in one scan: roots in the low 20 bits, big roots above; a block of consecutive
+  // runs per thread)
   int n_root = 0, n_bigc = 0;
-  for (int r0 = 0; r0 < R; r0 += kLblThreads) {
-    const int r = r0 + threadIdx.x;
-    const bool is_root = r < R && par[r] == r;
-    const bool is_big = is_root && (int)siz[r] > min_pts;
-    int tr, tb;
-    const int er = cta_scan_excl(is_root ? 1 : 0, s_tmp, &tr);
-    const int eb = cta_scan_excl(is_big ? 1 : 0, s_tmp, &tb);
-    if (is_root) {
-      const int label = n_root + er, slot = n_bigc + eb;
+  {
+    const int per = (R + kLblThreads - 1) / kLblThreads;
+    const int r_lo = min((int)threadIdx.x * per, R), r_hi = min(r_lo + per, R);
+    int mine = 0;
+    for (int r = r_lo; r < r_hi; ++r)
+      if (par[r] == r) mine += 1 + (((int)siz[r] > min_pts) ? (1 << 20) : 0);
+    int tot;
+    int run = cta_scan_excl(mine, s_tmp, &tot);
+    n_root = tot & 0xFFFFF;
+    n_bigc = tot >> 20;
+    for (int r = r_lo; r < r_hi; ++r) {
+      if (par[r] != r) continue;
+      const bool is_big = (int)siz[r] > min_pts;
+      const int label = run & 0xFFFFF, slot = run >> 20;
       const bool keep = is_big && slot < T;  // more big components than max_trees: the first T in label order
       siz[r] = ((uint32_t)label << 11) | (keep ? (uint32_t)(slot + 1) : 0u);
       if (keep) big_rank[(size_t)k * T + slot] = label;
+      run += 1 + (is_big ? (1 << 20) : 0);
     }
-    n_root += tr;
-    n_bigc += tb;
   }
   if (threadIdx.x == 0) {
     n_roots[k] = n_root;
@@ -1146,9 +1160,16 @@ __global__ void cc_labels_kernel(const DevParams *__restrict__ dp, int K, const 
   labels[g] = lab;
 }
 
+// runs per keyframe that cc_label_kernel keeps in shared memory (more: global scratch, slower).
+// A trunk is one run per scan line, so a context sized for many trees expects many runs; the
+// smaller the arrays, the more keyframes an SM works on at once.
 static int label_smem_runs(const sloam_ctx *c) {
-  const int rs = c->hp.N / 16;
-  return rs < 1024 ? 1024 : (rs > 8192 ? 8192 : rs);
+  const long long by_image = c->hp.N / 16, by_trees = (long long)c->hp.p.max_trees * c->hp.p.img_h / 2;
+  const long long rs = std::max(by_image, by_trees);
+  const int Nw = (c->hp.N + 31) / 32, Hw = (c->hp.p.img_h + 31) / 32;
+  // what fits next to the bit planes and the row masks in 200 KB
+  const long long fit = (200 * 1024 - 8ll * Nw - 4ll * c->hp.p.max_trees * Hw) / 12;
+  return (int)std::max(1024ll, std::min(std::min(rs, 16384ll), fit));
 }
 
 static int run_cc(sloam_ctx *c, int K, const sloam_point *tree, bool bits_ready, bool want_labels) {
