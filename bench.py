@@ -131,6 +131,11 @@ def host_state(capi, abi, p, cfg, k0, B):
     return scene, pose, maps, nmap
 
 
+# diagnostic only (the scaling control in profiles/): a sharded run without its result gather
+NO_GATHER = os.environ.get("SLOAM_BENCH_NO_GATHER") is not None
+GATHER_ONLY = os.environ.get("SLOAM_BENCH_GATHER_ONLY") is not None  # ... and the gather alone
+
+
 def make_inputs(capi, abi, ctx, p, cfg, B, k0, device):
     """Device-resident inputs of keyframes [k0, k0+B): generated on the GPU; prevGPlanes_ come
     from an untimed first-scan pass over the same keyframes (planes of keyframe k-1)."""
@@ -437,8 +442,9 @@ def main():
 
     def step():
         for b_inp, b_out, _, _ in batches:
-            ctx.run_keyframes_dev(B, b_inp, b_out)
-            if world > 1:
+            if not GATHER_ONLY:
+                ctx.run_keyframes_dev(B, b_inp, b_out)
+            if world > 1 and not NO_GATHER:
                 ctx.gather_results(B, b_out, gathered)
 
     def timed(fn, steps):

@@ -100,7 +100,11 @@ int sloam_b200_comm_init(sloam_ctx *c, int rank, int world, const void *id128) {
   std::memcpy(&id, id128, sizeof id);
   const int rc = a.CommInitRank(&s->comm, world, id, rank);
   if (rc != 0) { delete s; return nccl_err(c, rc, "ncclCommInitRank"); }
-  if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess ||
+  // highest priority: when a gather and the first kernels of the next batch become runnable
+  // together, the few CTAs of the gather are placed first instead of behind a full grid
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
       cudaEventCreateWithFlags(&s->ev_ready, cudaEventDisableTiming) != cudaSuccess ||
       (!c->ev_gather_done && cudaEventCreateWithFlags(&c->ev_gather_done, cudaEventDisableTiming) != cudaSuccess)) {
     a.CommDestroy(s->comm);

@@ -137,7 +137,8 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
                      uint8_t *__restrict__ ground_cell, int32_t *__restrict__ cell_count,
                      int32_t *__restrict__ tile_count, int ground_stride,
                      uint32_t *__restrict__ tree_bits, int sparse_tree,
-                     uint2 *__restrict__ ground_recs, uint32_t *__restrict__ seg_tab) {
+                     uint2 *__restrict__ ground_recs, uint32_t *__restrict__ seg_tab,
+                     int *__restrict__ tile_ctr) {
   __shared__ int s_pix[DO_PROJECT ? kSplitTile : 1];  // exact pixel indices of the queued points
   // per-tile cell counts and (round, warp) ground counts, double-buffered by tile parity: a
   // tile's counts are flushed / read while the next tile already fills the other buffer, which
@@ -152,6 +153,10 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
   // always has a full tile of loads in flight per CTA
   __shared__ __align__(128) sloam_point s_in[2][kSplitTile];
   __shared__ __align__(8) unsigned long long s_mbar[2];
+  // tiles are handed out by a global counter (tile_ctr, zero at launch), not by a fixed stride:
+  // a CTA that becomes resident late -- behind the CTAs of another stream's kernel, e.g. the
+  // result gather of the previous batch -- then takes fewer tiles instead of a full share
+  __shared__ int s_tile_id[2];
 
   const int N = dp->N;
   const int tiles = (N + kSplitTile - 1) / kSplitTile;
@@ -180,8 +185,12 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&s_mbar[0])));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&s_mbar[1])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if ((int)blockIdx.x < total_tiles) issue_tile((int)blockIdx.x, 0);
+    const int first = atomicAdd(tile_ctr, 1);
+    s_tile_id[0] = first;
+    if (first < total_tiles) issue_tile(first, 0);
   }
+  int fetched = total_tiles;  // (thread 0) the tile after the next one, claimed one iteration ahead
+  if (threadIdx.x == 0) fetched = atomicAdd(tile_ctr, 1);
   __syncthreads();
 
   // cell counts of a finished tile -> global (ground stage input)
@@ -194,8 +203,10 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
     }
   };
   int iter = 0, prev_k = -1, prev_tile = 0;
-  for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, ++iter) {
+  for (;; ++iter) {
   const int buf = iter & 1;
+  const int tile_id = s_tile_id[buf];  // written before the last barrier of the previous iteration
+  if (tile_id >= total_tiles) break;
   const int k = magic_tiles ? (int)__umulhi((unsigned)tile_id, magic_tiles) : tile_id / tiles, tile = tile_id - k * tiles;
   const size_t kbase = (size_t)k * N;
   int *const s_hist = s_hist2 + (DO_SPLIT ? buf * kMaxCells : 0);
@@ -204,7 +215,11 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
   if (threadIdx.x == 0) {
     s_nslow = 0;
     // the other buffer was last read two barriers ago (register loads of the previous tile)
-    if (tile_id + (int)gridDim.x < total_tiles) issue_tile(tile_id + (int)gridDim.x, buf ^ 1);
+    s_tile_id[buf ^ 1] = fetched;
+    if (fetched < total_tiles) {
+      issue_tile(fetched, buf ^ 1);
+      fetched = atomicAdd(tile_ctr, 1);  // not needed before the next iteration
+    }
   }
   if (DO_SPLIT)
     for (int c = threadIdx.x; c < kMaxCells; c += kThreads) s_hist[c] = 0;
@@ -500,15 +515,20 @@ int launch_project_split(sloam_ctx *c, int K, bool do_project, bool do_split,
   // The kernel always writes the tile-strided ground layout.  The fused pipeline consumes it
   // as is (ground == ws.ground); a stage entry gets the contiguous cloud by compaction.
   const bool strided_out = fused;
+  bool counters_prezeroed = false;
   if (do_split) {
     if ((c->zero_valid & 1u) && ground_count == c->ws.ground_count) {
       c->zero_valid &= ~1u;  // zeroed with the rest of the counters (pipeline.cu)
+      counters_prezeroed = true;
     } else {
       SB_CUDA(c, cudaMemsetAsync(ground_count, 0, sizeof(int32_t) * (size_t)K, c->stream));
       SB_CUDA(c, cudaMemsetAsync(c->ws.cell_count, 0, sizeof(int32_t) * (size_t)K * kMaxCells, c->stream));
     }
   }
-  // persistent CTAs: exactly the resident ones, each walks tiles blockIdx.x, + gridDim.x, ...
+  // persistent CTAs: exactly the resident ones, tiles handed out by a counter.  The counter is the
+  // first word of the per-run zero block; outside a fused run it is cleared here.
+  int *tile_ctr = c->ws.zero_begin;
+  if (!counters_prezeroed) SB_CUDA(c, cudaMemsetAsync(tile_ctr, 0, sizeof(int), c->stream));
   static int occ[4] = {0, 0, 0, 0};
   const int which = fused ? 3 : ((do_project && do_split) ? 0 : (do_project ? 1 : 2));
   if (occ[which] == 0) {
@@ -522,7 +542,7 @@ int launch_project_split(sloam_ctx *c, int K, bool do_project, bool do_split,
   const unsigned grid = (unsigned)std::min<long long>(all_tiles, (long long)c->sm_count * occ[which]);
 #define SB_K1_ARGS c->dp, K, points, mask, pix, rb, tree, c->ws.ground, ground_count, c->ws.ground_cell, \
                    c->ws.cell_count, c->ws.tile_count, N, tree_bits, sparse_tree ? 1 : 0,                 \
-                   reinterpret_cast<uint2 *>(c->ws.gscratch), c->ws.seg_tab
+                   reinterpret_cast<uint2 *>(c->ws.gscratch), c->ws.seg_tab, tile_ctr
   PROF_BEGIN(c, P_SPLIT);
   if (fused) project_split_kernel<true, true, true><<<grid, kThreads, 0, c->stream>>>(SB_K1_ARGS);
   else if (do_project && do_split) project_split_kernel<true, true, false><<<grid, kThreads, 0, c->stream>>>(SB_K1_ARGS);
