@@ -100,6 +100,8 @@ __device__ __forceinline__ int ground_cell_fast(const GroundGeom &g, float x, fl
   // pow_2 rounds the exact fp64 square of a float to float == the fp32 product
   const float rf = sqrtf(x * x + y * y);  // bit-identical to euclideanDist2D (utils.h:9-12)
   const double radius = (double)rf;
+  // (float thresholds with the same decisions -- the smallest float >= max_dist, the largest
+  // <= min_dist -- were tried: the kernel got 3 % slower, the DSETPs are not on its critical path)
   if (!(radius < g.max_dist && radius > g.min_dist)) return -1;
   const float theta = (yaw == yaw) ? -yaw : fast_atan2f(y, x);
   const float tb_f = (3.14159265f + theta) * g.inv_theta_step_f;
@@ -246,17 +248,22 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
   sloam_point pts[kRounds];
   int pixr[kRounds];
   float yawr[kRounds];
+  // the mask byte of a point is fetched as soon as its pixel is known, so that the gather's
+  // latency runs under phase B and its barriers instead of in front of the ballots of phase C
+  unsigned char mk[kRounds];
 #pragma unroll
   for (int j = 0; j < kRounds; ++j) {
     const int i = tile * kSplitTile + j * kThreads + threadIdx.x;
     pts[j] = sloam_point{0.f, 0.f, 0.f, 0.f};
     pixr[j] = 0;
     yawr[j] = qnan;
+    mk[j] = 0;
     if (i < N) {
       pts[j] = ld_point(&s_in[buf][j * kThreads + threadIdx.x]);
       if (DO_PROJECT) {
         pixr[j] = project_pixel_fast(pg, pts[j].x, pts[j].y, pts[j].z, mx, my, inv_fov, &yawr[j]);
         if (pixr[j] < 0) s_slow[atomicAdd(&s_nslow, 1)] = j * kThreads + threadIdx.x;
+        else if (DO_SPLIT) mk[j] = mask[kbase + pixr[j]];  // inference.cpp:242-243
       } else {
         pixr[j] = pix_io[kbase + i];
       }
@@ -277,7 +284,10 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
     for (int j = 0; j < kRounds; ++j) {
       const int i = tile * kSplitTile + j * kThreads + threadIdx.x;
       if (i < N) {
-        if (pixr[j] < 0) pixr[j] = s_pix[j * kThreads + threadIdx.x];
+        if (pixr[j] < 0) {
+          pixr[j] = s_pix[j * kThreads + threadIdx.x];
+          if (DO_SPLIT) mk[j] = mask[kbase + pixr[j]];
+        }
         // FUSED: the pixel indices (proj_xs / proj_ys, which the reference keeps only for
         // maskCloud, inference.cpp:131-132) feed the mask gather below and are not stored;
         // sloam_b200_get_intermediates recomputes them on demand
@@ -302,8 +312,8 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
   for (int j = 0; j < kRounds; ++j) {
     const int i = tile * kSplitTile + j * kThreads + threadIdx.x;
     const bool in = i < N;
-    unsigned char m = 0;
-    if (in) m = mask[kbase + pixr[j]];  // inference.cpp:242-243
+    unsigned char m = mk[j];
+    if (!DO_PROJECT && in) m = mask[kbase + pixr[j]];  // inference.cpp:242-243
     // dense mode (:247-251): the point or a NaN point with intensity 0.  With sparse_tree
     // (fused pipeline) only the tree points are written; tree_bits says which pixels hold one
     // and the NaN points are materialised on demand (pipeline.cu).

@@ -19,10 +19,11 @@
 
 namespace sb {
 
-#ifndef SLOAM_LM_THREADS
-#define SLOAM_LM_THREADS 64
+#ifndef SLOAM_LM_WARPS
+#define SLOAM_LM_WARPS 2  // measured per 1024 OS1-64 problems: 1 warp 102 us, 2 -> 91, 4 -> 118, 8 -> 178
 #endif
-constexpr int kLmThreads = SLOAM_LM_THREADS;  // 2 problems (warps) per CTA
+constexpr int kLmWarps = SLOAM_LM_WARPS;  // warps that share the residual rows of ONE problem (= one CTA)
+constexpr int kLmThreads = 32 * kLmWarps;
 
 // ---------------------------------------------------------------- matching --
 __global__ void __launch_bounds__(128)
@@ -157,21 +158,27 @@ build_matches_kernel(const DevParams *__restrict__ dp, const uint8_t *__restrict
 }
 
 // ---------------------------------------------------------------- LM solve --
-// One WARP per (keyframe, problem).  The 32 lanes split the residual rows of an evaluation
-// (row r on lane r % 32), reduce the J^T J / J^T r / cost partial sums with shuffles, and
-// then all run the scalar trust-region state machine of dev_lm.h on identical values: a
-// warp instruction costs the same issue slots with one lane or 32, so the redundancy is
-// free, and no block barrier or master/worker hand-over sits on the critical path.  The
-// scalar state (LMWork) is in shared memory, one copy per warp: every lane reads it by
-// broadcast and writes the same value to the same address.
-// The kernel is latency-bound on the dependent FP64 chain of one iteration, so what
-// matters is how many independent chains an SM holds: 2 warps per CTA, as many CTAs per SM
-// as the register file allows.
+// One CTA of kLmWarps warps per (keyframe, problem).  The threads split the residual rows of an
+// evaluation (row r on thread r % kLmThreads), reduce the J^T J / J^T r / cost partial sums
+// with shuffles inside each warp and through a double-buffered shared-memory table across the
+// warps (ONE block barrier per evaluation; every thread adds the warps' partial sums in the
+// same order), and then all run the scalar trust-region state machine of dev_lm.h on
+// identical values: a warp instruction costs the same issue slots with one lane or 32, so
+// the redundancy is free, and no master/worker hand-over sits on the critical path.  The
+// scalar state (LMWork) is in shared memory, one copy per WARP (warps run ahead of each other
+// between barriers): every lane reads it by broadcast and writes the same value to the same
+// address.
+// The kernel is latency-bound on the dependent FP64 chain of one iteration.  A tree problem
+// has ~260 rows, i.e. 8 sequential rows per lane with one warp; two warps halve that, but
+// every further warp repeats the scalar part (the 3x3 / 6x6 solve, step and ratio tests on
+// shared-memory state), which is most of an iteration: four and eight warps are slower.
 struct WarpEval {
   int mode;
   const double *tree_feat; const sloam_cylinder *tree_obj; int n_tree;
   const double *plane_feat; const sloam_plane *plane_obj; int n_plane;
   double huber_a;
+  double (*part)[kLmWarps][28];  // [2][warp][21 + 6 + 1] partial sums, shared memory
+  int n_eval = 0;
 
   // N = tangent dimension (6 joint, 3 for the two-step problems): a compile-time N keeps
   // the accumulators in registers
@@ -190,7 +197,7 @@ struct WarpEval {
 #pragma unroll
     for (int i = 0; i < N; ++i) accg[i] = 0.0;
     const int total = n_tree + n_plane;
-    for (int r = lane; r < total; r += 32) {
+    for (int r = threadIdx.x; r < total; r += kLmThreads) {
       double J[6];
       double res;
       if (r < n_tree) res = residual_row(mode, x, pre, tree_feat + 3 * (size_t)r, tree_obj + r, nullptr, J);
@@ -208,10 +215,36 @@ struct WarpEval {
       }
     }
 #pragma unroll
-    for (int i = 0; i < NP; ++i) A[i] = warp_sum_d(acc[i]);
+    for (int i = 0; i < NP; ++i) acc[i] = warp_sum_d(acc[i]);
 #pragma unroll
-    for (int i = 0; i < N; ++i) g[i] = warp_sum_d(accg[i]);
-    *cost = warp_sum_d(accc);
+    for (int i = 0; i < N; ++i) accg[i] = warp_sum_d(accg[i]);
+    accc = warp_sum_d(accc);
+    if (kLmWarps == 1) {
+#pragma unroll
+      for (int i = 0; i < NP; ++i) A[i] = acc[i];
+#pragma unroll
+      for (int i = 0; i < N; ++i) g[i] = accg[i];
+      *cost = accc;
+      return;
+    }
+    // across the warps: table of evaluation parity (the barrier of the next evaluation fences
+    // its reuse), summed by every thread in warp order
+    double (*tab)[28] = part[n_eval & 1];
+    ++n_eval;
+    const int warp = threadIdx.x >> 5;
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < NP; ++i) tab[warp][i] = acc[i];
+#pragma unroll
+      for (int i = 0; i < N; ++i) tab[warp][NP + i] = accg[i];
+      tab[warp][NP + N] = accc;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NP; ++i) { double v = tab[0][i]; for (int w = 1; w < kLmWarps; ++w) v += tab[w][i]; A[i] = v; }
+#pragma unroll
+    for (int i = 0; i < N; ++i) { double v = tab[0][NP + i]; for (int w = 1; w < kLmWarps; ++w) v += tab[w][NP + i]; g[i] = v; }
+    { double v = tab[0][NP + N]; for (int w = 1; w < kLmWarps; ++w) v += tab[w][NP + N]; *cost = v; }
   }
 
   __device__ void operator()(const double *xs, double *cost, double *A, double *g) {
@@ -223,9 +256,9 @@ struct WarpEval {
 };
 
 // problems: joint -> one per keyframe; two-step -> 2 per keyframe, problem 0 = XYYaw (trees),
-// 1 = ZRollPitch (planes).  Warp w of the grid solves problem w.
+// 1 = ZRollPitch (planes).  CTA b of the grid solves problem b.
 #ifndef SLOAM_LM_MIN_CTAS
-#define SLOAM_LM_MIN_CTAS 8  // 128 registers: measured best of 4 / 6 / 8 (latency-bound, occupancy wins)
+#define SLOAM_LM_MIN_CTAS (16 / SLOAM_LM_WARPS)  // 128 registers per thread
 #endif
 __global__ void __launch_bounds__(kLmThreads, SLOAM_LM_MIN_CTAS)
 lm_kernel(const DevParams *__restrict__ dp, int two_step, int K, const sloam_pose *__restrict__ pose_est,
@@ -233,11 +266,12 @@ lm_kernel(const DevParams *__restrict__ dp, int two_step, int K, const sloam_pos
           const int32_t *__restrict__ n_tree_res, int tf_stride, const double *__restrict__ plane_feat,
           const sloam_plane *__restrict__ plane_obj, const int32_t *__restrict__ n_plane_res, int pf_stride,
           const uint8_t *__restrict__ optim_flags, double *__restrict__ lm_x, int32_t *__restrict__ lm_info) {
-  __shared__ LMWork s_work[kLmThreads / 32];
+  __shared__ LMWork s_work[kLmWarps];
+  __shared__ double s_part[2][kLmWarps][28];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pid = blockIdx.x * (kLmThreads / 32) + warp;
+  const int pid = blockIdx.x;
   const int per_kf = two_step ? 2 : 1;
-  if (pid >= K * per_kf) return;  // warp-uniform; no block barrier below
+  if (pid >= K * per_kf) return;  // CTA-uniform
   const int k = pid / per_kf, prob = pid % per_kf;
   const bool optimTrees = optim_flags[2 * k] != 0, optimGround = optim_flags[2 * k + 1] != 0;
   double *xo = lm_x + ((size_t)k * 2 + prob) * 8;
@@ -272,15 +306,16 @@ lm_kernel(const DevParams *__restrict__ dp, int two_step, int K, const sloam_pos
     ev.plane_obj = plane_obj + (size_t)k * pf_stride;
     ev.n_plane = use_planes ? n_plane_res[k] : 0;
     ev.huber_a = dp->p.huber_delta;
+    ev.part = s_part;
     o = lm_minimize(ev, s_work[warp], mode, ev.n_tree + ev.n_plane, dp->p.lm_max_iterations, x);
   }
-  if (lane == 0) {
+  if (threadIdx.x == 0) {
     for (int i = 0; i < 7; ++i) xo[i] = x[i];
     xo[7] = o.final_cost;
     info[0] = o.iterations;
     info[1] = run ? o.termination : -1;
   }
-  if (!two_step && lane == 1) {  // the unused second problem slot of a joint solve
+  if (!two_step && threadIdx.x == 1) {  // the unused second problem slot of a joint solve
     int32_t *info1 = lm_info + ((size_t)k * 2 + 1) * 2;
     info1[0] = 0; info1[1] = -1;
   }
@@ -401,8 +436,8 @@ int launch_lm(sloam_ctx *c, int K, int two_step, const sloam_pose *pose_est, con
               const sloam_cylinder *tree_obj, const int32_t *n_tree_res, int tf_stride,
               const double *plane_feat, const sloam_plane *plane_obj, const int32_t *n_plane_res,
               int pf_stride, const uint8_t *optim_flags) {
-  const int problems = K * (two_step ? 2 : 1), per_cta = kLmThreads / 32;
-  lm_kernel<<<(problems + per_cta - 1) / per_cta, kLmThreads, 0, c->stream>>>(c->dp, two_step, K, pose_est, tree_feat, tree_obj, n_tree_res,
+  const int problems = K * (two_step ? 2 : 1);
+  lm_kernel<<<problems, kLmThreads, 0, c->stream>>>(c->dp, two_step, K, pose_est, tree_feat, tree_obj, n_tree_res,
                                                 tf_stride, plane_feat, plane_obj, n_plane_res, pf_stride,
                                                 optim_flags, c->ws.lm_x, c->ws.lm_info);
   SB_LAUNCH_CHECK(c);
