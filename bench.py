@@ -5,8 +5,9 @@ One step = one pass of the whole hot path (projection/split -> ground cells + pl
 -> tree clustering + vertices -> cylinder models -> association -> LM pose -> projection
 -> association) over one batch of synthetic keyframes.  Default workload: the one
 BASELINE.json's metric is quoted on, synthetic OS1-64 64x1024 forest scans (configs[0]'s
-scene: 20 trees + ground plane), 512 keyframes per step and GPU so that the inputs (570 MB)
-are far larger than the 126 MB L2.
+scene: 20 trees + ground plane), 1024 keyframes per step and GPU (the batch size of
+configs[1]; inputs 1.14 GB, far larger than the 126 MB L2; 256 / 512 / 2048 keyframes per
+step give 0.78 / 0.93 / 1.04 of its throughput).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
                     [--workload os1-64|vlp-16|os1-64-dense|os1-128|assoc-100k] [--keyframes B]
@@ -42,7 +43,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC_OS1_64 = "keyframes/sec (OS1-64 synthetic forest) at 1/2/4/8 B200; kernel HBM GB/s vs peak"
 WORKLOADS = {
     # name: (preset in sloam_b200/configs.py, default keyframes per step and GPU, metric, BASELINE config)
-    "os1-64": ("os1-64", 512, METRIC_OS1_64, "metric workload: configs[0]'s OS1-64 64x1024 scene (20 trees + ground), batched"),
+    "os1-64": ("os1-64", 1024, METRIC_OS1_64, "metric workload: configs[0]'s OS1-64 64x1024 scene (20 trees + ground), batched"),
     "vlp-16": ("vlp-16", 1000, "keyframes/sec (VLP-16 synthetic forest)", "configs[1]: VLP-16 sequence, 1000 keyframes, 50-tree scene"),
     "os1-64-dense": ("os1-64-dense", 64, "keyframes/sec (OS1-64 dense synthetic forest, 4096 RANSAC hypotheses/tree)",
                      "configs[2]: OS1-64 dense forest, 300 trees, 4096 hypotheses per tree"),

@@ -1168,8 +1168,14 @@ static int label_smem_runs(const sloam_ctx *c) {
   const long long rs = std::max(by_image, by_trees);
   const int Nw = (c->hp.N + 31) / 32, Hw = (c->hp.p.img_h + 31) / 32;
   // what fits next to the bit planes and the row masks in 200 KB
-  const long long fit = (200 * 1024 - 8ll * Nw - 4ll * c->hp.p.max_trees * Hw) / 12;
-  return (int)std::max(1024ll, std::min(std::min(rs, 16384ll), fit));
+  const long long fixed = 8ll * Nw + 4ll * c->hp.p.max_trees * Hw;
+  const long long fit = (200 * 1024 - fixed) / 12;
+  long long r = std::max(1024ll, std::min(std::min(rs, 16384ll), fit));
+  // four CTAs (the thread limit) instead of three per SM when that still leaves room for one
+  // run per 32 pixels: a batch of 512 keyframes is then one wave of CTAs instead of two
+  const long long four = (54 * 1024 - fixed) / 12;
+  if (four < r && four >= c->hp.N / 32) r = four;
+  return (int)r;
 }
 
 static int run_cc(sloam_ctx *c, int K, const sloam_point *tree, bool bits_ready, bool want_labels) {
