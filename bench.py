@@ -543,6 +543,27 @@ def main():
         e2e_xyzi_s = e2e_run(h_in)
         e2e_s = e2e_run(h_xyz)
 
+    # the gather, checked: one more batch, then every slice of the gathered arrays on every rank
+    # against a checksum of the buffers of the rank that produced it
+    gather_check = None
+    if world > 1 and not NO_GATHER:
+        import zlib
+        with torch.cuda.stream(ctx.stream):
+            ctx.run_keyframes_dev(B, inp, out)
+            ctx.gather_results(B, out, gathered)
+            ctx.comm_wait()
+        ctx.sync()
+        names = ("results", "matches", "tm", "tm_id")
+        mine = {k: zlib.crc32(capi.to_host(out[k], np.uint8).tobytes()) for k in names}
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        good = 0
+        for k in names:
+            buf = capi.to_host(gathered[k], np.uint8).reshape(world, -1)
+            good += sum(int(zlib.crc32(buf[r].tobytes()) == everyone[r][k]) for r in range(world))
+        worst = torch.tensor([good], device=device)
+        dist.all_reduce(worst, op=dist.ReduceOp.MIN)
+        gather_check = f"{int(worst.item())}/{len(names) * world} gathered slices byte-identical to the producing rank's buffers (min over ranks)"
     res = capi.to_host(out["results"], abi.KF_RESULT, (B,))
     peak, peak_src = load_peaks()
     value = world * share * args.steps / (ms * 1e-3)
@@ -589,6 +610,7 @@ def main():
         "run": {"lanes": args.lanes, "keyframes_per_step_per_gpu": share, "batches_per_step": n_batches,
                 "total_keyframes": world * share,
                 "gather": "sloam_b200_gather_results_dev (ncclAllGather, side stream)" if world > 1 else None,
+                "gather_check": gather_check,
                 "keyframes_ok": int((res["success"] == 1).sum()),
                 "mean_landmarks": float(res["n_landmarks"].mean()),
                 "lm_converged": int((res["lm_termination"][:, 0] == 0).sum()),

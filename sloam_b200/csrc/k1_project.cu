@@ -75,7 +75,7 @@ __device__ __forceinline__ float fast_asinf(float t) {
 // 0.5 (yaw / pi + 1) W deviates from the exact pipeline by < 9e-4 px, of
 // (1 - (pitch + |fov_down|) / fov) H by < 2e-4 px.  NaN / out-of-image -> -1.
 __device__ __forceinline__ int project_pixel_fast(const ProjGeom &g, float x, float y, float z, float mx,
-                                                  float my, float inv_fov, float *yaw_out) {
+                                                  float my, float kx, float ky, float cy, float *yaw_out) {
   // no-return beams (NaN x or y): yaw and pitch are NaN, both coordinates take the
   // clamp of inference.cpp:120,125 (std::min keeps its first argument) -> last pixel
   *yaw_out = __int_as_float(0x7fc00000);
@@ -84,10 +84,15 @@ __device__ __forceinline__ int project_pixel_fast(const ProjGeom &g, float x, fl
   *yaw_out = yaw;
   // z / range via rsqrt (<= 2 ulp): the estimate only has to be inside the margins
   const float pitch = fast_asinf(z * rsqrtf(x * x + y * y + z * z));
-  const float px = (0.5f * (yaw * 0.318309886f + 1.0f)) * g.Wf;
-  const float py = (1.0f - (pitch + g.fov_down_abs) * inv_fov) * g.Hf;
+  // one FMA per coordinate: 0.5 (yaw / pi + 1) W = yaw (W / 2 pi) + W / 2 and
+  // (1 - (pitch + |fov_down|) / fov) H = pitch (-H / fov) + H (1 - |fov_down| / fov), constants
+  // rounded once (relative 6e-8: < 7e-5 px at W = 2048, < 2e-5 px at H = 128) -- a smaller
+  // deviation from the exact pipeline than the four-operation form the budget above was made for
+  const float px = __fmaf_rn(yaw, kx, 0.5f * g.Wf);
+  const float py = __fmaf_rn(pitch, ky, cy);
   const float fx = floorf(px), fy = floorf(py);
-  const bool ok = (px - fx > mx) && (fx + 1.0f - px > mx) && (py - fy > my) && (fy + 1.0f - py > my) &&
+  const float tx = px - fx, ty = py - fy;  // exact
+  const bool ok = tx > mx && tx < 1.0f - mx && ty > my && ty < 1.0f - my &&
                   fx >= 0.0f && fx <= g.Wf - 1.0f && fy >= 0.0f && fy <= g.Hf - 1.0f;
   return ok ? (int)(fy * g.Wf + fx) : -1;
 }
@@ -104,11 +109,12 @@ __device__ __forceinline__ int ground_cell_fast(const GroundGeom &g, float x, fl
   // <= min_dist -- were tried: the kernel got 3 % slower, the DSETPs are not on its critical path)
   if (!(radius < g.max_dist && radius > g.min_dist)) return -1;
   const float theta = (yaw == yaw) ? -yaw : fast_atan2f(y, x);
-  const float tb_f = (3.14159265f + theta) * g.inv_theta_step_f;
+  const float tb_f = __fmaf_rn(theta, g.inv_theta_step_f, 3.14159265f * g.inv_theta_step_f);
   const float rb_f = rf * g.inv_radial_step_f;
   const float fl = floorf(tb_f), flr = floorf(rb_f);
+  const float tt = tb_f - fl, tr = rb_f - flr;  // exact
   // margins: atan2f 3 ulp + fp32 evaluation < 2e-5 bins for up to 255 bins
-  if (!(tb_f - fl > 1e-3f && fl + 1.0f - tb_f > 1e-3f && rb_f - flr > 1e-3f && flr + 1.0f - rb_f > 1e-3f))
+  if (!(tt > 1e-3f && tt < 0.999f && tr > 1e-3f && tr < 0.999f))
     return ground_cell_of(g, x, y);
   int rb = (int)flr;
   int tb = (int)fl;
@@ -170,7 +176,11 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
   const GroundGeom gg = dp->gg;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float qnan = __int_as_float(0x7fc00000);
-  const float mx = pg.Wf * 2.5e-6f + 1e-3f, my = 2e-3f, inv_fov = 1.0f / pg.fov;
+  const float mx = pg.Wf * 2.5e-6f + 1e-3f, my = 2e-3f;
+  // coefficients of the fp32 pixel estimate (project_pixel_fast), from double
+  const float kx = (float)(0.5 * (double)pg.Wf / 3.14159265358979323846);
+  const float ky = (float)(-(double)pg.Hf / (double)pg.fov);
+  const float cy = (float)((double)pg.Hf * (1.0 - (double)pg.fov_down_abs / (double)pg.fov));
   auto issue_tile = [&](int tile_id, int buf) {  // one thread
     const int kk = tile_id / tiles, tt = tile_id - kk * tiles;
     const int n_pts = min(kSplitTile, N - tt * kSplitTile);
@@ -261,7 +271,7 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
     if (i < N) {
       pts[j] = ld_point(&s_in[buf][j * kThreads + threadIdx.x]);
       if (DO_PROJECT) {
-        pixr[j] = project_pixel_fast(pg, pts[j].x, pts[j].y, pts[j].z, mx, my, inv_fov, &yawr[j]);
+        pixr[j] = project_pixel_fast(pg, pts[j].x, pts[j].y, pts[j].z, mx, my, kx, ky, cy, &yawr[j]);
         if (pixr[j] < 0) s_slow[atomicAdd(&s_nslow, 1)] = j * kThreads + threadIdx.x;
         else if (DO_SPLIT) mk[j] = mask[kbase + pixr[j]];  // inference.cpp:242-243
       } else {
