@@ -176,6 +176,7 @@ static void derive(DevParams &d) {
   d.gg.TB = p.groundThetaBins;
   d.gg.inv_radial_step_f = (float)(1.0 / d.gg.radial_step);
   d.gg.inv_theta_step_f = (float)(1.0 / d.gg.theta_step);
+  ground_geom_thresholds(d.gg);  // exact r^2 thresholds of the radius tests and the radial bin (proj_math.h)
   auto sq_cut = [](float t) {
     if (!(t > 0.f)) return 0.f;  // sqrtf(s) < t never holds for s >= 0
     float s = t * t;

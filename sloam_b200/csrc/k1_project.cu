@@ -8,22 +8,29 @@
 // (sloam::binGroundPoints, sloam.cpp:339-358) while it is in registers, so
 // stage a3 never re-reads the cloud to bin it.
 //
-// HBM-bound streaming kernel.  Algorithmic bytes per keyframe: 16N points +
-// 1N mask + 4N pix + 4N range image + 16T tree points + N/8 tree bits + 17G ground
-// points and cell tags (T tree-labelled, G ground-labelled points).  Persistent CTAs (one per
-// resident slot) walk tiles of kSplitTile consecutive points of one keyframe; the points of
-// the next tile are fetched by one TMA bulk copy (cp.async.bulk + mbarrier) into the other
-// half of a shared-memory double buffer while the current tile is processed; stores are
-// coalesced float4.
+// HBM-bound streaming kernel by design (issue-bound as measured).  Algorithmic bytes per keyframe
+// of the fused path: 16N points + 1N mask + 4N range image + N/8 tree bits + 16T tree points +
+// 9G ground records and cell tags (T tree-labelled, G ground-labelled points).  Persistent CTAs
+// (one per resident slot) take tiles of kSplitTile consecutive points of one keyframe from a
+// global counter; the points of the next tile are fetched by one TMA bulk copy (cp.async.bulk +
+// mbarrier) into the other half of a shared-memory double buffer while the current tile is
+// processed.  The tile stays in shared memory for the whole iteration: the phases re-read the
+// points they need instead of holding 4 x float4 per thread in registers across barriers, and
+// a thread carries one packed word (pixel index + theta bin) and the mask byte per point.
 //
 // Ground layout: the ground points of tile t are written, in input order, to slots
 // [t * kSplitTile, t * kSplitTile + tile_count[t]) of the keyframe's ground array
-// ("tile-strided").  The order of the slots is the input order, which is all the ground
+// ("tile-strided") -- as 8-byte (z key, point index) records on the fused path, as points for
+// the stage entries.  The order of the slots is the input order, which is all the ground
 // stage needs (it bins and sorts by (z, slot)), so no CTA ever waits for another one: the
 // single-pass compaction with a look-back scan that this replaces serialised the tiles of
 // a keyframe.  Callers that want the contiguous cloud of Segmentation::maskCloud (the stage
 // entries, the intermediates) get it from ground_compact_kernel.
 #include "common.cuh"
+
+#ifndef SLOAM_K1_EXP
+#define SLOAM_K1_EXP 0  // timing experiments only (wrong results): 1 no mask gather, 2 no range atomics,
+#endif                  // 4 no ground stores, 8 no tree stores, 16 no ground cell arithmetic
 
 namespace sb {
 
@@ -97,39 +104,54 @@ __device__ __forceinline__ int project_pixel_fast(const ProjGeom &g, float x, fl
   return ok ? (int)(fy * g.Wf + fx) : -1;
 }
 
-// Same idea for the polar ground cell: the radius bin is evaluated exactly (one
-// fp64 division), the theta bin from atan2f with a margin of 1e-4 bins, falling
-// back to the exact ground_cell_of() next to a bin edge (~2e-4 of the points).
-// `yaw` is the fp32 estimate of -atan2f(y, x) from the projection (NaN when unknown).
-__device__ __forceinline__ int ground_cell_fast(const GroundGeom &g, float x, float y, float yaw) {
-  // pow_2 rounds the exact fp64 square of a float to float == the fp32 product
-  const float rf = sqrtf(x * x + y * y);  // bit-identical to euclideanDist2D (utils.h:9-12)
-  const double radius = (double)rf;
-  // (float thresholds with the same decisions -- the smallest float >= max_dist, the largest
-  // <= min_dist -- were tried: the kernel got 3 % slower, the DSETPs are not on its critical path)
-  if (!(radius < g.max_dist && radius > g.min_dist)) return -1;
-  const float theta = (yaw == yaw) ? -yaw : fast_atan2f(y, x);
+// Same idea for the polar ground cell.  The theta bin comes from the yaw estimate of the
+// projection with a margin of 1e-3 bins (255 = next to a bin edge or unknown: decide exactly);
+// it is computed for every point while the yaw is at hand and travels in the spare byte of the
+// pixel word, so that no per-point float has to stay alive until the ground phase.
+__device__ __forceinline__ unsigned theta_bin_fast(const GroundGeom &g, float theta) {
   const float tb_f = __fmaf_rn(theta, g.inv_theta_step_f, 3.14159265f * g.inv_theta_step_f);
-  const float rb_f = rf * g.inv_radial_step_f;
-  const float fl = floorf(tb_f), flr = floorf(rb_f);
-  const float tt = tb_f - fl, tr = rb_f - flr;  // exact
-  // margins: atan2f 3 ulp + fp32 evaluation < 2e-5 bins for up to 255 bins
-  if (!(tt > 1e-3f && tt < 0.999f && tr > 1e-3f && tr < 0.999f))
-    return ground_cell_of(g, x, y);
-  int rb = (int)flr;
+  const float fl = floorf(tb_f);
+  const float tt = tb_f - fl;  // exact
+  // margins: atan2 estimate + fp32 evaluation < 2e-5 bins for up to 255 bins; NaN fails
+  if (!(tt > 1e-3f && tt < 0.999f) || g.TB > 255) return 255u;
   int tb = (int)fl;
-  rb = rb < g.RB - 1 ? rb : g.RB - 1;
-  rb = rb > 0 ? rb : 0;
   tb = tb < g.TB - 1 ? tb : g.TB - 1;
   tb = tb > 0 ? tb : 0;
-  return rb * g.TB + tb;
+  return (unsigned)tb;
+}
+// The radius tests (sloam.cpp:344) and the radial bin are exact threshold comparisons on
+// r2 = x*x + y*y (proj_math.h): pow_2 rounds the exact fp64 square of a float to float == the
+// fp32 product, so r2 is the argument of euclideanDist2D's sqrtf (utils.h:9-12) -- no square
+// root, no double arithmetic, no fallback for the radial coordinate (up to four radial bins;
+// more: estimate with the exact ground_cell_of() next to a bin edge).
+__device__ __forceinline__ int ground_cell_fast(const GroundGeom &g, float x, float y, unsigned tbv) {
+  const float r2 = x * x + y * y;
+  int rb = 0;
+  if (g.r2_bins >= 0) {
+    rb = ground_radial_bin_of_r2(g, r2);  // the thresholds are warp-uniform values
+    if (rb < 0) return -1;
+  } else if (!(r2 >= g.r2_in_lo && r2 < g.r2_in_hi)) {
+    return -1;
+  }
+  if (tbv == 255u) return ground_cell_of(g, x, y);
+  if (g.r2_bins < 0) {
+    const float rb_f = sqrtf(r2) * g.inv_radial_step_f;
+    const float flr = floorf(rb_f), tr = rb_f - flr;
+    if (!(tr > 1e-3f && tr < 0.999f)) return ground_cell_of(g, x, y);
+    rb = (int)flr;
+    rb = rb < g.RB - 1 ? rb : g.RB - 1;
+    rb = rb > 0 ? rb : 0;
+  }
+  return rb * g.TB + (int)tbv;
 }
 
 #ifndef SLOAM_K1_MIN_CTAS
 // round 1 (separate scan + flush barriers): 4 -> 427 us, 5 -> 384 us, 6 -> 390 us per 1000 VLP-16 keyframes.
-// round 2 (double-buffered counts, 4 barriers per tile): 5 CTAs / 48 registers spill 120 bytes -> 400 us,
-// 4 CTAs / 64 registers no spill -> 367 us per 512 OS1-64 keyframes
-#define SLOAM_K1_MIN_CTAS 4
+// round 2, points held in registers across the phases: 5 CTAs / 48 registers spill 120 bytes -> 400 us,
+// 4 CTAs / 64 registers -> 367 us per 512 OS1-64 keyframes; points re-read from shared memory
+// (one packed word per point in registers): 4 CTAs 581 us, 5 CTAs / 48 registers 568 us per 1024
+// keyframes (641 us before); 6 do not fit (42 KB of shared memory per CTA)
+#define SLOAM_K1_MIN_CTAS 5
 #endif
 // FUSED (the production path, with DO_PROJECT and DO_SPLIT): the ground points are not copied.
 // Every ground point becomes one 8-byte record (z key, point index) in the tile-strided layout
@@ -176,7 +198,11 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
   const GroundGeom gg = dp->gg;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float qnan = __int_as_float(0x7fc00000);
+#ifdef SLOAM_K1_EXPERIMENT_NO_EXACT  // timing experiment only (wrong pixels next to boundaries)
+  const float mx = -1.0f, my = -1.0f;
+#else
   const float mx = pg.Wf * 2.5e-6f + 1e-3f, my = 2e-3f;
+#endif
   // coefficients of the fp32 pixel estimate (project_pixel_fast), from double
   const float kx = (float)(0.5 * (double)pg.Wf / 3.14159265358979323846);
   const float ky = (float)(-(double)pg.Hf / (double)pg.fov);
@@ -224,15 +250,7 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
   int *const s_hist = s_hist2 + (DO_SPLIT ? buf * kMaxCells : 0);
   int *const s_cnt = s_cnt2[buf];
   uint32_t *tree_bits_k = tree_bits ? tree_bits + (size_t)k * ((N + 31) >> 5) : nullptr;
-  if (threadIdx.x == 0) {
-    s_nslow = 0;
-    // the other buffer was last read two barriers ago (register loads of the previous tile)
-    s_tile_id[buf ^ 1] = fetched;
-    if (fetched < total_tiles) {
-      issue_tile(fetched, buf ^ 1);
-      fetched = atomicAdd(tile_ctr, 1);  // not needed before the next iteration
-    }
-  }
+  if (threadIdx.x == 0) s_nslow = 0;
   if (DO_SPLIT)
     for (int c = threadIdx.x; c < kMaxCells; c += kThreads) s_hist[c] = 0;
   {  // wait for this tile's points
@@ -246,36 +264,61 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
     }
   }
   __syncthreads();
+  if (threadIdx.x == 0) {
+    // every warp is past its last read of the other buffer (the ground points of the previous
+    // tile are re-read from it at the very end of an iteration): start the copy of the next tile
+    s_tile_id[buf ^ 1] = fetched;
+    if (fetched < total_tiles) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue_tile(fetched, buf ^ 1);
+      fetched = atomicAdd(tile_ctr, 1);  // not needed before the next iteration
+    }
+  }
   // the previous tile of this CTA is complete behind that barrier: hand over its cell counts
   if (DO_SPLIT && prev_k >= 0) flush_hist(s_hist2 + (buf ^ 1) * kMaxCells, prev_k, prev_tile);
   prev_k = k; prev_tile = tile;
 
-  // ---- phase A: the tile from shared memory (kRounds float4 per thread stay in registers) and project.
+  // ---- phase A: project every point of the tile.
   // The pixel index is an integer derived from atan2f/asinf; the bit-exact evaluation
   // (proj_math.h, fp64) is ~230 DP instructions, so it only runs for the ~1.5 % of points
   // whose fast fp32 estimate lies within a proven error margin of a pixel boundary.
   // Those are queued and re-projected densely in phase B instead of diverging here.
-  sloam_point pts[kRounds];
-  int pixr[kRounds];
-  float yawr[kRounds];
-  // the mask byte of a point is fetched as soon as its pixel is known, so that the gather's
-  // latency runs under phase B and its barriers instead of in front of the ballots of phase C
+  // The points themselves are NOT kept in registers: the tile stays in shared memory until the
+  // end of the iteration and the later phases re-read what they need (one LDS.128).  What a
+  // thread carries per point is one word -- the pixel index in the low 24 bits (kSlowPix =
+  // queued) and the theta bin of the ground grid in the high 8 (255 = decide exactly) -- and
+  // the mask byte, fetched as soon as the pixel is known so that the gather's latency runs
+  // under phase B and its barriers.
+  constexpr unsigned kSlowPix = 0xFFFFFFu;
+  unsigned pixr[kRounds];
   unsigned char mk[kRounds];
+  const sloam_point *s_pts = &s_in[buf][0];
 #pragma unroll
   for (int j = 0; j < kRounds; ++j) {
     const int i = tile * kSplitTile + j * kThreads + threadIdx.x;
-    pts[j] = sloam_point{0.f, 0.f, 0.f, 0.f};
-    pixr[j] = 0;
-    yawr[j] = qnan;
+    pixr[j] = 0u;
     mk[j] = 0;
     if (i < N) {
-      pts[j] = ld_point(&s_in[buf][j * kThreads + threadIdx.x]);
       if (DO_PROJECT) {
-        pixr[j] = project_pixel_fast(pg, pts[j].x, pts[j].y, pts[j].z, mx, my, kx, ky, cy, &yawr[j]);
-        if (pixr[j] < 0) s_slow[atomicAdd(&s_nslow, 1)] = j * kThreads + threadIdx.x;
-        else if (DO_SPLIT) mk[j] = mask[kbase + pixr[j]];  // inference.cpp:242-243
+        const sloam_point p = ld_point(s_pts + j * kThreads + threadIdx.x);
+        float yaw;
+        const int pix = project_pixel_fast(pg, p.x, p.y, p.z, mx, my, kx, ky, cy, &yaw);
+        const unsigned tbv = DO_SPLIT ? theta_bin_fast(gg, -yaw) : 0u;
+        pixr[j] = (tbv << 24) | (pix < 0 ? kSlowPix : (unsigned)pix);
+        if (pix < 0) {
+          s_slow[atomicAdd(&s_nslow, 1)] = j * kThreads + threadIdx.x;
+        } else {
+          if (DO_SPLIT) mk[j] = (SLOAM_K1_EXP & 1) ? (unsigned char)((pix & 3) == 0 ? 1 : ((pix & 31) == 1 ? 255 : 0))
+                                                   : mask[kbase + pix];  // inference.cpp:242-243
+          // closest point wins (inference.cpp:135,160-162): minimum over the bit pattern of the
+          // non-negative SQUARED range (sqrtf is monotone, so the same point wins); the one
+          // square root per pixel is taken by range_finalize_kernel.  NaN ranges never write.
+          const float range_sq = p.x * p.x + p.y * p.y + p.z * p.z;
+          if (!(SLOAM_K1_EXP & 2) && range_bits != nullptr && range_sq == range_sq)
+            atomicMin(&range_bits[kbase + pix], __float_as_uint(range_sq));
+        }
       } else {
-        pixr[j] = pix_io[kbase + i];
+        pixr[j] = (unsigned)pix_io[kbase + i];
       }
     }
   }
@@ -285,7 +328,7 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
     const int ns = s_nslow;
     for (int q = threadIdx.x; q < ns; q += kThreads) {
       const int idx = s_slow[q];
-      const sloam_point p = ld_point(&s_in[buf][idx]);
+      const sloam_point p = ld_point(s_pts + idx);
       float range;
       s_pix[idx] = project_pixel(pg, p.x, p.y, p.z, &range);
     }
@@ -294,28 +337,26 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
     for (int j = 0; j < kRounds; ++j) {
       const int i = tile * kSplitTile + j * kThreads + threadIdx.x;
       if (i < N) {
-        if (pixr[j] < 0) {
-          pixr[j] = s_pix[j * kThreads + threadIdx.x];
-          if (DO_SPLIT) mk[j] = mask[kbase + pixr[j]];
+        if ((pixr[j] & kSlowPix) == kSlowPix) {  // a queued point: same steps as above with the exact pixel
+          const int pix = s_pix[j * kThreads + threadIdx.x];
+          pixr[j] = (pixr[j] & 0xFF000000u) | (unsigned)pix;
+          if (DO_SPLIT) mk[j] = mask[kbase + pix];
+          const sloam_point p = ld_point(s_pts + j * kThreads + threadIdx.x);
+          const float range_sq = p.x * p.x + p.y * p.y + p.z * p.z;
+          if (!(SLOAM_K1_EXP & 2) && range_bits != nullptr && range_sq == range_sq)
+            atomicMin(&range_bits[kbase + pix], __float_as_uint(range_sq));
         }
         // FUSED: the pixel indices (proj_xs / proj_ys, which the reference keeps only for
-        // maskCloud, inference.cpp:131-132) feed the mask gather below and are not stored;
+        // maskCloud, inference.cpp:131-132) feed the mask gather and are not stored;
         // sloam_b200_get_intermediates recomputes them on demand
-        if (!FUSED) pix_io[kbase + i] = pixr[j];
-        // closest point wins (inference.cpp:135,160-162): minimum over the bit pattern of the
-        // non-negative SQUARED range (sqrtf is monotone, so the same point wins); the one
-        // square root per pixel is taken by range_finalize_kernel.  NaN ranges never write.
-        const float range_sq = pts[j].x * pts[j].x + pts[j].y * pts[j].y + pts[j].z * pts[j].z;
-        if (range_bits != nullptr && range_sq == range_sq)
-          atomicMin(&range_bits[kbase + pixr[j]], __float_as_uint(range_sq));
+        if (!FUSED) pix_io[kbase + i] = (int)(pixr[j] & kSlowPix);
       }
     }
   }
 
-  // ---- phase C: mask gather, dense tree cloud, order-preserving ground compaction
+  // ---- phase C: dense tree cloud, order-preserving ground compaction
   if (!DO_SPLIT) { __syncthreads(); continue; }
-  // all mask gathers of the thread are issued back to back; the (round, warp) ballot counts
-  // give every ground point its slot in input order
+  // the (round, warp) ballot counts give every ground point its slot in input order
   unsigned bal[kRounds];
   unsigned gmask = 0;  // bit j: point j of this thread is ground
 #pragma unroll
@@ -328,9 +369,9 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
     // (fused pipeline) only the tree points are written; tree_bits says which pixels hold one
     // and the NaN points are materialised on demand (pipeline.cu).
     const bool is_t = in && (m == 255);
-    if (in && (is_t || !sparse_tree)) {
+    if (!(SLOAM_K1_EXP & 8) && in && (is_t || !sparse_tree)) {
       sloam_point t;
-      if (is_t) t = pts[j];
+      if (is_t) t = ld_point(s_pts + j * kThreads + threadIdx.x);
       else { t.x = qnan; t.y = qnan; t.z = qnan; t.intensity = 0.f; }
       st_point(tree + kbase + i, t);
     }
@@ -359,19 +400,21 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
       }
     }
   }
-  // ground points go straight from registers to their slots: the ground lanes of a warp
-  // own consecutive slots, so the 16-byte stores of a warp form contiguous runs
+  // ground points go straight to their slots: the ground lanes of a warp own consecutive
+  // slots, so the stores of a warp form contiguous runs
   sloam_point *gout = FUSED ? nullptr : ground + (size_t)k * ground_stride + (size_t)tile * kSplitTile;
   uint2 *rout = FUSED ? ground_recs + kbase + (size_t)tile * kSplitTile : nullptr;
   uint8_t *cout = ground_cell + (size_t)k * ground_stride + (size_t)tile * kSplitTile;
 #pragma unroll
   for (int j = 0; j < kRounds; ++j) {
     if ((gmask >> j) & 1u) {
-      const sloam_point p = pts[j];
+      const sloam_point p = ld_point(s_pts + j * kThreads + threadIdx.x);
       const int slot = unit_base[j] + __popc(bal[j] & ((1u << lane) - 1u));
-      const int cell = ground_cell_fast(gg, p.x, p.y, yawr[j]);
+      const unsigned tbv = DO_PROJECT ? (pixr[j] >> 24) : theta_bin_fast(gg, fast_atan2f(p.y, p.x));
+      const int cell = (SLOAM_K1_EXP & 16) ? (slot & 31) : ground_cell_fast(gg, p.x, p.y, tbv);
       // FUSED: the point itself is not copied -- an 8-byte (z key, point index) record is all the
       // ground stage sorts; it reads the few retained points from the input cloud
+      if (SLOAM_K1_EXP & 4) { if (cell >= 0) atomicAdd(&s_hist[cell], 1); continue; }
       if (FUSED) rout[slot] = make_uint2(float_key(p.z), (unsigned)(tile * kSplitTile + j * kThreads + threadIdx.x));
       else st_point(gout + slot, p);
       cout[slot] = (uint8_t)(cell < 0 ? 255 : cell);

@@ -7,6 +7,9 @@
 // include/sloam_b200_detmath.h.  Compiled with --fmad=false.
 #pragma once
 
+#include <cmath>
+#include <cstring>
+
 #include "../../include/sloam_b200_detmath.h"
 
 namespace sb {
@@ -45,6 +48,14 @@ struct GroundGeom {
   double theta_step;          // 2 * PIDEF / groundThetaBins
   int RB, TB;
   float inv_radial_step_f, inv_theta_step_f;  // for the fp32 estimate in k1_project.cu
+  // The radius tests and the radial bin as EXACT thresholds on r2 = x*x + y*y (fp32, the argument
+  // of the reference's sqrtf, utils.h:9-12): sqrtf is monotone, so every decision that
+  // ground_cell_of() takes on (double)sqrtf(r2) is one comparison of r2 with the smallest float
+  // for which the decision flips (found by bisection over the float bit patterns, ctx.cu).
+  float r2_in_lo;   // min{s : sqrtf(s) > min_dist}
+  float r2_in_hi;   // min{s : !(sqrtf(s) < max_dist)}
+  float r2_bin[3];  // r2_bin[j-1] = min{s : floor(sqrtf(s) / radial_step) >= j}, j = 1 .. RB-1; +inf beyond
+  int r2_bins;      // RB - 1 when RB <= 4, else -1: radial bin by estimate + exact fallback
 };
 
 // Polar cell (rb * TB + tb) of a ground point seen from the origin, or -1 when
@@ -65,6 +76,41 @@ SLOAM_HD int ground_cell_of(const GroundGeom &g, float x, float y) {
   tb = tb < g.TB - 1 ? tb : g.TB - 1;
   tb = tb > 0 ? tb : 0;
   return rb * g.TB + tb;
+}
+
+// Radial part of ground_cell_of() from r2 = x*x + y*y by the thresholds of GroundGeom:
+// -1 outside (min_dist, max_dist), else the clamped radial bin.  Only valid when g.r2_bins >= 0.
+SLOAM_HD int ground_radial_bin_of_r2(const GroundGeom &g, float r2) {
+  if (!(r2 >= g.r2_in_lo && r2 < g.r2_in_hi)) return -1;
+  const int rb = ((r2 >= g.r2_bin[0]) ? 1 : 0) + ((r2 >= g.r2_bin[1]) ? 1 : 0) + ((r2 >= g.r2_bin[2]) ? 1 : 0);
+  return rb < g.RB - 1 ? rb : g.RB - 1;
+}
+
+// Host only: fills the r2 thresholds from max_dist / min_dist / radial_step / RB.  Each is the
+// smallest non-negative float (+inf included) for which a monotone predicate on sqrtf(s) holds,
+// found by bisection over the bit patterns (non-negative floats order like their bits).
+template <class Pred>
+inline float sloam_first_float(Pred pred) {
+  unsigned lo = 0u, hi = 0x7f800000u;  // pred(+inf) holds for all uses below
+  while (lo < hi) {
+    const unsigned mid = lo + (hi - lo) / 2;
+    float f;
+    std::memcpy(&f, &mid, 4);
+    if (pred(f)) hi = mid; else lo = mid + 1;
+  }
+  float f;
+  std::memcpy(&f, &lo, 4);
+  return f;
+}
+inline void ground_geom_thresholds(GroundGeom &g) {
+  const double mn = g.min_dist, mx = g.max_dist, step = g.radial_step;
+  g.r2_in_lo = sloam_first_float([&](float s) { return (double)sqrtf(s) > mn; });
+  g.r2_in_hi = sloam_first_float([&](float s) { return !((double)sqrtf(s) < mx); });
+  g.r2_bins = (g.RB <= 4 && step > 0.0) ? g.RB - 1 : -1;
+  for (int j = 1; j <= 3; ++j)
+    g.r2_bin[j - 1] = (g.r2_bins >= j)
+        ? sloam_first_float([&](float s) { return floor((double)sqrtf(s) / step) >= (double)j; })
+        : INFINITY;
 }
 
 }  // namespace sb

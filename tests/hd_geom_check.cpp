@@ -36,6 +36,21 @@ void hd_ground_cells(const sloam_params *p, const sloam_point *pts, int n, int32
   g.inv_theta_step_f = (float)(1.0 / g.theta_step);
   for (int i = 0; i < n; ++i) cell[i] = ground_cell_of(g, pts[i].x, pts[i].y);
 }
+// the radial decisions of the same points from the r^2 thresholds (what project_split_kernel's
+// fast path uses): -1 outside the radius range, else the radial bin; -2 when RB > 4 (no thresholds)
+void hd_ground_radial_by_threshold(const sloam_params *p, const sloam_point *pts, int n, int32_t *rb) {
+  GroundGeom g;
+  g.max_dist = p->maxGroundLidarDist;
+  g.min_dist = p->minGroundLidarDist;
+  g.radial_step = p->maxGroundLidarDist / (double)p->groundRadiiBins;
+  g.theta_step = 2 * 3.14159265 / (double)p->groundThetaBins;
+  g.RB = p->groundRadiiBins;
+  g.TB = p->groundThetaBins;
+  g.inv_radial_step_f = g.inv_theta_step_f = 0.f;
+  ground_geom_thresholds(g);
+  for (int i = 0; i < n; ++i)
+    rb[i] = g.r2_bins < 0 ? -2 : ground_radial_bin_of_r2(g, pts[i].x * pts[i].x + pts[i].y * pts[i].y);
+}
 // angleCheck && heightCheck (sloam.cpp:401-409) as plane_finish_kernel evaluates it
 int hd_plane_accept(const sloam_pose *pose, const double *plane, const double *centroid, double tol) {
   return plane_accept(*pose, plane, centroid, tol) ? 1 : 0;

@@ -87,6 +87,48 @@ def test_ground_cells_match_the_oracle(hg, oracle, RB, TB, dmin, dmax):
     assert total.sum() < n and total.min() > 0
 
 
+@pytest.mark.parametrize("RB,TB,dmin,dmax", [(2, 18, 5.0, 25.0), (1, 18, 0.0, 30.0), (3, 7, 2.5, 40.0), (4, 36, 0.7, 12.3),
+                                              (4, 9, 1.0, 1e-3 + 33.333), (5, 18, 1.0, 20.0)])
+def test_radius_thresholds_equal_the_exact_radial_decisions(hg, oracle, RB, TB, dmin, dmax):
+    """project_split_kernel decides the radius tests and the radial bin by comparing
+    r2 = x*x + y*y with precomputed float thresholds (proj_math.h: ground_geom_thresholds).
+    They must give the decisions of the exact ground_cell_of() for every point -- here on
+    random radii and on the floats around every threshold radius (min, max, bin edges)."""
+    rng = np.random.default_rng(RB * 1000 + TB)
+    p = oracle.default_params(groundRadiiBins=RB, groundThetaBins=TB, minGroundLidarDist=dmin,
+                              maxGroundLidarDist=dmax, max_prev_planes=max(64, RB * TB))
+    edges = np.array([dmin, dmax] + [dmax / RB * j for j in range(1, RB)], np.float64)
+    near = []
+    for e in edges:                                   # +-64 floats around each edge radius
+        f = np.float32(e)
+        lo = f
+        for _ in range(64):
+            lo = np.nextafter(lo, np.float32(-np.inf))
+        xs = [lo]
+        for _ in range(128):
+            xs.append(np.nextafter(xs[-1], np.float32(np.inf)))
+        near.append(np.array(xs, np.float32))
+    near = np.concatenate(near)
+    r = np.concatenate([near, rng.uniform(0.0, dmax * 1.2, 100_000).astype(np.float32)])
+    # three families with different rounding of x*x + y*y: on an axis, on the diagonal, random
+    th = np.concatenate([np.zeros(near.size), rng.uniform(-np.pi, np.pi, 100_000)])
+    xyz = [np.stack([r * np.cos(th), r * np.sin(th), np.zeros(r.size)], 1),
+           np.stack([near / np.sqrt(2.0), near / np.sqrt(2.0), np.zeros(near.size)], 1),
+           np.stack([np.zeros(near.size), -near, np.zeros(near.size)], 1)]
+    pts = _points(np.concatenate(xyz).astype(np.float32))
+    n = pts.shape[0]
+    cell = np.zeros(n, np.int32)
+    rb = np.zeros(n, np.int32)
+    hg.hd_ground_cells(C.byref(p), abi.ptr(pts), n, abi.ptr(cell))
+    hg.hd_ground_radial_by_threshold(C.byref(p), abi.ptr(pts), n, abi.ptr(rb))
+    want = np.where(cell < 0, -1, cell // TB)
+    if RB > 4:                                        # no thresholds: the kernel uses estimate + exact fallback
+        assert (rb == -2).all()
+        return
+    assert np.array_equal(rb, want)
+    assert (want == -1).any() and all((want == j).any() for j in range(RB))
+
+
 def test_plane_acceptance_matches_the_oracle(hg, oracle):
     """The acceptance test (FromTwoVectors -> eulerAngles(0,1,2) -> tolerance, and the height
     check) decides which cells become planes; tilted grounds around the 0.1 rad tolerance and
