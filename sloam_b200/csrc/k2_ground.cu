@@ -666,7 +666,10 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
 // QR preconditioner; plane_finish_kernel finishes the 3 x 3 SVD.  Kept apart from the selection
 // so that the selection runs without the fit's registers and shared memory (twice the warps
 // per SM), and so that cells redone by the replay instance are fitted here like all others.
-__global__ void __launch_bounds__(32, 24)
+#ifndef SLOAM_FIT_MIN
+#define SLOAM_FIT_MIN 32  // 64 registers: fit + finish 156 -> 137 us per 1024 OS1-64 keyframes (24 CTAs: 80 registers)
+#endif
+__global__ void __launch_bounds__(32, SLOAM_FIT_MIN)
 ground_fit_kernel(const DevParams *__restrict__ dp, const sloam_point *__restrict__ ground, int stride,
                   const SelKey *__restrict__ members2, double *__restrict__ qscratch, float *__restrict__ pscratch,
                   FitRec *__restrict__ fit, sloam_point *__restrict__ cell_features) {
