@@ -508,6 +508,23 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
     for (int i = tid; i < n_c; i += kGThreads) s_z[i] = src[i].z;
   }
   CELL_SYNC();
+  // key range of the cell (selecting instance): the radix select below works on key - kmin,
+  // whose significant bits are few (a cell's z values span centimetres to metres), instead of
+  // on the raw key, whose top two bytes are nearly the same for every member
+  uint32_t kmin = 0u, krange = 0xFFFFFFFFu;
+  if (!REPLAY && do_sort) {
+    uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+    for (int i = tid; i < n_c; i += kGThreads) {
+      const uint32_t z = zc ? s_z[i] : list[i].z;
+      lo = min(lo, z); hi = max(hi, z);
+    }
+    if (kGThreads == 32) {
+      lo = __reduce_min_sync(kFull, lo); hi = __reduce_max_sync(kFull, hi);
+    } else {
+      for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(kFull, lo, o)); hi = max(hi, __shfl_xor_sync(kFull, hi, o)); }
+    }
+    kmin = lo; krange = hi - lo;
+  }
 
   // ---- select the r lowest (z, j) keys ----
   // kept records: in place in shared memory, or in the second member array for oversized
@@ -541,15 +558,21 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
       }
     }
   } else if (do_sort) {
-    // 8-bit MSD radix select on z for the r-th smallest (rank r-1)
+    // MSD radix select on (z key - kmin) for the r-th smallest (rank r-1): digits of up to 8
+    // bits from the highest significant bit of the range downwards, so the first pass already
+    // spreads the members over the bins (few shared-memory atomic conflicts) and a range of
+    // 2^22 keys -- 1 m of spread at |z| = 2 m -- takes three passes
     uint32_t prefix = 0, pmask = 0;
     int want = r - 1;  // 0-based rank among members matching the prefix
-    for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int top = 32 - __clz(krange | 1u); top > 0;) {
+      const int shift = top > 8 ? top - 8 : 0;
+      const uint32_t dmask = (1u << (top - shift)) - 1u;
+      top = shift;
       for (int b = tid; b < 256; b += kGThreads) s_hist[b] = 0;
       CELL_SYNC();
       for (int i = tid; i < n_c; i += kGThreads) {
-        const uint32_t z = zc ? s_z[i] : list[i].z;
-        if ((z & pmask) == prefix) atomicAdd(&s_hist[(z >> shift) & 0xFF], 1);
+        const uint32_t z = (zc ? s_z[i] : list[i].z) - kmin;
+        if ((z & pmask) == prefix) atomicAdd(&s_hist[(z >> shift) & dmask], 1);
       }
       CELL_SYNC();
       if (warp == 0) {  // bin that holds rank `want`: 8 bins per lane + a warp scan
@@ -571,11 +594,11 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
       }
       CELL_SYNC();
       prefix |= (uint32_t)s_misc[2] << shift;
-      pmask |= 0xFFu << shift;
+      pmask |= dmask << shift;
       want = s_misc[3];
       CELL_SYNC();
     }
-    const uint32_t pivot = prefix;   // z key of the r-th smallest
+    const uint32_t pivot = kmin + prefix;  // z key of the r-th smallest
     const int tie_quota = want + 1;  // members with z == pivot to keep, lowest j first
     // order-preserving compaction (the list is in j order, so ties come lowest j first)
     int kept = 0, ties_seen = 0;
