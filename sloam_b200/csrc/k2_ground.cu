@@ -589,14 +589,45 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
         if (excl <= want && want < inc) {  // exactly one lane
           int acc = excl, d = 0;
           for (; d < 7; ++d) { if (acc + loc[d] > want) break; acc += loc[d]; }
-          s_misc[2] = lane * 8 + d; s_misc[3] = want - acc;
+          s_misc[2] = lane * 8 + d; s_misc[3] = want - acc; s_misc[4] = s_hist[lane * 8 + d];
         }
       }
       CELL_SYNC();
       prefix |= (uint32_t)s_misc[2] << shift;
       pmask |= dmask << shift;
       want = s_misc[3];
+      const int in_bin = s_misc[4];
       CELL_SYNC();
+      if (kGThreads == 32 && top > 0 && in_bin <= 32) {
+        // At most a warp's worth of members left in the bin that holds the r-th smallest: finish
+        // among them directly instead of by further passes over the whole cell.  The candidates
+        // are collected in list order (one pass, ballots), every lane ranks its candidate among
+        // them with ties by list position, and the lane with rank `want` holds the pivot key.
+        int nc = 0;
+        for (int base = 0; base < n_c; base += 32) {
+          const int i = base + lane;
+          uint32_t z = 0;
+          bool hit = false;
+          if (i < n_c) { z = (zc ? s_z[i] : list[i].z) - kmin; hit = (z & pmask) == prefix; }
+          const unsigned bh = __ballot_sync(kFull, hit);
+          if (hit) s_hist[nc + __popc(bh & ((1u << lane) - 1u))] = (int)z;  // the histogram is consumed
+          nc += __popc(bh);
+        }
+        __syncwarp();
+        const uint32_t ck = lane < nc ? (uint32_t)s_hist[lane] : 0xFFFFFFFFu;
+        int rank = 0;
+        for (int m = 0; m < nc; ++m) {
+          const uint32_t km = __shfl_sync(kFull, ck, m);
+          rank += (km < ck || (km == ck && m < lane)) ? 1 : 0;
+        }
+        const unsigned bp = __ballot_sync(kFull, lane < nc && rank == want);  // exactly one lane
+        const uint32_t pk = __shfl_sync(kFull, ck, __ffs(bp) - 1);
+        const int lower = __popc(__ballot_sync(kFull, lane < nc && ck < pk));
+        prefix = pk;           // the full (offset) key of the r-th smallest
+        want -= lower;         // its position among the members with that key, in list order
+        top = 0;
+        __syncwarp();
+      }
     }
     const uint32_t pivot = kmin + prefix;  // z key of the r-th smallest
     const int tie_quota = want + 1;  // members with z == pivot to keep, lowest j first
