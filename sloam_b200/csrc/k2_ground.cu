@@ -500,12 +500,13 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
   // ---- the members (z key, input index), in input order: contiguous in `members` ----
   SelKey *src = members + (size_t)k * stride + off_all;
   SelKey *list = src;
+  uint32_t zlo = 0xFFFFFFFFu, zhi = 0u;  // key range of this lane's members (selecting instance)
   const bool zc = !REPLAY && n_c <= kZCap;  // z keys cached in shared memory
   if (REPLAY && n_c <= kCap) {
     list = s_list;
     for (int i = tid; i < n_c; i += kGThreads) s_list[i] = src[i];
   } else if (zc) {
-    for (int i = tid; i < n_c; i += kGThreads) s_z[i] = src[i].z;
+    for (int i = tid; i < n_c; i += kGThreads) { const uint32_t z = src[i].z; s_z[i] = z; zlo = min(zlo, z); zhi = max(zhi, z); }
   }
   CELL_SYNC();
   // key range of the cell (selecting instance): the radix select below works on key - kmin,
@@ -513,11 +514,9 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
   // on the raw key, whose top two bytes are nearly the same for every member
   uint32_t kmin = 0u, krange = 0xFFFFFFFFu;
   if (!REPLAY && do_sort) {
-    uint32_t lo = 0xFFFFFFFFu, hi = 0u;
-    for (int i = tid; i < n_c; i += kGThreads) {
-      const uint32_t z = zc ? s_z[i] : list[i].z;
-      lo = min(lo, z); hi = max(hi, z);
-    }
+    uint32_t lo = zlo, hi = zhi;  // gathered while the keys were copied to shared memory
+    if (!zc)
+      for (int i = tid; i < n_c; i += kGThreads) { const uint32_t z = list[i].z; lo = min(lo, z); hi = max(hi, z); }
     if (kGThreads == 32) {
       lo = __reduce_min_sync(kFull, lo); hi = __reduce_max_sync(kFull, hi);
     } else {
