@@ -359,8 +359,15 @@ cc_label_kernel(const DevParams *__restrict__ dp, const uint32_t *__restrict__ b
   }
   __syncthreads();
   // -- flatten, component sizes at the root
-  for (int r = threadIdx.x; r < R; r += kLblThreads) par[r] = uf_find(par, r);
-  __syncthreads();
+  // (finds and stores in separate phases, so that no find ever reads an entry another thread is
+  // rewriting -- harmless here, parents only move towards the root, but a reported race)
+  for (int r0 = 0; r0 < R; r0 += kLblThreads) {
+    const int r = r0 + threadIdx.x;
+    const int root = r < R ? uf_find(par, r) : 0;
+    __syncthreads();
+    if (r < R) par[r] = root;
+    __syncthreads();
+  }
   for (int r = threadIdx.x; r < R; r += kLblThreads) atomicAdd(&siz[par[r]], (uint32_t)len[r]);
   __syncthreads();
   // -- PCL label of every root (number of roots before it) and slot of every big component
@@ -630,14 +637,18 @@ __device__ __forceinline__ bool vertex_group(const DevParams *dp, GrpSmem &s, bo
   }
   const int lx = (int)fx, ly = (int)fy, lz = (int)fz;
   const bool mem = gl < n;
-  // z order; two members with the same count (an exact tie) collide on one slot: detected below
-  if (mem) s.ord[g0 + lz] = (int8_t)gl;
+  // z order.  Without ties the counts of an item's n members are a permutation of 0 .. n-1; two
+  // members with the same count are an exact z tie.  One REDUX over the warp ORs the bit
+  // (item's field + count) of every member: an item is tie-free iff its field has n bits set.
+  // Items with a tie do not write the order here (their members would collide on a slot).
+  const unsigned occ = __reduce_or_sync(kFull, mem ? (1u << (g0 + lz)) : 0u);
+  const unsigned field = G == 32 ? occ : ((occ >> g0) & ((1u << G) - 1u));
+  const bool ztie = __popc(field) != n;
+  if (mem && !ztie) s.ord[g0 + lz] = (int8_t)gl;
   unsigned bx = __ballot_sync(kFull, mem && lx == middle) & gmask;
   unsigned by = __ballot_sync(kFull, mem && ly == middle) & gmask;
   unsigned bz = __ballot_sync(kFull, mem && lz == middle) & gmask;
   __syncwarp();
-  const bool lost = mem && s.ord[g0 + lz] != (int8_t)gl;
-  const bool ztie = (__ballot_sync(kFull, lost) & gmask) != 0u;
   // a tie group straddling a median leaves no member with count == middle: stable ranks
   // (value, then index) decide, like a stable sort would (the median VALUE is what matters)
   if (__any_sync(kFull, active && (bx == 0u || by == 0u || bz == 0u))) {
@@ -757,7 +768,9 @@ __device__ bool build_vertex(const DevParams *dp, VtxSmem &s, unsigned long long
     if (REPLAY) {
       any_xtie |= __ballot_sync(kFull, m < n && ex > 1);
       any_ytie |= __ballot_sync(kFull, m < n && ey > 1);
-      if (m < n) { perm[lx] = (int16_t)m; perm[kVtxCap + ly] = (int16_t)m; }  // x / y order if tie-free
+      // x / y order, used only when that axis is tie-free (tied members would collide on a slot)
+      if (m < n && ex == 1) perm[lx] = (int16_t)m;
+      if (m < n && ey == 1) perm[kVtxCap + ly] = (int16_t)m;
     }
     const unsigned bx = __ballot_sync(kFull, m < n && lx == middle);
     const unsigned by = __ballot_sync(kFull, m < n && ly == middle);
