@@ -25,7 +25,7 @@ ncu --set full --clock-control none --import-source on -k "$K" -s 12 -c 12 -o $O
     python bench.py --lanes 1 --steps 1 --warmup 1 --cpu-seconds 0.05 --no-kernel-profile > $O/${TAG}_ncu_top.log 2>&1
 ncu --set full --clock-control none --import-source on -k 'regex:cylinder_kernel|cc_label' -s 2 -c 2 -o $O/${TAG}_dense \
     python bench.py --workload os1-64-dense --lanes 1 --steps 1 --warmup 1 --cpu-seconds 0.05 --no-kernel-profile > $O/${TAG}_ncu_dense.log 2>&1
-ncu --set full --clock-control none --import-source on -k 'regex:assoc' -s 1 -c 1 -o $O/${TAG}_assoc \
+ncu --set full --clock-control none --import-source on -k 'regex:assoc_kernel' -s 1 -c 1 -o $O/${TAG}_assoc \
     python bench.py --workload assoc-100k --steps 1 --warmup 1 --cpu-seconds 0.05 > $O/${TAG}_ncu_assoc.log 2>&1
 for r in top dense assoc; do
   python scripts/ncu_table.py $O/${TAG}_$r.ncu-rep > $O/${TAG}_ncu_$r.md 2>&1
