@@ -30,7 +30,7 @@
 
 #ifndef SLOAM_K1_EXP
 #define SLOAM_K1_EXP 0  // timing experiments only (wrong results): 1 no mask gather, 2 no range atomics,
-#endif                  // 4 no ground stores, 8 no tree stores, 16 no ground cell arithmetic
+#endif                  // 4 no ground stores, 8 no tree stores, 16 no ground cell arithmetic, 32 no projection
 
 namespace sb {
 
@@ -302,7 +302,7 @@ project_split_kernel(const DevParams *__restrict__ dp, int K, const sloam_point 
       if (DO_PROJECT) {
         const sloam_point p = ld_point(s_pts + j * kThreads + threadIdx.x);
         float yaw;
-        const int pix = project_pixel_fast(pg, p.x, p.y, p.z, mx, my, kx, ky, cy, &yaw);
+        const int pix = (SLOAM_K1_EXP & 32) ? ((yaw = p.x), i) : project_pixel_fast(pg, p.x, p.y, p.z, mx, my, kx, ky, cy, &yaw);
         const unsigned tbv = DO_SPLIT ? theta_bin_fast(gg, -yaw) : 0u;
         pixr[j] = (tbv << 24) | (pix < 0 ? kSlowPix : (unsigned)pix);
         if (pix < 0) {
