@@ -31,6 +31,7 @@
 
 #include "common.cuh"
 #include "dev_stdsort.h"
+#include "dev_warpsort.cuh"
 
 namespace sb {
 
@@ -578,6 +579,29 @@ __device__ __noinline__ void replay_sorts_packed(int16_t *order, unsigned long l
   for (int m = 0; m < n; ++m) order[m] = (int16_t)(pack[m] & 0xFFFFFFFFull);
 }
 
+// The same three sorts with the whole warp (dev_warpsort.cuh): records (key bits, member) in
+// `a`, sorted into `b` and back; lq / rq are the 64-entry stopper queues of the partition.
+static __device__ void replay_sorts_warp(int16_t *order, SelKey *a, SelKey *b, int *lq, int *rq, int n, int first,
+                                  const int16_t *init, const float *x, const float *y, const float *z) {
+  const int lane = threadIdx.x & 31;
+  const float *keys[3] = {x, y, z};
+  for (int m = lane; m < n; m += 32) {
+    const unsigned idx = first == 0 ? (unsigned)m : (unsigned)init[m];
+    a[m] = SelKey{__float_as_uint(keys[first][idx]), idx};
+  }
+  __syncwarp();
+  for (int ax = first; ax < 3; ++ax) {
+    if (ax > first) {
+      for (int m = lane; m < n; m += 32) a[m].z = __float_as_uint(keys[ax][a[m].j]);
+      __syncwarp();
+    }
+    warp_sort_prefix(a, n, n, b, lq, rq);  // std::sort(a, a + n): every position is needed
+    SelKey *t = a; a = b; b = t;
+  }
+  for (int m = lane; m < n; m += 32) order[m] = (int16_t)a[m].j;
+  __syncwarp();
+}
+
 // pixel of member m of an item whose members are spread over several runs (rare: a row of a
 // trunk split by a gap): walk the runs of the row between the first and the last one
 __device__ __forceinline__ int member_pixel(const VItem &it, int m, const int32_t *__restrict__ pix0_k,
@@ -722,7 +746,8 @@ __device__ __forceinline__ bool vertex_group(const DevParams *dp, GrpSmem &s, bo
 // must be redone by the REPLAY = true instance (nothing was written)
 template <bool REPLAY>
 __device__ bool build_vertex(const DevParams *dp, VtxSmem &s, unsigned long long *pack, int16_t *perm, int n,
-                             int row, sloam_vertex *out, sloam_point *pool, int base) {
+                             int row, sloam_vertex *out, sloam_point *pool, int base,
+                             SelKey *pack2 = nullptr, int *lq = nullptr, int *rq = nullptr) {
   const int lane = threadIdx.x & 31;
   const int middle = (int)(n / 2.0);  // trellis.cpp:66
   // Order statistics by counting: member m counts the members strictly below it on each
@@ -813,7 +838,9 @@ __device__ bool build_vertex(const DevParams *dp, VtxSmem &s, unsigned long long
       if (!REPLAY) return true;
       __syncwarp();
       const int first = any_ytie ? (any_xtie ? 0 : 1) : 2;
-      if (lane == 0) replay_sorts_packed(s.order, pack, n, first, first == 1 ? perm : perm + kVtxCap, s.x, s.y, s.z);
+      const int16_t *init = first == 1 ? perm : perm + kVtxCap;
+      if (pack2 != nullptr) replay_sorts_warp(s.order, reinterpret_cast<SelKey *>(pack), pack2, lq, rq, n, first, init, s.x, s.y, s.z);
+      else if (lane == 0) replay_sorts_packed(s.order, pack, n, first, init, s.x, s.y, s.z);
     } else
     for (int m = lane; m < n; m += 32) {
       const float xm = s.x[m], ym = s.y[m], zm = s.z[m];
@@ -976,6 +1003,8 @@ vertex_replay_kernel(const DevParams *__restrict__ dp, const sloam_point *__rest
   __shared__ __align__(16) VtxSmem sm[kVtxWarps];
   __shared__ unsigned long long s_pack[kVtxWarps * kVtxCap];  // replay scratch
   __shared__ int16_t s_perm[kVtxWarps * 2 * kVtxCap];         // members in x and in y order
+  __shared__ SelKey s_pack2[kVtxWarps * kVtxCap];             // second record array of the warp sort
+  __shared__ int s_lq[kVtxWarps][64], s_rq[kVtxWarps][64];    // its stopper queues
   const int N = dp->N, H = dp->p.img_h, T = dp->p.max_trees;
   const int item_shift = dp->vw_row_bits + dp->vw_slot_bits;
   const int warp = threadIdx.x >> 5;
@@ -990,7 +1019,7 @@ vertex_replay_kernel(const DevParams *__restrict__ dp, const sloam_point *__rest
     gather_members(dp, s, it, k, tree, run_pix0, run_info);
     sloam_vertex *out = slot_vertices + ((size_t)k * T + it.slot) * H + it.row;
     build_vertex<true>(dp, s, s_pack + warp * kVtxCap, s_perm + warp * 2 * kVtxCap, it.n, it.row, out,
-                       pool + (size_t)k * N, item_pool[gid]);
+                       pool + (size_t)k * N, item_pool[gid], s_pack2 + warp * kVtxCap, s_lq[warp], s_rq[warp]);
     __syncwarp();
   }
 }
