@@ -14,8 +14,11 @@ step give 0.78 / 0.93 / 1.04 of its throughput).
 
     os1-64        BASELINE metric workload (default)
     vlp-16        configs[1]: VLP-16 sequence, 1000 keyframes per step
-    os1-64-dense  configs[2]: 300 trees, 4096 RANSAC hypotheses per tree (fixed-count mode)
-    os1-128       configs[3]: OS1-128 2048 columns (the multi-GPU sequence; here per-GPU batches)
+    os1-64-dense  configs[2]: 300 trees, 4096 RANSAC hypotheses per tree (fixed-count mode), 256 keyframes per
+                  step (64 / 128 per step: 0.56 / 0.77 of its throughput -- the per-keyframe and per-tree
+                  kernels need that many to fill the GPU)
+    os1-128       configs[3]: OS1-128 2048 columns (the multi-GPU sequence; here per-GPU batches of 512;
+                  128 / 256 per step: 0.81 / 0.94)
     assoc-100k    configs[4]: association only, 100k map cylinders x 2k detections per keyframe
 
 Under torchrun (N > 1) every rank processes its own B keyframes (weak scaling, no data-path
@@ -45,9 +48,9 @@ WORKLOADS = {
     # name: (preset in sloam_b200/configs.py, default keyframes per step and GPU, metric, BASELINE config)
     "os1-64": ("os1-64", 1024, METRIC_OS1_64, "metric workload: configs[0]'s OS1-64 64x1024 scene (20 trees + ground), batched"),
     "vlp-16": ("vlp-16", 1000, "keyframes/sec (VLP-16 synthetic forest)", "configs[1]: VLP-16 sequence, 1000 keyframes, 50-tree scene"),
-    "os1-64-dense": ("os1-64-dense", 64, "keyframes/sec (OS1-64 dense synthetic forest, 4096 RANSAC hypotheses/tree)",
+    "os1-64-dense": ("os1-64-dense", 256, "keyframes/sec (OS1-64 dense synthetic forest, 4096 RANSAC hypotheses/tree)",
                      "configs[2]: OS1-64 dense forest, 300 trees, 4096 hypotheses per tree"),
-    "os1-128": ("os1-128", 128, "keyframes/sec (OS1-128 2048-column synthetic forest)", "configs[3]: OS1-128 2048-col sequence (per-GPU batch)"),
+    "os1-128": ("os1-128", 512, "keyframes/sec (OS1-128 2048-column synthetic forest)", "configs[3]: OS1-128 2048-col sequence (per-GPU batch)"),
     "assoc-100k": (None, 8, "keyframes/sec (data association only: 100k map cylinders, 2k detections/keyframe)",
                    "configs[4]: 100k cylinder landmarks, 2k detections per keyframe"),
 }
