@@ -40,8 +40,10 @@ namespace sb {
 #endif
 constexpr int kVtxWarps = SLOAM_VTX_WARPS;
 constexpr int kVtxCap = 128;   // members per (cluster,row) handled by the warp path
-constexpr int kLblThreads = 512;
-constexpr int kLblWarps = kLblThreads / 32;
+// cc_label_kernel runs with 512 threads per keyframe, or with 1024 when the image is so large
+// that shared memory, not threads, limits the CTAs per SM (OS1-128: 749 -> 471 us per 512
+// keyframes; OS1-64 is 3 % slower with 1024, so it keeps 512 and four CTAs per SM)
+constexpr int kLblThreads = 512, kLblThreadsMax = 1024;
 constexpr unsigned kSlotMask = 0x7FFu;  // slot code (slot + 1, 0 = none) in the low 11 bits of packed words
 
 // work item of the vertex stage: the members of one component in one row
@@ -224,6 +226,7 @@ cc_rows_kernel(const DevParams *__restrict__ dp, int K, const sloam_point *__res
 // ---- 2. per keyframe: runs, union-find, labels, work items -------------------
 // exclusive scan of one int per thread over the CTA; *total = sum.  s_tmp: kLblWarps + 1 ints
 __device__ __forceinline__ int cta_scan_excl(int v, int *s_tmp, int *total) {
+  const int kLblWarps = (int)(blockDim.x >> 5);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int inc = v;
 #pragma unroll
@@ -266,7 +269,7 @@ __device__ __forceinline__ uint32_t bits_at(const uint32_t *s_plane, int Nw, int
   return b ? ((lo >> b) | (hi << (32 - b))) : lo;
 }
 
-__global__ void __launch_bounds__(kLblThreads)
+__global__ void __launch_bounds__(kLblThreadsMax)
 cc_label_kernel(const DevParams *__restrict__ dp, const uint32_t *__restrict__ bits,
                 const uint4 *__restrict__ planes, int Rs, int32_t *__restrict__ g_par,
                 uint32_t *__restrict__ g_siz, int32_t *__restrict__ g_len, int32_t *__restrict__ run_pix0,
@@ -286,7 +289,8 @@ cc_label_kernel(const DevParams *__restrict__ dp, const uint32_t *__restrict__ b
   int32_t *s_wbase = reinterpret_cast<int32_t *>(s_start + Nw);        // [Nw]
   uint32_t *s_rows = reinterpret_cast<uint32_t *>(s_wbase + Nw);       // [T * Hw]
   int32_t *s_runs = reinterpret_cast<int32_t *>(s_rows + (size_t)T * Hw);  // 3 x [Rs]
-  __shared__ int s_tmp[kLblWarps + 1];
+  __shared__ int s_tmp[kLblThreadsMax / 32 + 1];
+  const int kLblThreads = (int)blockDim.x, kLblWarps = kLblThreads >> 5;  // 512 or 1024 (run_cc)
   __shared__ int s_nitems, s_pool;
   __shared__ int s_ccnt[kClsWide + 1], s_cbase[kClsWide + 1];
   const uint32_t *bk = bits + (size_t)k * Nw;
@@ -1250,7 +1254,10 @@ static int run_cc(sloam_ctx *c, int K, const sloam_point *tree, bool bits_ready,
   }
   const long long list_cap = (long long)c->max_k * T * p.img_h;
   PROF_BEGIN(c, P_CC_LABEL);
-  cc_label_kernel<<<K, kLblThreads, smem, c->stream>>>(
+  // four 512-thread CTAs per SM fit up to 54 KB each (label_smem_runs sizes the run arrays for
+  // that when it can); a larger image gets 1024 threads per keyframe
+  const int lbl_threads = smem <= 54 * 1024 ? kLblThreads : kLblThreadsMax;
+  cc_label_kernel<<<K, lbl_threads, smem, c->stream>>>(
       c->dp, w.tree_bits, reinterpret_cast<const uint4 *>(w.cc_planes), Rs, w.run_par, reinterpret_cast<uint32_t *>(w.run_siz),
       w.run_len, w.run_pix0, w.run_info, w.run_label, want_labels ? w.cc_wbase : nullptr, w.n_roots, w.n_big,
       w.big_rank, w.kf_flags, w.slot_rows, reinterpret_cast<VItem *>(w.vitems), w.vitem_pool, w.vlists, list_cap,
