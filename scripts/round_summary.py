@@ -58,7 +58,7 @@ if os.path.exists(ls):
             "`synth_*` generate the input, `project_split<0,1,0>` / `<1,0,0>`, `tree_fill`, `ground_compact` belong to the "
             "un-fused intermediates call that `bench.py` uses once for its label statistics):", "", "```"]
     out += open(ls).read().rstrip().splitlines() + ["```", ""]
-for r, title in (("top", "OS1-64, 1024 keyframes, one lane"), ("dense", "OS1-64 dense forest (configs[2]), 64 keyframes"),
+for r, title in (("top", "OS1-64, 1024 keyframes, one lane"), ("dense", "OS1-64 dense forest (configs[2])"),
                  ("assoc", "association only (configs[4])")):
     p = os.path.join(G, f"{tag}_ncu_{r}.md")
     if os.path.exists(p):
