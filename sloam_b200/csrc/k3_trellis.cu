@@ -1219,8 +1219,10 @@ static int label_smem_runs(const sloam_ctx *c) {
   long long r = std::max(1024ll, std::min(std::min(rs, 16384ll), fit));
   // four CTAs (the thread limit) instead of three per SM when that still leaves room for one
   // run per 32 pixels: a batch of 512 keyframes is then one wave of CTAs instead of two
+  // (not for a context sized for several times more trees than that leaves room for: a dense
+  // forest really has that many runs, and runs beyond the capacity live in global memory)
   const long long four = (54 * 1024 - fixed) / 12;
-  if (four < r && four >= c->hp.N / 32) r = four;
+  if (four < r && four >= c->hp.N / 32 && by_trees <= 2 * four) r = four;
   return (int)r;
 }
 
