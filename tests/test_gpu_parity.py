@@ -336,6 +336,54 @@ def test_compute_graph_edge_cases(capi, oracle):
     assert out["ntr"][0] == 0 and out["ntr"][1] == 1
 
 
+def test_vertex_tie_replay_stress(capi, oracle):
+    """Rows of 17 .. 128 members whose x, y and z values come from small value sets, so that
+    each of the three std::sort calls of computeVertexProperties (trellis.cpp:71-82) meets tie
+    groups of random sizes in random positions -- the case where the order of the kept points,
+    the radius and which points survive the centroid filter depend on libstdc++'s introsort
+    (SURVEY B-3; warp-parallel replay, dev_warpsort.cuh).  Every row of every blob is one
+    vertex; a wide max_dist_to_centroid keeps most points so that their order is compared."""
+    H, W = 32, 768
+    p = capi.default_params(img_h=H, img_w=W, min_cluster_points=20, min_tree_vertices=4,
+                            max_dist_to_centroid=0.5)
+    rng = np.random.default_rng(20260018)
+    clouds = []
+    for scene in range(6):
+        c = np.zeros(H * W, abi.POINT)
+        c["x"] = c["y"] = c["z"] = np.nan
+        col0 = 8
+        for blob in range(5):
+            width = int(rng.integers(17, 129))
+            for r in range(3, 3 + int(rng.integers(8, 24))):
+                n = int(rng.integers(max(17, width - 12), width + 1))
+                # 0: distinct, 1: pairs, 2: a handful of values, 3: one value
+                kinds = rng.integers(0, 4, 3)
+                axes = []
+                for a, kind in enumerate(kinds):
+                    base = [4.0, 0.3 * blob, 2.5 - 0.05 * r][a]
+                    step = [2e-3, 2e-3, 1e-4][a]
+                    if kind == 0:
+                        v = base + step * rng.permutation(n)
+                    elif kind == 1:
+                        v = base + step * (rng.permutation(n) // 2)
+                    elif kind == 2:
+                        v = base + step * rng.integers(0, int(rng.integers(2, 9)), n)
+                    else:
+                        v = np.full(n, base)
+                    axes.append(v.astype(np.float32))
+                i0 = r * W + col0
+                c["x"][i0:i0 + n], c["y"][i0:i0 + n], c["z"][i0:i0 + n] = axes
+            col0 += width + 8
+        clouds.append(c)
+    out = run_graph(capi, p, clouds)
+    n_vertices = 0
+    for k, c in enumerate(clouds):
+        exp = oracle.compute_graph(p, c)
+        compare_graph(capi, (out["trees"][k], out["ntr"][k], out["verts"][k], out["vpts"][k]), exp)
+        n_vertices += int(out["trees"][k]["n_vertices"][:out["ntr"][k]].sum())
+    assert n_vertices > 200
+
+
 # ------------------------------------------------------------------- stage a8..a10
 def run_models(capi, oracle, p, pts, mask, poses):
     """Oracle front end (projection, split, graph, planes) -> GPU vs oracle cylinders."""
