@@ -12,14 +12,17 @@
 // ground_scatter_kernel moves the records, one WARP per 1024-point tile, no barriers, no
 // atomics.  Caller-supplied clouds (stage entry): ground_bin_kernel, one CTA per keyframe.
 // ground_cells_kernel: one warp per (keyframe, cell) reads its members contiguously, selects
-// the r lowest z with an 8-bit radix select (ties by input order), sorts only those r, and
-// fits the plane:
+// the r lowest z with a radix select on (key - kmin) whose digits start at the top significant
+// bit of the cell's key range and which finishes among the members of the target bin once that
+// holds at most 32 (ties by input order), and sorts only those r; ground_fit_kernel (one warp
+// per cell with enough retained points) fits the plane:
 //   - centroid: float32 sequential sum in sorted order (utils.h:14-28), one lane;
 //   - 3 x n JacobiSVD: column-pivoted Householder QR of the n x 3 adjoint with
 //     warp-shuffle reductions, then the 3x3 two-sided Jacobi of dev_plane.h
 //     (plane_finish_kernel, one thread per cell).
 // Cells whose result depends on how libstdc++'s unstable std::sort orders exact z ties
-// (SURVEY B-3) are redone by a second instance that replays that sort (dev_stdsort.h).
+// (SURVEY B-3) are redone by a second instance that replays that sort with the whole warp
+// (dev_warpsort.cuh; dev_stdsort.h is the single-thread replay it must agree with).
 // Algorithmic bytes: 17 G in, 8 G member records, B * (72 + 16 F_g) out per keyframe.
 #include "common.cuh"
 #include "dev_plane.h"
@@ -299,7 +302,7 @@ ground_cells_kernel(const DevParams *__restrict__ dp, const sloam_point *__restr
   __shared__ SelKey s_list[kCap];
   __shared__ int s_lq[REPLAY ? 64 : 1], s_rq[REPLAY ? 64 : 1];  // stopper queues of warp_partition
   // the selecting instance keeps only what its passes re-read in shared memory: the z keys of
-  // the cell (4 radix passes) and the r kept records (rank sort); the member records
+  // the cell (the radix passes) and the r kept records (rank sort); the member records
   // themselves are streamed from global memory once, by the compaction
   constexpr int kZCap = REPLAY ? 1 : 2 * kSelCap, kKeepCap = REPLAY ? 1 : 128;
   __shared__ uint32_t s_z_[kW][kZCap];
